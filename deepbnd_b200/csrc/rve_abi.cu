@@ -1,0 +1,730 @@
+// rve_abi.cu — C-ABI of librve_b200.so (declared in include/rve_b200.h).
+// Host side: batch set-up, uploads, the PCG driver loop, epilogue downloads.  No torch types, no
+// CPU fallback: every entry point fails with RVE_E_CUDA if the device is unusable.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "rve_kernels.cuh"
+#include "rve_symbolic.hpp"
+
+namespace {
+
+thread_local std::string g_create_err;
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DBuf() { release(); }
+};
+
+}  // namespace
+
+struct rve_batch_s {
+    int device = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // host-side batch description
+    int n_sys = 0, model = 0, vref_nb = 0, nvref = 0;
+    bool have_batch = false, assembled = false, solved = false;
+    int K = 0, NL = 0;  // solver rhs count, load count of the last solve
+    Mat8 mat;
+    double vref_box[4];
+    std::vector<SysSym> sym;
+    std::vector<int> node_base, elem_base, row_base, bnd_base, bedge_base;
+    std::vector<long long> blk_base;
+    long long N = 0, E = 0, R = 0, NB = 0, NBN = 0, NBE = 0;
+    int n_chunks = 0;
+    int ncx = 0, ncy = 0;
+    Levels LV;
+    // device arrays
+    DBuf<double> node_xy, row_xy, box, bval, dinv, wmean, bnd_s, bedge_nl, samp_lam;
+    DBuf<int> node_row, node_bnd, node_sys, elem_node, elem_sys, bcol, d_row_base, cell_ptr, bnd_sys, bnd_node,
+        bedge, d_bedge_base, samp_elem, chunk_sys, chunk_row0, chunk_n, sys_chunk0, active, cnt, d_iters, n_active,
+        err_flag;
+    DBuf<unsigned char> elem_reg;
+    DBuf<unsigned> row_ptr;
+    DBuf<double> lvA[RVE_MAXLEV], lvD[RVE_MAXLEV], lvR[RVE_MAXLEV], lvX[RVE_MAXLEV], lvT[RVE_MAXLEV];
+    DBuf<double> p, q, x, r, b, part, sc;
+    DBuf<double> eps, eps_eff, Bmat, uD, gval, d_vbox, U, acc, sigL, sigT, aout, Bout, sol, Mx, Gaff, aaff;
+    DBuf<double> MWt, transl, Yd;
+    int* h_nactive = nullptr;  // pinned
+    std::vector<cudaEvent_t> evpool;  // per-iteration SpMV timing
+    double launches = 0;              // kernels launched since rve_create
+    double h2d_bytes = 0, d2h_bytes = 0;  // host<->device traffic since rve_create
+    double t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double c_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+#define H_CHECK(h)                                        \
+    if (!(h)) return RVE_E_ARG;                           \
+    if (cudaSetDevice((h)->device) != cudaSuccess) { (h)->err = "cudaSetDevice failed"; return RVE_E_CUDA; }
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return RVE_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+#define FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#define UPL(d, v) do { CU(upload((d), (v), st)); h->h2d_bytes += (double)(v).size() * sizeof((v)[0]); } while (0)
+
+template <class T>
+static cudaError_t upload(DBuf<T>& d, const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = d.alloc(v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+static ChunkTab chunk_tab(rve_batch_s* h) {
+    ChunkTab ct;
+    ct.chunk_sys = h->chunk_sys.p; ct.chunk_row0 = h->chunk_row0.p; ct.chunk_n = h->chunk_n.p;
+    ct.sys_chunk0 = h->sys_chunk0.p;
+    return ct;
+}
+
+extern "C" {
+
+int rve_create(int device, rve_handle_t* out) {
+    if (!out) return RVE_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return RVE_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return RVE_E_ARG; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return RVE_E_CUDA; }
+    rve_batch_s* h = new rve_batch_s();
+    h->device = device;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e); delete h; return RVE_E_CUDA;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+    cudaMallocHost((void**)&h->h_nactive, sizeof(int));
+    memset(&h->LV, 0, sizeof(Levels));
+    *out = h;
+    return 0;
+}
+
+int rve_destroy(rve_handle_t h) {
+    if (!h) return RVE_E_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
+    if (h->h_nactive) cudaFreeHost(h->h_nactive);
+    cudaStream_t s = h->stream;
+    delete h;
+    if (s) cudaStreamDestroy(s);
+    return 0;
+}
+
+const char* rve_last_error(rve_handle_t h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const int64_t* tri_off,
+                  const double* xy, const int32_t* tri, const int32_t* region, const double* mat,
+                  int32_t model, int32_t vref_nb, const double* vref_box) {
+    H_CHECK(h);
+    if (n_sys <= 0 || !vert_off || !tri_off || !xy || !tri || !region || !mat) FAIL(RVE_E_ARG, "null/empty argument");
+    if (model < RVE_MODEL_LIN || model > RVE_MODEL_MR) FAIL(RVE_E_ARG, "unknown model");
+    if (vref_nb != 0 && vref_nb < 2) FAIL(RVE_E_ARG, "vref_nb must be 0 or >= 2");
+    auto t0 = std::chrono::steady_clock::now();
+    h->have_batch = h->assembled = h->solved = false;
+    h->n_sys = n_sys; h->model = model; h->vref_nb = vref_nb;
+    h->nvref = vref_nb > 0 ? 4 * (vref_nb - 1) + 1 : 0;
+    for (int k = 0; k < 8; ++k) h->mat.v[k] = mat[k];
+    h->sym.clear();
+    h->sym.resize(n_sys);
+    std::vector<SysSym>& S = h->sym;
+    parallel_for(n_sys, [&](int s) {
+        sym_pass1(S[s], xy + 2 * vert_off[s], tri + 3 * tri_off[s], region + tri_off[s],
+                  (int)(vert_off[s + 1] - vert_off[s]), (int)(tri_off[s + 1] - tri_off[s]));
+    });
+    double ext = 0, Lx = 0, Ly = 0;
+    for (int s = 0; s < n_sys; ++s) {
+        if (!S[s].err.empty()) FAIL(RVE_E_MESH, "system " + std::to_string(s) + ": " + S[s].err);
+        ext = std::max(ext, S[s].max_ext);
+        if (s == 0) { Lx = S[s].box[2]; Ly = S[s].box[3]; }
+        else if (std::fabs(S[s].box[2] - Lx) > 1e-9 * Lx || std::fabs(S[s].box[3] - Ly) > 1e-9 * Ly)
+            FAIL(RVE_E_MESH, "all systems of a batch must share the box size");
+    }
+    SymParams P;
+    P.model = model; P.vref_nb = vref_nb; P.vref_box_given = vref_box != nullptr;
+    for (int k = 0; k < 4; ++k) P.vref_box[k] = vref_box ? vref_box[k] : 0.0;
+    P.ncx = pick_nc(Lx, ext); P.ncy = pick_nc(Ly, ext);
+    h->ncx = P.ncx; h->ncy = P.ncy;
+    parallel_for(n_sys, [&](int s) { sym_pass2(S[s], P); });
+    for (int s = 0; s < n_sys; ++s)
+        if (!S[s].err.empty()) FAIL(RVE_E_MESH, "system " + std::to_string(s) + ": " + S[s].err);
+    for (int k = 0; k < 4; ++k) h->vref_box[k] = vref_box ? vref_box[k] : S[0].box[k];
+
+    // prefix sums
+    h->node_base.assign(n_sys + 1, 0); h->elem_base.assign(n_sys + 1, 0); h->row_base.assign(n_sys + 1, 0);
+    h->bnd_base.assign(n_sys + 1, 0); h->bedge_base.assign(n_sys + 1, 0); h->blk_base.assign(n_sys + 1, 0);
+    std::vector<int> sys_chunk0(n_sys + 1, 0);
+    for (int s = 0; s < n_sys; ++s) {
+        long long nn = (long long)h->node_base[s] + S[s].nn, ne = (long long)h->elem_base[s] + S[s].nt;
+        long long nr = (long long)h->row_base[s] + S[s].na;
+        long long nb = h->blk_base[s] + (long long)S[s].bcol.size();
+        if (nn > 2000000000LL || ne > 2000000000LL || nr * 4 > 2000000000LL || nb > 4000000000LL)
+            FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
+        h->node_base[s + 1] = (int)nn; h->elem_base[s + 1] = (int)ne; h->row_base[s + 1] = (int)nr;
+        h->bnd_base[s + 1] = h->bnd_base[s] + S[s].nb; h->bedge_base[s + 1] = h->bedge_base[s] + S[s].nbe;
+        h->blk_base[s + 1] = nb;
+        sys_chunk0[s + 1] = sys_chunk0[s] + (S[s].na + RVE_CH - 1) / RVE_CH;
+    }
+    h->N = h->node_base[n_sys]; h->E = h->elem_base[n_sys]; h->R = h->row_base[n_sys];
+    h->NB = h->blk_base[n_sys]; h->NBN = h->bnd_base[n_sys]; h->NBE = h->bedge_base[n_sys];
+    h->n_chunks = sys_chunk0[n_sys];
+
+    // flatten (parallel over systems)
+    std::vector<double> node_xy(2 * h->N), row_xy(2 * h->R), box(4 * (size_t)n_sys), bnd_s, bedge_nl(2 * h->NBE), samp_lam;
+    std::vector<int> node_row(h->N), node_bnd(h->N), node_sys(h->N), elem_node(6 * h->E), elem_sys(h->E), bcol(h->NB),
+        cell_ptr((size_t)n_sys * (P.ncx * P.ncy + 1)), bnd_sys(h->NBN), bnd_node(h->NBN), bedge(3 * h->NBE), samp_elem,
+        chunk_sys(h->n_chunks), chunk_row0(h->n_chunks), chunk_n(h->n_chunks);
+    std::vector<unsigned char> elem_reg(h->E);
+    std::vector<unsigned> row_ptr(h->R + 1);
+    if (model == RVE_MODEL_DNN) bnd_s.resize(2 * h->NBN);
+    if (h->nvref) { samp_elem.resize((size_t)n_sys * h->nvref); samp_lam.resize(2 * (size_t)n_sys * h->nvref); }
+    parallel_for(n_sys, [&](int s) {
+        const SysSym& Y = S[s];
+        const int nb0 = h->node_base[s], eb0 = h->elem_base[s], rb0 = h->row_base[s];
+        const long long bb0 = h->blk_base[s];
+        for (int k = 0; k < 4; ++k) box[4 * (size_t)s + k] = Y.box[k];
+        for (int n = 0; n < Y.nn; ++n) {
+            node_xy[2 * ((size_t)nb0 + n)] = Y.node_xy[2 * n]; node_xy[2 * ((size_t)nb0 + n) + 1] = Y.node_xy[2 * n + 1];
+            node_row[nb0 + n] = Y.node_row[n] < 0 ? -1 : rb0 + Y.node_row[n];
+            node_bnd[nb0 + n] = Y.node_bnd[n] < 0 ? -1 : h->bnd_base[s] + Y.node_bnd[n];
+            node_sys[nb0 + n] = s;
+        }
+        for (int t = 0; t < Y.nt; ++t) {
+            for (int k = 0; k < 6; ++k) elem_node[6 * ((size_t)eb0 + t) + k] = nb0 + Y.elem_node[6 * t + k];
+            elem_reg[eb0 + t] = Y.reg[t]; elem_sys[eb0 + t] = s;
+        }
+        for (int r = 0; r < Y.na; ++r) {
+            row_xy[2 * ((size_t)rb0 + r)] = Y.node_xy[2 * Y.row_node[r]];
+            row_xy[2 * ((size_t)rb0 + r) + 1] = Y.node_xy[2 * Y.row_node[r] + 1];
+            row_ptr[rb0 + r] = (unsigned)(bb0 + Y.row_ptr[r]);
+        }
+        if (s == n_sys - 1) row_ptr[h->R] = (unsigned)h->NB;
+        for (size_t k = 0; k < Y.bcol.size(); ++k) bcol[bb0 + k] = rb0 + Y.bcol[k];
+        for (size_t k = 0; k < Y.cell_ptr.size(); ++k) cell_ptr[(size_t)s * (P.ncx * P.ncy + 1) + k] = Y.cell_ptr[k];
+        for (int i = 0; i < Y.nb; ++i) {
+            bnd_sys[h->bnd_base[s] + i] = s; bnd_node[h->bnd_base[s] + i] = nb0 + Y.bnd_node[i];
+            if (model == RVE_MODEL_DNN) {
+                bnd_s[2 * ((size_t)h->bnd_base[s] + i)] = Y.bnd_s[2 * i]; bnd_s[2 * ((size_t)h->bnd_base[s] + i) + 1] = Y.bnd_s[2 * i + 1];
+            }
+        }
+        for (int i = 0; i < Y.nbe; ++i) {
+            for (int k = 0; k < 3; ++k) bedge[3 * ((size_t)h->bedge_base[s] + i) + k] = nb0 + Y.bedge[3 * i + k];
+            bedge_nl[2 * ((size_t)h->bedge_base[s] + i)] = Y.bedge_nl[2 * i];
+            bedge_nl[2 * ((size_t)h->bedge_base[s] + i) + 1] = Y.bedge_nl[2 * i + 1];
+        }
+        for (int k = 0; k < h->nvref; ++k) {
+            samp_elem[(size_t)s * h->nvref + k] = eb0 + Y.samp_elem[k];
+            samp_lam[2 * ((size_t)s * h->nvref + k)] = Y.samp_lam[2 * k];
+            samp_lam[2 * ((size_t)s * h->nvref + k) + 1] = Y.samp_lam[2 * k + 1];
+        }
+        int c = sys_chunk0[s];
+        for (int r = 0; r < Y.na; r += RVE_CH, ++c) {
+            chunk_sys[c] = s; chunk_row0[c] = rb0 + r; chunk_n[c] = std::min(RVE_CH, Y.na - r);
+        }
+    });
+    auto t1 = std::chrono::steady_clock::now();
+    h->t_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+
+    cudaStream_t st = h->stream;
+    UPL(h->node_xy, node_xy); UPL(h->row_xy, row_xy); UPL(h->box, box);
+    UPL(h->node_row, node_row); UPL(h->node_bnd, node_bnd); UPL(h->node_sys, node_sys);
+    UPL(h->elem_node, elem_node); UPL(h->elem_sys, elem_sys); UPL(h->elem_reg, elem_reg);
+    UPL(h->row_ptr, row_ptr); UPL(h->bcol, bcol); UPL(h->d_row_base, h->row_base);
+    UPL(h->cell_ptr, cell_ptr); UPL(h->bnd_sys, bnd_sys); UPL(h->bnd_node, bnd_node);
+    UPL(h->bnd_s, bnd_s); UPL(h->bedge, bedge); UPL(h->bedge_nl, bedge_nl);
+    UPL(h->d_bedge_base, h->bedge_base); UPL(h->samp_elem, samp_elem); UPL(h->samp_lam, samp_lam);
+    UPL(h->chunk_sys, chunk_sys); UPL(h->chunk_row0, chunk_row0); UPL(h->chunk_n, chunk_n);
+    UPL(h->sys_chunk0, sys_chunk0);
+    std::vector<double> vb(h->vref_box, h->vref_box + 4);
+    UPL(h->d_vbox, vb);
+    CU(h->bval.alloc(4 * (size_t)h->NB)); CU(h->dinv.alloc(4 * (size_t)h->R)); CU(h->wmean.alloc(h->R));
+    CU(h->active.alloc(n_sys)); CU(h->cnt.alloc(n_sys)); CU(h->d_iters.alloc(n_sys)); CU(h->n_active.alloc(1));
+    CU(h->err_flag.alloc(1));
+    CU(h->part.alloc((size_t)h->n_chunks * 8)); CU(h->sc.alloc((size_t)n_sys * 4 * SC_N));
+    CU(h->Mx.alloc((size_t)n_sys * 16)); CU(h->Gaff.alloc((size_t)n_sys * 16)); CU(h->aaff.alloc((size_t)n_sys * 8));
+    CU(h->acc.alloc((size_t)n_sys * ACC_PER_SYS));
+    // coarse hierarchy
+    Levels& LV = h->LV;
+    memset(&LV, 0, sizeof(Levels));
+    int ncx = P.ncx, ncy = P.ncy, L = 0;
+    while (L < RVE_MAXLEV) {
+        Grid& g = LV.g[L];
+        g.ncx = ncx; g.ncy = ncy; g.nx = ncx + 1; g.ny = ncy + 1; g.G = g.nx * g.ny;
+        g.wrap = (model == RVE_MODEL_PER);
+        if (model == RVE_MODEL_LIN || model == RVE_MODEL_DNN) { g.lox = 1; g.loy = 1; g.hix = ncx - 1; g.hiy = ncy - 1; }
+        else if (model == RVE_MODEL_PER) { g.lox = 0; g.loy = 0; g.hix = ncx - 1; g.hiy = ncy - 1; }
+        else { g.lox = 0; g.loy = 0; g.hix = ncx; g.hiy = ncy; }
+        CU(h->lvA[L].alloc((size_t)n_sys * 100 * g.G)); CU(h->lvD[L].alloc((size_t)n_sys * 4 * g.G));
+        CU(h->lvR[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2)); CU(h->lvX[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2));
+        CU(h->lvT[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2));
+        LV.A[L] = h->lvA[L].p; LV.dinv[L] = h->lvD[L].p; LV.rc[L] = h->lvR[L].p; LV.xc[L] = h->lvX[L].p; LV.tc[L] = h->lvT[L].p;
+        ++L;
+        if ((ncx % 2) || (ncy % 2) || ncx / 2 < 2 || ncy / 2 < 2) break;
+        ncx /= 2; ncy /= 2;
+    }
+    LV.L = L;
+    CU(cudaStreamSynchronize(st));
+    auto t2 = std::chrono::steady_clock::now();
+    h->t_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    h->have_batch = true;
+    return 0;
+}
+
+int rve_assemble(rve_handle_t h) {
+    H_CHECK(h);
+    if (!h->have_batch) FAIL(RVE_E_STATE, "rve_assemble before rve_set_batch");
+    cudaStream_t st = h->stream;
+    CU(cudaEventRecord(h->ev[0], st));
+    CU(cudaMemsetAsync(h->bval.p, 0, h->bval.n * sizeof(double), st));
+    CU(cudaMemsetAsync(h->wmean.p, 0, h->wmean.n * sizeof(double), st));
+    CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), st));
+    k_assemble<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, h->elem_node.p, h->elem_reg.p, h->node_xy.p, h->node_row.p,
+                                               h->row_ptr.p, h->bcol.p, h->bval.p, h->wmean.p, h->mat);
+    k_dinv<<<cdiv(h->R, 256), 256, 0, st>>>((int)h->R, h->row_ptr.p, h->bcol.p, h->bval.p, h->dinv.p);
+    CU(cudaEventRecord(h->ev[1], st));
+    // two-level preconditioner: Galerkin hierarchy
+    Levels& LV = h->LV;
+    for (int l = 0; l < LV.L; ++l) CU(cudaMemsetAsync(LV.A[l], 0, h->lvA[l].n * sizeof(double), st));
+    k_galerkin1<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
+                                                h->node_row.p, h->box.p, LV.g[0], LV.A[0], h->mat, h->err_flag.p);
+    for (int l = 0; l + 1 < LV.L; ++l) {
+        long long n = (long long)h->n_sys * LV.g[l + 1].G * 25;
+        k_galerkin_coarse<<<cdiv(n, 256), 256, 0, st>>>(h->n_sys, LV.g[l], LV.g[l + 1], LV.A[l], LV.A[l + 1]);
+    }
+    for (int l = 0; l < LV.L; ++l) {
+        long long n = (long long)h->n_sys * LV.g[l].G;
+        k_coarse_dinv<<<cdiv(n, 256), 256, 0, st>>>(h->n_sys, LV.g[l], LV.A[l], LV.dinv[l]);
+    }
+    h->launches += 3 + (LV.L - 1) + LV.L;
+    CU(cudaEventRecord(h->ev[2], st));
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[2] = ms;
+    cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->t_ms[3] = ms;
+    if (flag) FAIL(RVE_E_MESH, "an element spans more than two level-1 coarse cells");
+    h->assembled = true;
+    return 0;
+}
+
+int rve_get_sizes(rve_handle_t h, int32_t sys, int64_t* n_nodes, int64_t* n_rows, int64_t* n_blocks, int64_t* n_elems) {
+    H_CHECK(h);
+    if (!h->have_batch || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_ARG, "bad system index");
+    if (n_nodes) *n_nodes = h->sym[sys].nn;
+    if (n_rows) *n_rows = h->sym[sys].na;
+    if (n_blocks) *n_blocks = (int64_t)h->sym[sys].bcol.size();
+    if (n_elems) *n_elems = h->sym[sys].nt;
+    return 0;
+}
+
+int rve_get_csr(rve_handle_t h, int32_t sys, int32_t* rowptr, int32_t* col, double* val) {
+    H_CHECK(h);
+    if (!h->assembled || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_STATE, "not assembled / bad system index");
+    const SysSym& Y = h->sym[sys];
+    const size_t nb = Y.bcol.size();
+    std::vector<double> bv(4 * nb);
+    CU(cudaMemcpy(bv.data(), h->bval.p + 4 * (size_t)h->blk_base[sys], 4 * nb * sizeof(double), cudaMemcpyDeviceToHost));
+    int64_t pos = 0;
+    for (int r = 0; r < Y.na; ++r)
+        for (int c = 0; c < 2; ++c) {
+            rowptr[2 * r + c] = (int32_t)pos;
+            for (unsigned k = Y.row_ptr[r]; k < Y.row_ptr[r + 1]; ++k)
+                for (int d = 0; d < 2; ++d) { col[pos] = 2 * Y.bcol[k] + d; val[pos] = bv[4 * (size_t)k + 2 * c + d]; ++pos; }
+        }
+    rowptr[2 * Y.na] = (int32_t)pos;
+    return 0;
+}
+
+int rve_get_rowmap(rve_handle_t h, int32_t sys, int32_t* va, int32_t* vb) {
+    H_CHECK(h);
+    if (!h->have_batch || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_ARG, "bad system index");
+    const SysSym& Y = h->sym[sys];
+    for (int r = 0; r < Y.na; ++r) { va[r] = Y.node_va[Y.row_node[r]]; vb[r] = Y.node_vb[Y.row_node[r]]; }
+    return 0;
+}
+
+int rve_get_nodemap(rve_handle_t h, int32_t sys, int32_t* va, int32_t* vb) {
+    H_CHECK(h);
+    if (!h->have_batch || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_ARG, "bad system index");
+    const SysSym& Y = h->sym[sys];
+    for (int n = 0; n < Y.nn; ++n) { va[n] = Y.node_va[n]; vb[n] = Y.node_vb[n]; }
+    return 0;
+}
+
+int rve_get_rhs(rve_handle_t h, int32_t sys, double* rhs) {
+    H_CHECK(h);
+    if (!h->solved || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_STATE, "no solve yet / bad system index");
+    CU(cudaMemcpy(rhs, h->b.p + (size_t)h->row_base[sys] * h->K * 2, (size_t)h->sym[sys].na * h->K * 2 * sizeof(double),
+                  cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int rve_get_solution(rve_handle_t h, int32_t sys, double* u) {
+    H_CHECK(h);
+    if (!h->solved || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_STATE, "no solve yet / bad system index");
+    CU(cudaMemcpy(u, h->U.p + (size_t)h->node_base[sys] * h->NL * 2, (size_t)h->sym[sys].nn * h->NL * 2 * sizeof(double),
+                  cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int rve_get_coarse_dim(rve_handle_t h, int32_t level, int32_t* G, int32_t* n_levels) {
+    H_CHECK(h);
+    if (!h->have_batch) FAIL(RVE_E_STATE, "no batch");
+    if (n_levels) *n_levels = h->LV.L;
+    if (G) { if (level < 0 || level >= h->LV.L) FAIL(RVE_E_ARG, "bad level"); *G = h->LV.g[level].G; }
+    return 0;
+}
+
+int rve_get_coarse_dense(rve_handle_t h, int32_t sys, int32_t level, double* dense) {
+    H_CHECK(h);
+    if (!h->assembled || sys < 0 || sys >= h->n_sys || level < 0 || level >= h->LV.L) FAIL(RVE_E_STATE, "bad state/arguments");
+    const Grid g = h->LV.g[level];
+    std::vector<double> A(100 * (size_t)g.G);
+    CU(cudaMemcpy(A.data(), h->LV.A[level] + (size_t)sys * 100 * g.G, A.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    const size_t n = 2 * (size_t)g.G;
+    std::fill(dense, dense + n * n, 0.0);
+    for (int j = 0; j < g.ny; ++j)
+        for (int i = 0; i < g.nx; ++i) {
+            if (i < g.lox || i > g.hix || j < g.loy || j > g.hiy) continue;
+            const int I = j * g.nx + i;
+            for (int dj = -2; dj <= 2; ++dj)
+                for (int di = -2; di <= 2; ++di) {
+                    int ii = i + di, jj = j + dj;
+                    if (g.wrap) { ii = ((ii % g.ncx) + g.ncx) % g.ncx; jj = ((jj % g.ncy) + g.ncy) % g.ncy; }
+                    else if (ii < g.lox || ii > g.hix || jj < g.loy || jj > g.hiy) continue;
+                    const int J = jj * g.nx + ii;
+                    const size_t slot = (size_t)(dj + 2) * 5 + (di + 2);
+                    for (int c = 0; c < 2; ++c)
+                        for (int d = 0; d < 2; ++d)
+                            dense[(2 * (size_t)I + c) * n + 2 * J + d] += A[(slot * 4 + 2 * c + d) * g.G + I];
+                }
+        }
+    return 0;
+}
+
+int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD, double rtol, int32_t maxit,
+              int32_t precond, int32_t* status, int32_t* iters) {
+    H_CHECK(h);
+    if (!h->assembled) FAIL(RVE_E_STATE, "rve_solve before rve_assemble");
+    if (n_rhs < 1 || n_rhs > 3 || !eps || maxit < 1 || rtol <= 0) FAIL(RVE_E_ARG, "bad solve arguments");
+    if (uD && h->model != RVE_MODEL_DNN) FAIL(RVE_E_ARG, "uD given but the batch model is not 'dnn'");
+    if (!uD && h->model == RVE_MODEL_DNN) FAIL(RVE_E_ARG, "'dnn' needs uD (use 'lin' for zero Dirichlet data)");
+    const int NL = n_rhs;
+    const int K = (h->model == RVE_MODEL_MR) ? 3 : n_rhs;
+    const int n_sys = h->n_sys;
+    h->K = K; h->NL = NL; h->solved = false;
+    cudaStream_t st = h->stream;
+    const size_t RK = (size_t)h->R * K * 2;
+    CU(h->p.alloc((size_t)h->R * 8)); CU(h->q.alloc(RK)); CU(h->x.alloc(RK)); CU(h->r.alloc(RK)); CU(h->b.alloc(RK));
+    CU(h->eps.alloc((size_t)n_sys * NL * 3)); CU(h->eps_eff.alloc((size_t)n_sys * NL * 3)); CU(h->Bmat.alloc((size_t)n_sys * NL * 4));
+    CU(h->U.alloc((size_t)h->N * NL * 2));
+    CU(cudaMemcpyAsync(h->eps.p, eps, (size_t)n_sys * NL * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    h->h2d_bytes += (double)n_sys * NL * 3 * sizeof(double) + (uD ? (double)n_sys * NL * 2 * h->nvref * sizeof(double) : 0.0);
+    h->d2h_bytes += 2.0 * n_sys * sizeof(int);
+    const int nside = h->vref_nb > 0 ? h->vref_nb - 1 : 0;
+    if (uD) {
+        CU(h->uD.alloc((size_t)n_sys * NL * 2 * h->nvref));
+        CU(cudaMemcpyAsync(h->uD.p, uD, h->uD.n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(h->gval.alloc((size_t)h->NBN * NL * 2));
+    }
+    CU(cudaEventRecord(h->ev[0], st));
+    k_dnn_prep<<<cdiv((long long)n_sys * NL, 128), 128, 0, st>>>(n_sys, NL, nside, h->d_vbox.p, uD ? h->uD.p : nullptr,
+                                                                  h->eps.p, h->eps_eff.p, h->Bmat.p);
+    if (uD)
+        k_bnd_values<<<cdiv(h->NBN * NL, 256), 256, 0, st>>>((int)h->NBN, NL, nside, h->bnd_sys.p, h->bnd_node.p, h->bnd_s.p,
+                                                              h->node_xy.p, h->uD.p, h->Bmat.p, h->gval.p);
+    CU(cudaMemsetAsync(h->b.p, 0, RK * sizeof(double), st));
+    CU(cudaMemsetAsync(h->sc.p, 0, h->sc.n * sizeof(double), st));
+    if (h->model == RVE_MODEL_MR)
+        k_rhs_mr<<<cdiv(h->NBE, 256), 256, 0, st>>>((int)h->NBE, h->bedge.p, h->bedge_nl.p, h->node_row.p, h->b.p);
+    else
+        k_rhs<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, K, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
+                                              h->node_row.p, h->node_bnd.p, h->eps_eff.p, uD ? h->gval.p : nullptr, h->b.p, h->sc.p, h->mat);
+    CU(cudaEventRecord(h->ev[1], st));
+    // ---- PCG
+    CU(cudaMemsetAsync(h->p.p, 0, h->p.n * sizeof(double), st));
+    CU(cudaMemsetAsync(h->q.p, 0, RK * sizeof(double), st));
+    CU(cudaMemsetAsync(h->x.p, 0, RK * sizeof(double), st));
+    CU(cudaMemcpyAsync(h->r.p, h->b.p, RK * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(h->cnt.p, 0, n_sys * sizeof(int), st));
+    CU(cudaMemsetAsync(h->d_iters.p, 0, n_sys * sizeof(int), st));
+    std::vector<int> ones(n_sys, 1);
+    CU(cudaMemcpyAsync(h->active.p, ones.data(), n_sys * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->n_active.p, &n_sys, sizeof(int), cudaMemcpyHostToDevice, st));
+    ChunkTab ct = chunk_tab(h);
+    Levels LV = h->LV;
+    LV.K = K;
+    const double rtol2 = rtol * rtol;
+    const int nch = h->n_chunks;
+    k_update<<<nch, 256, 0, st>>>((const double2*)h->p.p, (const double2*)h->q.p, (double2*)h->x.p, (double2*)h->r.p, h->dinv.p,
+                                  K, ct, h->active.p, h->part.p, h->cnt.p, h->sc.p, 1, -1, rtol2, precond, h->d_iters.p, h->n_active.p);
+    int it = 0, launched = 0;
+    const int CHECK = 8;
+    h->launches += 3 + (uD ? 1 : 0);
+    auto pool_event = [&](size_t i) -> cudaEvent_t {
+        while (h->evpool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); h->evpool.push_back(e); }
+        return h->evpool[i];
+    };
+    *h->h_nactive = n_sys;
+    while (it < maxit) {
+        for (int k = 0; k < CHECK && it < maxit; ++k, ++it) {
+            if (precond)
+                k_vcycle<<<n_sys, 256, 0, st>>>(LV, h->r.p, h->row_xy.p, h->d_row_base.p, h->cell_ptr.p, h->box.p, h->active.p,
+                                                h->sc.p, it == 0);
+            k_direction<<<nch, 256, 0, st>>>((double2*)h->p.p, (const double2*)h->r.p, h->dinv.p, h->row_xy.p, h->box.p, K, ct,
+                                             h->active.p, h->sc.p, precond, LV.g[0], LV.xc[0]);
+            cudaEventRecord(pool_event(2 * (size_t)it), st);
+            k_spmv_dot<<<nch, 256, 0, st>>>(h->row_ptr.p, h->bcol.p, (const double2*)h->bval.p, (const double2*)h->p.p,
+                                            (double2*)h->q.p, K, ct, h->active.p, h->part.p, h->cnt.p, h->sc.p);
+            cudaEventRecord(pool_event(2 * (size_t)it + 1), st);
+            k_update<<<nch, 256, 0, st>>>((const double2*)h->p.p, (const double2*)h->q.p, (double2*)h->x.p, (double2*)h->r.p,
+                                          h->dinv.p, K, ct, h->active.p, h->part.p, h->cnt.p, h->sc.p, 0, it, rtol2, precond,
+                                          h->d_iters.p, h->n_active.p);
+            ++launched;
+            h->launches += precond ? 4 : 3;
+        }
+        CU(cudaMemcpyAsync(h->h_nactive, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (*h->h_nactive <= 0) break;
+    }
+    CU(cudaEventRecord(h->ev[2], st));
+    // ---- constraint post-processing + nodal field
+    MixPtrs M; M.Mx = h->Mx.p; M.Gaff = h->Gaff.p; M.aaff = h->aaff.p;
+    k_mix_coeffs<<<n_sys, 256, 0, st>>>(h->model, K, NL, h->x.p, h->wmean.p, h->d_row_base.p, h->d_bedge_base.p, h->bedge.p,
+                                        h->bedge_nl.p, h->node_row.p, h->box.p, h->eps_eff.p, M);
+    k_nodal_field<<<cdiv(h->N * NL, 256), 256, 0, st>>>(h->N, K, NL, h->node_sys.p, h->node_row.p, h->node_bnd.p, h->node_xy.p,
+                                                        h->x.p, uD ? h->gval.p : nullptr, M, h->model != RVE_MODEL_MR, h->U.p);
+    CU(cudaEventRecord(h->ev[3], st));
+    std::vector<int> hit(n_sys), hact(n_sys);
+    CU(cudaMemcpyAsync(hit.data(), h->d_iters.p, n_sys * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hact.data(), h->active.p, n_sys * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[4] = ms;
+    cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->t_ms[5] = ms;
+    double spmv_ms = 0;
+    for (int i = 0; i < launched; ++i) { cudaEventElapsedTime(&ms, h->evpool[2 * i], h->evpool[2 * i + 1]); spmv_ms += ms; }
+    h->t_ms[6] = spmv_ms;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->c_cnt[5] = ms;  // constraint post-processing + nodal field
+    h->launches += 2;
+    bool allconv = true;
+    double sumit = 0;
+    for (int s = 0; s < n_sys; ++s) {
+        const int stt = hact[s] ? 1 : 0;
+        if (stt) { allconv = false; hit[s] = launched; }
+        if (status) status[s] = stt;
+        if (iters) iters[s] = hit[s];
+        sumit += hit[s];
+    }
+    h->c_cnt[0] = launched; h->c_cnt[2] = launched; h->c_cnt[3] = sumit;
+    // algorithmic SpMV bytes of the solve: sum over systems of iters * B_spmv(K)
+    double bytes = 0;
+    for (int s = 0; s < n_sys; ++s) {
+        const double n = 2.0 * h->sym[s].na, nnz = 4.0 * (double)h->sym[s].bcol.size();
+        bytes += hit[s] * (12.0 * nnz + 4.0 * (n + 1) + 16.0 * n * K);
+    }
+    h->c_cnt[1] = bytes;
+    h->solved = true;
+    if (!allconv) FAIL(RVE_E_NOCONV, "PCG did not converge for at least one system");
+    return 0;
+}
+
+static int run_epilogue(rve_handle_t h) {
+    cudaStream_t st = h->stream;
+    const int NL = h->NL, n_sys = h->n_sys;
+    CU(h->sigL.alloc((size_t)n_sys * NL * 3)); CU(h->sigT.alloc((size_t)n_sys * NL * 3));
+    CU(h->aout.alloc((size_t)n_sys * NL * 2)); CU(h->Bout.alloc((size_t)n_sys * NL * 4));
+    CU(cudaEventRecord(h->ev[0], st));
+    CU(cudaMemsetAsync(h->acc.p, 0, h->acc.n * sizeof(double), st));
+    k_epi_elements<<<cdiv(h->E, 128), 128, 0, st>>>((int)h->E, NL, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
+                                                    h->U.p, h->acc.p, h->mat);
+    k_epi_finalize<<<cdiv((long long)n_sys * NL, 128), 128, 0, st>>>(n_sys, NL, h->acc.p, h->eps_eff.p, h->mat, h->sigL.p,
+                                                                     h->sigT.p, h->aout.p, h->Bout.p);
+    if (h->nvref) {
+        CU(h->sol.alloc((size_t)n_sys * NL * 2 * h->nvref));
+        const long long n = (long long)n_sys * h->nvref * NL;
+        k_epi_sample<<<cdiv(n, 256), 256, 0, st>>>(n, h->nvref, NL, h->samp_elem.p, h->samp_lam.p, h->elem_node.p, h->U.p, h->sol.p);
+    }
+    h->launches += 2 + (h->nvref ? 1 : 0);
+    CU(cudaEventRecord(h->ev[1], st));
+    return 0;
+}
+
+int rve_epilogue_tangent(rve_handle_t h, double* C) {
+    H_CHECK(h);
+    if (!h->solved) FAIL(RVE_E_STATE, "rve_epilogue_tangent before rve_solve");
+    if (h->NL != 3 || !C) FAIL(RVE_E_ARG, "tangent needs the 3 unit load cases");
+    int rc = run_epilogue(h);
+    if (rc) return rc;
+    std::vector<double> s((size_t)h->n_sys * 9);
+    CU(cudaMemcpyAsync(s.data(), h->sigL.p, s.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    h->d2h_bytes += (double)s.size() * sizeof(double);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[7] = ms;
+    for (int sys = 0; sys < h->n_sys; ++sys)
+        for (int l = 0; l < 3; ++l)
+            for (int k = 0; k < 3; ++k) C[(size_t)sys * 9 + 3 * k + l] = s[((size_t)sys * 3 + l) * 3 + k];
+    return 0;
+}
+
+int rve_epilogue_snapshot(rve_handle_t h, double* sol, double* sigma, double* a, double* B, double* sigmaT) {
+    H_CHECK(h);
+    if (!h->solved) FAIL(RVE_E_STATE, "rve_epilogue_snapshot before rve_solve");
+    if (sol && !h->nvref) FAIL(RVE_E_ARG, "no Vref was given to rve_set_batch");
+    int rc = run_epilogue(h);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    const size_t n = (size_t)h->n_sys * h->NL;
+    h->d2h_bytes += (double)n * sizeof(double) * ((sol ? 2 * h->nvref : 0) + (sigma ? 3 : 0) + (sigmaT ? 3 : 0) + (a ? 2 : 0) + (B ? 4 : 0));
+    if (sol) CU(cudaMemcpyAsync(sol, h->sol.p, n * 2 * h->nvref * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (sigma) CU(cudaMemcpyAsync(sigma, h->sigL.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (sigmaT) CU(cudaMemcpyAsync(sigmaT, h->sigT.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (a) CU(cudaMemcpyAsync(a, h->aout.p, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (B) CU(cudaMemcpyAsync(B, h->Bout.p, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[7] = ms;
+    return 0;
+}
+
+int rve_project(rve_handle_t h, int32_t nmax, int32_t nh, const double* W, const double* M, const double* translate, double* Y) {
+    H_CHECK(h);
+    if (!h->solved || !h->sol.p) FAIL(RVE_E_STATE, "rve_project needs rve_epilogue_snapshot first");
+    if (nh != 2 * h->nvref || nmax < 1 || !W || !M || !Y) FAIL(RVE_E_ARG, "bad projection arguments");
+    const int NL = h->NL;
+    // MWt[l][q][j] = sum_k M[q][k] W[l][j][k]
+    std::vector<double> mwt((size_t)NL * nh * nmax);
+    for (int l = 0; l < NL; ++l)
+        for (int q = 0; q < nh; ++q)
+            for (int j = 0; j < nmax; ++j) {
+                double acc = 0;
+                const double* Mq = M + (size_t)q * nh;
+                const double* Wj = W + ((size_t)l * nmax + j) * nh;
+                for (int k = 0; k < nh; ++k) acc += Mq[k] * Wj[k];
+                mwt[((size_t)l * nh + q) * nmax + j] = acc;
+            }
+    cudaStream_t st = h->stream;
+    UPL(h->MWt, mwt);
+    const size_t n = (size_t)h->n_sys * NL;
+    if (translate) {
+        CU(h->transl.alloc(n * 2));
+        CU(cudaMemcpyAsync(h->transl.p, translate, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    CU(h->Yd.alloc(n * nmax));
+    h->launches += 1;
+    k_project<<<(unsigned)n, 128, nh * sizeof(double), st>>>(NL, nh, nmax, h->sol.p, translate ? h->transl.p : nullptr, h->MWt.p, h->Yd.p);
+    CU(cudaMemcpyAsync(Y, h->Yd.p, n * nmax * sizeof(double), cudaMemcpyDeviceToHost, st));
+    h->d2h_bytes += (double)n * nmax * sizeof(double);
+    h->h2d_bytes += (translate ? (double)n * 2 * sizeof(double) : 0.0);
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int rve_timings(rve_handle_t h, double* t, double* c) {
+    H_CHECK(h);
+    if (t) for (int k = 0; k < 8; ++k) t[k] = h->t_ms[k];
+    h->c_cnt[4] = h->launches; h->c_cnt[6] = h->h2d_bytes; h->c_cnt[7] = h->d2h_bytes;
+    if (c) for (int k = 0; k < 8; ++k) c[k] = h->c_cnt[k];
+    return 0;
+}
+
+int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_launch, double* alg_bytes_per_launch) {
+    H_CHECK(h);
+    if (!h->assembled) FAIL(RVE_E_STATE, "rve_bench_spmv before rve_assemble");
+    if (n_rhs < 1 || n_rhs > 3 || reps < 1) FAIL(RVE_E_ARG, "bad arguments");
+    cudaStream_t st = h->stream;
+    const int K = n_rhs, n_sys = h->n_sys;
+    DBuf<double> p, q, part, sc;
+    DBuf<int> active, cnt;
+    CU(p.alloc((size_t)h->R * 8)); CU(q.alloc((size_t)h->R * K * 2)); CU(part.alloc((size_t)h->n_chunks * 8));
+    CU(sc.alloc((size_t)n_sys * 4 * SC_N)); CU(active.alloc(n_sys)); CU(cnt.alloc(n_sys));
+    std::vector<double> hp((size_t)h->R * 8);
+    for (size_t i = 0; i < hp.size(); ++i) hp[i] = ((i & 7) < (size_t)(2 * K)) ? 1.0 + 1e-3 * (double)(i % 97) : 0.0;
+    CU(cudaMemcpyAsync(p.p, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<int> ones(n_sys, 1);
+    CU(cudaMemcpyAsync(active.p, ones.data(), n_sys * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(cnt.p, 0, n_sys * sizeof(int), st));
+    CU(cudaMemsetAsync(sc.p, 0, sc.n * sizeof(double), st));
+    ChunkTab ct = chunk_tab(h);
+    for (int wu = 0; wu < 3; ++wu)
+        k_spmv_dot<<<h->n_chunks, 256, 0, st>>>(h->row_ptr.p, h->bcol.p, (const double2*)h->bval.p, (const double2*)p.p,
+                                                (double2*)q.p, K, ct, active.p, part.p, cnt.p, sc.p);
+    CU(cudaEventRecord(h->ev[0], st));
+    for (int i = 0; i < reps; ++i)
+        k_spmv_dot<<<h->n_chunks, 256, 0, st>>>(h->row_ptr.p, h->bcol.p, (const double2*)h->bval.p, (const double2*)p.p,
+                                                (double2*)q.p, K, ct, active.p, part.p, cnt.p, sc.p);
+    CU(cudaEventRecord(h->ev[1], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    if (ms_per_launch) *ms_per_launch = ms / reps;
+    if (alg_bytes_per_launch) {
+        const double n = 2.0 * (double)h->R, nnz = 4.0 * (double)h->NB;
+        *alg_bytes_per_launch = 12.0 * nnz + 4.0 * (n + n_sys) + 16.0 * n * K;
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+// Host-only test hook (no CUDA call): symbolic phase of ONE system, so that the CPU test-suite can
+// check numbering, constraint maps and the block pattern against the oracle without a GPU.
+extern "C" int rve_host_symbolic(const double* xy, int32_t nv, const int32_t* tri, const int32_t* region, int32_t nt,
+                                 int32_t model, int32_t vref_nb, int32_t cap_rows, int32_t cap_blocks, int32_t* n_nodes,
+                                 int32_t* n_rows, int32_t* n_blocks, int32_t* nc, int32_t* rowptr, int32_t* bcol,
+                                 int32_t* row_va, int32_t* row_vb, int32_t* node_row, int32_t* samp_elem, double* samp_lam) {
+    SysSym S;
+    sym_pass1(S, xy, tri, region, nv, nt);
+    if (!S.err.empty()) return RVE_E_MESH;
+    SymParams P;
+    P.model = model; P.vref_nb = vref_nb; P.vref_box_given = false;
+    P.ncx = pick_nc(S.box[2], S.max_ext); P.ncy = pick_nc(S.box[3], S.max_ext);
+    sym_pass2(S, P);
+    if (!S.err.empty()) return RVE_E_MESH;
+    *n_nodes = S.nn; *n_rows = S.na; *n_blocks = (int32_t)S.bcol.size(); *nc = P.ncx;
+    if (S.na > cap_rows || (int)S.bcol.size() > cap_blocks) return RVE_E_ARG;
+    for (int r = 0; r <= S.na; ++r) rowptr[r] = (int32_t)S.row_ptr[r];
+    for (size_t k = 0; k < S.bcol.size(); ++k) bcol[k] = S.bcol[k];
+    for (int r = 0; r < S.na; ++r) { row_va[r] = S.node_va[S.row_node[r]]; row_vb[r] = S.node_vb[S.row_node[r]]; }
+    for (int n = 0; n < S.nn; ++n) node_row[n] = S.node_row[n];
+    if (vref_nb > 0 && samp_elem && samp_lam) {
+        const int nvref = 4 * (vref_nb - 1) + 1;
+        for (int k = 0; k < nvref; ++k) { samp_elem[k] = S.samp_elem[k]; samp_lam[2 * k] = S.samp_lam[2 * k]; samp_lam[2 * k + 1] = S.samp_lam[2 * k + 1]; }
+    }
+    return 0;
+}

@@ -1,0 +1,354 @@
+// rve_symbolic.hpp — host-side symbolic phase of rve_set_batch (multi-threaded over systems).
+//
+// For every RVE mesh: P2 numbering (vertices, then edges sorted by (va,vb) — the same order
+// numpy.unique gives the oracle), boundary detection, the constraint map of the BC model
+// (Dirichlet elimination for lin/dnn, periodic master map for per, identity for MR), active
+// block rows ordered by level-1 coarse cell, node-block CSR pattern, Vref sample location.
+// This replaces what dolfin's DofMap / multiphenics' BlockDofMap / PeriodicBoundary build
+// behind listMultiscaleModels[model](mesh, ...) (core/multiscale/micro_model.py:56-57).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/rve_b200.h"
+
+struct SysSym {
+    int nv = 0, nt = 0, ne = 0, nn = 0, na = 0, nb = 0, nbe = 0;
+    double box[4];                   // x0,y0,Lx,Ly (mesh bounding box)
+    std::vector<int> tri;            // [nt][3] CCW
+    std::vector<int> elem_node;      // [nt][6] local P2 node ids
+    std::vector<unsigned char> reg;  // [nt]
+    std::vector<double> node_xy;     // [nn][2]
+    std::vector<int> node_va, node_vb;
+    std::vector<int> node_row;       // [nn] local active row or -1
+    std::vector<int> node_bnd;       // [nn] index into the boundary-node list or -1
+    std::vector<int> row_node;       // [na] master node of the row
+    std::vector<int> cell_ptr;       // [ncx*ncy+1] rows sorted by level-1 cell
+    std::vector<unsigned> row_ptr;   // [na+1] local block offsets
+    std::vector<int> bcol;           // local row ids
+    std::vector<int> bnd_node;       // [nb]
+    std::vector<double> bnd_s;       // [nb][2] Vref perimeter parameters of the end vertices
+    std::vector<int> bedge;          // [nbe][3] boundary edges (a,b,m), outward normal to the right
+    std::vector<double> bedge_nl;    // [nbe][2] normal * length
+    std::vector<int> samp_elem;      // [nvref] local element id
+    std::vector<double> samp_lam;    // [nvref][2] (l1,l2)
+    double max_ext = 0;              // largest element bounding-box side
+    std::string err;
+};
+
+struct SymParams {
+    int model;
+    int ncx, ncy;        // level-1 grid
+    int vref_nb;         // 0: none
+    bool vref_box_given;
+    double vref_box[4];
+};
+
+// pass 1: everything that does not depend on the level-1 grid
+static void sym_pass1(SysSym& S, const double* xy, const int* tri, const int* region, int nv, int nt) {
+    S.nv = nv; S.nt = nt;
+    S.tri.assign(tri, tri + 3 * (size_t)nt);
+    int rmin = 1 << 30;
+    for (int t = 0; t < nt; ++t) rmin = std::min(rmin, region[t]);
+    S.reg.resize(nt);
+    double xmin = 1e300, ymin = 1e300, xmax = -1e300, ymax = -1e300;
+    for (int v = 0; v < nv; ++v) {
+        xmin = std::min(xmin, xy[2 * v]); xmax = std::max(xmax, xy[2 * v]);
+        ymin = std::min(ymin, xy[2 * v + 1]); ymax = std::max(ymax, xy[2 * v + 1]);
+    }
+    S.box[0] = xmin; S.box[1] = ymin; S.box[2] = xmax - xmin; S.box[3] = ymax - ymin;
+    double ext = 0;
+    for (int t = 0; t < nt; ++t) {
+        int r = region[t] - rmin;
+        if (r < 0 || r > 3) { S.err = "region tag out of range (need max-min <= 3)"; return; }
+        S.reg[t] = (unsigned char)r;
+        int* T = &S.tri[3 * t];
+        for (int k = 0; k < 3; ++k)
+            if (T[k] < 0 || T[k] >= nv) { S.err = "triangle vertex id out of range"; return; }
+        const double *p0 = xy + 2 * T[0], *p1 = xy + 2 * T[1], *p2 = xy + 2 * T[2];
+        double a2 = (p1[0] - p0[0]) * (p2[1] - p0[1]) - (p1[1] - p0[1]) * (p2[0] - p0[0]);
+        if (a2 == 0.0) { S.err = "degenerate triangle"; return; }
+        if (a2 < 0) std::swap(T[1], T[2]);
+        double ex = std::max({p0[0], p1[0], p2[0]}) - std::min({p0[0], p1[0], p2[0]});
+        double ey = std::max({p0[1], p1[1], p2[1]}) - std::min({p0[1], p1[1], p2[1]});
+        ext = std::max(ext, std::max(ex, ey));
+    }
+    S.max_ext = ext;
+    // edges: sort (key, slot)
+    std::vector<std::pair<uint64_t, int>> ek(3 * (size_t)nt);
+    for (int t = 0; t < nt; ++t)
+        for (int k = 0; k < 3; ++k) {
+            int a = S.tri[3 * t + k], b = S.tri[3 * t + (k + 1) % 3];
+            uint64_t key = ((uint64_t)std::min(a, b) << 32) | (uint64_t)std::max(a, b);
+            ek[3 * t + k] = {key, 3 * t + k};
+        }
+    std::sort(ek.begin(), ek.end());
+    S.elem_node.resize(6 * (size_t)nt);
+    std::vector<int> ecount;
+    std::vector<uint64_t> ekeys;
+    for (size_t i = 0; i < ek.size(); ++i) {
+        if (i == 0 || ek[i].first != ek[i - 1].first) { ekeys.push_back(ek[i].first); ecount.push_back(0); }
+        ecount.back()++;
+        int t = ek[i].second / 3, k = ek[i].second % 3;
+        S.elem_node[6 * t + 3 + k] = nv + (int)ekeys.size() - 1;
+    }
+    S.ne = (int)ekeys.size();
+    S.nn = nv + S.ne;
+    for (int t = 0; t < nt; ++t)
+        for (int k = 0; k < 3; ++k) S.elem_node[6 * t + k] = S.tri[3 * t + k];
+    S.node_xy.resize(2 * (size_t)S.nn);
+    S.node_va.resize(S.nn); S.node_vb.resize(S.nn);
+    for (int v = 0; v < nv; ++v) {
+        S.node_xy[2 * v] = xy[2 * v]; S.node_xy[2 * v + 1] = xy[2 * v + 1];
+        S.node_va[v] = S.node_vb[v] = v;
+    }
+    for (int e = 0; e < S.ne; ++e) {
+        int a = (int)(ekeys[e] >> 32), b = (int)(ekeys[e] & 0xffffffffu);
+        S.node_xy[2 * (nv + e)] = 0.5 * (xy[2 * a] + xy[2 * b]);
+        S.node_xy[2 * (nv + e) + 1] = 0.5 * (xy[2 * a + 1] + xy[2 * b + 1]);
+        S.node_va[nv + e] = a; S.node_vb[nv + e] = b;
+    }
+    // boundary edges with outward normal (owning triangle is CCW -> outward is to the right of a->b)
+    S.node_bnd.assign(S.nn, -1);
+    for (int t = 0; t < nt; ++t)
+        for (int k = 0; k < 3; ++k) {
+            int m = S.elem_node[6 * t + 3 + k];
+            if (ecount[m - nv] == 1) {
+                int a = S.tri[3 * t + k], b = S.tri[3 * t + (k + 1) % 3];
+                S.bedge.push_back(a); S.bedge.push_back(b); S.bedge.push_back(m);
+                double dx = xy[2 * b] - xy[2 * a], dy = xy[2 * b + 1] - xy[2 * a + 1];
+                S.bedge_nl.push_back(dy); S.bedge_nl.push_back(-dx);
+                S.node_bnd[a] = S.node_bnd[b] = S.node_bnd[m] = 0;
+            } else if (ecount[m - nv] != 2) {
+                S.err = "non-manifold edge"; return;
+            }
+        }
+    S.nbe = (int)S.bedge.size() / 3;
+    for (int n = 0; n < S.nn; ++n)
+        if (S.node_bnd[n] == 0) { S.node_bnd[n] = (int)S.bnd_node.size(); S.bnd_node.push_back(n); }
+    S.nb = (int)S.bnd_node.size();
+}
+
+// Vref perimeter parameter of a point on the box boundary: node k of Vref sits at s = k.
+static double perimeter_param(double x, double y, const double* vb, int nside) {
+    double x0 = vb[0], y0 = vb[1], Lx = vb[2], Ly = vb[3];
+    double tol = 1e-9 * std::max(Lx, Ly);
+    if (std::fabs(y - y0) < tol && x < x0 + Lx - tol) return (x - x0) / Lx * nside;
+    if (std::fabs(x - (x0 + Lx)) < tol && y < y0 + Ly - tol) return nside + (y - y0) / Ly * nside;
+    if (std::fabs(y - (y0 + Ly)) < tol && x > x0 + tol) return 2 * nside + (x0 + Lx - x) / Lx * nside;
+    if (std::fabs(x - x0) < tol) return 3 * nside + (y0 + Ly - y) / Ly * nside;
+    return -1.0;
+}
+
+// pass 2: constraint map, rows ordered by level-1 cell, node-block pattern, Vref samples
+static void sym_pass2(SysSym& S, const SymParams& P) {
+    const int nn = S.nn, nt = S.nt;
+    const double x0 = S.box[0], y0 = S.box[1], Lx = S.box[2], Ly = S.box[3];
+    const double tol = 1e-9 * std::max(Lx, Ly);
+    std::vector<int> master(nn);
+    for (int n = 0; n < nn; ++n) master[n] = n;
+    if (P.model == RVE_MODEL_LIN || P.model == RVE_MODEL_DNN) {
+        for (int i = 0; i < S.nb; ++i) master[S.bnd_node[i]] = -1;
+    } else if (P.model == RVE_MODEL_PER) {
+        // slaves: x = x1 -> x0, y = y1 -> y0 (corners -> (x0,y0)); match by the other coordinate
+        std::vector<std::pair<double, int>> left, bottom;
+        for (int i = 0; i < S.nb; ++i) {
+            int n = S.bnd_node[i];
+            double x = S.node_xy[2 * n], y = S.node_xy[2 * n + 1];
+            if (std::fabs(x - x0) < tol) left.push_back({y, n});
+            if (std::fabs(y - y0) < tol) bottom.push_back({x, n});
+        }
+        std::sort(left.begin(), left.end());
+        std::sort(bottom.begin(), bottom.end());
+        auto find = [&](const std::vector<std::pair<double, int>>& L, double key) -> int {
+            auto it = std::lower_bound(L.begin(), L.end(), std::make_pair(key - 1e-7 * std::max(Lx, Ly), -1));
+            if (it == L.end() || std::fabs(it->first - key) > 1e-7 * std::max(Lx, Ly)) return -1;
+            return it->second;
+        };
+        for (int i = 0; i < S.nb; ++i) {
+            int n = S.bnd_node[i];
+            double x = S.node_xy[2 * n], y = S.node_xy[2 * n + 1];
+            bool onr = std::fabs(x - (x0 + Lx)) < tol, ont = std::fabs(y - (y0 + Ly)) < tol;
+            int m = n;
+            if (onr) { m = find(left, y); if (m < 0) { S.err = "periodic: left/right boundary nodes do not match"; return; } y = S.node_xy[2 * m + 1]; }
+            if (ont) {
+                double xm = S.node_xy[2 * m];
+                m = find(bottom, xm);
+                if (m < 0) { S.err = "periodic: bottom/top boundary nodes do not match"; return; }
+            }
+            master[n] = m;
+        }
+        for (int it = 0; it < 3; ++it)
+            for (int n = 0; n < nn; ++n) if (master[n] >= 0) master[n] = master[master[n]];
+    }
+    // active rows sorted by level-1 cell (row-major), ties by node id
+    const int ncx = P.ncx, ncy = P.ncy;
+    const double invHx = ncx / Lx, invHy = ncy / Ly;
+    std::vector<std::pair<int, int>> keyed;
+    keyed.reserve(nn);
+    for (int n = 0; n < nn; ++n)
+        if (master[n] == n) {
+            int ci = (int)((S.node_xy[2 * n] - x0) * invHx), cj = (int)((S.node_xy[2 * n + 1] - y0) * invHy);
+            ci = std::min(std::max(ci, 0), ncx - 1); cj = std::min(std::max(cj, 0), ncy - 1);
+            keyed.push_back({cj * ncx + ci, n});
+        }
+    std::sort(keyed.begin(), keyed.end());
+    S.na = (int)keyed.size();
+    S.row_node.resize(S.na);
+    S.cell_ptr.assign(ncx * ncy + 1, 0);
+    std::vector<int> rowof(nn, -1);
+    for (int r = 0; r < S.na; ++r) {
+        S.row_node[r] = keyed[r].second;
+        rowof[keyed[r].second] = r;
+        S.cell_ptr[keyed[r].first + 1]++;
+    }
+    for (int c = 0; c < ncx * ncy; ++c) S.cell_ptr[c + 1] += S.cell_ptr[c];
+    S.node_row.resize(nn);
+    for (int n = 0; n < nn; ++n) S.node_row[n] = master[n] < 0 ? -1 : rowof[master[n]];
+    // row -> elements adjacency
+    std::vector<int> adj_ptr(S.na + 1, 0);
+    for (int t = 0; t < nt; ++t)
+        for (int k = 0; k < 6; ++k) {
+            int r = S.node_row[S.elem_node[6 * t + k]];
+            if (r >= 0) adj_ptr[r + 1]++;
+        }
+    for (int r = 0; r < S.na; ++r) adj_ptr[r + 1] += adj_ptr[r];
+    std::vector<int> adj(adj_ptr[S.na]), fill(adj_ptr.begin(), adj_ptr.end() - 1);
+    for (int t = 0; t < nt; ++t)
+        for (int k = 0; k < 6; ++k) {
+            int r = S.node_row[S.elem_node[6 * t + k]];
+            if (r >= 0) adj[fill[r]++] = t;
+        }
+    S.row_ptr.assign(S.na + 1, 0);
+    S.bcol.clear();
+    S.bcol.reserve((size_t)S.na * 12);
+    std::vector<int> cand;
+    for (int r = 0; r < S.na; ++r) {
+        cand.clear();
+        for (int i = adj_ptr[r]; i < adj_ptr[r + 1]; ++i) {
+            int t = adj[i];
+            for (int k = 0; k < 6; ++k) {
+                int c = S.node_row[S.elem_node[6 * t + k]];
+                if (c >= 0) cand.push_back(c);
+            }
+        }
+        std::sort(cand.begin(), cand.end());
+        cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+        S.bcol.insert(S.bcol.end(), cand.begin(), cand.end());
+        S.row_ptr[r + 1] = (unsigned)S.bcol.size();
+    }
+    // Dirichlet boundary parameters / Vref samples
+    double vb[4];
+    for (int k = 0; k < 4; ++k) vb[k] = P.vref_box_given ? P.vref_box[k] : S.box[k];
+    const int nside = P.vref_nb > 0 ? P.vref_nb - 1 : 0;
+    if (P.model == RVE_MODEL_DNN) {
+        if (nside == 0) { S.err = "dnn model needs vref_nb > 0"; return; }
+        S.bnd_s.resize(2 * (size_t)S.nb);
+        for (int i = 0; i < S.nb; ++i) {
+            int n = S.bnd_node[i];
+            int a = S.node_va[n], b = S.node_vb[n];
+            double sa = perimeter_param(S.node_xy[2 * a], S.node_xy[2 * a + 1], vb, nside);
+            double sb = perimeter_param(S.node_xy[2 * b], S.node_xy[2 * b + 1], vb, nside);
+            if (sa < 0 || sb < 0) { S.err = "dnn: mesh boundary does not coincide with the Vref box"; return; }
+            S.bnd_s[2 * i] = sa; S.bnd_s[2 * i + 1] = sb;
+        }
+    }
+    if (nside > 0) {
+        const int nvref = 4 * nside + 1;
+        S.samp_elem.assign(nvref, -1);
+        S.samp_lam.assign(2 * (size_t)nvref, 0.0);
+        // bin elements on a uniform grid for point location
+        const int gb = std::max(1, (int)std::sqrt((double)nt / 4.0));
+        std::vector<int> bptr((size_t)gb * gb + 1, 0), blist;
+        auto cellrange = [&](int t, int& i0, int& i1, int& j0, int& j1) {
+            double xa = 1e300, xb = -1e300, ya = 1e300, yb = -1e300;
+            for (int k = 0; k < 3; ++k) {
+                int v = S.tri[3 * t + k];
+                xa = std::min(xa, S.node_xy[2 * v]); xb = std::max(xb, S.node_xy[2 * v]);
+                ya = std::min(ya, S.node_xy[2 * v + 1]); yb = std::max(yb, S.node_xy[2 * v + 1]);
+            }
+            i0 = std::min(std::max((int)((xa - x0) / Lx * gb - 1e-9), 0), gb - 1);
+            i1 = std::min(std::max((int)((xb - x0) / Lx * gb + 1e-9), 0), gb - 1);
+            j0 = std::min(std::max((int)((ya - y0) / Ly * gb - 1e-9), 0), gb - 1);
+            j1 = std::min(std::max((int)((yb - y0) / Ly * gb + 1e-9), 0), gb - 1);
+        };
+        for (int pass = 0; pass < 2; ++pass) {
+            std::vector<int> f(bptr.begin(), bptr.end() - 1);
+            for (int t = 0; t < nt; ++t) {
+                int i0, i1, j0, j1;
+                cellrange(t, i0, i1, j0, j1);
+                for (int j = j0; j <= j1; ++j)
+                    for (int i = i0; i <= i1; ++i) {
+                        if (pass == 0) bptr[(size_t)j * gb + i + 1]++;
+                        else blist[f[(size_t)j * gb + i]++] = t;
+                    }
+            }
+            if (pass == 0) {
+                for (size_t c = 0; c < (size_t)gb * gb; ++c) bptr[c + 1] += bptr[c];
+                blist.resize(bptr.back());
+            }
+        }
+        for (int k = 0; k < nvref; ++k) {
+            double px, py;
+            if (k == 4 * nside) { px = vb[0] + 0.5 * vb[2]; py = vb[1] + 0.5 * vb[3]; }
+            else {
+                int side = k / nside; double f = (double)(k % nside) / nside;
+                if (side == 0) { px = vb[0] + vb[2] * f; py = vb[1]; }
+                else if (side == 1) { px = vb[0] + vb[2]; py = vb[1] + vb[3] * f; }
+                else if (side == 2) { px = vb[0] + vb[2] * (1 - f); py = vb[1] + vb[3]; }
+                else { px = vb[0]; py = vb[1] + vb[3] * (1 - f); }
+            }
+            int bi = std::min(std::max((int)((px - x0) / Lx * gb), 0), gb - 1);
+            int bj = std::min(std::max((int)((py - y0) / Ly * gb), 0), gb - 1);
+            double best = -1e300; int bt = -1; double bl1 = 0, bl2 = 0;
+            for (int dj = -1; dj <= 1; ++dj)
+                for (int di = -1; di <= 1; ++di) {
+                    int i = bi + di, j = bj + dj;
+                    if (i < 0 || j < 0 || i >= gb || j >= gb) continue;
+                    for (int q = bptr[(size_t)j * gb + i]; q < bptr[(size_t)j * gb + i + 1]; ++q) {
+                        int t = blist[q];
+                        const double* p0 = &S.node_xy[2 * S.tri[3 * t]];
+                        const double* p1 = &S.node_xy[2 * S.tri[3 * t + 1]];
+                        const double* p2 = &S.node_xy[2 * S.tri[3 * t + 2]];
+                        double twoA = (p1[0] - p0[0]) * (p2[1] - p0[1]) - (p1[1] - p0[1]) * (p2[0] - p0[0]);
+                        double l1 = ((px - p0[0]) * (p2[1] - p0[1]) - (py - p0[1]) * (p2[0] - p0[0])) / twoA;
+                        double l2 = ((p1[0] - p0[0]) * (py - p0[1]) - (p1[1] - p0[1]) * (px - p0[0])) / twoA;
+                        double l0 = 1.0 - l1 - l2;
+                        double mn = std::min(l0, std::min(l1, l2));
+                        // deterministic tie-break: best min-lambda, then lowest element id
+                        if (mn > best + 1e-12) { best = mn; bt = t; bl1 = l1; bl2 = l2; }
+                    }
+                }
+            if (bt < 0 || best < -1e-8) { S.err = "Vref sample point outside the mesh"; return; }
+            S.samp_elem[k] = bt; S.samp_lam[2 * k] = bl1; S.samp_lam[2 * k + 1] = bl2;
+        }
+    }
+}
+
+// level-1 grid size: largest n = m*2^j (m in {2,3}, j>=0) with L/n >= ext (so that an element
+// never spans more than two coarse cells per direction) and n >= 2.
+static int pick_nc(double L, double ext) {
+    int best = 2;
+    double lim = L / (ext * 1.0000001);
+    for (int m = 2; m <= 3; ++m)
+        for (int n = m; n <= 4096; n *= 2)
+            if ((double)n <= lim) best = std::max(best, n);
+    return best;
+}
+
+template <class F>
+static void parallel_for(int n, F f) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nth = (int)std::min<unsigned>(hw ? hw : 4, 64);
+    nth = std::min(nth, std::max(1, n / 4));
+    if (nth <= 1) { for (int i = 0; i < n; ++i) f(i); return; }
+    std::vector<std::thread> th;
+    for (int w = 0; w < nth; ++w)
+        th.emplace_back([=]() { for (int i = w; i < n; i += nth) f(i); });
+    for (auto& t : th) t.join();
+}

@@ -1,0 +1,258 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same
+meshes.  Tolerances: 1e-8 relative (BASELINE.json north_star) on nodal displacement, Vref samples,
+RB coefficients and tangent entries; assembled matrices/vectors to 1e-12."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import smooth_uD
+
+pytestmark = pytest.mark.gpu
+
+PARAM = (0.3, 10.0, 0.3, 1.0)
+EPS3 = np.eye(3)
+
+
+def _oracle_rows(o, model):
+    from oracle.rve_oracle import periodic_map
+    m = o.mesh
+    if o._lu is None:
+        o._factor()
+    if model in ("lin", "dnn"):
+        return o.free[0::2] // 2
+    if model == "per":
+        return np.unique(periodic_map(m))
+    return np.arange(m.nn)
+
+
+def _perm(batch, sys, o, model):
+    """position in the oracle's active ordering of every library row"""
+    m = o.mesh
+    va, vb = batch.rowmap(sys)
+    ed = {(int(a), int(b)): m.nv + i for i, (a, b) in enumerate(m.edges)}
+    rown = np.array([a if a == b else ed[(int(a), int(b))] for a, b in zip(va, vb)])
+    pos = {int(n): i for i, n in enumerate(_oracle_rows(o, model))}
+    return np.array([pos[int(n)] for n in rown]), rown
+
+
+def _oracle_matrix(o, model):
+    o._factor()
+    if model in ("lin", "dnn"):
+        return o.K[o.free][:, o.free].tocsr()
+    if model == "per":
+        return (o.P.T @ o.K @ o.P).tocsr()
+    return o.K.tocsr()
+
+
+@pytest.mark.parametrize("model", ["lin", "per", "MR"])
+def test_assembly_matches_oracle(reduced_meshes, model):
+    from deepbnd_b200.batch import RVEBatch
+    from oracle.rve_oracle import OracleRVE
+    b = RVEBatch().set_meshes(reduced_meshes, PARAM, model=model).assemble()
+    for s in (0, 2):
+        o = OracleRVE(*reduced_meshes[s], param=PARAM, model=model)
+        A = _oracle_matrix(o, model)
+        perm, _ = _perm(b, s, o, model)
+        dperm = np.stack([2 * perm, 2 * perm + 1], 1).ravel()
+        Al = b.csr(s)
+        D = (Al - A[dperm][:, dperm]).tocsr()
+        err = np.abs(D.data).max() if D.nnz else 0.0
+        assert err <= 1e-12 * np.abs(A.data).max(), (model, s, err)
+    b.close()
+
+
+@pytest.mark.parametrize("model", ["lin", "per", "MR"])
+def test_coarse_operators_are_galerkin(reduced_meshes, model):
+    """level-1 operator == Z^T A Z with the bilinear Z rebuilt in numpy; deeper levels == P^T A P."""
+    from deepbnd_b200.batch import RVEBatch
+    from oracle.rve_oracle import OracleRVE
+    meshes = reduced_meshes[:2]
+    b = RVEBatch().set_meshes(meshes, PARAM, model=model).assemble()
+    dims = b.coarse_levels()
+    s = 1
+    o = OracleRVE(*meshes[s], param=PARAM, model=model)
+    m = o.mesh
+    _, rown = _perm(b, s, o, model)
+    Al = b.csr(s)
+    nx = int(round(np.sqrt(dims[0])))
+    nc = nx - 1
+    xy = m.xy[rown]
+    H = (m.x1 - m.x0) / nc
+    fx, fy = (xy[:, 0] - m.x0) / H, (xy[:, 1] - m.y0) / H
+    ci = np.clip(fx.astype(int), 0, nc - 1)
+    cj = np.clip(fy.astype(int), 0, nc - 1)
+    sx, ty = np.clip(fx - ci, 0, 1), np.clip(fy - cj, 0, 1)
+
+    def node(i, j, ncl):
+        nxl = ncl + 1
+        if model == "per":
+            return (j % ncl) * nxl + (i % ncl), np.ones_like(i, dtype=bool)
+        if model == "lin":
+            ok = (i >= 1) & (i <= ncl - 1) & (j >= 1) & (j <= ncl - 1)
+        else:
+            ok = np.ones_like(i, dtype=bool)
+        return j * nxl + i, ok
+
+    rows, cols, vals = [], [], []
+    for di, dj, w in ((0, 0, (1 - sx) * (1 - ty)), (1, 0, sx * (1 - ty)), (0, 1, (1 - sx) * ty), (1, 1, sx * ty)):
+        nd, ok = node(ci + di, cj + dj, nc)
+        for c in range(2):
+            rows.append(2 * np.arange(len(xy))[ok] + c)
+            cols.append(2 * nd[ok] + c)
+            vals.append(w[ok])
+    Z = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                      shape=(Al.shape[0], 2 * dims[0])).tocsr()
+    A1 = (Z.T @ Al @ Z).toarray()
+    A1l = b.coarse_dense(s, 0)
+    assert np.abs(A1 - A1l).max() <= 1e-11 * np.abs(A1).max(), np.abs(A1 - A1l).max()
+    # next level
+    if len(dims) > 1:
+        ncc = nc // 2
+        rows, cols, vals = [], [], []
+        for j in range(nc + 1):
+            for i in range(nc + 1):
+                nf, okf = node(np.array([i]), np.array([j]), nc)
+                if not okf[0] or (model == "per" and (i >= nc or j >= nc)):
+                    continue
+                for I, wi in ([(i // 2, 1.0)] if i % 2 == 0 else [(i // 2, 0.5), (i // 2 + 1, 0.5)]):
+                    for J, wj in ([(j // 2, 1.0)] if j % 2 == 0 else [(j // 2, 0.5), (j // 2 + 1, 0.5)]):
+                        ncd, okc = node(np.array([I]), np.array([J]), ncc)
+                        if okc[0]:
+                            for c in range(2):
+                                rows.append(2 * nf[0] + c); cols.append(2 * ncd[0] + c); vals.append(wi * wj)
+        P = sp.coo_matrix((vals, (rows, cols)), shape=(2 * dims[0], 2 * dims[1])).tocsr()
+        A2 = (P.T @ sp.csr_matrix(A1l) @ P).toarray()
+        A2l = b.coarse_dense(s, 1)
+        assert np.abs(A2 - A2l).max() <= 1e-11 * np.abs(A2).max(), np.abs(A2 - A2l).max()
+    b.close()
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "twolevel"])
+@pytest.mark.parametrize("model", ["lin", "dnn", "per", "MR"])
+def test_solution_tangent_snapshot_match_oracle(reduced_meshes, model, precond):
+    from deepbnd_b200.batch import RVEBatch
+    from oracle.rve_oracle import OracleRVE, vref_points, macro_strain
+    meshes = reduced_meshes
+    n = len(meshes)
+    pts = vref_points(-1, -1, 2, 2, 21)
+    b = RVEBatch().set_meshes(meshes, PARAM, model=model, vref_nb=21).assemble()
+    eps = np.broadcast_to(EPS3, (n, 3, 3)).copy()
+    uD = None
+    if model == "dnn":
+        uD = np.stack([np.stack([smooth_uD(81, 100 * s + i) for i in range(3)]) for s in range(n)])
+    status, iters = b.solve(eps, uD=uD, rtol=1e-11, maxit=6000, precond=precond)
+    assert (status == 0).all()
+    print(model, precond, "iters", iters)
+    C = b.tangent()
+    snap = b.snapshot()
+    for s in range(n):
+        o = OracleRVE(*meshes[s], param=PARAM, model=model)
+        Co = o.compute_tangent(uD_list=None if uD is None else uD[s], pts=pts)
+        U = b.solution(s)
+        for i in range(3):
+            uo = o.sol[i].reshape(-1, 2)
+            err = np.linalg.norm(U[:, i, :] - uo) / max(np.linalg.norm(uo), 1e-300)
+            assert err < 1e-8, (model, precond, s, i, err)
+        assert np.abs(C[s] - Co).max() < 1e-8 * np.abs(Co).max(), (model, s, np.abs(C[s] - Co).max())
+        for i in range(3):
+            a_o, B_o = o.affine_local(i, (0, 1))
+            sig_o = o.homogenise([0, 1], i).flatten()[[0, 3, 2]]
+            sigT_o = o.homogenise([0, 1, 2, 3], i).flatten()[[0, 3, 2]]
+            sol_o = o.eval_at(o.sol[i], pts).ravel()
+            sc = max(np.abs(sol_o).max(), 1e-300)
+            assert np.abs(snap["sol"][s, i] - sol_o).max() < 1e-8 * sc
+            assert np.abs(snap["sigma"][s, i] - sig_o).max() < 1e-8 * np.abs(sig_o).max()
+            assert np.abs(snap["sigmaT"][s, i] - sigT_o).max() < 1e-8 * np.abs(sigT_o).max()
+            assert np.abs(snap["a"][s, i] - a_o).max() < 1e-8 * max(np.abs(a_o).max(), sc)
+            assert np.abs(snap["B"][s, i] - B_o).max() < 1e-8 * max(np.abs(B_o).max(), sc)
+    b.close()
+
+
+def test_rhs_matches_oracle(reduced_meshes):
+    from deepbnd_b200.batch import RVEBatch
+    from oracle.rve_oracle import OracleRVE, load_vector, vref_points, macro_strain, strain2voigt
+    meshes = reduced_meshes[:2]
+    pts = vref_points(-1, -1, 2, 2, 21)
+    b = RVEBatch().set_meshes(meshes, PARAM, model="dnn", vref_nb=21).assemble()
+    uD = np.stack([np.stack([smooth_uD(81, 7 * s + i) for i in range(3)]) for s in range(2)])
+    eps = np.broadcast_to(EPS3, (2, 3, 3)).copy()
+    b.solve(eps, uD=uD, rtol=1e-6, maxit=500)
+    for s in range(2):
+        o = OracleRVE(*meshes[s], param=PARAM, model="dnn")
+        o._factor()
+        m = o.mesh
+        perm, _ = _perm(b, s, o, "dnn")
+        rl = b.rhs(s)
+        for i in range(3):
+            g, B = o.dirichlet_from_vref(uD[s, i], pts)
+            F = load_vector(m, o.ed, strain2voigt(macro_strain(i) - B))
+            u = np.zeros(2 * m.nn)
+            u[2 * m.bnd_nodes] = g[:, 0]
+            u[2 * m.bnd_nodes + 1] = g[:, 1]
+            ro = (F - o.K @ u)[o.free].reshape(-1, 2)[perm]
+            assert np.abs(rl[:, i, :] - ro).max() < 1e-12 * np.abs(ro).max()
+    b.close()
+
+
+def test_full_mesh_snapshot_per_and_projection(full_mesh):
+    """config-1 style: one 'full' RVE, periodic model, loads S (2) and A (0), Vref = internal boundary,
+    plus the RB projection Y = U M W^T against numpy."""
+    from deepbnd_b200.batch import RVEBatch
+    from oracle.rve_oracle import OracleRVE, vref_points, vref_mass, rb_project
+    pts = vref_points(-1, -1, 2, 2, 21)
+    for model in ("per", "MR"):
+        b = RVEBatch().set_meshes([full_mesh], PARAM, model=model, vref_nb=21, vref_box=(-1, -1, 2, 2)).assemble()
+        eps = np.array([[[0, 0, 1.0], [1.0, 0, 0]]])
+        status, iters = b.solve(eps, rtol=1e-11, maxit=8000)
+        snap = b.snapshot()
+        o = OracleRVE(*full_mesh, param=PARAM, model=model)
+        so = o.snapshot(pts)
+        for k, lab in enumerate(("S", "A")):
+            for key, okey in (("sol", "solutions_"), ("sigma", "sigma_"), ("sigmaT", "sigmaTotal_"), ("a", "a_"), ("B", "B_")):
+                ref = np.asarray(so[okey + lab]).ravel()
+                got = snap[key][0, k].ravel()
+                assert np.abs(got - ref).max() < 1e-8 * max(np.abs(ref).max(), 1e-3), (model, key, lab)
+        rng = np.random.RandomState(0)
+        W = np.linalg.qr(rng.randn(162, 160))[0].T
+        M = vref_mass(pts)
+        Y = b.project(np.stack([W, W]), M, translate=snap["a"])
+        for k in range(2):
+            Ut = snap["sol"][0, k].reshape(-1, 2) + snap["a"][0, k]
+            Yo = rb_project(Ut.ravel()[None], W, M)[0]
+            assert np.abs(Y[0, k] - Yo).max() < 1e-10 * np.abs(Yo).max()
+        b.close()
+
+
+def test_homogeneous_material_known_answer(coarse_reduced_meshes):
+    """analytic known answer: homogeneous material => u~ = 0, C = plane-stress D, every model."""
+    from deepbnd_b200.batch import RVEBatch
+    from deepbnd_b200.elasticity import getLameTable
+    lam, mu = getLameTable(0.3, 1.0, 0.3, 1.0)[0]
+    D = np.array([[lam + 2 * mu, lam, 0], [lam, lam + 2 * mu, 0], [0, 0, mu]])
+    n = len(coarse_reduced_meshes)
+    eps = np.broadcast_to(EPS3, (n, 3, 3)).copy()
+    for model in ("lin", "per", "MR"):
+        b = RVEBatch().set_meshes(coarse_reduced_meshes, (0.3, 1.0, 0.3, 1.0), model=model).assemble()
+        b.solve(eps, rtol=1e-11, maxit=4000)
+        C = b.tangent()
+        assert np.abs(C - D[None]).max() < 1e-9, (model, np.abs(C - D[None]).max())
+        b.close()
+
+
+def test_energy_ordering_and_symmetry(coarse_reduced_meshes):
+    """MR <= per <= lin in the energy sense; tangents symmetric positive definite."""
+    from deepbnd_b200.batch import RVEBatch
+    n = len(coarse_reduced_meshes)
+    eps = np.broadcast_to(EPS3, (n, 3, 3)).copy()
+    C = {}
+    for model in ("lin", "per", "MR"):
+        b = RVEBatch().set_meshes(coarse_reduced_meshes, PARAM, model=model).assemble()
+        b.solve(eps, rtol=1e-11, maxit=4000)
+        C[model] = b.tangent()
+        b.close()
+    for s in range(n):
+        for model in C:
+            assert np.abs(C[model][s] - C[model][s].T).max() < 1e-8
+            assert np.linalg.eigvalsh(0.5 * (C[model][s] + C[model][s].T)).min() > 0
+        assert np.linalg.eigvalsh(C["per"][s] - C["MR"][s]).min() > -1e-9
+        assert np.linalg.eigvalsh(C["lin"][s] - C["per"][s]).min() > -1e-9
