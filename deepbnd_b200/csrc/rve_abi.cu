@@ -19,14 +19,17 @@ thread_local std::string g_create_err;
 template <class T>
 struct DBuf {
     T* p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap = 0;
+    // grow-only: repeated passes over same-sized batches never touch cudaMalloc/cudaFree again
     cudaError_t alloc(size_t count) {
+        if (count <= cap && p) { n = count; return cudaSuccess; }
         release();
-        n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc((void**)&p, count * sizeof(T));
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) { n = count; cap = count; }
+        return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; cap = 0; }
     ~DBuf() { release(); }
 };
 
@@ -44,19 +47,22 @@ struct rve_batch_s {
     Mat8 mat;
     double vref_box[4];
     std::vector<SysSym> sym;
-    std::vector<int> node_base, elem_base, row_base, bnd_base, bedge_base;
-    std::vector<long long> blk_base;
-    long long N = 0, E = 0, R = 0, NB = 0, NBN = 0, NBE = 0;
-    int n_chunks = 0;
+    std::vector<int> node_base, elem_base, row_base, bnd_base, bedge_base, win_base, slice_base, halo_base, cn_base;
+    std::vector<long long> blk_base, grp_base, ent_base;
+    long long N = 0, E = 0, R = 0, NB = 0, NBN = 0, NBE = 0, NG = 0;
+    int n_win = 0, max_tile = 0, max_cn = 0;
     int ncx = 0, ncy = 0;
     Levels LV;
     // device arrays
-    DBuf<double> node_xy, row_xy, box, bval, dinv, wmean, bnd_s, bedge_nl, samp_lam;
-    DBuf<int> node_row, node_bnd, node_sys, elem_node, elem_sys, bcol, d_row_base, cell_ptr, bnd_sys, bnd_node,
-        bedge, d_bedge_base, samp_elem, chunk_sys, chunk_row0, chunk_n, sys_chunk0, active, cnt, d_iters, n_active,
-        err_flag;
+    DBuf<double> node_xy, box, bval, wmean, bnd_s, bedge_nl, samp_lam;
+    DBuf<float4> dinv;
+    DBuf<int> node_row, node_bnd, node_sys, elem_node, elem_sys, d_row_base, bnd_sys, bnd_node,
+        bedge, d_bedge_base, samp_elem, win_sys, win_row0, win_n, win_slice0, win_halo0, win_cn0, sys_win0, halo,
+        cn_node, active, cnt, d_iters, n_active, err_flag;
     DBuf<unsigned char> elem_reg;
-    DBuf<unsigned> row_ptr;
+    DBuf<unsigned> slice_ptr, cn_beg;
+    DBuf<uint16_t> scol, cn_ent;
+    DBuf<RowInfo> rowinfo;
     DBuf<double> lvA[RVE_MAXLEV], lvD[RVE_MAXLEV], lvR[RVE_MAXLEV], lvX[RVE_MAXLEV], lvT[RVE_MAXLEV];
     DBuf<double> p, q, x, r, b, part, sc;
     DBuf<double> eps, eps_eff, Bmat, uD, gval, d_vbox, U, acc, sigL, sigT, aout, Bout, sol, Mx, Gaff, aaff;
@@ -95,12 +101,68 @@ static cudaError_t upload(DBuf<T>& d, const std::vector<T>& v, cudaStream_t s) {
     return cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
-static ChunkTab chunk_tab(rve_batch_s* h) {
-    ChunkTab ct;
-    ct.chunk_sys = h->chunk_sys.p; ct.chunk_row0 = h->chunk_row0.p; ct.chunk_n = h->chunk_n.p;
-    ct.sys_chunk0 = h->sys_chunk0.p;
-    return ct;
+static WinTab win_tab(rve_batch_s* h) {
+    WinTab wt;
+    wt.win_sys = h->win_sys.p; wt.win_row0 = h->win_row0.p; wt.win_n = h->win_n.p; wt.win_slice0 = h->win_slice0.p;
+    wt.win_halo0 = h->win_halo0.p; wt.win_cn0 = h->win_cn0.p; wt.sys_win0 = h->sys_win0.p; wt.row_base = h->d_row_base.p;
+    return wt;
 }
+
+static Sell sell_tab(rve_batch_s* h) {
+    Sell sl;
+    sl.slice_ptr = h->slice_ptr.p; sl.scol = h->scol.p; sl.halo = h->halo.p;
+    return sl;
+}
+
+// dynamic shared memory of the PCG kernels
+static size_t smem_spmv(rve_batch_s* h, int K) { return (size_t)(h->max_tile + RVE_WIN) * K * sizeof(double2); }
+static size_t smem_update(int K) { return (size_t)RVE_WIN * K * sizeof(double2) + RVE_WIN * sizeof(float2) + 4 * RVE_WIN * sizeof(uint16_t); }
+static size_t smem_direction(rve_batch_s* h, int K) { return (size_t)h->max_cn * K * sizeof(double2); }
+
+template <int K>
+static cudaError_t pcg_attrs(rve_batch_s* h) {
+    cudaError_t e = cudaFuncSetAttribute(k_spmv<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_spmv(h, K));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_update<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_update(K));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_direction<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_direction(h, K));
+}
+
+struct PcgArgs {
+    WinTab wt; Sell sl; Levels LV;
+    int n_win, n_sys, K, precond;
+    double rtol2;
+    size_t sm_spmv, sm_upd, sm_dir;
+};
+
+template <int K>
+static void launch_spmv(rve_batch_s* h, const PcgArgs& a, const double* p, double* q, int* active, double* part, int* cnt,
+                        double* sc, cudaStream_t st) {
+    k_spmv<K><<<a.n_win, RVE_WIN, a.sm_spmv, st>>>(a.wt, a.sl, (const double2*)h->bval.p, (const double2*)p, (double2*)q,
+                                                  active, part, cnt, sc);
+}
+
+template <int K>
+static void launch_update(rve_batch_s* h, const PcgArgs& a, int init, int iter, cudaStream_t st) {
+    k_update<K><<<a.n_win, RVE_WIN, a.sm_upd, st>>>(a.wt, (const double2*)h->p.p, (const double2*)h->q.p, (double2*)h->x.p,
+                                                   (double2*)h->r.p, h->dinv.p, h->rowinfo.p, h->cn_node.p, h->cn_beg.p,
+                                                   h->cn_ent.p, a.LV.rc[0], a.LV.g[0].G, h->active.p, h->part.p, h->cnt.p,
+                                                   h->sc.p, init, iter, a.rtol2, a.precond, h->d_iters.p, h->n_active.p);
+}
+
+template <int K>
+static void launch_direction(rve_batch_s* h, const PcgArgs& a, cudaStream_t st) {
+    k_direction<K><<<a.n_win, RVE_WIN, a.sm_dir, st>>>(a.wt, (double2*)h->p.p, (const double2*)h->r.p, h->dinv.p, h->rowinfo.p,
+                                                      h->cn_node.p, (const double2*)a.LV.xc[0], a.LV.g[0].G, h->active.p,
+                                                      h->sc.p, a.precond);
+}
+
+#define K_DISPATCH(K, call)              \
+    do {                                 \
+        if ((K) == 1) { call(1); }       \
+        else if ((K) == 2) { call(2); }  \
+        else { call(3); }                \
+    } while (0)
 
 extern "C" {
 
@@ -182,35 +244,47 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     // prefix sums
     h->node_base.assign(n_sys + 1, 0); h->elem_base.assign(n_sys + 1, 0); h->row_base.assign(n_sys + 1, 0);
     h->bnd_base.assign(n_sys + 1, 0); h->bedge_base.assign(n_sys + 1, 0); h->blk_base.assign(n_sys + 1, 0);
-    std::vector<int> sys_chunk0(n_sys + 1, 0);
+    h->win_base.assign(n_sys + 1, 0); h->slice_base.assign(n_sys + 1, 0); h->halo_base.assign(n_sys + 1, 0);
+    h->cn_base.assign(n_sys + 1, 0); h->grp_base.assign(n_sys + 1, 0); h->ent_base.assign(n_sys + 1, 0);
+    h->max_tile = 0; h->max_cn = 0;
     for (int s = 0; s < n_sys; ++s) {
         long long nn = (long long)h->node_base[s] + S[s].nn, ne = (long long)h->elem_base[s] + S[s].nt;
         long long nr = (long long)h->row_base[s] + S[s].na;
         long long nb = h->blk_base[s] + (long long)S[s].bcol.size();
-        if (nn > 2000000000LL || ne > 2000000000LL || nr * 4 > 2000000000LL || nb > 4000000000LL)
+        long long ng = h->grp_base[s] + (long long)S[s].slice_ptr.back();
+        long long nh = (long long)h->halo_base[s] + (long long)S[s].halo.size();
+        long long nent = h->ent_base[s] + (long long)S[s].cn_ent.size();
+        if (nn > 2000000000LL || ne > 2000000000LL || nr * 4 > 2000000000LL || ng > 4000000000LL || nh > 2000000000LL ||
+            nent > 4000000000LL)
             FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
         h->node_base[s + 1] = (int)nn; h->elem_base[s + 1] = (int)ne; h->row_base[s + 1] = (int)nr;
         h->bnd_base[s + 1] = h->bnd_base[s] + S[s].nb; h->bedge_base[s + 1] = h->bedge_base[s] + S[s].nbe;
-        h->blk_base[s + 1] = nb;
-        sys_chunk0[s + 1] = sys_chunk0[s] + (S[s].na + RVE_CH - 1) / RVE_CH;
+        h->blk_base[s + 1] = nb; h->grp_base[s + 1] = ng; h->halo_base[s + 1] = (int)nh; h->ent_base[s + 1] = nent;
+        h->win_base[s + 1] = h->win_base[s] + S[s].nwin;
+        h->slice_base[s + 1] = h->slice_base[s] + (int)S[s].slice_ptr.size() - 1;
+        h->cn_base[s + 1] = h->cn_base[s] + (int)S[s].cn_node.size();
+        h->max_tile = std::max(h->max_tile, S[s].max_tile); h->max_cn = std::max(h->max_cn, S[s].max_cn);
     }
     h->N = h->node_base[n_sys]; h->E = h->elem_base[n_sys]; h->R = h->row_base[n_sys];
     h->NB = h->blk_base[n_sys]; h->NBN = h->bnd_base[n_sys]; h->NBE = h->bedge_base[n_sys];
-    h->n_chunks = sys_chunk0[n_sys];
+    h->NG = h->grp_base[n_sys]; h->n_win = h->win_base[n_sys];
+    const int n_win = h->n_win, n_slice = h->slice_base[n_sys], n_cn = h->cn_base[n_sys];
+    if ((size_t)(h->max_tile + RVE_WIN) * 3 * sizeof(double2) > 200 * 1024) FAIL(RVE_E_MESH, "window halo too large for shared memory");
 
     // flatten (parallel over systems)
-    std::vector<double> node_xy(2 * h->N), row_xy(2 * h->R), box(4 * (size_t)n_sys), bnd_s, bedge_nl(2 * h->NBE), samp_lam;
-    std::vector<int> node_row(h->N), node_bnd(h->N), node_sys(h->N), elem_node(6 * h->E), elem_sys(h->E), bcol(h->NB),
-        cell_ptr((size_t)n_sys * (P.ncx * P.ncy + 1)), bnd_sys(h->NBN), bnd_node(h->NBN), bedge(3 * h->NBE), samp_elem,
-        chunk_sys(h->n_chunks), chunk_row0(h->n_chunks), chunk_n(h->n_chunks);
+    std::vector<double> node_xy(2 * h->N), box(4 * (size_t)n_sys), bnd_s, bedge_nl(2 * h->NBE), samp_lam;
+    std::vector<int> node_row(h->N), node_bnd(h->N), node_sys(h->N), elem_node(6 * h->E), elem_sys(h->E),
+        bnd_sys(h->NBN), bnd_node(h->NBN), bedge(3 * h->NBE), samp_elem, win_sys(n_win), win_row0(n_win), win_n(n_win),
+        win_slice0(n_win), win_halo0(n_win + 1), win_cn0(n_win + 1), halo(h->halo_base[n_sys]), cn_node(n_cn);
     std::vector<unsigned char> elem_reg(h->E);
-    std::vector<unsigned> row_ptr(h->R + 1);
+    std::vector<unsigned> slice_ptr(n_slice + 1), cn_beg(n_cn + 1);
+    std::vector<uint16_t> scol((size_t)h->NG * 32), cn_ent(h->ent_base[n_sys]);
+    std::vector<RowInfo> rowinfo(h->R);
     if (model == RVE_MODEL_DNN) bnd_s.resize(2 * h->NBN);
     if (h->nvref) { samp_elem.resize((size_t)n_sys * h->nvref); samp_lam.resize(2 * (size_t)n_sys * h->nvref); }
     parallel_for(n_sys, [&](int s) {
         const SysSym& Y = S[s];
         const int nb0 = h->node_base[s], eb0 = h->elem_base[s], rb0 = h->row_base[s];
-        const long long bb0 = h->blk_base[s];
         for (int k = 0; k < 4; ++k) box[4 * (size_t)s + k] = Y.box[k];
         for (int n = 0; n < Y.nn; ++n) {
             node_xy[2 * ((size_t)nb0 + n)] = Y.node_xy[2 * n]; node_xy[2 * ((size_t)nb0 + n) + 1] = Y.node_xy[2 * n + 1];
@@ -222,14 +296,21 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
             for (int k = 0; k < 6; ++k) elem_node[6 * ((size_t)eb0 + t) + k] = nb0 + Y.elem_node[6 * t + k];
             elem_reg[eb0 + t] = Y.reg[t]; elem_sys[eb0 + t] = s;
         }
-        for (int r = 0; r < Y.na; ++r) {
-            row_xy[2 * ((size_t)rb0 + r)] = Y.node_xy[2 * Y.row_node[r]];
-            row_xy[2 * ((size_t)rb0 + r) + 1] = Y.node_xy[2 * Y.row_node[r] + 1];
-            row_ptr[rb0 + r] = (unsigned)(bb0 + Y.row_ptr[r]);
+        for (int r = 0; r < Y.na; ++r) rowinfo[(size_t)rb0 + r] = Y.rowinfo[r];
+        const int w0 = h->win_base[s], sl0 = h->slice_base[s], hb0 = h->halo_base[s], cb0 = h->cn_base[s];
+        for (int w = 0; w < Y.nwin; ++w) {
+            win_sys[w0 + w] = s; win_row0[w0 + w] = rb0 + w * RVE_WIN; win_n[w0 + w] = Y.win_n[w];
+            win_slice0[w0 + w] = sl0 + Y.win_slice0[w]; win_halo0[w0 + w] = hb0 + Y.win_halo0[w];
+            win_cn0[w0 + w] = cb0 + Y.win_cn0[w];
         }
-        if (s == n_sys - 1) row_ptr[h->R] = (unsigned)h->NB;
-        for (size_t k = 0; k < Y.bcol.size(); ++k) bcol[bb0 + k] = rb0 + Y.bcol[k];
-        for (size_t k = 0; k < Y.cell_ptr.size(); ++k) cell_ptr[(size_t)s * (P.ncx * P.ncy + 1) + k] = Y.cell_ptr[k];
+        if (s == n_sys - 1) { win_halo0[n_win] = h->halo_base[n_sys]; win_cn0[n_win] = n_cn; }
+        for (size_t k = 0; k + 1 < Y.slice_ptr.size(); ++k) slice_ptr[sl0 + k] = (unsigned)(h->grp_base[s] + Y.slice_ptr[k]);
+        if (s == n_sys - 1) slice_ptr[n_slice] = (unsigned)h->NG;
+        std::copy(Y.scol.begin(), Y.scol.end(), scol.begin() + (size_t)h->grp_base[s] * 32);
+        for (size_t k = 0; k < Y.halo.size(); ++k) halo[hb0 + k] = rb0 + Y.halo[k];
+        for (size_t k = 0; k < Y.cn_node.size(); ++k) { cn_node[cb0 + k] = Y.cn_node[k]; cn_beg[cb0 + k] = (unsigned)(h->ent_base[s] + Y.cn_beg[k]); }
+        if (s == n_sys - 1) cn_beg[n_cn] = (unsigned)h->ent_base[n_sys];
+        std::copy(Y.cn_ent.begin(), Y.cn_ent.end(), cn_ent.begin() + h->ent_base[s]);
         for (int i = 0; i < Y.nb; ++i) {
             bnd_sys[h->bnd_base[s] + i] = s; bnd_node[h->bnd_base[s] + i] = nb0 + Y.bnd_node[i];
             if (model == RVE_MODEL_DNN) {
@@ -246,30 +327,28 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
             samp_lam[2 * ((size_t)s * h->nvref + k)] = Y.samp_lam[2 * k];
             samp_lam[2 * ((size_t)s * h->nvref + k) + 1] = Y.samp_lam[2 * k + 1];
         }
-        int c = sys_chunk0[s];
-        for (int r = 0; r < Y.na; r += RVE_CH, ++c) {
-            chunk_sys[c] = s; chunk_row0[c] = rb0 + r; chunk_n[c] = std::min(RVE_CH, Y.na - r);
-        }
     });
     auto t1 = std::chrono::steady_clock::now();
     h->t_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
 
     cudaStream_t st = h->stream;
-    UPL(h->node_xy, node_xy); UPL(h->row_xy, row_xy); UPL(h->box, box);
+    UPL(h->node_xy, node_xy); UPL(h->box, box);
     UPL(h->node_row, node_row); UPL(h->node_bnd, node_bnd); UPL(h->node_sys, node_sys);
     UPL(h->elem_node, elem_node); UPL(h->elem_sys, elem_sys); UPL(h->elem_reg, elem_reg);
-    UPL(h->row_ptr, row_ptr); UPL(h->bcol, bcol); UPL(h->d_row_base, h->row_base);
-    UPL(h->cell_ptr, cell_ptr); UPL(h->bnd_sys, bnd_sys); UPL(h->bnd_node, bnd_node);
+    UPL(h->d_row_base, h->row_base);
+    UPL(h->bnd_sys, bnd_sys); UPL(h->bnd_node, bnd_node);
     UPL(h->bnd_s, bnd_s); UPL(h->bedge, bedge); UPL(h->bedge_nl, bedge_nl);
     UPL(h->d_bedge_base, h->bedge_base); UPL(h->samp_elem, samp_elem); UPL(h->samp_lam, samp_lam);
-    UPL(h->chunk_sys, chunk_sys); UPL(h->chunk_row0, chunk_row0); UPL(h->chunk_n, chunk_n);
-    UPL(h->sys_chunk0, sys_chunk0);
+    UPL(h->win_sys, win_sys); UPL(h->win_row0, win_row0); UPL(h->win_n, win_n); UPL(h->win_slice0, win_slice0);
+    UPL(h->win_halo0, win_halo0); UPL(h->win_cn0, win_cn0); UPL(h->sys_win0, h->win_base);
+    UPL(h->slice_ptr, slice_ptr); UPL(h->scol, scol); UPL(h->halo, halo); UPL(h->cn_node, cn_node);
+    UPL(h->cn_beg, cn_beg); UPL(h->cn_ent, cn_ent); UPL(h->rowinfo, rowinfo);
     std::vector<double> vb(h->vref_box, h->vref_box + 4);
     UPL(h->d_vbox, vb);
-    CU(h->bval.alloc(4 * (size_t)h->NB)); CU(h->dinv.alloc(4 * (size_t)h->R)); CU(h->wmean.alloc(h->R));
+    CU(h->bval.alloc(128 * (size_t)h->NG)); CU(h->dinv.alloc((size_t)h->R)); CU(h->wmean.alloc(h->R));
     CU(h->active.alloc(n_sys)); CU(h->cnt.alloc(n_sys)); CU(h->d_iters.alloc(n_sys)); CU(h->n_active.alloc(1));
     CU(h->err_flag.alloc(1));
-    CU(h->part.alloc((size_t)h->n_chunks * 8)); CU(h->sc.alloc((size_t)n_sys * 4 * SC_N));
+    CU(h->part.alloc((size_t)h->n_win * 8)); CU(h->sc.alloc((size_t)n_sys * 4 * SC_N));
     CU(h->Mx.alloc((size_t)n_sys * 16)); CU(h->Gaff.alloc((size_t)n_sys * 16)); CU(h->aaff.alloc((size_t)n_sys * 8));
     CU(h->acc.alloc((size_t)n_sys * ACC_PER_SYS));
     // coarse hierarchy
@@ -307,9 +386,9 @@ int rve_assemble(rve_handle_t h) {
     CU(cudaMemsetAsync(h->bval.p, 0, h->bval.n * sizeof(double), st));
     CU(cudaMemsetAsync(h->wmean.p, 0, h->wmean.n * sizeof(double), st));
     CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), st));
-    k_assemble<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, h->elem_node.p, h->elem_reg.p, h->node_xy.p, h->node_row.p,
-                                               h->row_ptr.p, h->bcol.p, h->bval.p, h->wmean.p, h->mat);
-    k_dinv<<<cdiv(h->R, 256), 256, 0, st>>>((int)h->R, h->row_ptr.p, h->bcol.p, h->bval.p, h->dinv.p);
+    k_assemble<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
+                                               h->node_row.p, win_tab(h), sell_tab(h), h->bval.p, h->wmean.p, h->mat);
+    k_dinv<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), sell_tab(h), h->bval.p, h->dinv.p);
     CU(cudaEventRecord(h->ev[1], st));
     // two-level preconditioner: Galerkin hierarchy
     Levels& LV = h->LV;
@@ -352,16 +431,22 @@ int rve_get_csr(rve_handle_t h, int32_t sys, int32_t* rowptr, int32_t* col, doub
     H_CHECK(h);
     if (!h->assembled || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_STATE, "not assembled / bad system index");
     const SysSym& Y = h->sym[sys];
-    const size_t nb = Y.bcol.size();
-    std::vector<double> bv(4 * nb);
-    CU(cudaMemcpy(bv.data(), h->bval.p + 4 * (size_t)h->blk_base[sys], 4 * nb * sizeof(double), cudaMemcpyDeviceToHost));
+    const size_t ng = Y.slice_ptr.back();
+    std::vector<double> bv(128 * ng);
+    CU(cudaMemcpy(bv.data(), h->bval.p + 128 * (size_t)h->grp_base[sys], bv.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    // SELL slot j of a row holds the j-th (sorted) CSR column of that row
     int64_t pos = 0;
-    for (int r = 0; r < Y.na; ++r)
+    for (int r = 0; r < Y.na; ++r) {
+        const int w = r / RVE_WIN, rl = r % RVE_WIN, lane = rl & 31;
+        const size_t g0 = Y.slice_ptr[Y.win_slice0[w] + (rl >> 5)];
         for (int c = 0; c < 2; ++c) {
             rowptr[2 * r + c] = (int32_t)pos;
-            for (unsigned k = Y.row_ptr[r]; k < Y.row_ptr[r + 1]; ++k)
-                for (int d = 0; d < 2; ++d) { col[pos] = 2 * Y.bcol[k] + d; val[pos] = bv[4 * (size_t)k + 2 * c + d]; ++pos; }
+            for (unsigned k = Y.row_ptr[r]; k < Y.row_ptr[r + 1]; ++k) {
+                const size_t g = g0 + (k - Y.row_ptr[r]);
+                for (int d = 0; d < 2; ++d) { col[pos] = 2 * Y.bcol[k] + d; val[pos] = bv[128 * g + 64 * c + 2 * lane + d]; ++pos; }
+            }
         }
+    }
     rowptr[2 * Y.na] = (int32_t)pos;
     return 0;
 }
@@ -446,7 +531,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     h->K = K; h->NL = NL; h->solved = false;
     cudaStream_t st = h->stream;
     const size_t RK = (size_t)h->R * K * 2;
-    CU(h->p.alloc((size_t)h->R * 8)); CU(h->q.alloc(RK)); CU(h->x.alloc(RK)); CU(h->r.alloc(RK)); CU(h->b.alloc(RK));
+    CU(h->p.alloc(RK)); CU(h->q.alloc(RK)); CU(h->x.alloc(RK)); CU(h->r.alloc(RK)); CU(h->b.alloc(RK));
     CU(h->eps.alloc((size_t)n_sys * NL * 3)); CU(h->eps_eff.alloc((size_t)n_sys * NL * 3)); CU(h->Bmat.alloc((size_t)n_sys * NL * 4));
     CU(h->U.alloc((size_t)h->N * NL * 2));
     CU(cudaMemcpyAsync(h->eps.p, eps, (size_t)n_sys * NL * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -482,13 +567,18 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     std::vector<int> ones(n_sys, 1);
     CU(cudaMemcpyAsync(h->active.p, ones.data(), n_sys * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->n_active.p, &n_sys, sizeof(int), cudaMemcpyHostToDevice, st));
-    ChunkTab ct = chunk_tab(h);
-    Levels LV = h->LV;
-    LV.K = K;
-    const double rtol2 = rtol * rtol;
-    const int nch = h->n_chunks;
-    k_update<<<nch, 256, 0, st>>>((const double2*)h->p.p, (const double2*)h->q.p, (double2*)h->x.p, (double2*)h->r.p, h->dinv.p,
-                                  K, ct, h->active.p, h->part.p, h->cnt.p, h->sc.p, 1, -1, rtol2, precond, h->d_iters.p, h->n_active.p);
+    PcgArgs pa;
+    pa.wt = win_tab(h); pa.sl = sell_tab(h); pa.LV = h->LV; pa.LV.K = K;
+    pa.n_win = h->n_win; pa.n_sys = n_sys; pa.K = K; pa.precond = precond; pa.rtol2 = rtol * rtol;
+    pa.sm_spmv = smem_spmv(h, K); pa.sm_upd = smem_update(K); pa.sm_dir = smem_direction(h, K);
+#define ATTR_(KK) CU(pcg_attrs<KK>(h))
+    K_DISPATCH(K, ATTR_);
+#undef ATTR_
+    const Levels& LV = pa.LV;
+    CU(cudaMemsetAsync(LV.rc[0], 0, h->lvR[0].n * sizeof(double), st));
+#define UPD0_(KK) launch_update<KK>(h, pa, 1, -1, st)
+    K_DISPATCH(K, UPD0_);
+#undef UPD0_
     int it = 0, launched = 0;
     const int CHECK = 8;
     h->launches += 3 + (uD ? 1 : 0);
@@ -499,18 +589,18 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     *h->h_nactive = n_sys;
     while (it < maxit) {
         for (int k = 0; k < CHECK && it < maxit; ++k, ++it) {
-            if (precond)
-                k_vcycle<<<n_sys, 256, 0, st>>>(LV, h->r.p, h->row_xy.p, h->d_row_base.p, h->cell_ptr.p, h->box.p, h->active.p,
-                                                h->sc.p, it == 0);
-            k_direction<<<nch, 256, 0, st>>>((double2*)h->p.p, (const double2*)h->r.p, h->dinv.p, h->row_xy.p, h->box.p, K, ct,
-                                             h->active.p, h->sc.p, precond, LV.g[0], LV.xc[0]);
+            if (precond) k_vcycle<<<n_sys, 256, 0, st>>>(LV, h->active.p, h->sc.p, it == 0);
+#define DIR_(KK) launch_direction<KK>(h, pa, st)
+            K_DISPATCH(K, DIR_);
+#undef DIR_
             cudaEventRecord(pool_event(2 * (size_t)it), st);
-            k_spmv_dot<<<nch, 256, 0, st>>>(h->row_ptr.p, h->bcol.p, (const double2*)h->bval.p, (const double2*)h->p.p,
-                                            (double2*)h->q.p, K, ct, h->active.p, h->part.p, h->cnt.p, h->sc.p);
+#define SPMV_(KK) launch_spmv<KK>(h, pa, h->p.p, h->q.p, h->active.p, h->part.p, h->cnt.p, h->sc.p, st)
+            K_DISPATCH(K, SPMV_);
+#undef SPMV_
             cudaEventRecord(pool_event(2 * (size_t)it + 1), st);
-            k_update<<<nch, 256, 0, st>>>((const double2*)h->p.p, (const double2*)h->q.p, (double2*)h->x.p, (double2*)h->r.p,
-                                          h->dinv.p, K, ct, h->active.p, h->part.p, h->cnt.p, h->sc.p, 0, it, rtol2, precond,
-                                          h->d_iters.p, h->n_active.p);
+#define UPD_(KK) launch_update<KK>(h, pa, 0, it, st)
+            K_DISPATCH(K, UPD_);
+#undef UPD_
             ++launched;
             h->launches += precond ? 4 : 3;
         }
@@ -670,23 +760,26 @@ int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_l
     const int K = n_rhs, n_sys = h->n_sys;
     DBuf<double> p, q, part, sc;
     DBuf<int> active, cnt;
-    CU(p.alloc((size_t)h->R * 8)); CU(q.alloc((size_t)h->R * K * 2)); CU(part.alloc((size_t)h->n_chunks * 8));
+    CU(p.alloc((size_t)h->R * K * 2)); CU(q.alloc((size_t)h->R * K * 2)); CU(part.alloc((size_t)h->n_win * 8));
     CU(sc.alloc((size_t)n_sys * 4 * SC_N)); CU(active.alloc(n_sys)); CU(cnt.alloc(n_sys));
-    std::vector<double> hp((size_t)h->R * 8);
-    for (size_t i = 0; i < hp.size(); ++i) hp[i] = ((i & 7) < (size_t)(2 * K)) ? 1.0 + 1e-3 * (double)(i % 97) : 0.0;
+    std::vector<double> hp((size_t)h->R * K * 2);
+    for (size_t i = 0; i < hp.size(); ++i) hp[i] = 1.0 + 1e-3 * (double)(i % 97);
     CU(cudaMemcpyAsync(p.p, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     std::vector<int> ones(n_sys, 1);
     CU(cudaMemcpyAsync(active.p, ones.data(), n_sys * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(cnt.p, 0, n_sys * sizeof(int), st));
     CU(cudaMemsetAsync(sc.p, 0, sc.n * sizeof(double), st));
-    ChunkTab ct = chunk_tab(h);
-    for (int wu = 0; wu < 3; ++wu)
-        k_spmv_dot<<<h->n_chunks, 256, 0, st>>>(h->row_ptr.p, h->bcol.p, (const double2*)h->bval.p, (const double2*)p.p,
-                                                (double2*)q.p, K, ct, active.p, part.p, cnt.p, sc.p);
+    PcgArgs pa;
+    pa.wt = win_tab(h); pa.sl = sell_tab(h); pa.LV = h->LV; pa.n_win = h->n_win; pa.n_sys = n_sys; pa.K = K;
+    pa.precond = 0; pa.rtol2 = 0; pa.sm_spmv = smem_spmv(h, K); pa.sm_upd = smem_update(K); pa.sm_dir = smem_direction(h, K);
+#define ATTR_(KK) CU(pcg_attrs<KK>(h))
+    K_DISPATCH(K, ATTR_);
+#undef ATTR_
+#define SPMV_(KK) launch_spmv<KK>(h, pa, p.p, q.p, active.p, part.p, cnt.p, sc.p, st)
+    for (int wu = 0; wu < 3; ++wu) K_DISPATCH(K, SPMV_);
     CU(cudaEventRecord(h->ev[0], st));
-    for (int i = 0; i < reps; ++i)
-        k_spmv_dot<<<h->n_chunks, 256, 0, st>>>(h->row_ptr.p, h->bcol.p, (const double2*)h->bval.p, (const double2*)p.p,
-                                                (double2*)q.p, K, ct, active.p, part.p, cnt.p, sc.p);
+    for (int i = 0; i < reps; ++i) K_DISPATCH(K, SPMV_);
+#undef SPMV_
     CU(cudaEventRecord(h->ev[1], st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
@@ -716,6 +809,7 @@ extern "C" int rve_host_symbolic(const double* xy, int32_t nv, const int32_t* tr
     P.ncx = pick_nc(S.box[2], S.max_ext); P.ncy = pick_nc(S.box[3], S.max_ext);
     sym_pass2(S, P);
     if (!S.err.empty()) return RVE_E_MESH;
+    if (!sym_selfcheck(S).empty()) return RVE_E_STATE;
     *n_nodes = S.nn; *n_rows = S.na; *n_blocks = (int32_t)S.bcol.size(); *nc = P.ncx;
     if (S.na > cap_rows || (int)S.bcol.size() > cap_blocks) return RVE_E_ARG;
     for (int r = 0; r <= S.na; ++r) rowptr[r] = (int32_t)S.row_ptr[r];

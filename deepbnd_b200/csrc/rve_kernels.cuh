@@ -2,22 +2,29 @@
 //
 // Data layout (all systems of a batch concatenated; "row" = active P2 node = 2x2 block row):
 //   node_xy[N][2], node_row[N] (global row or -1), node_bnd[N]; elem_node[E][6] (global node ids),
-//   elem_reg[E], elem_sys[E];  row_ptr[R+1] (uint32 block offsets), bcol[NB] (global row ids),
-//   bval[NB][4] (K00 K01 K10 K11), dinv[R][4], row_xy[R][2], wmean[R].
-//   PCG vectors: p[R][4][2] (padded: one 64-byte line segment per gathered node),
-//                x,r,q,b[R][K][2] compact.
+//   elem_reg[E], elem_sys[E].
+//   Rows of a system are ordered along the Morton curve of the level-1 coarse cells and cut into
+//   WINDOWS of RVE_WIN (=256) rows (one CTA of the PCG kernels each); inside a window rows are
+//   sorted by length so that the 32-row SELL slices are uniform.  Matrix storage (SELL-32):
+//     slice_ptr[S+1]  offsets in 32-entry groups;  group g = slot j of one slice
+//     scol[g][32]     uint16 column, LOCAL to the window's p-tile (own rows, then the halo rows)
+//     bval[g][2][32]  double2: (K00,K01) and (K10,K11) of the block of lane's row
+//     halo[]          global row ids each window gathers into its shared-memory p-tile
+//   PCG vectors p,x,r,q,b[R][K][2] (K = number of right-hand sides, compile-time in the kernels),
+//   dinv32[R] float4 (block-Jacobi, preconditioner only), wmean[R], rowinfo[R] (bilinear weights and
+//   window-local slots of the 4 level-1 nodes around the row), cn_node/cn_beg/cn_ent (per window: the
+//   level-1 nodes it touches and, per node, the (row, corner) pairs restricting to it).
 //   Coarse level l (structured (ncx+1)x(ncy+1) grid per system, 25-point block stencil):
 //                A[sys][slot 25][4][G], dinv[sys][G][4], vectors [sys][G][K][2].
-// Rows are processed in chunks of <= RVE_CH rows that never straddle a system; per-chunk partial
-// dot products are combined in a fixed order by the last CTA of each system (deterministic).
+// Per-window partial dot products are combined in a fixed order by the last CTA of each system.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/rve_b200.h"
 #include "rve_math.cuh"
+#include "rve_symbolic.hpp"   // RVE_WIN, RowInfo
 
-#define RVE_CH 64          // rows per chunk (CTA of 256 threads: 8 warps x 8 rows, or 64 rows x 4 rhs)
 #define RVE_MAXLEV 8
 #define RVE_OMEGA 0.8      // damped block-Jacobi smoother on the coarse levels
 
@@ -40,11 +47,21 @@ struct Levels {
     double* tc[RVE_MAXLEV];
 };
 
-struct ChunkTab {
-    const int* chunk_sys;   // [n_chunks]
-    const int* chunk_row0;  // global first row
-    const int* chunk_n;     // rows in the chunk
-    const int* sys_chunk0;  // [n_sys+1]
+struct WinTab {
+    const int* win_sys;      // [n_win]
+    const int* win_row0;     // global first row
+    const int* win_n;        // rows in the window (<= RVE_WIN)
+    const int* win_slice0;   // global first slice (ceil(n/32) slices)
+    const int* win_halo0;    // [n_win+1] offsets into halo
+    const int* win_cn0;      // [n_win+1] offsets into cn_node / cn_beg
+    const int* sys_win0;     // [n_sys+1]
+    const int* row_base;     // [n_sys+1] first global row of a system
+};
+
+struct Sell {
+    const unsigned* slice_ptr;
+    const uint16_t* scol;
+    const int* halo;
 };
 
 // per (system, rhs) scalars
@@ -82,32 +99,48 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ---------------------------------------------------------------------------------------------
 // (1) numeric assembly: warp per element, 21 lanes compute the upper-triangular 2x2 blocks and
-//     scatter them (and their transposes) with fp64 atomics into the node-block CSR.
+//     scatter them (and their transposes) with fp64 atomics into the SELL block storage.
 //     Connectivity / coordinates are staged through warp shuffles, the material table lives in
 //     shared memory.  Replaces mp.block_assemble(a) (micro_model.py:60).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int find_block(const unsigned* __restrict__ row_ptr, const int* __restrict__ bcol,
-                                          int row, int col) {
-    unsigned lo = row_ptr[row], hi = row_ptr[row + 1];
-    while (lo < hi) {
-        unsigned mid = (lo + hi) >> 1;
-        int c = bcol[mid];
-        if (c < col) lo = mid + 1; else hi = mid;
+// entry index (group*32 + lane) of block (ra, rb), both global rows of system sys
+__device__ __forceinline__ long long sell_find(const WinTab& wt, const Sell& sl, int sys, int ra, int rb) {
+    const int w = wt.sys_win0[sys] + (ra - wt.row_base[sys]) / RVE_WIN;
+    const int r0 = wt.win_row0[w], n = wt.win_n[w];
+    int lc;
+    if (rb >= r0 && rb < r0 + n) {
+        lc = rb - r0;
+    } else {
+        int lo = wt.win_halo0[w], hi = wt.win_halo0[w + 1];
+        const int h0 = lo;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (sl.halo[mid] < rb) lo = mid + 1; else hi = mid;
+        }
+        lc = n + (lo - h0);
     }
-    return (int)lo;  // caller guarantees presence
+    const int rl = ra - r0, lane = rl & 31;
+    const int slice = wt.win_slice0[w] + (rl >> 5);
+    const unsigned g0 = sl.slice_ptr[slice], g1 = sl.slice_ptr[slice + 1];
+    for (unsigned g = g0; g < g1; ++g)
+        if (sl.scol[(size_t)g * 32 + lane] == lc) return (long long)g * 32 + lane;
+    return -1;  // cannot happen for a pattern built from the same mesh
 }
+
+// doubles of entry e=(g,lane): K00,K01 at 128 g + 2 lane, K10,K11 at 128 g + 64 + 2 lane
+__device__ __forceinline__ size_t sell_val0(long long e) { return (size_t)(e >> 5) * 128 + 2 * (size_t)(e & 31); }
 
 __global__ void __launch_bounds__(256)
 k_assemble(int n_elem, const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
-           const double* __restrict__ node_xy, const int* __restrict__ node_row,
-           const unsigned* __restrict__ row_ptr, const int* __restrict__ bcol, double* __restrict__ bval,
-           double* __restrict__ wmean, Mat8 mat) {
+           const int* __restrict__ elem_sys, const double* __restrict__ node_xy, const int* __restrict__ node_row,
+           WinTab wt, Sell sl, double* __restrict__ bval, double* __restrict__ wmean, Mat8 mat) {
     __shared__ double s_mat[8];
     if (threadIdx.x < 8) s_mat[threadIdx.x] = mat.v[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (e >= n_elem) return;
+    const int sys = elem_sys[e];
     int node = 0, row = -1;
     double px = 0, py = 0;
     if (lane < 6) {
@@ -130,28 +163,47 @@ k_assemble(int n_elem, const int* __restrict__ elem_node, const unsigned char* _
     if (lane < 21 && ra >= 0 && rb >= 0) {
         double K[4];
         p2_stiff_block(g, a, b, lam, mu, K);
-        double* d = bval + 4 * (size_t)find_block(row_ptr, bcol, ra, rb);
-        atomicAdd(d + 0, K[0]); atomicAdd(d + 1, K[1]); atomicAdd(d + 2, K[2]); atomicAdd(d + 3, K[3]);
-        if (a != b) {
-            double* dt = bval + 4 * (size_t)find_block(row_ptr, bcol, rb, ra);
-            atomicAdd(dt + 0, K[0]); atomicAdd(dt + 1, K[2]); atomicAdd(dt + 2, K[1]); atomicAdd(dt + 3, K[3]);
+        const long long e0 = sell_find(wt, sl, sys, ra, rb);
+        if (e0 >= 0) {
+            double* d = bval + sell_val0(e0);
+            atomicAdd(d + 0, K[0]); atomicAdd(d + 1, K[1]); atomicAdd(d + 64, K[2]); atomicAdd(d + 65, K[3]);
+        }
+        if (ra != rb) {   // (two local nodes can share a row only under the periodic map: then a==b terms add up)
+            const long long e1 = sell_find(wt, sl, sys, rb, ra);
+            if (e1 >= 0) {
+                double* dt = bval + sell_val0(e1);
+                atomicAdd(dt + 0, K[0]); atomicAdd(dt + 1, K[2]); atomicAdd(dt + 64, K[1]); atomicAdd(dt + 65, K[3]);
+            }
+        } else if (a != b) {
+            // distinct local nodes mapped to the same row: the transposed block lands on the same entry
+            const long long e1 = e0;
+            if (e1 >= 0) {
+                double* dt = bval + sell_val0(e1);
+                atomicAdd(dt + 0, K[0]); atomicAdd(dt + 1, K[2]); atomicAdd(dt + 64, K[1]); atomicAdd(dt + 65, K[3]);
+            }
         }
     }
     // int phi_a dx: A/3 for the mid-edge functions (mean-value constraint of 'per' / 'MR')
     if (lane >= 3 && lane < 6 && row >= 0) atomicAdd(wmean + row, g.area * (1.0 / 3.0));
 }
 
-// 2x2 inverse of the diagonal blocks (block-Jacobi)
-__global__ void k_dinv(int n_rows, const unsigned* __restrict__ row_ptr, const int* __restrict__ bcol,
-                       const double* __restrict__ bval, double* __restrict__ dinv) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
-    const double* d = bval + 4 * (size_t)find_block(row_ptr, bcol, r, r);
-    double a = d[0], b = d[1], c = d[2], e = d[3];
-    double det = a * e - b * c;
-    double inv = det != 0.0 ? 1.0 / det : 0.0;
-    dinv[4 * (size_t)r + 0] = e * inv; dinv[4 * (size_t)r + 1] = -b * inv;
-    dinv[4 * (size_t)r + 2] = -c * inv; dinv[4 * (size_t)r + 3] = a * inv;
+// 2x2 inverse of the diagonal blocks (block-Jacobi), stored in fp32: CTA per window, thread per row
+__global__ void __launch_bounds__(RVE_WIN)
+k_dinv(WinTab wt, Sell sl, const double* __restrict__ bval, float4* __restrict__ dinv32) {
+    const int w = blockIdx.x, t = threadIdx.x;
+    if (t >= wt.win_n[w]) return;
+    const int lane = t & 31, slice = wt.win_slice0[w] + (t >> 5);
+    const unsigned g0 = sl.slice_ptr[slice], g1 = sl.slice_ptr[slice + 1];
+    double a = 0, b = 0, c = 0, e = 0;
+    for (unsigned g = g0; g < g1; ++g)
+        if (sl.scol[(size_t)g * 32 + lane] == t) {
+            const double* d = bval + (size_t)g * 128 + 2 * lane;
+            a = d[0]; b = d[1]; c = d[64]; e = d[65];
+            break;
+        }
+    const double det = a * e - b * c;
+    const double inv = det != 0.0 ? 1.0 / det : 0.0;
+    dinv32[wt.win_row0[w] + t] = make_float4((float)(e * inv), (float)(-b * inv), (float)(-c * inv), (float)(a * inv));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -321,19 +373,19 @@ __global__ void k_coarse_dinv(int n_sys, Grid g, const double* __restrict__ A, d
 }
 
 // ---------------------------------------------------------------------------------------------
-// (3) PCG kernels
+// (3) PCG kernels (one CTA of RVE_WIN threads per window)
 // ---------------------------------------------------------------------------------------------
 
-// Deterministic combination of per-chunk partials by the last CTA of a system.
-// part layout: [chunk][4][NQ]; result written to out[rq][q] (shared) for rq<4, q<NQ.
+// Deterministic combination of per-window partials by the last CTA of a system.
+// part layout: [window][4][NQ]; thread tid < 4*NQ contributes my (value index tid = rq*NQ + q);
+// result written to s_out[rq][q] (shared).
 template <int NQ>
-__device__ __forceinline__ bool last_block_sum(double* part, int* cnt, int sys, int chunk, int c0, int c1,
-                                               const double* my /*[4*NQ] valid in thread 0..4*NQ-1? */,
-                                               double (*s_out)[NQ]) {
+__device__ __forceinline__ bool last_block_sum(double* part, int* cnt, int sys, int win, int c0, int c1,
+                                               double my, double (*s_out)[NQ]) {
     __shared__ int s_last;
     __shared__ double s_red[256];
     const int tid = threadIdx.x;
-    if (tid < 4 * NQ) part[(size_t)chunk * 4 * NQ + tid] = my[0];
+    if (tid < 4 * NQ) part[(size_t)win * 4 * NQ + tid] = my;
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -344,7 +396,6 @@ __device__ __forceinline__ bool last_block_sum(double* part, int* cnt, int sys, 
     __syncthreads();
     if (!s_last) return false;
     __threadfence();
-    // 256 threads: value v = tid % (4*NQ), lane group = tid / (4*NQ)
     const int nv = 4 * NQ;
     const int grp = tid / nv, v = tid % nv, ngrp = 256 / nv;
     double acc = 0.0;
@@ -361,118 +412,190 @@ __device__ __forceinline__ bool last_block_sum(double* part, int* cnt, int sys, 
     return true;
 }
 
-// q = A p, pq = p.q  — warp per block row, lane quad per 2x2 block, lane (lane&3) owns one rhs.
-// Per 8-block pass a warp issues: 2 LDG.128 on a contiguous 256 B of bval, one LDG on 32 B of bcol
-// and one LDG.128 gather that touches exactly one 64-byte segment of p per block.
-__global__ void __launch_bounds__(256)
-k_spmv_dot(const unsigned* __restrict__ row_ptr, const int* __restrict__ bcol,
-           const double2* __restrict__ bval, const double2* __restrict__ p, double2* __restrict__ q,
-           int K, ChunkTab ct, const int* __restrict__ active, double* part, int* cnt, double* sc) {
-    const int chunk = blockIdx.x;
-    const int sys = ct.chunk_sys[chunk];
+// q = A p, pq = p.q.  The CTA first stages the p entries its window needs (own rows: one coalesced
+// copy; halo rows: list-driven gather) in shared memory, then every thread owns one row of a SELL-32
+// slice: per slot one coalesced 2-byte column load, two coalesced LDG.128 of the 2x2 block and K
+// LDS.128 gathers from the tile.  No cross-lane reduction; q leaves through shared memory so the
+// global store is coalesced.
+template <int K>
+__global__ void __launch_bounds__(RVE_WIN)
+k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __restrict__ p,
+       double2* __restrict__ q, const int* __restrict__ active, double* part, int* cnt, double* sc) {
+    extern __shared__ double2 s_tile[];           // [(n + nhalo) * K] p-tile, then [RVE_WIN * K] q staging
+    const int win = blockIdx.x;
+    const int sys = wt.win_sys[win];
     if (!active[sys]) return;
-    const int row0 = ct.chunk_row0[chunk], nrow = ct.chunk_n[chunk];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int grp = lane >> 2, rq = lane & 3;
-    double dot = 0.0;
-    for (int lr = w; lr < nrow; lr += 8) {
-        const int row = row0 + lr;
-        const unsigned beg = row_ptr[row], end = row_ptr[row + 1];
-        double y0 = 0.0, y1 = 0.0;
-        unsigned b = beg + grp;
-        // two passes in flight
-        for (; b + 8 < end; b += 16) {
-            const int c0 = bcol[b], c1 = bcol[b + 8];
-            const double2 k00 = bval[2 * (size_t)b], k01 = bval[2 * (size_t)b + 1];
-            const double2 k10 = bval[2 * (size_t)(b + 8)], k11 = bval[2 * (size_t)(b + 8) + 1];
-            const double2 xa = p[(size_t)c0 * 4 + rq], xb = p[(size_t)c1 * 4 + rq];
-            y0 += k00.x * xa.x + k00.y * xa.y; y1 += k01.x * xa.x + k01.y * xa.y;
-            y0 += k10.x * xb.x + k10.y * xb.y; y1 += k11.x * xb.x + k11.y * xb.y;
-        }
-        if (b < end) {
-            const int c0 = bcol[b];
-            const double2 k00 = bval[2 * (size_t)b], k01 = bval[2 * (size_t)b + 1];
-            const double2 xa = p[(size_t)c0 * 4 + rq];
-            y0 += k00.x * xa.x + k00.y * xa.y; y1 += k01.x * xa.x + k01.y * xa.y;
-        }
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-            y0 += __shfl_xor_sync(0xffffffffu, y0, o);
-            y1 += __shfl_xor_sync(0xffffffffu, y1, o);
-        }
-        if (grp == 0 && rq < K) {
-            q[(size_t)row * K + rq] = make_double2(y0, y1);
-            const double2 pv = p[(size_t)row * 4 + rq];
-            dot += y0 * pv.x + y1 * pv.y;
+    const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int row0 = wt.win_row0[win], n = wt.win_n[win];
+    const int h0 = wt.win_halo0[win], nh = wt.win_halo0[win + 1] - h0;
+    // issue the first matrix loads before waiting for the tile
+    const int slice = wt.win_slice0[win] + wv;
+    unsigned g0 = 0, g1 = 0;
+    if (wv * 32 < n) { g0 = sl.slice_ptr[slice]; g1 = sl.slice_ptr[slice + 1]; }
+    {
+        const double2* src = p + (size_t)row0 * K;
+        for (int e = tid; e < n * K; e += RVE_WIN) s_tile[e] = src[e];
+        double2* dst = s_tile + n * K;
+        for (int e = tid; e < nh * K; e += RVE_WIN) {
+            const int hr = sl.halo[h0 + e / K];
+            dst[e] = p[(size_t)hr * K + (e % K)];
         }
     }
-    // CTA reduction of the 4 per-rhs dots in a fixed order
+    __syncthreads();
+    double2 y[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) y[k] = make_double2(0.0, 0.0);
+    const uint16_t* cp = sl.scol + (size_t)g0 * 32 + lane;
+    const double2* vp = bval + (size_t)g0 * 64 + lane;
+    const int ng = (int)(g1 - g0);
+    int j = 0;
+    for (; j + 2 <= ng; j += 2) {
+        const int c0 = cp[(size_t)j * 32], c1 = cp[(size_t)(j + 1) * 32];
+        const double2 a0 = vp[(size_t)j * 64], a1 = vp[(size_t)j * 64 + 32];
+        const double2 b0 = vp[(size_t)(j + 1) * 64], b1 = vp[(size_t)(j + 1) * 64 + 32];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double2 xa = s_tile[c0 * K + k], xb = s_tile[c1 * K + k];
+            y[k].x += a0.x * xa.x + a0.y * xa.y; y[k].y += a1.x * xa.x + a1.y * xa.y;
+            y[k].x += b0.x * xb.x + b0.y * xb.y; y[k].y += b1.x * xb.x + b1.y * xb.y;
+        }
+    }
+    if (j < ng) {
+        const int c0 = cp[(size_t)j * 32];
+        const double2 a0 = vp[(size_t)j * 64], a1 = vp[(size_t)j * 64 + 32];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double2 xa = s_tile[c0 * K + k];
+            y[k].x += a0.x * xa.x + a0.y * xa.y; y[k].y += a1.x * xa.x + a1.y * xa.y;
+        }
+    }
+    // dot with the own p entries, q through shared memory
+    double2* s_q = s_tile + (size_t)(n + nh) * K;
+    double dot[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) dot[k] = 0.0;
+    if (tid < n) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double2 pv = s_tile[tid * K + k];
+            dot[k] = y[k].x * pv.x + y[k].y * pv.y;
+            s_q[tid * K + k] = y[k];
+        }
+    }
     __shared__ double s_dot[8][4];
     __shared__ double s_out[4][1];
-    if (grp == 0) s_dot[w][rq] = dot;
-    __syncthreads();
-    double my = 0.0;
-    if (threadIdx.x < 4) {
-        for (int i = 0; i < 8; ++i) my += s_dot[i][threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double v = warp_sum(dot[k]);
+        if (lane == 0) s_dot[wv][k] = v;
     }
-    const int c0 = ct.sys_chunk0[sys], c1 = ct.sys_chunk0[sys + 1];
-    if (last_block_sum<1>(part, cnt, sys, chunk, c0, c1, &my, s_out)) {
-        if (threadIdx.x < 4) {
-            double* s = sc + ((size_t)sys * 4 + threadIdx.x) * SC_N;
-            const double pq = s_out[threadIdx.x][0];
+    __syncthreads();
+    {
+        double2* dst = q + (size_t)row0 * K;
+        for (int e = tid; e < n * K; e += RVE_WIN) dst[e] = s_q[e];
+    }
+    double my = 0.0;
+    if (tid < K)
+        for (int i = 0; i < 8; ++i) my += s_dot[i][tid];
+    const int c0 = wt.sys_win0[sys], c1 = wt.sys_win0[sys + 1];
+    if (last_block_sum<1>(part, cnt, sys, win, c0, c1, my, s_out)) {
+        if (tid < K) {
+            double* s = sc + ((size_t)sys * 4 + tid) * SC_N;
+            const double pq = s_out[tid][0];
             s[SC_PQ] = pq;
             s[SC_ALPHA] = (pq > 0.0) ? s[SC_RZ] / pq : 0.0;
         }
     }
 }
 
-// x += alpha p ; r -= alpha q ; partial rr and r.Dinv r ; convergence test by the last CTA.
-// thread = (row in chunk, rhs).
-__global__ void __launch_bounds__(256)
-k_update(const double2* __restrict__ p, const double2* __restrict__ q, double2* __restrict__ x,
-         double2* __restrict__ r, const double* __restrict__ dinv, int K, ChunkTab ct, int* active,
-         double* part, int* cnt, double* sc, int init, int iter, double rtol2, int precond,
-         int* iters, int* n_active) {
-    const int chunk = blockIdx.x;
-    const int sys = ct.chunk_sys[chunk];
+// x += alpha p ; r -= alpha q ; partial rr and r.Dinv r ; restriction of the new residual to the
+// level-1 grid (rc += Z^T r, per-window partial sums then one RED per touched coarse value);
+// convergence test by the last CTA of the system.  Thread = one (row, rhs) pair, flat and coalesced.
+template <int K>
+__global__ void __launch_bounds__(RVE_WIN)
+k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q, double2* __restrict__ x,
+         double2* __restrict__ r, const float4* __restrict__ dinv32, const RowInfo* __restrict__ rowinfo,
+         const int* __restrict__ cn_node, const unsigned* __restrict__ cn_beg, const uint16_t* __restrict__ cn_ent,
+         double* __restrict__ rc1, int G, int* active, double* part, int* cnt, double* sc, int init, int iter,
+         double rtol2, int precond, int* iters, int* n_active) {
+    extern __shared__ double2 s_r[];              // [n*K] new residual, then float2 s_st[n], uint16 s_ent[4n]
+    constexpr int TPB = (RVE_WIN / K) * K;        // active threads: a thread keeps its rhs index
+    const int win = blockIdx.x;
+    const int sys = wt.win_sys[win];
     if (!active[sys]) return;
-    const int row0 = ct.chunk_row0[chunk], nrow = ct.chunk_n[chunk];
-    const int lr = threadIdx.x >> 2, rq = threadIdx.x & 3;
+    const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int row0 = wt.win_row0[win], n = wt.win_n[win];
+    const int k = tid % K;
+    float2* s_st = (float2*)(s_r + (size_t)RVE_WIN * K);
+    uint16_t* s_ent = (uint16_t*)(s_st + RVE_WIN);
+    const int cn0 = wt.win_cn0[win], ncn = wt.win_cn0[win + 1] - cn0;
+    unsigned ent0 = 0, nent = 0;
+    if (precond) {
+        ent0 = cn_beg[cn0]; nent = cn_beg[cn0 + ncn] - ent0;
+        for (unsigned e = tid; e < nent; e += RVE_WIN) s_ent[e] = cn_ent[ent0 + e];
+        if (tid < n) { const RowInfo ri = rowinfo[row0 + tid]; s_st[tid] = make_float2(ri.s, ri.t); }
+    }
+    const double alpha = sc[((size_t)sys * 4 + k) * SC_N + SC_ALPHA];
     double rr = 0.0, rdr = 0.0;
-    if (lr < nrow && rq < K) {
-        const int row = row0 + lr;
-        const double alpha = sc[((size_t)sys * 4 + rq) * SC_N + SC_ALPHA];
-        const size_t i = (size_t)row * K + rq;
-        double2 rv = r[i];
-        if (!init) {
-            const double2 pv = p[(size_t)row * 4 + rq], qv = q[i];
-            double2 xv = x[i];
-            xv.x += alpha * pv.x; xv.y += alpha * pv.y;
-            rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
-            x[i] = xv; r[i] = rv;
+    if (tid < TPB) {
+        const size_t base = (size_t)row0 * K;
+        for (int e = tid; e < n * K; e += TPB) {
+            double2 rv = r[base + e];
+            if (!init) {
+                const double2 pv = p[base + e], qv = q[base + e];
+                double2 xv = x[base + e];
+                xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+                rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
+                x[base + e] = xv; r[base + e] = rv;
+            }
+            const float4 d = dinv32[row0 + e / K];
+            rr += rv.x * rv.x + rv.y * rv.y;
+            rdr += rv.x * ((double)d.x * rv.x + (double)d.y * rv.y) + rv.y * ((double)d.z * rv.x + (double)d.w * rv.y);
+            s_r[e] = rv;
         }
-        const double* d = dinv + 4 * (size_t)row;
-        rr = rv.x * rv.x + rv.y * rv.y;
-        rdr = rv.x * (d[0] * rv.x + d[1] * rv.y) + rv.y * (d[2] * rv.x + d[3] * rv.y);
     }
-    __shared__ double s_a[256], s_b[256];
+    __shared__ double s_a[RVE_WIN], s_b[RVE_WIN];
+    __shared__ double s_fin[8];
     __shared__ double s_out[4][2];
-    s_a[threadIdx.x] = rr; s_b[threadIdx.x] = rdr;
+    s_a[tid] = rr; s_b[tid] = rdr;
+    if (tid < 8) s_fin[tid] = 0.0;
     __syncthreads();
-    for (int st = 128; st >= 4; st >>= 1) {
-        if (threadIdx.x < st) { s_a[threadIdx.x] += s_a[threadIdx.x + st]; s_b[threadIdx.x] += s_b[threadIdx.x + st]; }
-        __syncthreads();
+    // class sums: warp 2k+which adds the entries of rhs k
+    if (wv < 2 * K) {
+        const int kk = wv >> 1;
+        const double* src = (wv & 1) ? s_b : s_a;
+        double acc = 0.0;
+        for (int m = lane; m < TPB / K; m += 32) acc += src[kk + K * m];
+        acc = warp_sum(acc);
+        if (lane == 0) s_fin[wv] = acc;
     }
-    // thread t<8 publishes value (rq = t/2, which = t%2)
-    double my = 0.0;
-    if (threadIdx.x < 8) my = (threadIdx.x & 1) ? s_b[threadIdx.x >> 1] : s_a[threadIdx.x >> 1];
-    const int c0 = ct.sys_chunk0[sys], c1 = ct.sys_chunk0[sys + 1];
-    if (last_block_sum<2>(part, cnt, sys, chunk, c0, c1, &my, s_out)) {
-        if (threadIdx.x == 0) {
+    // restriction: task = (coarse node of the window, rhs); weights from the staged (s,t)
+    if (precond) {
+        for (int t = tid; t < ncn * K; t += RVE_WIN) {
+            const int jn = t / K, kk = t % K;
+            const unsigned b0 = cn_beg[cn0 + jn] - ent0, b1 = cn_beg[cn0 + jn + 1] - ent0;
+            double a0 = 0.0, a1 = 0.0;
+            for (unsigned e = b0; e < b1; ++e) {
+                const int en = s_ent[e];
+                const int rl = en >> 2, c = en & 3;
+                const float2 st = s_st[rl];
+                const double wgt = (double)((c & 1) ? st.x : 1.0f - st.x) * (double)((c & 2) ? st.y : 1.0f - st.y);
+                const double2 v = s_r[rl * K + kk];
+                a0 += wgt * v.x; a1 += wgt * v.y;
+            }
+            double* d = rc1 + (((size_t)sys * G + cn_node[cn0 + jn]) * K + kk) * 2;
+            atomicAdd(d, a0); atomicAdd(d + 1, a1);
+        }
+    }
+    __syncthreads();
+    const double my = (tid < 8) ? s_fin[tid] : 0.0;   // value index tid = rq*2 + which
+    const int c0 = wt.sys_win0[sys], c1 = wt.sys_win0[sys + 1];
+    if (last_block_sum<2>(part, cnt, sys, win, c0, c1, my, s_out)) {
+        if (tid == 0) {
             bool done = true;
-            for (int k = 0; k < K; ++k) {
-                double* s = sc + ((size_t)sys * 4 + k) * SC_N;
-                const double vrr = s_out[k][0], vrdr = s_out[k][1];
+            for (int kk = 0; kk < K; ++kk) {
+                double* s = sc + ((size_t)sys * 4 + kk) * SC_N;
+                const double vrr = s_out[kk][0], vrdr = s_out[kk][1];
                 if (init) s[SC_BB] = vrr;
                 s[SC_RR] = vrr; s[SC_RDR] = vrdr;
                 if (!(vrr <= rtol2 * s[SC_BB] || vrr <= 1e-28 * s[SC_BREF])) done = false;
@@ -492,8 +615,9 @@ k_update(const double2* __restrict__ p, const double2* __restrict__ q, double2* 
     }
 }
 
-// Coarse V-cycle: ONE CTA per system runs restriction from the fine residual, all structured
-// levels (25-point block stencils, damped block-Jacobi smoothing) and the coarse part of r.z.
+
+// Coarse V-cycle: ONE CTA per system runs all structured levels (25-point block stencils, damped
+// block-Jacobi smoothing) on the restricted residual and adds the coarse part of r.z.
 __device__ __forceinline__ void stencil_apply(const Grid& g, const double* __restrict__ A,
                                               const double* x, int K, int i, int j, double* out) {
     const int idx = j * g.nx + i;
@@ -516,49 +640,12 @@ __device__ __forceinline__ void stencil_apply(const Grid& g, const double* __res
 }
 
 __global__ void __launch_bounds__(256)
-k_vcycle(Levels LV, const double* __restrict__ r, const double* __restrict__ row_xy,
-         const int* __restrict__ row_base, const int* __restrict__ cell_ptr, const double* __restrict__ box,
-         const int* __restrict__ active, double* sc, int first) {
+k_vcycle(Levels LV, const int* __restrict__ active, double* sc, int first) {
     const int sys = blockIdx.x;
     if (!active[sys]) return;
     const int K = LV.K, tid = threadIdx.x, nth = blockDim.x;
     const double om = RVE_OMEGA;
-    // --- restrict fine residual to level 1:  rc = Z^T r
-    {
-        const Grid g = LV.g[0];
-        double* rc = LV.rc[0] + (size_t)sys * g.G * K * 2;
-        const int* cp = cell_ptr + (size_t)sys * (g.ncx * g.ncy + 1);
-        const int rb = row_base[sys];
-        const double bx0 = box[4 * sys], by0 = box[4 * sys + 1];
-        const double invHx = g.ncx / box[4 * sys + 2], invHy = g.ncy / box[4 * sys + 3];
-        for (int idx = tid; idx < g.G; idx += nth) {
-            const int i = idx % g.nx, j = idx / g.nx;
-            if (!grid_valid(g, i, j)) continue;
-            double acc[2 * RVE_MAX_RHS];
-#pragma unroll
-            for (int k = 0; k < 2 * RVE_MAX_RHS; ++k) acc[k] = 0.0;
-            for (int dj = -1; dj <= 0; ++dj)
-                for (int di = -1; di <= 0; ++di) {
-                    int ci = i + di, cj = j + dj;
-                    if (g.wrap) { ci = (ci + g.ncx) % g.ncx; cj = (cj + g.ncy) % g.ncy; }
-                    else if (ci < 0 || cj < 0 || ci >= g.ncx || cj >= g.ncy) continue;
-                    const int c = cj * g.ncx + ci;
-                    for (int rr = cp[c]; rr < cp[c + 1]; ++rr) {
-                        const size_t row = (size_t)rb + rr;
-                        int qi, qj; double s, t;
-                        coarse_cell(row_xy[2 * row], row_xy[2 * row + 1], bx0, by0, invHx, invHy, g.ncx, g.ncy, qi, qj, s, t);
-                        const double wgt = (di ? s : 1.0 - s) * (dj ? t : 1.0 - t);
-                        const double* rv = r + row * K * 2;
-#pragma unroll
-                        for (int k = 0; k < 2 * RVE_MAX_RHS; ++k)
-                            if (k < 2 * K) acc[k] += wgt * rv[k];
-                    }
-                }
-            double* o = rc + (size_t)idx * K * 2;
-            for (int k = 0; k < 2 * K; ++k) o[k] = acc[k];
-        }
-    }
-    __syncthreads();
+    // level-1 residual rc = Z^T r was accumulated by k_update (REDs); it is cleared again at the end
     // --- down sweep
     for (int l = 0; l < LV.L; ++l) {
         const Grid g = LV.g[l];
@@ -709,46 +796,59 @@ k_vcycle(Levels LV, const double* __restrict__ r, const double* __restrict__ row
             s[SC_RZ] = rz;
             s[SC_BETA] = (!first && rzold > 0.0) ? rz / rzold : 0.0;
         }
+        // clear the accumulator for the next iteration's restriction
+        double* rcw = LV.rc[0] + (size_t)sys * g.G * K * 2;
+        for (int idx = tid; idx < g.G * K * 2; idx += nth) rcw[idx] = 0.0;
     }
 }
 
-// p = Dinv r + Z xc1 + beta p     (thread = (row in chunk, rhs))
-__global__ void __launch_bounds__(256)
-k_direction(double2* __restrict__ p, const double2* __restrict__ r, const double* __restrict__ dinv,
-            const double* __restrict__ row_xy, const double* __restrict__ box, int K, ChunkTab ct,
-            const int* __restrict__ active, const double* __restrict__ sc, int precond, Grid g1,
-            const double* xc1) {
-    const int chunk = blockIdx.x;
-    const int sys = ct.chunk_sys[chunk];
+// p = Dinv r + Z xc1 + beta p     (thread = one (row, rhs) pair; the level-1 values the window
+// touches are staged in shared memory)
+template <int K>
+__global__ void __launch_bounds__(RVE_WIN)
+k_direction(WinTab wt, double2* __restrict__ p, const double2* __restrict__ r, const float4* __restrict__ dinv32,
+            const RowInfo* __restrict__ rowinfo, const int* __restrict__ cn_node, const double2* __restrict__ xc1,
+            int G, const int* __restrict__ active, const double* __restrict__ sc, int precond) {
+    extern __shared__ double2 s_xc[];             // [ncn*K]
+    constexpr int TPB = (RVE_WIN / K) * K;
+    const int win = blockIdx.x;
+    const int sys = wt.win_sys[win];
     if (!active[sys]) return;
-    const int row0 = ct.chunk_row0[chunk], nrow = ct.chunk_n[chunk];
-    const int lr = threadIdx.x >> 2, rq = threadIdx.x & 3;
-    if (lr >= nrow || rq >= K) return;
-    const int row = row0 + lr;
-    const double beta = sc[((size_t)sys * 4 + rq) * SC_N + SC_BETA];
-    const double2 rv = r[(size_t)row * K + rq];
-    const double* d = dinv + 4 * (size_t)row;
-    double z0 = d[0] * rv.x + d[1] * rv.y, z1 = d[2] * rv.x + d[3] * rv.y;
+    const int tid = threadIdx.x;
+    const int row0 = wt.win_row0[win], n = wt.win_n[win];
+    const int k = tid % K;
     if (precond) {
-        int ci, cj; double s, t;
-        coarse_cell(row_xy[2 * (size_t)row], row_xy[2 * (size_t)row + 1], box[4 * sys], box[4 * sys + 1],
-                    g1.ncx / box[4 * sys + 2], g1.ncy / box[4 * sys + 3], g1.ncx, g1.ncy, ci, cj, s, t);
-        const double* xs = xc1 + (size_t)sys * g1.G * K * 2;
-#pragma unroll
-        for (int dj = 0; dj < 2; ++dj)
-#pragma unroll
-            for (int di = 0; di < 2; ++di) {
-                int nc;
-                if (!grid_node(g1, ci + di, cj + dj, nc)) continue;
-                const double wgt = (di ? s : 1.0 - s) * (dj ? t : 1.0 - t);
-                z0 += wgt * xs[((size_t)nc * K + rq) * 2];
-                z1 += wgt * xs[((size_t)nc * K + rq) * 2 + 1];
-            }
+        const int cn0 = wt.win_cn0[win], ncn = wt.win_cn0[win + 1] - cn0;
+        for (int t = tid; t < ncn * K; t += RVE_WIN)
+            s_xc[t] = xc1[((size_t)sys * G + cn_node[cn0 + t / K]) * K + (t % K)];
+        __syncthreads();
     }
-    double2 pv = p[(size_t)row * 4 + rq];
-    pv.x = z0 + beta * pv.x; pv.y = z1 + beta * pv.y;
-    p[(size_t)row * 4 + rq] = pv;
+    if (tid >= TPB) return;
+    const double beta = sc[((size_t)sys * 4 + k) * SC_N + SC_BETA];
+    const size_t base = (size_t)row0 * K;
+    for (int e = tid; e < n * K; e += TPB) {
+        const int rl = e / K;
+        const double2 rv = r[base + e];
+        const float4 d = dinv32[row0 + rl];
+        double z0 = (double)d.x * rv.x + (double)d.y * rv.y, z1 = (double)d.z * rv.x + (double)d.w * rv.y;
+        if (precond) {
+            const RowInfo ri = rowinfo[row0 + rl];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int slot = ri.slot[c];
+                if (slot != 0xffff) {
+                    const double wgt = (double)((c & 1) ? ri.s : 1.0f - ri.s) * (double)((c & 2) ? ri.t : 1.0f - ri.t);
+                    const double2 v = s_xc[slot * K + k];
+                    z0 += wgt * v.x; z1 += wgt * v.y;
+                }
+            }
+        }
+        double2 pv = p[base + e];
+        pv.x = z0 + beta * pv.x; pv.y = z1 + beta * pv.y;
+        p[base + e] = pv;
+    }
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // (4) right-hand sides

@@ -16,6 +16,13 @@
 #include <vector>
 
 #include "../../include/rve_b200.h"
+#include "rve_math.cuh"
+
+#define RVE_WIN 256   // rows per window = rows per CTA of the PCG kernels
+
+// per active row: position in its level-1 coarse cell (fp32: preconditioner only) and the
+// window-local slots of the 4 cell corners (0xffff = corner not in the coarse space)
+struct RowInfo { float s, t; uint16_t slot[4]; };
 
 struct SysSym {
     int nv = 0, nt = 0, ne = 0, nn = 0, na = 0, nb = 0, nbe = 0;
@@ -28,9 +35,21 @@ struct SysSym {
     std::vector<int> node_row;       // [nn] local active row or -1
     std::vector<int> node_bnd;       // [nn] index into the boundary-node list or -1
     std::vector<int> row_node;       // [na] master node of the row
-    std::vector<int> cell_ptr;       // [ncx*ncy+1] rows sorted by level-1 cell
-    std::vector<unsigned> row_ptr;   // [na+1] local block offsets
+    std::vector<unsigned> row_ptr;   // [na+1] local block offsets (CSR in the final numbering, host only)
     std::vector<int> bcol;           // local row ids
+    // device layout: windows of <= RVE_WIN rows, SELL-32 slices, window-local 16-bit columns
+    int nwin = 0, max_tile = 0, max_cn = 0;
+    std::vector<int> win_n;          // [nwin] rows of the window
+    std::vector<int> win_slice0;     // [nwin+1] first slice
+    std::vector<int> win_halo0;      // [nwin+1] offset into halo
+    std::vector<int> win_cn0;        // [nwin+1] offset into cn_node
+    std::vector<unsigned> slice_ptr; // [nslices+1] offsets in 32-entry groups
+    std::vector<uint16_t> scol;      // [groups][32] window-local column (own rows, then halo)
+    std::vector<int> halo;           // local row ids gathered by each window
+    std::vector<int> cn_node;        // level-1 grid nodes touched by each window
+    std::vector<unsigned> cn_beg;    // [sum ncn + 1] offsets into cn_ent
+    std::vector<uint16_t> cn_ent;    // (row_in_window << 2) | corner
+    std::vector<RowInfo> rowinfo;    // [na] bilinear weights + window-local coarse slots
     std::vector<int> bnd_node;       // [nb]
     std::vector<double> bnd_s;       // [nb][2] Vref perimeter parameters of the end vertices
     std::vector<int> bedge;          // [nbe][3] boundary edges (a,b,m), outward normal to the right
@@ -186,61 +205,180 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
         for (int it = 0; it < 3; ++it)
             for (int n = 0; n < nn; ++n) if (master[n] >= 0) master[n] = master[master[n]];
     }
-    // active rows sorted by level-1 cell (row-major), ties by node id
+    // ---- active rows ordered along the Morton curve of the level-1 cells (compact row windows)
     const int ncx = P.ncx, ncy = P.ncy;
     const double invHx = ncx / Lx, invHy = ncy / Ly;
-    std::vector<std::pair<int, int>> keyed;
+    auto spread = [](unsigned v) -> uint64_t {
+        uint64_t x = v & 0xffffu;
+        x = (x | (x << 8)) & 0x00ff00ffull; x = (x | (x << 4)) & 0x0f0f0f0full;
+        x = (x | (x << 2)) & 0x33333333ull; x = (x | (x << 1)) & 0x55555555ull;
+        return x;
+    };
+    std::vector<std::pair<uint64_t, int>> keyed;
     keyed.reserve(nn);
     for (int n = 0; n < nn; ++n)
         if (master[n] == n) {
-            int ci = (int)((S.node_xy[2 * n] - x0) * invHx), cj = (int)((S.node_xy[2 * n + 1] - y0) * invHy);
-            ci = std::min(std::max(ci, 0), ncx - 1); cj = std::min(std::max(cj, 0), ncy - 1);
-            keyed.push_back({cj * ncx + ci, n});
+            int ci, cj; double s, t;
+            coarse_cell(S.node_xy[2 * n], S.node_xy[2 * n + 1], x0, y0, invHx, invHy, ncx, ncy, ci, cj, s, t);
+            keyed.push_back({spread((unsigned)ci) | (spread((unsigned)cj) << 1), n});
         }
     std::sort(keyed.begin(), keyed.end());
     S.na = (int)keyed.size();
-    S.row_node.resize(S.na);
-    S.cell_ptr.assign(ncx * ncy + 1, 0);
-    std::vector<int> rowof(nn, -1);
-    for (int r = 0; r < S.na; ++r) {
-        S.row_node[r] = keyed[r].second;
-        rowof[keyed[r].second] = r;
-        S.cell_ptr[keyed[r].first + 1]++;
-    }
-    for (int c = 0; c < ncx * ncy; ++c) S.cell_ptr[c + 1] += S.cell_ptr[c];
-    S.node_row.resize(nn);
-    for (int n = 0; n < nn; ++n) S.node_row[n] = master[n] < 0 ? -1 : rowof[master[n]];
-    // row -> elements adjacency
-    std::vector<int> adj_ptr(S.na + 1, 0);
+    const int na = S.na;
+    // preliminary numbering = Morton order; pattern in that numbering gives the row lengths
+    std::vector<int> prow(nn, -1), pnode(na);
+    for (int r = 0; r < na; ++r) { pnode[r] = keyed[r].second; prow[keyed[r].second] = r; }
+    std::vector<int> nrow0(nn);
+    for (int n = 0; n < nn; ++n) nrow0[n] = master[n] < 0 ? -1 : prow[master[n]];
+    std::vector<int> adj_ptr(na + 1, 0);
     for (int t = 0; t < nt; ++t)
         for (int k = 0; k < 6; ++k) {
-            int r = S.node_row[S.elem_node[6 * t + k]];
+            int r = nrow0[S.elem_node[6 * t + k]];
             if (r >= 0) adj_ptr[r + 1]++;
         }
-    for (int r = 0; r < S.na; ++r) adj_ptr[r + 1] += adj_ptr[r];
-    std::vector<int> adj(adj_ptr[S.na]), fill(adj_ptr.begin(), adj_ptr.end() - 1);
+    for (int r = 0; r < na; ++r) adj_ptr[r + 1] += adj_ptr[r];
+    std::vector<int> adj(adj_ptr[na]), fill(adj_ptr.begin(), adj_ptr.end() - 1);
     for (int t = 0; t < nt; ++t)
         for (int k = 0; k < 6; ++k) {
-            int r = S.node_row[S.elem_node[6 * t + k]];
+            int r = nrow0[S.elem_node[6 * t + k]];
             if (r >= 0) adj[fill[r]++] = t;
         }
-    S.row_ptr.assign(S.na + 1, 0);
-    S.bcol.clear();
-    S.bcol.reserve((size_t)S.na * 12);
+    std::vector<unsigned> rp0(na + 1, 0);
+    std::vector<int> bc0;
+    bc0.reserve((size_t)na * 12);
     std::vector<int> cand;
-    for (int r = 0; r < S.na; ++r) {
+    for (int r = 0; r < na; ++r) {
         cand.clear();
         for (int i = adj_ptr[r]; i < adj_ptr[r + 1]; ++i) {
             int t = adj[i];
             for (int k = 0; k < 6; ++k) {
-                int c = S.node_row[S.elem_node[6 * t + k]];
+                int c = nrow0[S.elem_node[6 * t + k]];
                 if (c >= 0) cand.push_back(c);
             }
         }
         std::sort(cand.begin(), cand.end());
         cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
-        S.bcol.insert(S.bcol.end(), cand.begin(), cand.end());
-        S.row_ptr[r + 1] = (unsigned)S.bcol.size();
+        bc0.insert(bc0.end(), cand.begin(), cand.end());
+        rp0[r + 1] = (unsigned)bc0.size();
+    }
+    // windows of RVE_WIN consecutive rows; inside a window rows are sorted by descending length so
+    // that the 32-row SELL slices are nearly uniform (vertex rows ~19 blocks, mid-edge rows ~9)
+    const int nwin = (na + RVE_WIN - 1) / RVE_WIN;
+    S.nwin = nwin;
+    std::vector<int> newid(na), oldid(na);
+    {
+        std::vector<int> idx;
+        for (int w = 0; w < nwin; ++w) {
+            const int r0 = w * RVE_WIN, r1 = std::min(na, r0 + RVE_WIN);
+            idx.resize(r1 - r0);
+            for (int r = r0; r < r1; ++r) idx[r - r0] = r;
+            std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return rp0[a + 1] - rp0[a] > rp0[b + 1] - rp0[b]; });
+            for (int k = 0; k < r1 - r0; ++k) { newid[idx[k]] = r0 + k; oldid[r0 + k] = idx[k]; }
+        }
+    }
+    S.row_node.resize(na);
+    for (int r = 0; r < na; ++r) S.row_node[r] = pnode[oldid[r]];
+    S.node_row.resize(nn);
+    for (int n = 0; n < nn; ++n) S.node_row[n] = nrow0[n] < 0 ? -1 : newid[nrow0[n]];
+    // CSR pattern in the final numbering (sorted columns) — kept on the host for accessors/tests
+    S.row_ptr.assign(na + 1, 0);
+    S.bcol.resize(bc0.size());
+    for (int r = 0; r < na; ++r) S.row_ptr[r + 1] = S.row_ptr[r] + (rp0[oldid[r] + 1] - rp0[oldid[r]]);
+    for (int r = 0; r < na; ++r) {
+        int* dst = &S.bcol[S.row_ptr[r]];
+        const int o = oldid[r], len = (int)(rp0[o + 1] - rp0[o]);
+        for (int k = 0; k < len; ++k) dst[k] = newid[bc0[rp0[o] + k]];
+        std::sort(dst, dst + len);
+    }
+    // per window: halo list, SELL-32 slices with window-local 16-bit columns, coarse-node lists
+    S.win_n.assign(nwin, 0); S.win_slice0.assign(nwin + 1, 0); S.win_halo0.assign(nwin + 1, 0); S.win_cn0.assign(nwin + 1, 0);
+    S.slice_ptr.assign(1, 0u);
+    S.scol.clear(); S.halo.clear(); S.cn_node.clear(); S.cn_beg.assign(1, 0u); S.cn_ent.clear();
+    S.rowinfo.resize(na);
+    S.max_tile = 0; S.max_cn = 0;
+    const int nxg = ncx + 1;
+    auto cnode = [&](int i, int j) -> int {   // same validity rules as grid_node() on the device
+        if (P.model == RVE_MODEL_PER) { i = ((i % ncx) + ncx) % ncx; j = ((j % ncy) + ncy) % ncy; return j * nxg + i; }
+        const int lo = (P.model == RVE_MODEL_MR) ? 0 : 1, hix = (P.model == RVE_MODEL_MR) ? ncx : ncx - 1,
+                  hiy = (P.model == RVE_MODEL_MR) ? ncy : ncy - 1;
+        if (i < lo || i > hix || j < lo || j > hiy) return -1;
+        return j * nxg + i;
+    };
+    std::vector<int> hal, cns;
+    std::vector<int> corner(4 * (size_t)RVE_WIN);
+    for (int w = 0; w < nwin; ++w) {
+        const int r0 = w * RVE_WIN, r1 = std::min(na, r0 + RVE_WIN), wn = r1 - r0;
+        S.win_n[w] = wn;
+        hal.clear();
+        for (unsigned k = S.row_ptr[r0]; k < S.row_ptr[r1]; ++k) {
+            int c = S.bcol[k];
+            if (c < r0 || c >= r1) hal.push_back(c);
+        }
+        std::sort(hal.begin(), hal.end());
+        hal.erase(std::unique(hal.begin(), hal.end()), hal.end());
+        if (wn + (int)hal.size() > 65535) { S.err = "window halo too large for 16-bit local columns"; return; }
+        S.max_tile = std::max(S.max_tile, wn + (int)hal.size());
+        S.halo.insert(S.halo.end(), hal.begin(), hal.end());
+        S.win_halo0[w + 1] = (int)S.halo.size();
+        const int nsl = (wn + 31) / 32;
+        for (int sl = 0; sl < nsl; ++sl) {
+            const int a0 = r0 + 32 * sl, a1 = std::min(r1, a0 + 32);
+            int width = 0;
+            for (int r = a0; r < a1; ++r) width = std::max(width, (int)(S.row_ptr[r + 1] - S.row_ptr[r]));
+            const size_t base = S.scol.size();
+            S.scol.resize(base + (size_t)width * 32);
+            for (int lane = 0; lane < 32; ++lane) {
+                const int r = a0 + lane;
+                const int len = r < a1 ? (int)(S.row_ptr[r + 1] - S.row_ptr[r]) : 0;
+                const int self = r < a1 ? r - r0 : 0;
+                for (int j = 0; j < width; ++j) {
+                    int lc = self;   // padding: zero block against a valid tile entry
+                    if (j < len) {
+                        const int c = S.bcol[S.row_ptr[r] + j];
+                        lc = (c >= r0 && c < r1) ? c - r0
+                                                 : wn + (int)(std::lower_bound(hal.begin(), hal.end(), c) - hal.begin());
+                    }
+                    S.scol[base + (size_t)j * 32 + lane] = (uint16_t)lc;
+                }
+            }
+            S.slice_ptr.push_back(S.slice_ptr.back() + (unsigned)width);
+        }
+        S.win_slice0[w + 1] = S.win_slice0[w] + nsl;
+        // coarse nodes touched by the window and the (row, corner) lists of each of them
+        cns.clear();
+        for (int r = r0; r < r1; ++r) {
+            const int n = S.row_node[r];
+            int ci, cj; double s, t;
+            coarse_cell(S.node_xy[2 * n], S.node_xy[2 * n + 1], x0, y0, invHx, invHy, ncx, ncy, ci, cj, s, t);
+            S.rowinfo[r].s = (float)s; S.rowinfo[r].t = (float)t;
+            for (int c = 0; c < 4; ++c) {
+                const int nd = cnode(ci + (c & 1), cj + (c >> 1));
+                corner[4 * (size_t)(r - r0) + c] = nd;
+                if (nd >= 0) cns.push_back(nd);
+            }
+        }
+        std::sort(cns.begin(), cns.end());
+        cns.erase(std::unique(cns.begin(), cns.end()), cns.end());
+        S.max_cn = std::max(S.max_cn, (int)cns.size());
+        const size_t cn0 = S.cn_node.size();
+        S.cn_node.insert(S.cn_node.end(), cns.begin(), cns.end());
+        std::vector<std::vector<uint16_t>> lists(cns.size());
+        for (int r = r0; r < r1; ++r)
+            for (int c = 0; c < 4; ++c) {
+                const int nd = corner[4 * (size_t)(r - r0) + c];
+                uint16_t slot = 0xffffu;
+                if (nd >= 0) {
+                    slot = (uint16_t)(std::lower_bound(cns.begin(), cns.end(), nd) - cns.begin());
+                    lists[slot].push_back((uint16_t)(((r - r0) << 2) | c));
+                }
+                S.rowinfo[r].slot[c] = slot;
+            }
+        for (size_t j = 0; j < cns.size(); ++j) {
+            S.cn_ent.insert(S.cn_ent.end(), lists[j].begin(), lists[j].end());
+            S.cn_beg.push_back((unsigned)S.cn_ent.size());
+        }
+        (void)cn0;
+        S.win_cn0[w + 1] = (int)S.cn_node.size();
     }
     // Dirichlet boundary parameters / Vref samples
     double vb[4];
@@ -328,6 +466,58 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
             S.samp_elem[k] = bt; S.samp_lam[2 * k] = bl1; S.samp_lam[2 * k + 1] = bl2;
         }
     }
+}
+
+// Consistency check of the device layout against the host CSR pattern (used by the CPU test hook):
+// every CSR block must sit in the SELL slot of its row with the right window-local column, padding
+// must point at the row itself, halo lists must be sorted and outside their window, and every
+// (row, corner) pair must appear exactly once in the coarse-node lists.  Returns "" when consistent.
+static std::string sym_selfcheck(const SysSym& S) {
+    const int na = S.na;
+    if (S.nwin != (na + RVE_WIN - 1) / RVE_WIN) return "window count";
+    size_t npairs = 0;
+    for (int w = 0; w < S.nwin; ++w) {
+        const int r0 = w * RVE_WIN, wn = S.win_n[w];
+        if (wn != std::min(RVE_WIN, na - r0)) return "window size";
+        const int h0 = S.win_halo0[w], h1 = S.win_halo0[w + 1];
+        for (int k = h0; k < h1; ++k) {
+            if (S.halo[k] >= r0 && S.halo[k] < r0 + wn) return "halo inside window";
+            if (k > h0 && S.halo[k] <= S.halo[k - 1]) return "halo not sorted";
+        }
+        for (int rl = 0; rl < wn; ++rl) {
+            const int r = r0 + rl, lane = rl & 31, slice = S.win_slice0[w] + (rl >> 5);
+            const unsigned g0 = S.slice_ptr[slice], g1 = S.slice_ptr[slice + 1];
+            const int len = (int)(S.row_ptr[r + 1] - S.row_ptr[r]);
+            if ((int)(g1 - g0) < len) return "slice narrower than a row";
+            for (unsigned g = g0; g < g1; ++g) {
+                const int lc = S.scol[(size_t)g * 32 + lane];
+                const int j = (int)(g - g0);
+                if (j >= len) { if (lc != rl) return "padding column"; continue; }
+                const int c = lc < wn ? r0 + lc : (lc - wn < h1 - h0 ? S.halo[h0 + lc - wn] : -1);
+                if (c != S.bcol[S.row_ptr[r] + j]) return "SELL column mismatch";
+            }
+            // length-sorted inside the window
+            if (rl > 0 && len > (int)(S.row_ptr[r] - S.row_ptr[r - 1])) return "rows not sorted by length";
+        }
+        const int c0 = S.win_cn0[w], c1 = S.win_cn0[w + 1];
+        std::vector<int> seen(4 * (size_t)wn, 0);
+        for (int j = c0; j < c1; ++j) {
+            if (j > c0 && S.cn_node[j] <= S.cn_node[j - 1]) return "coarse nodes not sorted";
+            for (unsigned e = S.cn_beg[j]; e < S.cn_beg[j + 1]; ++e) {
+                const int rl = S.cn_ent[e] >> 2, c = S.cn_ent[e] & 3;
+                if (rl >= wn) return "restriction entry row";
+                if (S.rowinfo[r0 + rl].slot[c] != j - c0) return "restriction entry slot";
+                seen[4 * (size_t)rl + c]++; ++npairs;
+            }
+        }
+        for (int rl = 0; rl < wn; ++rl)
+            for (int c = 0; c < 4; ++c) {
+                const bool valid = S.rowinfo[r0 + rl].slot[c] != 0xffff;
+                if (seen[4 * (size_t)rl + c] != (valid ? 1 : 0)) return "restriction pair count";
+            }
+    }
+    if (npairs != S.cn_ent.size()) return "restriction entry total";
+    return "";
 }
 
 // level-1 grid size: largest n = m*2^j (m in {2,3}, j>=0) with L/n >= ext (so that an element

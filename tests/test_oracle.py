@@ -1,0 +1,130 @@
+"""CPU tests that pin the oracle (PARITY UNPINNED against FEniCS — see oracle/rve_oracle.py header):
+reference constants and goldens that exist (material table, mesh volume fractions of
+tests/test_meshes.py:58-59), analytic known answers, and structural properties of the models."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import smooth_uD
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PARAM = (0.3, 10.0, 0.3, 1.0)      # simulation_snapshots.py:120-123 (nu=0.3, E matrix 1, contrast 10)
+
+
+def test_material_table_matches_reference_formulas():
+    from oracle.rve_oracle import lame_table, eng2mu, eng2lambPlane
+    from deepbnd_b200.elasticity import getLameTable
+    t = lame_table(*PARAM)
+    # closed forms: mu = E/2(1+nu), plane-stress lambda* = E nu / (1-nu^2)
+    for row, (nu, E) in zip(t, [(0.3, 10.0), (0.3, 1.0), (0.3, 10.0), (0.3, 1.0)]):
+        assert np.isclose(row[1], E / 2.6, rtol=1e-15)
+        assert np.isclose(row[0], E * nu / (1 - nu * nu), rtol=1e-14)
+    assert np.array_equal(t, getLameTable(*PARAM))
+    assert eng2mu(0.3, 1.0) == 1.0 / 2.6 and np.isclose(eng2lambPlane(0.3, 1.0), 0.3 / 0.91)
+
+
+@pytest.mark.parametrize("size,vol,frac", [("reduced", 4.000000000000001, 0.22481976337016096),
+                                           ("full", 36.00000000000007, 0.29270474461987417)])
+def test_mesher_reproduces_reference_volume_goldens(size, vol, frac):
+    """the reference pins total volume and inclusion volume fraction of buildRVEmesh on this table
+    (tests/test_meshes.py:58-59, np.allclose); like the reference test, the SAME array is meshed twice,
+    'reduced' then 'full', each call permuting it in place (mesh_RVE.py:45-50)."""
+    from deepbnd_b200.mesh.rve_mesher import buildRVEmesh_arrays
+    p = np.loadtxt(os.path.join(GOLD, "paramRVE_test_meshes.txt"))
+    if size == "full":
+        buildRVEmesh_arrays(p, size="reduced", lcar=0.2)      # first call of the reference test: permutes p
+    xy, tri, reg = buildRVEmesh_arrays(p, size=size)
+    a = xy[tri]
+    area = 0.5 * ((a[:, 1, 0] - a[:, 0, 0]) * (a[:, 2, 1] - a[:, 0, 1]) - (a[:, 1, 1] - a[:, 0, 1]) * (a[:, 2, 0] - a[:, 0, 0]))
+    assert (area > 0).all()
+    v0 = area[(reg == 0) | (reg == 2)].sum()
+    v1 = area[(reg == 1) | (reg == 3)].sum()
+    assert np.allclose([v0 + v1, v0 / (v0 + v1)], [vol, frac])
+
+
+def test_ordered_indexes_are_a_layered_permutation():
+    """generation_inclusions.py:68-92: first NL entries = the internal 2x2 block of the 6x6 grid."""
+    from deepbnd_b200.mesh.rve_mesher import orderedIndexesTotal
+    perm = orderedIndexesTotal(6, 6, 2)
+    assert sorted(perm.tolist()) == list(range(36))
+    assert sorted(perm[:4].tolist()) == [14, 15, 20, 21]
+    assert sorted(perm[:16].tolist()) == sorted([6 * j + i for j in range(1, 5) for i in range(1, 5)])
+
+
+@pytest.mark.parametrize("model", ["lin", "per", "MR"])
+def test_homogeneous_material_gives_plane_stress_D(coarse_reduced_meshes, model):
+    from oracle.rve_oracle import OracleRVE, lame_table
+    lam, mu = lame_table(0.3, 1.0, 0.3, 1.0)[0]
+    D = np.array([[lam + 2 * mu, lam, 0], [lam, lam + 2 * mu, 0], [0, 0, mu]])
+    o = OracleRVE(*coarse_reduced_meshes[0], param=(0.3, 1.0, 0.3, 1.0), model=model)
+    C = o.compute_tangent()
+    assert np.abs(C - D).max() < 1e-10
+    for i in range(3):
+        u = o.sol[i].reshape(-1, 2)
+        if model != "MR":
+            assert np.abs(u).max() < 1e-10
+    
+
+def test_energy_ordering_symmetry_and_bounds(coarse_reduced_meshes):
+    from oracle.rve_oracle import OracleRVE, lame_table
+    mesh = coarse_reduced_meshes[2]
+    C = {m: OracleRVE(*mesh, param=PARAM, model=m).compute_tangent() for m in ("lin", "per", "MR")}
+    for m, c in C.items():
+        assert np.abs(c - c.T).max() < 1e-9 * np.abs(c).max()
+        assert np.linalg.eigvalsh(0.5 * (c + c.T)).min() > 0
+    assert np.linalg.eigvalsh(C["per"] - C["MR"]).min() > -1e-9
+    assert np.linalg.eigvalsh(C["lin"] - C["per"]).min() > -1e-9
+    # Voigt/Reuss bounds on C11 from the volume fraction
+    xy, tri, reg = mesh
+    a = xy[tri]
+    area = 0.5 * ((a[:, 1, 0] - a[:, 0, 0]) * (a[:, 2, 1] - a[:, 0, 1]) - (a[:, 1, 1] - a[:, 0, 1]) * (a[:, 2, 0] - a[:, 0, 0]))
+    f = abs(area[reg == reg.min()].sum()) / abs(area).sum()
+    t = lame_table(*PARAM)
+    c_i, c_m = t[0, 0] + 2 * t[0, 1], t[1, 0] + 2 * t[1, 1]
+    for c in C.values():
+        assert 1.0 / (f / c_i + (1 - f) / c_m) * 0.8 < c[0, 0] < f * c_i + (1 - f) * c_m
+
+
+def test_dnn_model_with_zero_data_equals_lin(coarse_reduced_meshes):
+    from oracle.rve_oracle import OracleRVE, vref_points
+    mesh = coarse_reduced_meshes[0]
+    pts = vref_points(-1, -1, 2, 2, 21)
+    C0 = OracleRVE(*mesh, param=PARAM, model="lin").compute_tangent()
+    C1 = OracleRVE(*mesh, param=PARAM, model="dnn").compute_tangent(uD_list=[np.zeros(162)] * 3, pts=pts)
+    assert np.abs(C0 - C1).max() < 1e-12
+
+
+def test_dnn_affine_boundary_data_is_absorbed_by_B(coarse_reduced_meshes):
+    """micro_model_dnn.py:85-94: for uD = G x the correction gives B = -G, uD + Bx = 0 and the effective macro
+    strain eps - B = eps + G; the tangent column must equal C_lin (eps + sym G)."""
+    from oracle.rve_oracle import OracleRVE, vref_points, macro_strain, strain2voigt
+    mesh = coarse_reduced_meshes[0]
+    pts = vref_points(-1, -1, 2, 2, 21)
+    G = np.array([[0.02, -0.01], [0.03, 0.015]])
+    uD = (pts @ G.T).ravel()
+    Clin = OracleRVE(*mesh, param=PARAM, model="lin").compute_tangent()
+    o = OracleRVE(*mesh, param=PARAM, model="dnn")
+    C = o.compute_tangent(uD_list=[uD] * 3, pts=pts)
+    for i in range(3):
+        e = strain2voigt(macro_strain(i) + G)
+        assert np.abs(C[:, i] - Clin @ e).max() < 1e-9
+
+
+def test_snapshot_outputs_and_rb_projection(coarse_reduced_meshes):
+    from oracle.rve_oracle import OracleRVE, vref_points, vref_mass, rb_project
+    mesh = coarse_reduced_meshes[0]
+    pts = vref_points(-0.5, -0.5, 1.0, 1.0, 21)
+    o = OracleRVE(*mesh, param=PARAM, model="per")
+    s = o.snapshot(pts)
+    assert s["solutions_S"].shape == (162,) and s["sigma_A"].shape == (3,) and s["B_S"].shape == (2, 2)
+    M = vref_mass(pts)
+    assert np.abs(M - M.T).max() == 0 and np.abs(M[160:]).max() == 0       # centre rows are zero
+    assert np.isclose(M.sum(), 2 * 4.0)                                     # 2 comps x perimeter
+    W = np.linalg.qr(np.random.RandomState(0).randn(162, 160))[0].T
+    U = np.stack([s["solutions_S"], s["solutions_A"]])
+    Y = rb_project(U, W, M)
+    assert np.allclose(Y, np.einsum("nq,qk,jk->nj", U, M, W))
+    # affine data: B is minus the average gradient over the regions {0,1} == whole reduced RVE
+    a, B = o.affine_local(0)
+    assert np.allclose(B, s["B_A"]) and np.allclose(a, s["a_A"])
