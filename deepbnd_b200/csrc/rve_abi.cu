@@ -64,7 +64,8 @@ struct rve_batch_s {
     DBuf<uint16_t> scol, cn_ent;
     DBuf<RowInfo> rowinfo;
     DBuf<double> lvA[RVE_MAXLEV], lvD[RVE_MAXLEV], lvR[RVE_MAXLEV], lvX[RVE_MAXLEV], lvT[RVE_MAXLEV];
-    DBuf<double> p, q, x, r, b, part, sc;
+    DBuf<float4> lvA4[RVE_MAXLEV], lvH4[RVE_MAXLEV];
+    DBuf<double> p, q, x, r, b, part, sc, cpart;
     DBuf<double> eps, eps_eff, Bmat, uD, gval, d_vbox, U, acc, sigL, sigT, aout, Bout, sol, Mx, Gaff, aaff;
     DBuf<double> MWt, transl, Yd;
     int* h_nactive = nullptr;  // pinned
@@ -150,10 +151,20 @@ static void launch_update(rve_batch_s* h, const PcgArgs& a, int init, int iter, 
                                                    h->sc.p, init, iter, a.rtol2, a.precond, h->d_iters.p, h->n_active.p);
 }
 
+// coarse V-cycle: level 1 as two grid-wide kernels (thread per coarse node), levels >= 2 in one CTA per system
+template <int K>
+static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStream_t st) {
+    const int G = a.LV.g[0].G;
+    const dim3 grid((unsigned)((G + 255) / 256), (unsigned)a.n_sys);
+    k_vc_down1<K><<<grid, 256, 0, st>>>(a.LV, h->active.p);
+    if (a.LV.L > 1) k_vc_mid<K><<<a.n_sys, a.LV.g[1].G <= 128 ? 128 : 256, 0, st>>>(a.LV, h->active.p);
+    k_vc_up1<K><<<grid, 256, 0, st>>>(a.LV, h->active.p, h->sc.p, h->cpart.p, h->cnt.p, first);
+}
+
 template <int K>
 static void launch_direction(rve_batch_s* h, const PcgArgs& a, cudaStream_t st) {
     k_direction<K><<<a.n_win, RVE_WIN, a.sm_dir, st>>>(a.wt, (double2*)h->p.p, (const double2*)h->r.p, h->dinv.p, h->rowinfo.p,
-                                                      h->cn_node.p, (const double2*)a.LV.xc[0], a.LV.g[0].G, h->active.p,
+                                                      h->cn_node.p, (const double2*)a.LV.tc[0], a.LV.g[0].G, h->active.p,
                                                       h->sc.p, a.precond);
 }
 
@@ -348,7 +359,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     CU(h->bval.alloc(128 * (size_t)h->NG)); CU(h->dinv.alloc((size_t)h->R)); CU(h->wmean.alloc(h->R));
     CU(h->active.alloc(n_sys)); CU(h->cnt.alloc(n_sys)); CU(h->d_iters.alloc(n_sys)); CU(h->n_active.alloc(1));
     CU(h->err_flag.alloc(1));
-    CU(h->part.alloc((size_t)h->n_win * 8)); CU(h->sc.alloc((size_t)n_sys * 4 * SC_N));
+    CU(h->part.alloc((size_t)h->n_win * 8));  CU(h->sc.alloc((size_t)n_sys * 4 * SC_N));
     CU(h->Mx.alloc((size_t)n_sys * 16)); CU(h->Gaff.alloc((size_t)n_sys * 16)); CU(h->aaff.alloc((size_t)n_sys * 8));
     CU(h->acc.alloc((size_t)n_sys * ACC_PER_SYS));
     // coarse hierarchy
@@ -365,12 +376,16 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         CU(h->lvA[L].alloc((size_t)n_sys * 100 * g.G)); CU(h->lvD[L].alloc((size_t)n_sys * 4 * g.G));
         CU(h->lvR[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2)); CU(h->lvX[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2));
         CU(h->lvT[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2));
+        CU(h->lvA4[L].alloc((size_t)n_sys * 25 * g.G)); CU(h->lvH4[L].alloc((size_t)n_sys * 25 * g.G));
         LV.A[L] = h->lvA[L].p; LV.dinv[L] = h->lvD[L].p; LV.rc[L] = h->lvR[L].p; LV.xc[L] = h->lvX[L].p; LV.tc[L] = h->lvT[L].p;
+        LV.A4[L] = h->lvA4[L].p; LV.H4[L] = h->lvH4[L].p;
         ++L;
         if ((ncx % 2) || (ncy % 2) || ncx / 2 < 2 || ncy / 2 < 2) break;
         ncx /= 2; ncy /= 2;
     }
     LV.L = L;
+    CU(h->cpart.alloc((size_t)n_sys * ((LV.g[0].G + 255) / 256) * 4));
+    if (n_sys > 65535) FAIL(RVE_E_ARG, "more than 65535 systems in one batch: split it");
     CU(cudaStreamSynchronize(st));
     auto t2 = std::chrono::steady_clock::now();
     h->t_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
@@ -402,8 +417,9 @@ int rve_assemble(rve_handle_t h) {
     for (int l = 0; l < LV.L; ++l) {
         long long n = (long long)h->n_sys * LV.g[l].G;
         k_coarse_dinv<<<cdiv(n, 256), 256, 0, st>>>(h->n_sys, LV.g[l], LV.A[l], LV.dinv[l]);
+        k_coarse_pack<<<cdiv(25 * n, 256), 256, 0, st>>>(h->n_sys, LV.g[l], LV.A[l], LV.dinv[l], LV.A4[l], LV.H4[l]);
     }
-    h->launches += 3 + (LV.L - 1) + LV.L;
+    h->launches += 3 + (LV.L - 1) + 2 * LV.L;
     CU(cudaEventRecord(h->ev[2], st));
     int flag = 0;
     CU(cudaMemcpyAsync(&flag, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -589,7 +605,11 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     *h->h_nactive = n_sys;
     while (it < maxit) {
         for (int k = 0; k < CHECK && it < maxit; ++k, ++it) {
-            if (precond) k_vcycle<<<n_sys, 256, 0, st>>>(LV, h->active.p, h->sc.p, it == 0);
+            if (precond) {
+#define VC_(KK) launch_vcycle<KK>(h, pa, it == 0, st)
+                K_DISPATCH(K, VC_);
+#undef VC_
+            }
 #define DIR_(KK) launch_direction<KK>(h, pa, st)
             K_DISPATCH(K, DIR_);
 #undef DIR_
@@ -602,7 +622,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
             K_DISPATCH(K, UPD_);
 #undef UPD_
             ++launched;
-            h->launches += precond ? 4 : 3;
+            h->launches += precond ? (LV.L > 1 ? 6 : 5) : 3;
         }
         CU(cudaMemcpyAsync(h->h_nactive, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

@@ -45,6 +45,8 @@ struct Levels {
     double* rc[RVE_MAXLEV];     // [n_sys][G][K][2]
     double* xc[RVE_MAXLEV];
     double* tc[RVE_MAXLEV];
+    float4* A4[RVE_MAXLEV];     // [n_sys][25][G] fp32 copy of A (a00,a01,a10,a11): preconditioner arithmetic only
+    float4* H4[RVE_MAXLEV];     // [n_sys][25][G] A_ij * (omega Dinv_j): residual after the first Jacobi step
 };
 
 struct WinTab {
@@ -80,6 +82,19 @@ __device__ __forceinline__ bool grid_node(const Grid& g, int i, int j, int& idx)
     if (g.wrap) {
         i = i % g.ncx; if (i < 0) i += g.ncx;
         j = j % g.ncy; if (j < 0) j += g.ncy;
+    } else if (i < g.lox || i > g.hix || j < g.loy || j > g.hiy) {
+        return false;
+    }
+    idx = j * g.nx + i;
+    return true;
+}
+
+// same as grid_node for |offset| <= ncx (one conditional wrap instead of two integer modulos):
+// every index the V-cycle kernels form is within [-2, ncx+2] and ncx >= 2
+__device__ __forceinline__ bool grid_node_fast(const Grid& g, int i, int j, int& idx) {
+    if (g.wrap) {
+        i += (i < 0) ? g.ncx : 0; i -= (i >= g.ncx) ? g.ncx : 0;
+        j += (j < 0) ? g.ncy : 0; j -= (j >= g.ncy) ? g.ncy : 0;
     } else if (i < g.lox || i > g.hix || j < g.loy || j > g.hiy) {
         return false;
     }
@@ -385,8 +400,9 @@ __device__ __forceinline__ bool last_block_sum(double* part, int* cnt, int sys, 
     __shared__ int s_last;
     __shared__ double s_red[256];
     const int tid = threadIdx.x;
-    if (tid < 4 * NQ) part[(size_t)win * 4 * NQ + tid] = my;
-    __threadfence();
+    // only the publishing threads fence (a fence by every thread would make the whole CTA wait for
+    // its x/r/q stores to land)
+    if (tid < 4 * NQ) { part[(size_t)win * 4 * NQ + tid] = my; __threadfence(); }
     __syncthreads();
     if (tid == 0) {
         int old = atomicAdd(cnt + sys, 1);
@@ -428,10 +444,18 @@ k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __re
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
     const int h0 = wt.win_halo0[win], nh = wt.win_halo0[win + 1] - h0;
-    // issue the first matrix loads before waiting for the tile
+    // software pipeline over slot pairs: the loads of the next pair are in flight while the current
+    // pair is multiplied; the first pair is requested before the p-tile is staged
     const int slice = wt.win_slice0[win] + wv;
     unsigned g0 = 0, g1 = 0;
     if (wv * 32 < n) { g0 = sl.slice_ptr[slice]; g1 = sl.slice_ptr[slice + 1]; }
+    const uint16_t* cp = sl.scol + (size_t)g0 * 32 + lane;
+    const double2* vp = bval + (size_t)g0 * 64 + lane;
+    const int ng = (int)(g1 - g0);
+    int c0 = 0, c1 = 0;
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0;
+    if (0 < ng) { c0 = cp[0]; a0 = vp[0]; a1 = vp[32]; }
+    if (1 < ng) { c1 = cp[32]; b0 = vp[64]; b1 = vp[96]; }
     {
         const double2* src = p + (size_t)row0 * K;
         for (int e = tid; e < n * K; e += RVE_WIN) s_tile[e] = src[e];
@@ -445,29 +469,19 @@ k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __re
     double2 y[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) y[k] = make_double2(0.0, 0.0);
-    const uint16_t* cp = sl.scol + (size_t)g0 * 32 + lane;
-    const double2* vp = bval + (size_t)g0 * 64 + lane;
-    const int ng = (int)(g1 - g0);
-    int j = 0;
-    for (; j + 2 <= ng; j += 2) {
-        const int c0 = cp[(size_t)j * 32], c1 = cp[(size_t)(j + 1) * 32];
-        const double2 a0 = vp[(size_t)j * 64], a1 = vp[(size_t)j * 64 + 32];
-        const double2 b0 = vp[(size_t)(j + 1) * 64], b1 = vp[(size_t)(j + 1) * 64 + 32];
+    for (int j = 0; j < ng; j += 2) {
+        int nc0 = 0, nc1 = 0;
+        double2 na0 = make_double2(0.0, 0.0), na1 = na0, nb0 = na0, nb1 = na0;
+        if (j + 2 < ng) { nc0 = cp[(size_t)(j + 2) * 32]; na0 = vp[(size_t)(j + 2) * 64]; na1 = vp[(size_t)(j + 2) * 64 + 32]; }
+        if (j + 3 < ng) { nc1 = cp[(size_t)(j + 3) * 32]; nb0 = vp[(size_t)(j + 3) * 64]; nb1 = vp[(size_t)(j + 3) * 64 + 32]; }
+        // a pair past the end of the slice carries zero blocks against column 0 of the tile
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const double2 xa = s_tile[c0 * K + k], xb = s_tile[c1 * K + k];
             y[k].x += a0.x * xa.x + a0.y * xa.y; y[k].y += a1.x * xa.x + a1.y * xa.y;
             y[k].x += b0.x * xb.x + b0.y * xb.y; y[k].y += b1.x * xb.x + b1.y * xb.y;
         }
-    }
-    if (j < ng) {
-        const int c0 = cp[(size_t)j * 32];
-        const double2 a0 = vp[(size_t)j * 64], a1 = vp[(size_t)j * 64 + 32];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const double2 xa = s_tile[c0 * K + k];
-            y[k].x += a0.x * xa.x + a0.y * xa.y; y[k].y += a1.x * xa.x + a1.y * xa.y;
-        }
+        c0 = nc0; c1 = nc1; a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
     }
     // dot with the own p entries, q through shared memory
     double2* s_q = s_tile + (size_t)(n + nh) * K;
@@ -497,8 +511,8 @@ k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __re
     double my = 0.0;
     if (tid < K)
         for (int i = 0; i < 8; ++i) my += s_dot[i][tid];
-    const int c0 = wt.sys_win0[sys], c1 = wt.sys_win0[sys + 1];
-    if (last_block_sum<1>(part, cnt, sys, win, c0, c1, my, s_out)) {
+    const int w0 = wt.sys_win0[sys], w1 = wt.sys_win0[sys + 1];
+    if (last_block_sum<1>(part, cnt, sys, win, w0, w1, my, s_out)) {
         if (tid < K) {
             double* s = sc + ((size_t)sys * 4 + tid) * SC_N;
             const double pq = s_out[tid][0];
@@ -538,20 +552,36 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
     const double alpha = sc[((size_t)sys * 4 + k) * SC_N + SC_ALPHA];
     double rr = 0.0, rdr = 0.0;
     if (tid < TPB) {
+        // all loads of the thread's (row, rhs) pairs are issued before the first use
+        constexpr int NIT = (RVE_WIN * K + TPB - 1) / TPB;
         const size_t base = (size_t)row0 * K;
-        for (int e = tid; e < n * K; e += TPB) {
-            double2 rv = r[base + e];
-            if (!init) {
-                const double2 pv = p[base + e], qv = q[base + e];
-                double2 xv = x[base + e];
-                xv.x += alpha * pv.x; xv.y += alpha * pv.y;
-                rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
-                x[base + e] = xv; r[base + e] = rv;
+        double2 rv[NIT], pv[NIT], qv[NIT], xv[NIT];
+        float4 dv[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int e = tid + it * TPB;
+            if (e < n * K) {
+                rv[it] = r[base + e];
+                dv[it] = dinv32[row0 + e / K];
+                if (!init) { pv[it] = p[base + e]; qv[it] = q[base + e]; xv[it] = x[base + e]; }
             }
-            const float4 d = dinv32[row0 + e / K];
-            rr += rv.x * rv.x + rv.y * rv.y;
-            rdr += rv.x * ((double)d.x * rv.x + (double)d.y * rv.y) + rv.y * ((double)d.z * rv.x + (double)d.w * rv.y);
-            s_r[e] = rv;
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int e = tid + it * TPB;
+            if (e < n * K) {
+                double2 rw = rv[it];
+                if (!init) {
+                    double2 xw = xv[it];
+                    xw.x += alpha * pv[it].x; xw.y += alpha * pv[it].y;
+                    rw.x -= alpha * qv[it].x; rw.y -= alpha * qv[it].y;
+                    x[base + e] = xw; r[base + e] = rw;
+                }
+                const float4 d = dv[it];
+                rr += rw.x * rw.x + rw.y * rw.y;
+                rdr += rw.x * ((double)d.x * rw.x + (double)d.y * rw.y) + rw.y * ((double)d.z * rw.x + (double)d.w * rw.y);
+                s_r[e] = rw;
+            }
         }
     }
     __shared__ double s_a[RVE_WIN], s_b[RVE_WIN];
@@ -569,22 +599,31 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
         acc = warp_sum(acc);
         if (lane == 0) s_fin[wv] = acc;
     }
-    // restriction: task = (coarse node of the window, rhs); weights from the staged (s,t)
+    // restriction: 4 threads per (coarse node of the window, rhs) split the node's (row, corner) list;
+    // weights from the staged (s,t)
     if (precond) {
-        for (int t = tid; t < ncn * K; t += RVE_WIN) {
-            const int jn = t / K, kk = t % K;
-            const unsigned b0 = cn_beg[cn0 + jn] - ent0, b1 = cn_beg[cn0 + jn + 1] - ent0;
+        for (int t = tid; t < ((ncn * K * 4 + 31) & ~31); t += RVE_WIN) {
+            const int task = t >> 2, sub = t & 3;
             double a0 = 0.0, a1 = 0.0;
-            for (unsigned e = b0; e < b1; ++e) {
-                const int en = s_ent[e];
-                const int rl = en >> 2, c = en & 3;
-                const float2 st = s_st[rl];
-                const double wgt = (double)((c & 1) ? st.x : 1.0f - st.x) * (double)((c & 2) ? st.y : 1.0f - st.y);
-                const double2 v = s_r[rl * K + kk];
-                a0 += wgt * v.x; a1 += wgt * v.y;
+            int jn = 0, kk = 0;
+            if (task < ncn * K) {
+                jn = task / K; kk = task % K;
+                const unsigned b0 = cn_beg[cn0 + jn] - ent0, b1 = cn_beg[cn0 + jn + 1] - ent0;
+                for (unsigned e = b0 + sub; e < b1; e += 4) {
+                    const int en = s_ent[e];
+                    const int rl = en >> 2, c = en & 3;
+                    const float2 st = s_st[rl];
+                    const double wgt = (double)((c & 1) ? st.x : 1.0f - st.x) * (double)((c & 2) ? st.y : 1.0f - st.y);
+                    const double2 v = s_r[rl * K + kk];
+                    a0 += wgt * v.x; a1 += wgt * v.y;
+                }
             }
-            double* d = rc1 + (((size_t)sys * G + cn_node[cn0 + jn]) * K + kk) * 2;
-            atomicAdd(d, a0); atomicAdd(d + 1, a1);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 2); a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+            if (task < ncn * K && sub == 0) {
+                double* d = rc1 + (((size_t)sys * G + cn_node[cn0 + jn]) * K + kk) * 2;
+                atomicAdd(d, a0); atomicAdd(d + 1, a1);
+            }
         }
     }
     __syncthreads();
@@ -616,189 +655,292 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
 }
 
 
-// Coarse V-cycle: ONE CTA per system runs all structured levels (25-point block stencils, damped
-// block-Jacobi smoothing) on the restricted residual and adds the coarse part of r.z.
-__device__ __forceinline__ void stencil_apply(const Grid& g, const double* __restrict__ A,
-                                              const double* x, int K, int i, int j, double* out) {
+// fp32 copies of a coarse level: A4 = A, H4_ij = A_ij (omega Dinv_j) (so that the residual after the
+// first damped-Jacobi step, rc - A (omega Dinv rc), is ONE stencil pass over rc).  thread per (sys,slot,node)
+__global__ void k_coarse_pack(int n_sys, Grid g, const double* __restrict__ A, const double* __restrict__ dinv,
+                              float4* __restrict__ A4, float4* __restrict__ H4) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n_sys * 25 * g.G) return;
+    const int I = (int)(gid % g.G);
+    const int slot = (int)((gid / g.G) % 25);
+    const int sys = (int)(gid / ((long long)25 * g.G));
+    const double* a = A + (size_t)sys * 100 * g.G + (size_t)slot * 4 * g.G + I;
+    const double a00 = a[0], a01 = a[g.G], a10 = a[2 * (size_t)g.G], a11 = a[3 * (size_t)g.G];
+    A4[gid] = make_float4((float)a00, (float)a01, (float)a10, (float)a11);
+    int nb;
+    double h00 = 0, h01 = 0, h10 = 0, h11 = 0;
+    if (grid_node(g, I % g.nx + slot % 5 - 2, I / g.nx + slot / 5 - 2, nb)) {
+        const double* d = dinv + ((size_t)sys * g.G + nb) * 4;
+        const double om = RVE_OMEGA;
+        h00 = om * (a00 * d[0] + a01 * d[2]); h01 = om * (a00 * d[1] + a01 * d[3]);
+        h10 = om * (a10 * d[0] + a11 * d[2]); h11 = om * (a10 * d[1] + a11 * d[3]);
+    }
+    H4[gid] = make_float4((float)h00, (float)h01, (float)h10, (float)h11);
+}
+
+// Coarse V-cycle on the restricted residual (damped block-Jacobi V(1,1) on 25-point block stencils).
+// out += S x over the 25 slots of node (i,j); branch-free: entries towards nodes outside the coarse
+// space are zero by construction, so their x is read from the node itself.
+template <int K>
+__device__ __forceinline__ void stencil_apply(const Grid& g, const float4* __restrict__ S4,
+                                              const double2* __restrict__ x, int i, int j, double2* out) {
     const int idx = j * g.nx + i;
+#pragma unroll
     for (int dj = -2; dj <= 2; ++dj)
+#pragma unroll
         for (int di = -2; di <= 2; ++di) {
             int nb;
-            if (!grid_node(g, i + di, j + dj, nb)) continue;
-            const double* a = A + (size_t)((dj + 2) * 5 + (di + 2)) * 4 * g.G + idx;
-            const double a00 = a[0], a01 = a[g.G], a10 = a[2 * (size_t)g.G], a11 = a[3 * (size_t)g.G];
-            if (a00 == 0.0 && a01 == 0.0 && a10 == 0.0 && a11 == 0.0) continue;
-            const double* xn = x + (size_t)nb * K * 2;
+            if (!grid_node_fast(g, i + di, j + dj, nb)) nb = idx;
+            const float4 a = S4[(size_t)((dj + 2) * 5 + (di + 2)) * g.G + idx];
+            const double2* xn = x + (size_t)nb * K;
 #pragma unroll
-            for (int k = 0; k < RVE_MAX_RHS; ++k)
-                if (k < K) {
-                    const double x0 = xn[2 * k], x1 = xn[2 * k + 1];
-                    out[2 * k] += a00 * x0 + a01 * x1;
-                    out[2 * k + 1] += a10 * x0 + a11 * x1;
-                }
+            for (int k = 0; k < K; ++k) {
+                const double2 xv = xn[k];
+                out[k].x += (double)a.x * xv.x + (double)a.y * xv.y;
+                out[k].y += (double)a.z * xv.x + (double)a.w * xv.y;
+            }
         }
 }
 
+// level-1 down: x1 = om Dinv rc ; t1 = rc - H rc.   thread per (sys, node), grid (ceil(G/256), n_sys)
+template <int K>
 __global__ void __launch_bounds__(256)
-k_vcycle(Levels LV, const int* __restrict__ active, double* sc, int first) {
+k_vc_down1(Levels LV, const int* __restrict__ active) {
+    const int sys = blockIdx.y;
+    if (!active[sys]) return;
+    const Grid g = LV.g[0];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.G) return;
+    const double2* rc = (const double2*)LV.rc[0] + (size_t)sys * g.G * K;
+    double2* xc = (double2*)LV.xc[0] + (size_t)sys * g.G * K;
+    double2* tc = (double2*)LV.tc[0] + (size_t)sys * g.G * K;
+    const double* d = LV.dinv[0] + ((size_t)sys * g.G + idx) * 4;
+    const double om = RVE_OMEGA;
+    const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
+    double2 acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+    stencil_apply<K>(g, LV.H4[0] + (size_t)sys * 25 * g.G, rc, idx % g.nx, idx / g.nx, acc);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double2 rv = rc[(size_t)idx * K + k];
+        xc[(size_t)idx * K + k] = make_double2(d0 * rv.x + d1 * rv.y, d2 * rv.x + d3 * rv.y);
+        tc[(size_t)idx * K + k] = make_double2(rv.x - acc[k].x, rv.y - acc[k].y);
+    }
+}
+
+// levels >= 2: one CTA per system.  Restricts t1, runs the rest of the V-cycle, prolongs the level-2
+// correction into x1.
+template <int K>
+__global__ void __launch_bounds__(256, 2)
+k_vc_mid(Levels LV, const int* __restrict__ active) {
     const int sys = blockIdx.x;
     if (!active[sys]) return;
-    const int K = LV.K, tid = threadIdx.x, nth = blockDim.x;
+    const int nth = blockDim.x, tid = threadIdx.x;
     const double om = RVE_OMEGA;
-    // level-1 residual rc = Z^T r was accumulated by k_update (REDs); it is cleared again at the end
-    // --- down sweep
-    for (int l = 0; l < LV.L; ++l) {
-        const Grid g = LV.g[l];
-        const double* A = LV.A[l] + (size_t)sys * 100 * g.G;
+    for (int l = 1; l < LV.L; ++l) {
+        const Grid g = LV.g[l], gf = LV.g[l - 1];
         const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
-        double* rc = LV.rc[l] + (size_t)sys * g.G * K * 2;
-        double* xc = LV.xc[l] + (size_t)sys * g.G * K * 2;
-        double* tc = LV.tc[l] + (size_t)sys * g.G * K * 2;
-        // x = om Dinv rc
+        double2* rc = (double2*)LV.rc[l] + (size_t)sys * g.G * K;
+        double2* xc = (double2*)LV.xc[l] + (size_t)sys * g.G * K;
+        double2* tc = (double2*)LV.tc[l] + (size_t)sys * g.G * K;
+        const double2* tf = (const double2*)LV.tc[l - 1] + (size_t)sys * gf.G * K;
+        // rc_l = P^T t_{l-1} (full weighting; t vanishes outside the coarse space)
         for (int idx = tid; idx < g.G; idx += nth) {
-            if (!grid_valid(g, idx % g.nx, idx / g.nx)) continue;
+            const int I = idx % g.nx, J = idx / g.nx;
+            double2 acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+            if (grid_valid(g, I, J)) {
+#pragma unroll
+                for (int aj = -1; aj <= 1; ++aj)
+#pragma unroll
+                    for (int ai = -1; ai <= 1; ++ai) {
+                        int nf;
+                        if (!grid_node_fast(gf, 2 * I + ai, 2 * J + aj, nf)) continue;
+                        const double wgt = (ai ? 0.5 : 1.0) * (aj ? 0.5 : 1.0);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const double2 tv = tf[(size_t)nf * K + k];
+                            acc[k].x += wgt * tv.x; acc[k].y += wgt * tv.y;
+                        }
+                    }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) rc[(size_t)idx * K + k] = acc[k];
+        }
+        __syncthreads();
+        // x = om Dinv rc ; t = rc - H rc
+        const float4* H4 = LV.H4[l] + (size_t)sys * 25 * g.G;
+        for (int idx = tid; idx < g.G; idx += nth) {
             const double* d = Di + 4 * (size_t)idx;
+            const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
+            double2 acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+            stencil_apply<K>(g, H4, rc, idx % g.nx, idx / g.nx, acc);
+#pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double r0 = rc[((size_t)idx * K + k) * 2], r1 = rc[((size_t)idx * K + k) * 2 + 1];
-                xc[((size_t)idx * K + k) * 2] = om * (d[0] * r0 + d[1] * r1);
-                xc[((size_t)idx * K + k) * 2 + 1] = om * (d[2] * r0 + d[3] * r1);
+                const double2 rv = rc[(size_t)idx * K + k];
+                xc[(size_t)idx * K + k] = make_double2(d0 * rv.x + d1 * rv.y, d2 * rv.x + d3 * rv.y);
+                tc[(size_t)idx * K + k] = make_double2(rv.x - acc[k].x, rv.y - acc[k].y);
             }
         }
         __syncthreads();
-        const bool coarsest = (l == LV.L - 1);
-        const int nsw = coarsest ? 3 : 0;  // extra Jacobi sweeps on the coarsest level
-        for (int sw = 0; sw < (coarsest ? nsw : 1); ++sw) {
-            // t = rc - A x
+    }
+    // coarsest level: two more damped-Jacobi sweeps (x += om Dinv t ; t = rc - A x)
+    {
+        const int l = LV.L - 1;
+        const Grid g = LV.g[l];
+        const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
+        const float4* A4 = LV.A4[l] + (size_t)sys * 25 * g.G;
+        const double2* rc = (const double2*)LV.rc[l] + (size_t)sys * g.G * K;
+        double2* xc = (double2*)LV.xc[l] + (size_t)sys * g.G * K;
+        double2* tc = (double2*)LV.tc[l] + (size_t)sys * g.G * K;
+        for (int sw = 0; sw < 2; ++sw) {
             for (int idx = tid; idx < g.G; idx += nth) {
-                const int i = idx % g.nx, j = idx / g.nx;
-                if (!grid_valid(g, i, j)) continue;
-                double acc[2 * RVE_MAX_RHS];
+                const double* d = Di + 4 * (size_t)idx;
+                const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
 #pragma unroll
-                for (int k = 0; k < 2 * RVE_MAX_RHS; ++k) acc[k] = 0.0;
-                stencil_apply(g, A, xc, K, i, j, acc);
-                for (int k = 0; k < 2 * K; ++k) tc[(size_t)idx * K * 2 + k] = rc[(size_t)idx * K * 2 + k] - acc[k];
+                for (int k = 0; k < K; ++k) {
+                    const double2 tv = tc[(size_t)idx * K + k];
+                    double2 xv = xc[(size_t)idx * K + k];
+                    xv.x += d0 * tv.x + d1 * tv.y; xv.y += d2 * tv.x + d3 * tv.y;
+                    xc[(size_t)idx * K + k] = xv;
+                }
             }
             __syncthreads();
-            if (coarsest) {
-                for (int idx = tid; idx < g.G; idx += nth) {
-                    if (!grid_valid(g, idx % g.nx, idx / g.nx)) continue;
-                    const double* d = Di + 4 * (size_t)idx;
-                    for (int k = 0; k < K; ++k) {
-                        const double t0 = tc[((size_t)idx * K + k) * 2], t1 = tc[((size_t)idx * K + k) * 2 + 1];
-                        xc[((size_t)idx * K + k) * 2] += om * (d[0] * t0 + d[1] * t1);
-                        xc[((size_t)idx * K + k) * 2 + 1] += om * (d[2] * t0 + d[3] * t1);
-                    }
+            if (sw == 1) break;
+            for (int idx = tid; idx < g.G; idx += nth) {
+                double2 acc[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+                stencil_apply<K>(g, A4, xc, idx % g.nx, idx / g.nx, acc);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const double2 rv = rc[(size_t)idx * K + k];
+                    tc[(size_t)idx * K + k] = make_double2(rv.x - acc[k].x, rv.y - acc[k].y);
                 }
-                __syncthreads();
-            }
-        }
-        if (!coarsest) {
-            // restrict t to level l+1 (full weighting = P^T)
-            const Grid gc = LV.g[l + 1];
-            double* rcc = LV.rc[l + 1] + (size_t)sys * gc.G * K * 2;
-            for (int idx = tid; idx < gc.G; idx += nth) {
-                const int I = idx % gc.nx, J = idx / gc.nx;
-                if (!grid_valid(gc, I, J)) continue;
-                double acc[2 * RVE_MAX_RHS];
-#pragma unroll
-                for (int k = 0; k < 2 * RVE_MAX_RHS; ++k) acc[k] = 0.0;
-                for (int aj = -1; aj <= 1; ++aj)
-                    for (int ai = -1; ai <= 1; ++ai) {
-                        int nf;
-                        if (!grid_node(g, 2 * I + ai, 2 * J + aj, nf)) continue;
-                        const double wgt = (ai ? 0.5 : 1.0) * (aj ? 0.5 : 1.0);
-                        const double* tv = tc + (size_t)nf * K * 2;
-#pragma unroll
-                        for (int k = 0; k < 2 * RVE_MAX_RHS; ++k)
-                            if (k < 2 * K) acc[k] += wgt * tv[k];
-                    }
-                for (int k = 0; k < 2 * K; ++k) rcc[(size_t)idx * K * 2 + k] = acc[k];
             }
             __syncthreads();
         }
     }
-    // --- up sweep
+    // up sweep: x_l += P x_{l+1}, then (for l >= 1) post-smoothing; level 0 is post-smoothed by k_vc_up1
     for (int l = LV.L - 2; l >= 0; --l) {
-        const Grid g = LV.g[l];
-        const Grid gc = LV.g[l + 1];
-        const double* A = LV.A[l] + (size_t)sys * 100 * g.G;
-        const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
-        double* rc = LV.rc[l] + (size_t)sys * g.G * K * 2;
-        double* xc = LV.xc[l] + (size_t)sys * g.G * K * 2;
-        double* tc = LV.tc[l] + (size_t)sys * g.G * K * 2;
-        const double* xcc = LV.xc[l + 1] + (size_t)sys * gc.G * K * 2;
-        // x += P xc
+        const Grid g = LV.g[l], gc = LV.g[l + 1];
+        double2* xc = (double2*)LV.xc[l] + (size_t)sys * g.G * K;
+        const double2* xcc = (const double2*)LV.xc[l + 1] + (size_t)sys * gc.G * K;
         for (int idx = tid; idx < g.G; idx += nth) {
             const int i = idx % g.nx, j = idx / g.nx;
             if (!grid_valid(g, i, j)) continue;
             const int I0 = i >> 1, J0 = j >> 1;
             const int ni = (i & 1) ? 2 : 1, nj = (j & 1) ? 2 : 1;
+            const double wgt = ((i & 1) ? 0.5 : 1.0) * ((j & 1) ? 0.5 : 1.0);
+            double2 acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = xc[(size_t)idx * K + k];
             for (int bj = 0; bj < nj; ++bj)
                 for (int bi = 0; bi < ni; ++bi) {
                     int nc;
-                    if (!grid_node(gc, I0 + bi, J0 + bj, nc)) continue;
-                    const double wgt = ((i & 1) ? 0.5 : 1.0) * ((j & 1) ? 0.5 : 1.0);
-                    for (int k = 0; k < 2 * K; ++k) xc[(size_t)idx * K * 2 + k] += wgt * xcc[(size_t)nc * K * 2 + k];
-                }
-        }
-        __syncthreads();
-        // post-smoothing: t = rc - A x ; x += om Dinv t
-        for (int idx = tid; idx < g.G; idx += nth) {
-            const int i = idx % g.nx, j = idx / g.nx;
-            if (!grid_valid(g, i, j)) continue;
-            double acc[2 * RVE_MAX_RHS];
+                    if (!grid_node_fast(gc, I0 + bi, J0 + bj, nc)) continue;
 #pragma unroll
-            for (int k = 0; k < 2 * RVE_MAX_RHS; ++k) acc[k] = 0.0;
-            stencil_apply(g, A, xc, K, i, j, acc);
-            for (int k = 0; k < 2 * K; ++k) tc[(size_t)idx * K * 2 + k] = rc[(size_t)idx * K * 2 + k] - acc[k];
+                    for (int k = 0; k < K; ++k) {
+                        const double2 v = xcc[(size_t)nc * K + k];
+                        acc[k].x += wgt * v.x; acc[k].y += wgt * v.y;
+                    }
+                }
+#pragma unroll
+            for (int k = 0; k < K; ++k) xc[(size_t)idx * K + k] = acc[k];
+        }
+        __syncthreads();
+        if (l == 0) break;
+        const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
+        const float4* A4 = LV.A4[l] + (size_t)sys * 25 * g.G;
+        const double2* rc = (const double2*)LV.rc[l] + (size_t)sys * g.G * K;
+        double2* tc = (double2*)LV.tc[l] + (size_t)sys * g.G * K;
+        for (int idx = tid; idx < g.G; idx += nth) {
+            double2 acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+            stencil_apply<K>(g, A4, xc, idx % g.nx, idx / g.nx, acc);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double2 rv = rc[(size_t)idx * K + k];
+                tc[(size_t)idx * K + k] = make_double2(rv.x - acc[k].x, rv.y - acc[k].y);
+            }
         }
         __syncthreads();
         for (int idx = tid; idx < g.G; idx += nth) {
-            if (!grid_valid(g, idx % g.nx, idx / g.nx)) continue;
             const double* d = Di + 4 * (size_t)idx;
+            const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
+#pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double t0 = tc[((size_t)idx * K + k) * 2], t1 = tc[((size_t)idx * K + k) * 2 + 1];
-                xc[((size_t)idx * K + k) * 2] += om * (d[0] * t0 + d[1] * t1);
-                xc[((size_t)idx * K + k) * 2 + 1] += om * (d[2] * t0 + d[3] * t1);
+                const double2 tv = tc[(size_t)idx * K + k];
+                double2 xv = xc[(size_t)idx * K + k];
+                xv.x += d0 * tv.x + d1 * tv.y; xv.y += d2 * tv.x + d3 * tv.y;
+                xc[(size_t)idx * K + k] = xv;
             }
         }
         __syncthreads();
     }
-    // --- coarse part of r.z = rc1 . xc1, then beta
-    {
-        const Grid g = LV.g[0];
-        const double* rc = LV.rc[0] + (size_t)sys * g.G * K * 2;
-        const double* xc = LV.xc[0] + (size_t)sys * g.G * K * 2;
-        double acc[RVE_MAX_RHS] = {0, 0, 0, 0};
-        for (int idx = tid; idx < g.G; idx += nth) {
-            if (!grid_valid(g, idx % g.nx, idx / g.nx)) continue;
+}
+
+// level-1 up: z1 = x1 + om Dinv (rc - A x1) written to tc[0] (k_direction prolongs it), coarse part of
+// r.z = rc . z1, beta; clears rc for the next restriction.  grid (ceil(G/256), n_sys)
+template <int K>
+__global__ void __launch_bounds__(256)
+k_vc_up1(Levels LV, const int* __restrict__ active, double* sc, double* part, int* cnt, int first) {
+    const int sys = blockIdx.y;
+    if (!active[sys]) return;
+    const Grid g = LV.g[0];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    double dot[K];
 #pragma unroll
-            for (int k = 0; k < RVE_MAX_RHS; ++k)
-                if (k < K)
-                    acc[k] += rc[((size_t)idx * K + k) * 2] * xc[((size_t)idx * K + k) * 2] +
-                              rc[((size_t)idx * K + k) * 2 + 1] * xc[((size_t)idx * K + k) * 2 + 1];
+    for (int k = 0; k < K; ++k) dot[k] = 0.0;
+    if (idx < g.G) {
+        double2* rc = (double2*)LV.rc[0] + (size_t)sys * g.G * K;
+        const double2* xc = (const double2*)LV.xc[0] + (size_t)sys * g.G * K;
+        double2* zc = (double2*)LV.tc[0] + (size_t)sys * g.G * K;
+        const double* d = LV.dinv[0] + ((size_t)sys * g.G + idx) * 4;
+        const double om = RVE_OMEGA;
+        const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
+        double2 acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+        stencil_apply<K>(g, LV.A4[0] + (size_t)sys * 25 * g.G, xc, idx % g.nx, idx / g.nx, acc);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double2 rv = rc[(size_t)idx * K + k];
+            const double t0 = rv.x - acc[k].x, t1 = rv.y - acc[k].y;
+            double2 xv = xc[(size_t)idx * K + k];
+            xv.x += d0 * t0 + d1 * t1; xv.y += d2 * t0 + d3 * t1;
+            zc[(size_t)idx * K + k] = xv;
+            dot[k] = rv.x * xv.x + rv.y * xv.y;
+            rc[(size_t)idx * K + k] = make_double2(0.0, 0.0);
         }
-        __shared__ double s_red[256][RVE_MAX_RHS];
+    }
+    __shared__ double s_dot[8][4];
+    __shared__ double s_out[4][1];
 #pragma unroll
-        for (int k = 0; k < RVE_MAX_RHS; ++k) s_red[tid][k] = acc[k];
-        __syncthreads();
-        for (int st = nth >> 1; st > 0; st >>= 1) {
-            if (tid < st)
-#pragma unroll
-                for (int k = 0; k < RVE_MAX_RHS; ++k) s_red[tid][k] += s_red[tid + st][k];
-            __syncthreads();
-        }
-        if (tid < K) {
-            double* s = sc + ((size_t)sys * 4 + tid) * SC_N;
-            const double rz = s[SC_RDR] + s_red[0][tid];
+    for (int k = 0; k < K; ++k) {
+        const double v = warp_sum(dot[k]);
+        if (lane == 0) s_dot[wv][k] = v;
+    }
+    __syncthreads();
+    double my = 0.0;
+    if (threadIdx.x < K)
+        for (int i = 0; i < 8; ++i) my += s_dot[i][threadIdx.x];
+    const int nb = gridDim.x;
+    if (last_block_sum<1>(part, cnt, sys, sys * nb + blockIdx.x, sys * nb, sys * nb + nb, my, s_out)) {
+        if (threadIdx.x < K) {
+            double* s = sc + ((size_t)sys * 4 + threadIdx.x) * SC_N;
+            const double rz = s[SC_RDR] + s_out[threadIdx.x][0];
             const double rzold = s[SC_RZ];
             s[SC_RZOLD] = rzold;
             s[SC_RZ] = rz;
             s[SC_BETA] = (!first && rzold > 0.0) ? rz / rzold : 0.0;
         }
-        // clear the accumulator for the next iteration's restriction
-        double* rcw = LV.rc[0] + (size_t)sys * g.G * K * 2;
-        for (int idx = tid; idx < g.G * K * 2; idx += nth) rcw[idx] = 0.0;
     }
 }
 
@@ -817,6 +959,24 @@ k_direction(WinTab wt, double2* __restrict__ p, const double2* __restrict__ r, c
     const int tid = threadIdx.x;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
     const int k = tid % K;
+    const double beta = sc[((size_t)sys * 4 + k) * SC_N + SC_BETA];
+    const size_t base = (size_t)row0 * K;
+    constexpr int NIT = (RVE_WIN * K + TPB - 1) / TPB;
+    double2 rv[NIT], pv[NIT];
+    float4 dv[NIT];
+    RowInfo ri[NIT];
+    // the streaming loads do not depend on the staged coarse values: request them first
+    if (tid < TPB) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int e = tid + it * TPB;
+            if (e < n * K) {
+                rv[it] = r[base + e]; pv[it] = p[base + e];
+                dv[it] = dinv32[row0 + e / K];
+                if (precond) ri[it] = rowinfo[row0 + e / K];
+            }
+        }
+    }
     if (precond) {
         const int cn0 = wt.win_cn0[win], ncn = wt.win_cn0[win + 1] - cn0;
         for (int t = tid; t < ncn * K; t += RVE_WIN)
@@ -824,31 +984,27 @@ k_direction(WinTab wt, double2* __restrict__ p, const double2* __restrict__ r, c
         __syncthreads();
     }
     if (tid >= TPB) return;
-    const double beta = sc[((size_t)sys * 4 + k) * SC_N + SC_BETA];
-    const size_t base = (size_t)row0 * K;
-    for (int e = tid; e < n * K; e += TPB) {
-        const int rl = e / K;
-        const double2 rv = r[base + e];
-        const float4 d = dinv32[row0 + rl];
-        double z0 = (double)d.x * rv.x + (double)d.y * rv.y, z1 = (double)d.z * rv.x + (double)d.w * rv.y;
-        if (precond) {
-            const RowInfo ri = rowinfo[row0 + rl];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int slot = ri.slot[c];
-                if (slot != 0xffff) {
-                    const double wgt = (double)((c & 1) ? ri.s : 1.0f - ri.s) * (double)((c & 2) ? ri.t : 1.0f - ri.t);
-                    const double2 v = s_xc[slot * K + k];
-                    z0 += wgt * v.x; z1 += wgt * v.y;
+    for (int it = 0; it < NIT; ++it) {
+        const int e = tid + it * TPB;
+        if (e < n * K) {
+            const float4 d = dv[it];
+            double z0 = (double)d.x * rv[it].x + (double)d.y * rv[it].y, z1 = (double)d.z * rv[it].x + (double)d.w * rv[it].y;
+            if (precond) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int slot = ri[it].slot[c];
+                    if (slot != 0xffff) {
+                        const double wgt = (double)((c & 1) ? ri[it].s : 1.0f - ri[it].s) * (double)((c & 2) ? ri[it].t : 1.0f - ri[it].t);
+                        const double2 v = s_xc[slot * K + k];
+                        z0 += wgt * v.x; z1 += wgt * v.y;
+                    }
                 }
             }
+            p[base + e] = make_double2(z0 + beta * pv[it].x, z1 + beta * pv[it].y);
         }
-        double2 pv = p[base + e];
-        pv.x = z0 + beta * pv.x; pv.y = z1 + beta * pv.y;
-        p[base + e] = pv;
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // (4) right-hand sides

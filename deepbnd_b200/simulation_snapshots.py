@@ -1,0 +1,131 @@
+"""Drop-in for creation_model/dataset/simulation_snapshots.py (reference :42-107): builds
+snapshots{suffix}_{run}.hd5 — for each RVE of paramRVEdataset.hd5 the fluctuation on the internal
+boundary (Vref samples), (a, B) affine data and homogenised stresses for the shear 'S' (Voigt 2) and
+axial 'A' (Voigt 0) loads — but solves the RVEs in BATCHES on one B200 through the C-ABI instead of
+one FEniCS/multiphenics LU at a time.
+
+Same call signature, same rank-strided split (`ids_run = arange(run, ns, num_runs)`, :76), same
+datasets and shapes (:80-83), same in-place permutation of the param rows by the mesher (:97-98).
+Extra keyword arguments only add what a GPU run needs (device, batch size, mesh cache directory).
+"""
+import multiprocessing as mp
+import os
+from timeit import default_timer as timer
+
+import numpy as np
+
+from . import wrapper_h5py as myhd
+from .batch import RVEBatch
+from .elasticity import macro_strain_voigt
+from .mesh.mesh_io import cache_name, load_mesh, read_xdmf_mesh, save_mesh_cache
+from .mesh.rve_mesher import buildRVEmesh_arrays, paramRVE_default
+
+LABELS = ['id', 'solutions_S', 'sigma_S', 'a_S', 'B_S', 'sigmaTotal_S',
+          'solutions_A', 'sigma_A', 'a_A', 'B_A', 'sigmaTotal_A']
+
+
+def vref_box_from_mesh(bndMeshname):
+    """Bounding box (x0, y0, Lx, Ly) and Nb of the internal-boundary reference mesh
+    (degeneratedBoundaryRectangleMesh, core/mesh/degenerated_rectangle_mesh.py:3-35).  Falls back to the
+    reference's constants (paramRVE_default: [-1,1]^2, Nb = 21) when the file is absent."""
+    p = paramRVE_default()
+    box, nb = (p.x0L, p.y0L, p.LxL, p.LyL), 21
+    if bndMeshname and os.path.exists(bndMeshname):
+        try:
+            pts, tri, _ = read_xdmf_mesh(bndMeshname)
+            x0, y0 = pts.min(axis=0)
+            Lx, Ly = np.ptp(pts[:, 0]), np.ptp(pts[:, 1])
+            box, nb = (x0, y0, Lx, Ly), (len(pts) - 1) // 4 + 1
+        except Exception:                                       # noqa: BLE001 - markers are optional for Vref
+            pass
+    return box, nb
+
+
+def _mesh_job(args):
+    row, meshname, size, createMesh = args
+    if createMesh or not (os.path.exists(cache_name(meshname)) or os.path.exists(meshname)):
+        mesh = buildRVEmesh_arrays(row, isOrdered=False, size=size)        # permutes `row` in place
+        save_mesh_cache(meshname, mesh)
+        return mesh, row
+    return load_mesh(meshname), row
+
+
+def get_meshes(paramRVEdata, meshnames, size, createMesh, nproc=None):
+    """Mesh every row (multi-process, results cached as .npz next to the reference's mesh name)."""
+    jobs = [(paramRVEdata[i], meshnames[i], size, createMesh) for i in range(len(meshnames))]
+    nproc = nproc or min(len(jobs), os.cpu_count() or 1)
+    if nproc <= 1 or len(jobs) < 4:
+        res = [_mesh_job(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(nproc) as pool:
+            res = pool.map(_mesh_job, jobs, chunksize=max(1, len(jobs) // (4 * nproc)))
+    for i, (_, row) in enumerate(res):
+        paramRVEdata[i] = row                                               # keep the reference's in-place permutation
+    return [m for m, _ in res]
+
+
+def solve_snapshot_batch(rows, meshes, paramMaterial, opModel, datasets, batch, vref, rtol=1e-10):
+    """Batch twin of solve_snapshot (reference :42-64): fills rows `rows` of the 11 datasets."""
+    ids, sol_S, sigma_S, a_S, B_S, sigmaT_S, sol_A, sigma_A, a_A, B_A, sigmaT_A = datasets
+    box, nb = vref
+    start = timer()
+    batch.set_meshes(meshes, tuple(paramMaterial), model=opModel, vref_nb=nb, vref_box=box).assemble()
+    n = len(meshes)
+    eps = np.broadcast_to(np.stack([macro_strain_voigt(2), macro_strain_voigt(0)]), (n, 2, 3)).copy()
+    batch.solve(eps, rtol=rtol)
+    out = batch.snapshot()
+    for k, (sol, sigma, a, B, sigmaT) in enumerate(((sol_S, sigma_S, a_S, B_S, sigmaT_S),
+                                                     (sol_A, sigma_A, a_A, B_A, sigmaT_A))):
+        sol[rows, :] = out["sol"][:, k]
+        sigma[rows, :] = out["sigma"][:, k]
+        a[rows, :] = out["a"][:, k]
+        B[rows, :, :] = out["B"][:, k]
+        sigmaT[rows, :] = out["sigmaT"][:, k]
+    print("batch of", n, "snapshots concluded in ", timer() - start)
+    return out
+
+
+def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs, comm_self=None,
+                   device=None, batch_size=256, rtol=1e-10, nproc=None):
+    bndMeshname, paramRVEname, snapshotsname, meshname = filesnames
+    vref = vref_box_from_mesh(bndMeshname)
+    nh = 2 * (4 * (vref[1] - 1) + 1)                                        # Vref.dim()
+
+    ns = len(myhd.loadhd5(paramRVEname, 'param')[:, 0])
+    ids_run = np.arange(run, ns, num_runs).astype('int')
+    nrun = len(ids_run)
+
+    if os.path.exists(snapshotsname):
+        os.remove(snapshotsname)
+    snapshots, fsnaps = myhd.zeros_openFile(filename=snapshotsname,
+                                            shape=[(nrun,)] + 2 * [(nrun, nh), (nrun, 3), (nrun, 2), (nrun, 2, 2), (nrun, 3)],
+                                            label=LABELS, mode='w-')
+    ids = snapshots[0]
+    paramRVEdata = myhd.loadhd5(paramRVEname, 'param')[ids_run]
+
+    batch = RVEBatch(run if device is None else device)
+    for b0 in range(0, nrun, batch_size):
+        rows = np.arange(b0, min(nrun, b0 + batch_size))
+        ids[rows] = ids_run[rows]
+        print("Solving snapshots", int(ids[rows[0]]), "..", int(ids[rows[-1]]))
+        # the reference reuses ONE temporary mesh name per rank; a batch needs one cache entry per snapshot
+        names = [meshname if len(rows) == 1 and not createMesh else
+                 meshname.replace(".xdmf", "_%d.xdmf" % int(ids_run[i])) for i in rows]
+        meshes = get_meshes(paramRVEdata[rows], names, 'full', createMesh, nproc)
+        solve_snapshot_batch(rows, meshes, paramMaterial, opModel, snapshots, batch, vref, rtol)
+        fsnaps.flush()
+    fsnaps.close()
+    batch.close()
+
+
+if __name__ == '__main__':
+    import sys
+    run = int(os.environ.get("RANK", sys.argv[1] if len(sys.argv) > 1 else 0))
+    num_runs = int(os.environ.get("WORLD_SIZE", sys.argv[2] if len(sys.argv) > 2 else 1))
+    folder = os.environ.get("DEEPBND_DATA", "./deepBND_data") + "/deepBND/dataset/"
+    suffix, opModel, createMesh = "_validation", 'per', True
+    contrast, E2, nu = 10.0, 1.0, 0.3
+    paramMaterial = [nu, E2 * contrast, nu, E2]
+    filesnames = [folder + 'boundaryMesh.xdmf', folder + 'paramRVEdataset{0}.hd5'.format(suffix),
+                  folder + 'snapshots{0}_{1}.hd5'.format(suffix, run), folder + "meshes/mesh_temp_{0}.xdmf".format(run)]
+    buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs)

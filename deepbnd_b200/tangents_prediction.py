@@ -1,0 +1,76 @@
+"""Drop-in for creation_model/prediction/tangents_prediction.py (reference :30-100): homogenised
+tangents of every RVE of paramRVEdataset.hd5 under the boundary model `modelBnd` ('dnn' with the
+predicted fluctuations of bcs.hd5, 'lin' = zero fluctuation, 'per', 'MR'), written to tangents.hd5 as
+`id (n,)`, `tangent (n,3,3)`, `center (n,2)` (:56-57) — batched on one B200 per rank.
+
+The reference reads the rank from a module-level `run`; here `num` is that rank (the signature keeps the
+reference's positional order)."""
+import os
+import sys
+from timeit import default_timer as timer
+
+import numpy as np
+
+from . import wrapper_h5py as myhd
+from .batch import RVEBatch
+from .elasticity import macro_strain_voigt
+from .simulation_snapshots import get_meshes, vref_box_from_mesh
+
+
+def predictTangents(num, num_runs, modelBnd, namefiles, createMesh, meshSize, device=None, batch_size=2048,
+                    rtol=1e-10, nproc=None):
+    nameMeshRefBnd, paramRVEname, tangentName, BCname, meshMicroName = namefiles
+    run = num
+    start = timer()
+    vref = vref_box_from_mesh(nameMeshRefBnd)
+
+    paramRVEdata = myhd.loadhd5(paramRVEname, 'param')[run::num_runs]
+    ns = len(paramRVEdata)                                            # per rank
+    if myhd.checkExistenceDataset(paramRVEname, 'id'):
+        ids = myhd.loadhd5(paramRVEname, 'id')[run::num_runs].astype('int')
+        centers = myhd.loadhd5(paramRVEname, 'center')[ids, :]
+    else:                                                             # dummy (reference :52-54)
+        ids = np.zeros(ns)
+        centers = np.zeros((ns, 2))
+
+    if os.path.exists(tangentName):
+        os.remove(tangentName)
+    (Iid, Itangent, Icenter), f = myhd.zeros_openFile(tangentName, [(ns,), (ns, 3, 3), (ns, 2)],
+                                                      ['id', 'tangent', 'center'], mode='w')
+    uD_all = None
+    if modelBnd == 'dnn':
+        uD_all = np.stack([myhd.loadhd5(BCname, 'u%d' % k)[run::num_runs, :] for k in range(3)], axis=1)
+
+    contrast, E2, nu = 10.0, 1.0, 0.3
+    param = [nu, E2 * contrast, nu, E2]
+    batch = RVEBatch(run if device is None else device)
+    eps3 = np.stack([macro_strain_voigt(i) for i in range(3)])
+    for b0 in range(0, ns, batch_size):
+        rows = np.arange(b0, min(ns, b0 + batch_size))
+        Iid[rows] = ids[rows]
+        print(run, rows[0], rows[-1], ids[rows[0]])
+        names = [meshMicroName.format(int(Iid[i]) if np.any(ids) else int(i), meshSize) for i in rows]
+        meshes = get_meshes(paramRVEdata[rows], names, meshSize, createMesh, nproc)
+        # a 'dnn' batch whose predictions are all zero is the 'lin' model (reference :86-90)
+        model, uD = modelBnd, None
+        if modelBnd == 'dnn':
+            uD = uD_all[rows]
+        batch.set_meshes(meshes, tuple(param), model=model, vref_nb=vref[1], vref_box=vref[0]).assemble()
+        batch.solve(np.broadcast_to(eps3, (len(rows), 3, 3)).copy(), uD=uD, rtol=rtol)
+        Itangent[rows, :, :] = batch.tangent()
+        Icenter[rows, :] = centers[rows, :]
+        f.flush()
+        sys.stdout.flush()
+    f.close()
+    batch.close()
+    print("tangents of", ns, "RVEs concluded in", timer() - start)
+
+
+if __name__ == '__main__':
+    run = int(sys.argv[1]) if len(sys.argv) > 1 else int(os.environ.get("RANK", 0))
+    num_runs = int(sys.argv[2]) if len(sys.argv) > 2 else int(os.environ.get("WORLD_SIZE", 1))
+    folder = os.environ.get("DEEPBND_DATA", "./deepBND_data") + "/deepBND/"
+    namefiles = [folder + 'dataset/boundaryMesh.xdmf', folder + 'prediction/paramRVEdataset.hd5',
+                 folder + 'prediction/tangents_{0}.hd5'.format(run), folder + 'prediction/bcs.hd5',
+                 folder + 'prediction/meshes/mesh_micro_{0}_{1}.xdmf']
+    predictTangents(run, num_runs, 'dnn', namefiles, True, 'reduced')
