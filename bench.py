@@ -254,23 +254,40 @@ def main():
                 M[2 * k + c, 2 * k + c] += 0.1 / 3; M[2 * k2 + c, 2 * k2 + c] += 0.1 / 3
                 M[2 * k + c, 2 * k2 + c] += 0.1 / 6; M[2 * k2 + c, 2 * k + c] += 0.1 / 6
 
-    b = RVEBatch(local_rank)
+    # two handles: while one batch is on the GPU, the host prepares (symbolic phase + H2D) the next
+    # one on the other handle from a second host thread (ctypes releases the GIL)
+    from concurrent.futures import ThreadPoolExecutor
+    hb = [RVEBatch(local_rank), RVEBatch(local_rank)]
+    b = hb[0]
+    pool = ThreadPoolExecutor(max_workers=1)
     maxit = 4000
 
-    def device_pass():
-        b.assemble()
-        status, iters = b.solve(eps, uD=uD, rtol=args.rtol, maxit=maxit, precond=args.precond)
+    def device_pass(bb=None):
+        bb = bb or b
+        bb.assemble()
+        status, iters = bb.solve(eps, uD=uD, rtol=args.rtol, maxit=maxit, precond=args.precond)
         if nl == 3:
-            out = b.tangent()
+            out = bb.tangent()
         else:
-            out = b.snapshot()
+            out = bb.snapshot()
             if wl["project"]:
-                out["Y"] = b.project(W, M, translate=out["a"])
+                out["Y"] = bb.project(W, M, translate=out["a"])
         return out, iters
 
-    def host_pass():
-        b.set_batch(voff, toff, xy, tri, reg, param=PARAM_MAT, model=wl["model"], vref_nb=21, vref_box=vref_box)
-        return device_pass()
+    def set_pass(bb):
+        bb.set_batch(voff, toff, xy, tri, reg, param=PARAM_MAT, model=wl["model"], vref_nb=21, vref_box=vref_box)
+
+    def e2e_steps(nsteps):
+        """nsteps full passes from HOST mesh arrays: set_batch (symbolic + H2D) of step i+1 overlaps the
+        device work + D2H of step i"""
+        set_pass(hb[0])
+        r = None
+        for i in range(nsteps):
+            fut = pool.submit(set_pass, hb[(i + 1) % 2]) if i + 1 < nsteps else None
+            r = device_pass(hb[i % 2])
+            if fut is not None:
+                fut.result()
+        return r
 
     def barrier():
         torch.cuda.synchronize()
@@ -278,23 +295,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, nsteps):
+    def timed(fn, *a):
         barrier()
         t = time.perf_counter()
-        for _ in range(nsteps):
-            r = fn()
+        r = fn(*a)
         barrier()
         return time.perf_counter() - t, r
 
+    def counters():
+        t0_, c0_ = hb[0].timings()
+        t1_, c1_ = hb[1].timings()
+        return {k_: c0_[k_] + c1_[k_] for k_ in c0_}
+
     # e2e loop (host buffers in, outputs out)
-    timed(host_pass, max(1, args.warmup - 1))
-    tim0, cnt0 = b.timings()
+    timed(e2e_steps, max(3, args.warmup))
+    cnt0 = counters()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    t_e2e, (out, iters) = timed(host_pass, args.steps)
-    tim1, cnt1 = b.timings()
+    t_e2e, (out, iters) = timed(e2e_steps, args.steps)
+    cnt1 = counters()
     # device-resident loop (batch already in HBM): `value`
-    timed(device_pass, 1)
+    set_pass(b)
+    timed(device_pass)
     spmv_ms, spmv_bytes, launches0 = 0.0, 0.0, b.timings()[1]["kernel_launches"]
     barrier()
     t = time.perf_counter()
@@ -346,7 +368,8 @@ def main():
                        "precond": args.precond, "mean_pcg_iters": float(np.mean(iters)),
                        "l2": "per-iteration working set >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "mesh_gen_s": t_mesh, "phase_ms": phase},
-            "e2e": {"value": e2e_val, "unit": "RVE/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_val, "unit": "RVE/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "pipeline": "2 handles: host symbolic phase + H2D of step i+1 overlap device work + D2H of step i"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_spmv_dot", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -174,6 +174,33 @@ class RVEBatch:
         return ms.value, by.value
 
 
+class DoubleBuffer:
+    """Two handles on one GPU: `prepare(job, handle)` (meshing, symbolic phase, H2D — host bound) of job
+    i+1 runs on a second host thread while `consume(job, handle, prepared)` (device work, D2H) of job i
+    runs on the caller's thread.  ctypes releases the GIL during the library calls."""
+
+    def __init__(self, device=0):
+        from concurrent.futures import ThreadPoolExecutor
+        self.h = [RVEBatch(device), RVEBatch(device)]
+        self.pool = ThreadPoolExecutor(max_workers=1)
+
+    def run(self, jobs, prepare, consume):
+        jobs = list(jobs)
+        if not jobs:
+            return
+        fut = self.pool.submit(prepare, jobs[0], self.h[0])
+        for i, job in enumerate(jobs):
+            prepared = fut.result()
+            if i + 1 < len(jobs):
+                fut = self.pool.submit(prepare, jobs[i + 1], self.h[(i + 1) % 2])
+            consume(job, self.h[i % 2], prepared)
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+        for b in self.h:
+            b.close()
+
+
 def host_symbolic(xy, tri, region, model="lin", vref_nb=0):
     """CPU-only test hook (rve_host_symbolic): symbolic phase of one system."""
     lib = L.load()

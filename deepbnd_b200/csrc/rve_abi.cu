@@ -33,6 +33,43 @@ struct DBuf {
     ~DBuf() { release(); }
 };
 
+// typed view into the pinned staging arena (same surface as the std::vector it replaces)
+template <class T>
+struct Span {
+    T* p = nullptr;
+    size_t n = 0;
+    T& operator[](size_t i) const { return p[i]; }
+    T* data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T* begin() const { return p; }
+};
+
+// grow-only page-locked host buffer: the flattened batch is built directly in it so that every
+// cudaMemcpyAsync is a true asynchronous DMA at PCIe speed
+struct PinnedArena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+    cudaError_t reserve(size_t bytes) {
+        off = 0;
+        if (bytes <= cap) return cudaSuccess;
+        if (base) cudaFreeHost(base);
+        base = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc((void**)&base, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    template <class T>
+    Span<T> take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        Span<T> sp; sp.p = (T*)(base + off); sp.n = count;
+        off += count * sizeof(T);
+        return sp;
+    }
+    static size_t need(size_t count, size_t elem) { return ((count * elem + 255) & ~(size_t)255) + 256; }
+    void release() { if (base) cudaFreeHost(base); base = nullptr; cap = 0; }
+};
+
 }  // namespace
 
 struct rve_batch_s {
@@ -69,6 +106,7 @@ struct rve_batch_s {
     DBuf<double> eps, eps_eff, Bmat, uD, gval, d_vbox, U, acc, sigL, sigT, aout, Bout, sol, Mx, Gaff, aaff;
     DBuf<double> MWt, transl, Yd;
     int* h_nactive = nullptr;  // pinned
+    PinnedArena arena;
     std::vector<cudaEvent_t> evpool;  // per-iteration SpMV timing
     double launches = 0;              // kernels launched since rve_create
     double h2d_bytes = 0, d2h_bytes = 0;  // host<->device traffic since rve_create
@@ -94,6 +132,13 @@ struct rve_batch_s {
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 #define UPL(d, v) do { CU(upload((d), (v), st)); h->h2d_bytes += (double)(v).size() * sizeof((v)[0]); } while (0)
+
+template <class T>
+static cudaError_t upload(DBuf<T>& d, const Span<T>& v, cudaStream_t s) {
+    cudaError_t e = d.alloc(v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
 
 template <class T>
 static cudaError_t upload(DBuf<T>& d, const std::vector<T>& v, cudaStream_t s) {
@@ -207,6 +252,7 @@ int rve_destroy(rve_handle_t h) {
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
+    h->arena.release();
     cudaStream_t s = h->stream;
     delete h;
     if (s) cudaStreamDestroy(s);
@@ -282,17 +328,33 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     const int n_win = h->n_win, n_slice = h->slice_base[n_sys], n_cn = h->cn_base[n_sys];
     if ((size_t)(h->max_tile + RVE_WIN) * 3 * sizeof(double2) > 200 * 1024) FAIL(RVE_E_MESH, "window halo too large for shared memory");
 
-    // flatten (parallel over systems)
-    std::vector<double> node_xy(2 * h->N), box(4 * (size_t)n_sys), bnd_s, bedge_nl(2 * h->NBE), samp_lam;
-    std::vector<int> node_row(h->N), node_bnd(h->N), node_sys(h->N), elem_node(6 * h->E), elem_sys(h->E),
-        bnd_sys(h->NBN), bnd_node(h->NBN), bedge(3 * h->NBE), samp_elem, win_sys(n_win), win_row0(n_win), win_n(n_win),
-        win_slice0(n_win), win_halo0(n_win + 1), win_cn0(n_win + 1), halo(h->halo_base[n_sys]), cn_node(n_cn);
-    std::vector<unsigned char> elem_reg(h->E);
-    std::vector<unsigned> slice_ptr(n_slice + 1), cn_beg(n_cn + 1);
-    std::vector<uint16_t> scol((size_t)h->NG * 32), cn_ent(h->ent_base[n_sys]);
-    std::vector<RowInfo> rowinfo(h->R);
-    if (model == RVE_MODEL_DNN) bnd_s.resize(2 * h->NBN);
-    if (h->nvref) { samp_elem.resize((size_t)n_sys * h->nvref); samp_lam.resize(2 * (size_t)n_sys * h->nvref); }
+    // flatten (parallel over systems) straight into the pinned staging arena
+    const size_t nvs = (size_t)n_sys * h->nvref;
+    const size_t n_bnds = model == RVE_MODEL_DNN ? 2 * (size_t)h->NBN : 0;
+    {
+        size_t bytes = 0;
+        auto add = [&](size_t c, size_t e) { bytes += PinnedArena::need(c, e); };
+        add(2 * h->N, 8); add(4 * (size_t)n_sys, 8); add(n_bnds, 8); add(2 * h->NBE, 8); add(2 * nvs, 8);
+        add(h->N, 4); add(h->N, 4); add(h->N, 4); add(6 * h->E, 4); add(h->E, 4); add(h->NBN, 4); add(h->NBN, 4);
+        add(3 * h->NBE, 4); add(nvs, 4); for (int k = 0; k < 4; ++k) add(n_win, 4);
+        add(n_win + 1, 4); add(n_win + 1, 4); add(h->halo_base[n_sys], 4); add(n_cn, 4); add(h->E, 1);
+        add(n_slice + 1, 4); add(n_cn + 1, 4); add((size_t)h->NG * 32, 2); add(h->ent_base[n_sys], 2); add(h->R, sizeof(RowInfo));
+        CU(cudaStreamSynchronize(h->stream));          // the previous batch's copies out of the arena are done
+        CU(h->arena.reserve(bytes));
+    }
+    PinnedArena& AR = h->arena;
+    Span<double> node_xy = AR.take<double>(2 * h->N), box = AR.take<double>(4 * (size_t)n_sys), bnd_s = AR.take<double>(n_bnds),
+                 bedge_nl = AR.take<double>(2 * h->NBE), samp_lam = AR.take<double>(2 * nvs);
+    Span<int> node_row = AR.take<int>(h->N), node_bnd = AR.take<int>(h->N), node_sys = AR.take<int>(h->N),
+              elem_node = AR.take<int>(6 * h->E), elem_sys = AR.take<int>(h->E), bnd_sys = AR.take<int>(h->NBN),
+              bnd_node = AR.take<int>(h->NBN), bedge = AR.take<int>(3 * h->NBE), samp_elem = AR.take<int>(nvs),
+              win_sys = AR.take<int>(n_win), win_row0 = AR.take<int>(n_win), win_n = AR.take<int>(n_win),
+              win_slice0 = AR.take<int>(n_win), win_halo0 = AR.take<int>(n_win + 1), win_cn0 = AR.take<int>(n_win + 1),
+              halo = AR.take<int>(h->halo_base[n_sys]), cn_node = AR.take<int>(n_cn);
+    Span<unsigned char> elem_reg = AR.take<unsigned char>(h->E);
+    Span<unsigned> slice_ptr = AR.take<unsigned>(n_slice + 1), cn_beg = AR.take<unsigned>(n_cn + 1);
+    Span<uint16_t> scol = AR.take<uint16_t>((size_t)h->NG * 32), cn_ent = AR.take<uint16_t>(h->ent_base[n_sys]);
+    Span<RowInfo> rowinfo = AR.take<RowInfo>(h->R);
     parallel_for(n_sys, [&](int s) {
         const SysSym& Y = S[s];
         const int nb0 = h->node_base[s], eb0 = h->elem_base[s], rb0 = h->row_base[s];

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -98,23 +99,45 @@ static void sym_pass1(SysSym& S, const double* xy, const int* tri, const int* re
         ext = std::max(ext, std::max(ex, ey));
     }
     S.max_ext = ext;
-    // edges: sort (key, slot)
-    std::vector<std::pair<uint64_t, int>> ek(3 * (size_t)nt);
+    // edges: bucket the 3*nt half-edges by their smaller vertex (counting sort), then order each
+    // bucket (<= ~10 entries) by the larger vertex: same numbering as a global sort by (va,vb)
+    std::vector<int> vptr(nv + 1, 0);
     for (int t = 0; t < nt; ++t)
         for (int k = 0; k < 3; ++k) {
             int a = S.tri[3 * t + k], b = S.tri[3 * t + (k + 1) % 3];
-            uint64_t key = ((uint64_t)std::min(a, b) << 32) | (uint64_t)std::max(a, b);
-            ek[3 * t + k] = {key, 3 * t + k};
+            vptr[std::min(a, b) + 1]++;
         }
-    std::sort(ek.begin(), ek.end());
+    for (int v = 0; v < nv; ++v) vptr[v + 1] += vptr[v];
+    std::vector<std::pair<int, int>> he(3 * (size_t)nt);          // (larger vertex, slot)
+    {
+        std::vector<int> vf(vptr.begin(), vptr.end() - 1);
+        for (int t = 0; t < nt; ++t)
+            for (int k = 0; k < 3; ++k) {
+                int a = S.tri[3 * t + k], b = S.tri[3 * t + (k + 1) % 3];
+                he[vf[std::min(a, b)]++] = {std::max(a, b), 3 * t + k};
+            }
+    }
     S.elem_node.resize(6 * (size_t)nt);
     std::vector<int> ecount;
     std::vector<uint64_t> ekeys;
-    for (size_t i = 0; i < ek.size(); ++i) {
-        if (i == 0 || ek[i].first != ek[i - 1].first) { ekeys.push_back(ek[i].first); ecount.push_back(0); }
-        ecount.back()++;
-        int t = ek[i].second / 3, k = ek[i].second % 3;
-        S.elem_node[6 * t + 3 + k] = nv + (int)ekeys.size() - 1;
+    ecount.reserve(3 * (size_t)nt / 2 + nv); ekeys.reserve(3 * (size_t)nt / 2 + nv);
+    for (int v = 0; v < nv; ++v) {
+        std::pair<int, int>* b0 = he.data() + vptr[v];
+        const int m = vptr[v + 1] - vptr[v];
+        for (int i = 1; i < m; ++i) {
+            const std::pair<int, int> x = b0[i];
+            int j = i - 1;
+            while (j >= 0 && b0[j] > x) { b0[j + 1] = b0[j]; --j; }
+            b0[j + 1] = x;
+        }
+        for (int i = 0; i < m; ++i) {
+            if (i == 0 || b0[i].first != b0[i - 1].first) {
+                ekeys.push_back(((uint64_t)v << 32) | (uint64_t)b0[i].first); ecount.push_back(0);
+            }
+            ecount.back()++;
+            const int t = b0[i].second / 3, k = b0[i].second % 3;
+            S.elem_node[6 * t + 3 + k] = nv + (int)ekeys.size() - 1;
+        }
     }
     S.ne = (int)ekeys.size();
     S.nn = nv + S.ne;
@@ -214,52 +237,60 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
         x = (x | (x << 2)) & 0x33333333ull; x = (x | (x << 1)) & 0x55555555ull;
         return x;
     };
-    std::vector<std::pair<uint64_t, int>> keyed;
-    keyed.reserve(nn);
+    // counting sort of the active nodes by the Morton rank of their cell (ties keep node order)
+    std::vector<int> cellrank((size_t)ncx * ncy);
+    {
+        std::vector<std::pair<uint64_t, int>> ck((size_t)ncx * ncy);
+        for (int cj = 0; cj < ncy; ++cj)
+            for (int ci = 0; ci < ncx; ++ci) ck[(size_t)cj * ncx + ci] = {spread((unsigned)ci) | (spread((unsigned)cj) << 1), cj * ncx + ci};
+        std::sort(ck.begin(), ck.end());
+        for (size_t k = 0; k < ck.size(); ++k) cellrank[ck[k].second] = (int)k;
+    }
+    std::vector<int> ncell(nn, -1), cptr((size_t)ncx * ncy + 1, 0);
     for (int n = 0; n < nn; ++n)
         if (master[n] == n) {
             int ci, cj; double s, t;
             coarse_cell(S.node_xy[2 * n], S.node_xy[2 * n + 1], x0, y0, invHx, invHy, ncx, ncy, ci, cj, s, t);
-            keyed.push_back({spread((unsigned)ci) | (spread((unsigned)cj) << 1), n});
+            ncell[n] = cellrank[cj * ncx + ci];
+            cptr[ncell[n] + 1]++;
         }
-    std::sort(keyed.begin(), keyed.end());
+    for (size_t c = 0; c < (size_t)ncx * ncy; ++c) cptr[c + 1] += cptr[c];
+    std::vector<std::pair<uint64_t, int>> keyed(cptr.back());
+    for (int n = 0; n < nn; ++n)
+        if (ncell[n] >= 0) keyed[cptr[ncell[n]]++] = {(uint64_t)ncell[n], n};
     S.na = (int)keyed.size();
     const int na = S.na;
-    // preliminary numbering = Morton order; pattern in that numbering gives the row lengths
+    // preliminary numbering = Morton order; row lengths by a marker-array dedupe over the adjacent elements
     std::vector<int> prow(nn, -1), pnode(na);
     for (int r = 0; r < na; ++r) { pnode[r] = keyed[r].second; prow[keyed[r].second] = r; }
     std::vector<int> nrow0(nn);
     for (int n = 0; n < nn; ++n) nrow0[n] = master[n] < 0 ? -1 : prow[master[n]];
+    std::vector<int> erow(6 * (size_t)nt);                 // element -> preliminary rows
     std::vector<int> adj_ptr(na + 1, 0);
     for (int t = 0; t < nt; ++t)
         for (int k = 0; k < 6; ++k) {
-            int r = nrow0[S.elem_node[6 * t + k]];
+            const int r = nrow0[S.elem_node[6 * t + k]];
+            erow[6 * (size_t)t + k] = r;
             if (r >= 0) adj_ptr[r + 1]++;
         }
     for (int r = 0; r < na; ++r) adj_ptr[r + 1] += adj_ptr[r];
     std::vector<int> adj(adj_ptr[na]), fill(adj_ptr.begin(), adj_ptr.end() - 1);
     for (int t = 0; t < nt; ++t)
         for (int k = 0; k < 6; ++k) {
-            int r = nrow0[S.elem_node[6 * t + k]];
+            const int r = erow[6 * (size_t)t + k];
             if (r >= 0) adj[fill[r]++] = t;
         }
-    std::vector<unsigned> rp0(na + 1, 0);
-    std::vector<int> bc0;
-    bc0.reserve((size_t)na * 12);
-    std::vector<int> cand;
+    std::vector<int> mark(na, -1), len0(na);
     for (int r = 0; r < na; ++r) {
-        cand.clear();
+        int cnt = 0;
         for (int i = adj_ptr[r]; i < adj_ptr[r + 1]; ++i) {
-            int t = adj[i];
+            const int* er = &erow[6 * (size_t)adj[i]];
             for (int k = 0; k < 6; ++k) {
-                int c = nrow0[S.elem_node[6 * t + k]];
-                if (c >= 0) cand.push_back(c);
+                const int c = er[k];
+                if (c >= 0 && mark[c] != r) { mark[c] = r; ++cnt; }
             }
         }
-        std::sort(cand.begin(), cand.end());
-        cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
-        bc0.insert(bc0.end(), cand.begin(), cand.end());
-        rp0[r + 1] = (unsigned)bc0.size();
+        len0[r] = cnt;
     }
     // windows of RVE_WIN consecutive rows; inside a window rows are sorted by descending length so
     // that the 32-row SELL slices are nearly uniform (vertex rows ~19 blocks, mid-edge rows ~9)
@@ -267,33 +298,45 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
     S.nwin = nwin;
     std::vector<int> newid(na), oldid(na);
     {
-        std::vector<int> idx;
-        for (int w = 0; w < nwin; ++w) {
+        int bucket[64];
+        for (int w = 0; w < nwin; ++w) {                    // stable counting sort by length (lengths < 64)
             const int r0 = w * RVE_WIN, r1 = std::min(na, r0 + RVE_WIN);
-            idx.resize(r1 - r0);
-            for (int r = r0; r < r1; ++r) idx[r - r0] = r;
-            std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return rp0[a + 1] - rp0[a] > rp0[b + 1] - rp0[b]; });
-            for (int k = 0; k < r1 - r0; ++k) { newid[idx[k]] = r0 + k; oldid[r0 + k] = idx[k]; }
+            for (int k = 0; k < 64; ++k) bucket[k] = 0;
+            for (int r = r0; r < r1; ++r) bucket[63 - std::min(len0[r], 63)]++;
+            int acc = 0;
+            for (int k = 0; k < 64; ++k) { const int c = bucket[k]; bucket[k] = acc; acc += c; }
+            for (int r = r0; r < r1; ++r) {
+                const int pos = r0 + bucket[63 - std::min(len0[r], 63)]++;
+                newid[r] = pos; oldid[pos] = r;
+            }
         }
     }
     S.row_node.resize(na);
     for (int r = 0; r < na; ++r) S.row_node[r] = pnode[oldid[r]];
     S.node_row.resize(nn);
     for (int n = 0; n < nn; ++n) S.node_row[n] = nrow0[n] < 0 ? -1 : newid[nrow0[n]];
-    // CSR pattern in the final numbering (sorted columns) — kept on the host for accessors/tests
+    // CSR pattern directly in the final numbering (columns in discovery order) — kept on the host for accessors/tests
     S.row_ptr.assign(na + 1, 0);
-    S.bcol.resize(bc0.size());
-    for (int r = 0; r < na; ++r) S.row_ptr[r + 1] = S.row_ptr[r] + (rp0[oldid[r] + 1] - rp0[oldid[r]]);
+    for (int r = 0; r < na; ++r) S.row_ptr[r + 1] = S.row_ptr[r] + (unsigned)len0[oldid[r]];
+    S.bcol.resize(S.row_ptr[na]);
+    std::fill(mark.begin(), mark.end(), -1);
     for (int r = 0; r < na; ++r) {
+        const int o = oldid[r];
         int* dst = &S.bcol[S.row_ptr[r]];
-        const int o = oldid[r], len = (int)(rp0[o + 1] - rp0[o]);
-        for (int k = 0; k < len; ++k) dst[k] = newid[bc0[rp0[o] + k]];
-        std::sort(dst, dst + len);
+        int cnt = 0;
+        for (int i = adj_ptr[o]; i < adj_ptr[o + 1]; ++i) {
+            const int* er = &erow[6 * (size_t)adj[i]];
+            for (int k = 0; k < 6; ++k) {
+                const int c = er[k];
+                if (c >= 0 && mark[c] != r) { mark[c] = r; dst[cnt++] = newid[c]; }
+            }
+        }
     }
     // per window: halo list, SELL-32 slices with window-local 16-bit columns, coarse-node lists
     S.win_n.assign(nwin, 0); S.win_slice0.assign(nwin + 1, 0); S.win_halo0.assign(nwin + 1, 0); S.win_cn0.assign(nwin + 1, 0);
     S.slice_ptr.assign(1, 0u);
     S.scol.clear(); S.halo.clear(); S.cn_node.clear(); S.cn_beg.assign(1, 0u); S.cn_ent.clear();
+    S.scol.reserve((size_t)S.bcol.size() + S.bcol.size() / 6);
     S.rowinfo.resize(na);
     S.max_tile = 0; S.max_cn = 0;
     const int nxg = ncx + 1;
@@ -304,18 +347,18 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
         if (i < lo || i > hix || j < lo || j > hiy) return -1;
         return j * nxg + i;
     };
-    std::vector<int> hal, cns;
+    std::vector<int> hal, cns, hpos(na, -1), cpos((size_t)nxg * (ncy + 1), -1), ccount, cfill;
     std::vector<int> corner(4 * (size_t)RVE_WIN);
     for (int w = 0; w < nwin; ++w) {
         const int r0 = w * RVE_WIN, r1 = std::min(na, r0 + RVE_WIN), wn = r1 - r0;
         S.win_n[w] = wn;
         hal.clear();
         for (unsigned k = S.row_ptr[r0]; k < S.row_ptr[r1]; ++k) {
-            int c = S.bcol[k];
-            if (c < r0 || c >= r1) hal.push_back(c);
+            const int c = S.bcol[k];
+            if ((c < r0 || c >= r1) && hpos[c] < 0) { hpos[c] = 0; hal.push_back(c); }
         }
         std::sort(hal.begin(), hal.end());
-        hal.erase(std::unique(hal.begin(), hal.end()), hal.end());
+        for (size_t k = 0; k < hal.size(); ++k) hpos[hal[k]] = wn + (int)k;
         if (wn + (int)hal.size() > 65535) { S.err = "window halo too large for 16-bit local columns"; return; }
         S.max_tile = std::max(S.max_tile, wn + (int)hal.size());
         S.halo.insert(S.halo.end(), hal.begin(), hal.end());
@@ -327,22 +370,21 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
             for (int r = a0; r < a1; ++r) width = std::max(width, (int)(S.row_ptr[r + 1] - S.row_ptr[r]));
             const size_t base = S.scol.size();
             S.scol.resize(base + (size_t)width * 32);
+            uint16_t* sc = &S.scol[base];
             for (int lane = 0; lane < 32; ++lane) {
                 const int r = a0 + lane;
                 const int len = r < a1 ? (int)(S.row_ptr[r + 1] - S.row_ptr[r]) : 0;
-                const int self = r < a1 ? r - r0 : 0;
-                for (int j = 0; j < width; ++j) {
-                    int lc = self;   // padding: zero block against a valid tile entry
-                    if (j < len) {
-                        const int c = S.bcol[S.row_ptr[r] + j];
-                        lc = (c >= r0 && c < r1) ? c - r0
-                                                 : wn + (int)(std::lower_bound(hal.begin(), hal.end(), c) - hal.begin());
-                    }
-                    S.scol[base + (size_t)j * 32 + lane] = (uint16_t)lc;
+                const uint16_t self = (uint16_t)(r < a1 ? r - r0 : 0);
+                const int* cols = r < a1 ? &S.bcol[S.row_ptr[r]] : nullptr;
+                for (int j = 0; j < len; ++j) {
+                    const int c = cols[j];
+                    sc[(size_t)j * 32 + lane] = (uint16_t)((c >= r0 && c < r1) ? c - r0 : hpos[c]);
                 }
+                for (int j = len; j < width; ++j) sc[(size_t)j * 32 + lane] = self;   // padding: zero block
             }
             S.slice_ptr.push_back(S.slice_ptr.back() + (unsigned)width);
         }
+        for (size_t k = 0; k < hal.size(); ++k) hpos[hal[k]] = -1;
         S.win_slice0[w + 1] = S.win_slice0[w] + nsl;
         // coarse nodes touched by the window and the (row, corner) lists of each of them
         cns.clear();
@@ -354,30 +396,31 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
             for (int c = 0; c < 4; ++c) {
                 const int nd = cnode(ci + (c & 1), cj + (c >> 1));
                 corner[4 * (size_t)(r - r0) + c] = nd;
-                if (nd >= 0) cns.push_back(nd);
+                if (nd >= 0 && cpos[nd] < 0) { cpos[nd] = 0; cns.push_back(nd); }
             }
         }
         std::sort(cns.begin(), cns.end());
-        cns.erase(std::unique(cns.begin(), cns.end()), cns.end());
-        S.max_cn = std::max(S.max_cn, (int)cns.size());
-        const size_t cn0 = S.cn_node.size();
+        const int ncn = (int)cns.size();
+        for (int j = 0; j < ncn; ++j) cpos[cns[j]] = j;
+        S.max_cn = std::max(S.max_cn, ncn);
         S.cn_node.insert(S.cn_node.end(), cns.begin(), cns.end());
-        std::vector<std::vector<uint16_t>> lists(cns.size());
-        for (int r = r0; r < r1; ++r)
+        ccount.assign(ncn + 1, 0);
+        for (int i = 0; i < 4 * wn; ++i) if (corner[i] >= 0) ccount[cpos[corner[i]] + 1]++;
+        for (int j = 0; j < ncn; ++j) ccount[j + 1] += ccount[j];
+        const size_t ebase = S.cn_ent.size();
+        S.cn_ent.resize(ebase + ccount[ncn]);
+        cfill.assign(ccount.begin(), ccount.end() - 1);
+        for (int rl = 0; rl < wn; ++rl)
             for (int c = 0; c < 4; ++c) {
-                const int nd = corner[4 * (size_t)(r - r0) + c];
+                const int nd = corner[4 * (size_t)rl + c];
                 uint16_t slot = 0xffffu;
                 if (nd >= 0) {
-                    slot = (uint16_t)(std::lower_bound(cns.begin(), cns.end(), nd) - cns.begin());
-                    lists[slot].push_back((uint16_t)(((r - r0) << 2) | c));
+                    slot = (uint16_t)cpos[nd];
+                    S.cn_ent[ebase + cfill[slot]++] = (uint16_t)((rl << 2) | c);
                 }
-                S.rowinfo[r].slot[c] = slot;
+                S.rowinfo[r0 + rl].slot[c] = slot;
             }
-        for (size_t j = 0; j < cns.size(); ++j) {
-            S.cn_ent.insert(S.cn_ent.end(), lists[j].begin(), lists[j].end());
-            S.cn_beg.push_back((unsigned)S.cn_ent.size());
-        }
-        (void)cn0;
+        for (int j = 0; j < ncn; ++j) { S.cn_beg.push_back((unsigned)(ebase + ccount[j + 1])); cpos[cns[j]] = -1; }
         S.win_cn0[w + 1] = (int)S.cn_node.size();
     }
     // Dirichlet boundary parameters / Vref samples
@@ -535,6 +578,7 @@ template <class F>
 static void parallel_for(int n, F f) {
     unsigned hw = std::thread::hardware_concurrency();
     int nth = (int)std::min<unsigned>(hw ? hw : 4, 64);
+    if (const char* e = std::getenv("RVE_HOST_THREADS")) { const int v = std::atoi(e); if (v > 0) nth = v; }
     nth = std::min(nth, std::max(1, n / 4));
     if (nth <= 1) { for (int i = 0; i < n; ++i) f(i); return; }
     std::vector<std::thread> th;

@@ -15,7 +15,7 @@ from timeit import default_timer as timer
 import numpy as np
 
 from . import wrapper_h5py as myhd
-from .batch import RVEBatch
+from .batch import DoubleBuffer
 from .elasticity import macro_strain_voigt
 from .mesh.mesh_io import cache_name, load_mesh, read_xdmf_mesh, save_mesh_cache
 from .mesh.rve_mesher import buildRVEmesh_arrays, paramRVE_default
@@ -64,13 +64,13 @@ def get_meshes(paramRVEdata, meshnames, size, createMesh, nproc=None):
     return [m for m, _ in res]
 
 
-def solve_snapshot_batch(rows, meshes, paramMaterial, opModel, datasets, batch, vref, rtol=1e-10):
-    """Batch twin of solve_snapshot (reference :42-64): fills rows `rows` of the 11 datasets."""
+def solve_snapshot_batch(rows, batch, datasets, rtol=1e-10):
+    """Batch twin of solve_snapshot (reference :42-64) on a batch already set on the GPU: fills rows `rows`
+    of the 11 datasets."""
     ids, sol_S, sigma_S, a_S, B_S, sigmaT_S, sol_A, sigma_A, a_A, B_A, sigmaT_A = datasets
-    box, nb = vref
     start = timer()
-    batch.set_meshes(meshes, tuple(paramMaterial), model=opModel, vref_nb=nb, vref_box=box).assemble()
-    n = len(meshes)
+    batch.assemble()
+    n = batch.n_sys
     eps = np.broadcast_to(np.stack([macro_strain_voigt(2), macro_strain_voigt(0)]), (n, 2, 3)).copy()
     batch.solve(eps, rtol=rtol)
     out = batch.snapshot()
@@ -88,8 +88,8 @@ def solve_snapshot_batch(rows, meshes, paramMaterial, opModel, datasets, batch, 
 def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs, comm_self=None,
                    device=None, batch_size=256, rtol=1e-10, nproc=None):
     bndMeshname, paramRVEname, snapshotsname, meshname = filesnames
-    vref = vref_box_from_mesh(bndMeshname)
-    nh = 2 * (4 * (vref[1] - 1) + 1)                                        # Vref.dim()
+    box, nb = vref_box_from_mesh(bndMeshname)
+    nh = 2 * (4 * (nb - 1) + 1)                                             # Vref.dim()
 
     ns = len(myhd.loadhd5(paramRVEname, 'param')[:, 0])
     ids_run = np.arange(run, ns, num_runs).astype('int')
@@ -103,19 +103,22 @@ def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs
     ids = snapshots[0]
     paramRVEdata = myhd.loadhd5(paramRVEname, 'param')[ids_run]
 
-    batch = RVEBatch(run if device is None else device)
-    for b0 in range(0, nrun, batch_size):
-        rows = np.arange(b0, min(nrun, b0 + batch_size))
+    def prepare(rows, batch):
+        # the reference reuses ONE temporary mesh name per rank; a batch needs one cache entry per snapshot
+        names = [meshname.replace(".xdmf", "_%d.xdmf" % int(ids_run[i])) for i in rows]
+        meshes = get_meshes(paramRVEdata[rows], names, 'full', createMesh, nproc)
+        batch.set_meshes(meshes, tuple(paramMaterial), model=opModel, vref_nb=nb, vref_box=box)
+
+    def consume(rows, batch, _):
         ids[rows] = ids_run[rows]
         print("Solving snapshots", int(ids[rows[0]]), "..", int(ids[rows[-1]]))
-        # the reference reuses ONE temporary mesh name per rank; a batch needs one cache entry per snapshot
-        names = [meshname if len(rows) == 1 and not createMesh else
-                 meshname.replace(".xdmf", "_%d.xdmf" % int(ids_run[i])) for i in rows]
-        meshes = get_meshes(paramRVEdata[rows], names, 'full', createMesh, nproc)
-        solve_snapshot_batch(rows, meshes, paramMaterial, opModel, snapshots, batch, vref, rtol)
+        solve_snapshot_batch(rows, batch, snapshots, rtol)
         fsnaps.flush()
+
+    db = DoubleBuffer(run if device is None else device)
+    db.run([np.arange(b0, min(nrun, b0 + batch_size)) for b0 in range(0, nrun, batch_size)], prepare, consume)
+    db.close()
     fsnaps.close()
-    batch.close()
 
 
 if __name__ == '__main__':

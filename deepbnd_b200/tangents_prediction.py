@@ -12,7 +12,7 @@ from timeit import default_timer as timer
 import numpy as np
 
 from . import wrapper_h5py as myhd
-from .batch import RVEBatch
+from .batch import DoubleBuffer
 from .elasticity import macro_strain_voigt
 from .simulation_snapshots import get_meshes, vref_box_from_mesh
 
@@ -43,26 +43,28 @@ def predictTangents(num, num_runs, modelBnd, namefiles, createMesh, meshSize, de
 
     contrast, E2, nu = 10.0, 1.0, 0.3
     param = [nu, E2 * contrast, nu, E2]
-    batch = RVEBatch(run if device is None else device)
     eps3 = np.stack([macro_strain_voigt(i) for i in range(3)])
-    for b0 in range(0, ns, batch_size):
-        rows = np.arange(b0, min(ns, b0 + batch_size))
+    box, nb = vref
+
+    def prepare(rows, batch):
+        names = [meshMicroName.format(int(ids[i]) if np.any(ids) else int(i), meshSize) for i in rows]
+        meshes = get_meshes(paramRVEdata[rows], names, meshSize, createMesh, nproc)
+        batch.set_meshes(meshes, tuple(param), model=modelBnd, vref_nb=nb, vref_box=box)
+
+    def consume(rows, batch, _):
         Iid[rows] = ids[rows]
         print(run, rows[0], rows[-1], ids[rows[0]])
-        names = [meshMicroName.format(int(Iid[i]) if np.any(ids) else int(i), meshSize) for i in rows]
-        meshes = get_meshes(paramRVEdata[rows], names, meshSize, createMesh, nproc)
-        # a 'dnn' batch whose predictions are all zero is the 'lin' model (reference :86-90)
-        model, uD = modelBnd, None
-        if modelBnd == 'dnn':
-            uD = uD_all[rows]
-        batch.set_meshes(meshes, tuple(param), model=model, vref_nb=vref[1], vref_box=vref[0]).assemble()
-        batch.solve(np.broadcast_to(eps3, (len(rows), 3, 3)).copy(), uD=uD, rtol=rtol)
+        batch.assemble()
+        batch.solve(np.broadcast_to(eps3, (len(rows), 3, 3)).copy(), uD=uD_all[rows] if modelBnd == 'dnn' else None, rtol=rtol)
         Itangent[rows, :, :] = batch.tangent()
         Icenter[rows, :] = centers[rows, :]
         f.flush()
         sys.stdout.flush()
+
+    db = DoubleBuffer(run if device is None else device)
+    db.run([np.arange(b0, min(ns, b0 + batch_size)) for b0 in range(0, ns, batch_size)], prepare, consume)
+    db.close()
     f.close()
-    batch.close()
     print("tangents of", ns, "RVEs concluded in", timer() - start)
 
 
