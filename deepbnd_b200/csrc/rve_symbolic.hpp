@@ -58,6 +58,7 @@ struct SysSym {
     std::vector<int> samp_elem;      // [nvref] local element id
     std::vector<double> samp_lam;    // [nvref][2] (l1,l2)
     double max_ext = 0;              // largest element bounding-box side
+    double mean_ext = 0;             // mean element bounding-box side
     std::string err;
 };
 
@@ -82,7 +83,7 @@ static void sym_pass1(SysSym& S, const double* xy, const int* tri, const int* re
         ymin = std::min(ymin, xy[2 * v + 1]); ymax = std::max(ymax, xy[2 * v + 1]);
     }
     S.box[0] = xmin; S.box[1] = ymin; S.box[2] = xmax - xmin; S.box[3] = ymax - ymin;
-    double ext = 0;
+    double ext = 0, ext_sum = 0;
     for (int t = 0; t < nt; ++t) {
         int r = region[t] - rmin;
         if (r < 0 || r > 3) { S.err = "region tag out of range (need max-min <= 3)"; return; }
@@ -97,8 +98,10 @@ static void sym_pass1(SysSym& S, const double* xy, const int* tri, const int* re
         double ex = std::max({p0[0], p1[0], p2[0]}) - std::min({p0[0], p1[0], p2[0]});
         double ey = std::max({p0[1], p1[1], p2[1]}) - std::min({p0[1], p1[1], p2[1]});
         ext = std::max(ext, std::max(ex, ey));
+        ext_sum += std::max(ex, ey);
     }
     S.max_ext = ext;
+    S.mean_ext = nt > 0 ? ext_sum / nt : 0.0;
     // edges: bucket the 3*nt half-edges by their smaller vertex (counting sort), then order each
     // bucket (<= ~10 entries) by the larger vertex: same numbering as a global sort by (va,vb)
     std::vector<int> vptr(nv + 1, 0);
@@ -563,11 +566,16 @@ static std::string sym_selfcheck(const SysSym& S) {
     return "";
 }
 
-// level-1 grid size: largest n = m*2^j (m in {2,3}, j>=0) with L/n >= ext (so that an element
-// never spans more than two coarse cells per direction) and n >= 2.
-static int pick_nc(double L, double ext) {
+// level-1 grid size: largest n = m*2^j (m in {2,3}, j>=0), n >= 2, whose cell H = L/n is at least
+// RVE_CELL_FACTOR mean element extents.  Elements larger than a cell are allowed: the Galerkin kernel
+// clamps the few nodes that fall outside the element's 3x3 coarse-node window (k_galerkin1), which keeps
+// the coarse operator a sum of SPSD element terms.  Finer grids cut the PCG iterations (full meshes:
+// n=32 -> 117, n=48 -> 80, n=64 -> 63 iterations) at a growing V-cycle cost; 1.1 balances the two
+// (lcar = 2/30: n = 24 on the 2x2 'reduced' box, n = 64 on the 6x6 'full' box).
+#define RVE_CELL_FACTOR 1.1
+static int pick_nc(double L, double mean_ext) {
     int best = 2;
-    double lim = L / (ext * 1.0000001);
+    double lim = L / (RVE_CELL_FACTOR * mean_ext * 1.0000001);
     for (int m = 2; m <= 3; ++m)
         for (int n = m; n <= 4096; n *= 2)
             if ((double)n <= lim) best = std::max(best, n);
@@ -577,7 +585,8 @@ static int pick_nc(double L, double ext) {
 template <class F>
 static void parallel_for(int n, F f) {
     unsigned hw = std::thread::hardware_concurrency();
-    int nth = (int)std::min<unsigned>(hw ? hw : 4, 64);
+    // leave two cores to the thread that is feeding kernels of the previous batch to the GPU
+    int nth = (int)std::min<unsigned>(hw > 3 ? hw - 2 : (hw ? hw : 4), 64);
     if (const char* e = std::getenv("RVE_HOST_THREADS")) { const int v = std::atoi(e); if (v > 0) nth = v; }
     nth = std::min(nth, std::max(1, n / 4));
     if (nth <= 1) { for (int i = 0; i < n; ++i) f(i); return; }

@@ -61,9 +61,62 @@ def test_assembly_matches_oracle(reduced_meshes, model):
     b.close()
 
 
+def _level1_reference(o, model, rown, nc):
+    """A1 = sum_e Z_e^T K_e Z_e with the bilinear transfer Z and the library's clamping rule for elements
+    that reach a third coarse cell (k_galerkin1): identical to Z^T A Z when no element does."""
+    from oracle.rve_oracle import periodic_map
+    m = o.mesh
+    nx = nc + 1
+    master = np.arange(m.nn)
+    if model == "lin":
+        master[m.bnd_nodes] = -1
+    elif model == "per":
+        master = periodic_map(m)
+    pos = -np.ones(m.nn, dtype=np.int64)
+    pos[rown] = np.arange(len(rown))
+    node_row = np.where(master >= 0, pos[np.maximum(master, 0)], -1)
+    X = m.xy[m.cells]
+    H = (m.x1 - m.x0) / nc
+    fx, fy = (X[:, :, 0] - m.x0) / H, (X[:, :, 1] - m.y0) / H
+    ci, cj = np.clip(fx.astype(int), 0, nc - 1), np.clip(fy.astype(int), 0, nc - 1)
+    s, t = np.clip(fx - ci, 0, 1), np.clip(fy - cj, 0, 1)
+    imin, jmin = ci.min(1, keepdims=True), cj.min(1, keepdims=True)
+    far_i, far_j = (ci - imin) >= 2, (cj - jmin) >= 2
+    ci, s = np.where(far_i, imin + 1, ci), np.where(far_i, 1.0, s)
+    cj, t = np.where(far_j, jmin + 1, cj), np.where(far_j, 1.0, t)
+    R = node_row[m.cells]
+    W, N = [], []
+    for di, dj, w in ((0, 0, (1 - s) * (1 - t)), (1, 0, s * (1 - t)), (0, 1, (1 - s) * t), (1, 1, s * t)):
+        i, j = ci + di, cj + dj
+        if model == "per":
+            nd, ok = (j % nc) * nx + (i % nc), np.ones_like(i, dtype=bool)
+        elif model == "lin":
+            ok, nd = (i >= 1) & (i <= nc - 1) & (j >= 1) & (j <= nc - 1), j * nx + i
+        else:
+            ok, nd = np.ones_like(i, dtype=bool), j * nx + i
+        ok = ok & (R >= 0)
+        W.append(np.where(ok, w, 0.0))
+        N.append(np.where(ok, nd, 0))
+    W, N = np.stack(W, 2), np.stack(N, 2)
+    nt = m.nt
+    Ke4 = o.ed['Ke'].reshape(nt, 6, 2, 6, 2)
+    I, J, V = [], [], []
+    for ca in range(4):
+        for cb in range(4):
+            ww = W[:, :, ca][:, :, None] * W[:, :, cb][:, None, :]
+            for c in range(2):
+                for d in range(2):
+                    I.append((2 * N[:, :, ca][:, :, None] + c + 0 * N[:, :, cb][:, None, :]).ravel())
+                    J.append((2 * N[:, :, cb][:, None, :] + d + 0 * N[:, :, ca][:, :, None]).ravel())
+                    V.append((ww * Ke4[:, :, c, :, d]).ravel())
+    A1 = sp.coo_matrix((np.concatenate(V), (np.concatenate(I), np.concatenate(J))), shape=(2 * nx * nx, 2 * nx * nx))
+    return A1.toarray(), int((far_i | far_j).any(1).sum())
+
+
 @pytest.mark.parametrize("model", ["lin", "per", "MR"])
 def test_coarse_operators_are_galerkin(reduced_meshes, model):
-    """level-1 operator == Z^T A Z with the bilinear Z rebuilt in numpy; deeper levels == P^T A P."""
+    """level-1 operator == sum_e Z_e^T K_e Z_e (Z^T A Z up to the clamping of over-long elements);
+    deeper levels == P^T A P."""
     from deepbnd_b200.batch import RVEBatch
     from oracle.rve_oracle import OracleRVE
     meshes = reduced_meshes[:2]
@@ -73,15 +126,8 @@ def test_coarse_operators_are_galerkin(reduced_meshes, model):
     o = OracleRVE(*meshes[s], param=PARAM, model=model)
     m = o.mesh
     _, rown = _perm(b, s, o, model)
-    Al = b.csr(s)
     nx = int(round(np.sqrt(dims[0])))
     nc = nx - 1
-    xy = m.xy[rown]
-    H = (m.x1 - m.x0) / nc
-    fx, fy = (xy[:, 0] - m.x0) / H, (xy[:, 1] - m.y0) / H
-    ci = np.clip(fx.astype(int), 0, nc - 1)
-    cj = np.clip(fy.astype(int), 0, nc - 1)
-    sx, ty = np.clip(fx - ci, 0, 1), np.clip(fy - cj, 0, 1)
 
     def node(i, j, ncl):
         nxl = ncl + 1
@@ -93,16 +139,8 @@ def test_coarse_operators_are_galerkin(reduced_meshes, model):
             ok = np.ones_like(i, dtype=bool)
         return j * nxl + i, ok
 
-    rows, cols, vals = [], [], []
-    for di, dj, w in ((0, 0, (1 - sx) * (1 - ty)), (1, 0, sx * (1 - ty)), (0, 1, (1 - sx) * ty), (1, 1, sx * ty)):
-        nd, ok = node(ci + di, cj + dj, nc)
-        for c in range(2):
-            rows.append(2 * np.arange(len(xy))[ok] + c)
-            cols.append(2 * nd[ok] + c)
-            vals.append(w[ok])
-    Z = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
-                      shape=(Al.shape[0], 2 * dims[0])).tocsr()
-    A1 = (Z.T @ Al @ Z).toarray()
+    A1, nclamped = _level1_reference(o, model, rown, nc)
+    print("level-1 grid", nc, "clamped elements", nclamped)
     A1l = b.coarse_dense(s, 0)
     assert np.abs(A1 - A1l).max() <= 1e-11 * np.abs(A1).max(), np.abs(A1 - A1l).max()
     # next level
@@ -257,3 +295,33 @@ def test_energy_ordering_and_symmetry(coarse_reduced_meshes):
             assert np.linalg.eigvalsh(0.5 * (C[model][s] + C[model][s].T)).min() > 0
         assert np.linalg.eigvalsh(C["per"][s] - C["MR"][s]).min() > -1e-9
         assert np.linalg.eigvalsh(C["lin"][s] - C["per"][s]).min() > -1e-9
+
+
+def test_config1_against_committed_goldens():
+    """BASELINE config 1: the single RVE of the reference's parameter table (tests/test_meshes.py:63-98) on the
+    GPU against tests/golden/c1_oracle.npz (oracle sparse LU; generator: tests/golden/make_goldens.py)."""
+    import os
+    from deepbnd_b200.batch import RVEBatch
+    from deepbnd_b200.mesh.rve_mesher import buildRVEmesh_arrays
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = np.load(os.path.join(gdir, "c1_oracle.npz"))
+    table = np.loadtxt(os.path.join(gdir, "paramRVE_test_meshes.txt"))
+    reduced = buildRVEmesh_arrays(table.copy(), size="reduced")
+    for model in ("lin", "per", "MR"):
+        b = RVEBatch().set_meshes([reduced], PARAM, model=model).assemble()
+        b.solve(EPS3[None].copy(), rtol=1e-11, maxit=6000)
+        C = b.tangent()[0]
+        ref = gold["tangent_reduced_" + model]
+        assert np.abs(C - ref).max() < 1e-8 * np.abs(ref).max(), model
+        b.close()
+    full = buildRVEmesh_arrays(table.copy(), size="full")
+    for model in ("per", "MR"):
+        b = RVEBatch().set_meshes([full], PARAM, model=model, vref_nb=21, vref_box=(-1, -1, 2, 2)).assemble()
+        b.solve(np.array([[[0, 0, 1.0], [1.0, 0, 0]]]), rtol=1e-11, maxit=8000)
+        snap = b.snapshot()
+        for k, lab in enumerate(("S", "A")):
+            for key, okey in (("sol", "solutions_"), ("sigma", "sigma_"), ("sigmaT", "sigmaTotal_"), ("a", "a_"), ("B", "B_")):
+                ref = gold["full_%s_%s%s" % (model, okey, lab)].ravel()
+                got = snap[key][0, k].ravel()
+                assert np.abs(got - ref).max() < 1e-8 * max(np.abs(ref).max(), 1e-3), (model, key, lab)
+        b.close()

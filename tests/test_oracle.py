@@ -128,3 +128,16 @@ def test_snapshot_outputs_and_rb_projection(coarse_reduced_meshes):
     # affine data: B is minus the average gradient over the regions {0,1} == whole reduced RVE
     a, B = o.affine_local(0)
     assert np.allclose(B, s["B_A"]) and np.allclose(a, s["a_A"])
+
+
+def test_oracle_reproduces_committed_c1_goldens():
+    """tests/golden/c1_oracle.npz (made by tests/golden/make_goldens.py) pins the oracle itself for BASELINE
+    config 1 (the reference's parameter table, reduced mesh; the full-mesh entries are checked on the GPU)."""
+    from deepbnd_b200.mesh.rve_mesher import buildRVEmesh_arrays
+    from oracle.rve_oracle import OracleRVE
+    gold = np.load(os.path.join(GOLD, "c1_oracle.npz"))
+    p = np.loadtxt(os.path.join(GOLD, "paramRVE_test_meshes.txt"))
+    mesh = buildRVEmesh_arrays(p, size="reduced")
+    for model in ("lin", "per", "MR"):
+        C = OracleRVE(*mesh, param=PARAM, model=model).compute_tangent()
+        assert np.abs(C - gold["tangent_reduced_" + model]).max() < 1e-10 * np.abs(C).max(), model
