@@ -175,6 +175,8 @@ def main():
     lcar = args.lcar if args.lcar > 0 else None
     ncpu = os.cpu_count() or 1
     nproc_local = max(1, ncpu // max(1, world))
+    if world > 1:                                   # ranks share the host cores of the box
+        os.environ.setdefault("RVE_HOST_THREADS", str(max(1, ncpu // world - 1)))
     from conftest import synthetic_param, smooth_uD
 
     if args.impl == "reference":

@@ -460,6 +460,13 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
             i1 = std::min(std::max((int)((xb - x0) / Lx * gb + 1e-9), 0), gb - 1);
             j0 = std::min(std::max((int)((ya - y0) / Ly * gb - 1e-9), 0), gb - 1);
             j1 = std::min(std::max((int)((yb - y0) / Ly * gb + 1e-9), 0), gb - 1);
+            // only elements that can hold a sample point are binned: those touching the outline of the
+            // Vref box, or its centre
+            const double e = 1e-9 * std::max(Lx, Ly), cxv = vb[0] + 0.5 * vb[2], cyv = vb[1] + 0.5 * vb[3];
+            const bool hits = xa <= vb[0] + vb[2] + e && xb >= vb[0] - e && ya <= vb[1] + vb[3] + e && yb >= vb[1] - e;
+            const bool inside = xa > vb[0] + e && xb < vb[0] + vb[2] - e && ya > vb[1] + e && yb < vb[1] + vb[3] - e;
+            const bool centre = xa <= cxv + e && xb >= cxv - e && ya <= cyv + e && yb >= cyv - e;
+            if (!((hits && !inside) || centre)) { i0 = 1; i1 = 0; }
         };
         for (int pass = 0; pass < 2; ++pass) {
             std::vector<int> f(bptr.begin(), bptr.end() - 1);
