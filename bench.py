@@ -29,6 +29,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+_OUT = sys.stdout
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -152,6 +153,12 @@ class ClockSampler:
 
 
 def main():
+    # the contract is ONE JSON line on stdout: anything a library prints there (NCCL's version banner, ...)
+    # is sent to stderr instead; the line itself goes to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -207,7 +214,8 @@ def main():
                 "cpu_baseline": {"value": val, "unit": "RVE/s", "cores": ncpu, "kind": "port",
                                  "sample": "%d RVEs per step, %d serial worker processes, scipy splu" % (nsamp, ncpu)},
                 "e2e": {"value": val, "unit": "RVE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        _OUT.write(json.dumps(line) + "\n")
+        _OUT.flush()
         return
 
     # ---------------- B200 arm ----------------
@@ -379,7 +387,8 @@ def main():
                          "launches_timed": int(spmv_launches * args.steps),
                          "alg_bytes_per_launch": spmv_bytes / max(1.0, spmv_launches * args.steps)},
             "cpu_baseline": cpu}
-    print(json.dumps(line))
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -161,7 +161,7 @@ static Sell sell_tab(rve_batch_s* h) {
 }
 
 // dynamic shared memory of the PCG kernels
-static size_t smem_spmv(rve_batch_s* h, int K) { return (size_t)(h->max_tile + RVE_WIN) * K * sizeof(double2); }
+static size_t smem_spmv(rve_batch_s* h, int K) { return (size_t)h->max_tile * K * sizeof(double2); }
 static size_t smem_update(int K) { return (size_t)RVE_WIN * K * sizeof(double2) + RVE_WIN * sizeof(float2) + 4 * RVE_WIN * sizeof(uint16_t); }
 static size_t smem_direction(rve_batch_s* h, int K) { return (size_t)h->max_cn * K * sizeof(double2); }
 
@@ -184,7 +184,7 @@ struct PcgArgs {
 template <int K>
 static void launch_spmv(rve_batch_s* h, const PcgArgs& a, const double* p, double* q, int* active, double* part, int* cnt,
                         double* sc, cudaStream_t st) {
-    k_spmv<K><<<a.n_win, RVE_WIN, a.sm_spmv, st>>>(a.wt, a.sl, (const double2*)h->bval.p, (const double2*)p, (double2*)q,
+    k_spmv<K><<<a.n_win, RVE_SPMV_THREADS, a.sm_spmv, st>>>(a.wt, a.sl, (const double2*)h->bval.p, (const double2*)p, (double2*)q,
                                                   active, part, cnt, sc);
 }
 

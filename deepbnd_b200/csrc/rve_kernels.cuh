@@ -415,7 +415,7 @@ __device__ __forceinline__ bool last_block_sum(double* part, int* cnt, int sys, 
     if (!s_last) return false;
     __threadfence();
     const int nv = 4 * NQ;
-    const int grp = tid / nv, v = tid % nv, ngrp = 256 / nv;
+    const int grp = tid / nv, v = tid % nv, ngrp = (int)blockDim.x / nv;
     double acc = 0.0;
     if (grp < ngrp)
         for (int c = c0 + grp; c < c1; c += ngrp) acc += __ldcg(part + (size_t)c * nv + v);
@@ -430,75 +430,105 @@ __device__ __forceinline__ bool last_block_sum(double* part, int* cnt, int sys, 
     return true;
 }
 
-// q = A p, pq = p.q.  The CTA first stages the p entries its window needs (own rows: one coalesced
-// copy; halo rows: list-driven gather) in shared memory, then every thread owns one row of a SELL-32
-// slice: per slot one coalesced 2-byte column load, two coalesced LDG.128 of the 2x2 block and K
-// LDS.128 gathers from the tile.  No cross-lane reduction; q leaves through shared memory so the
-// global store is coalesced.
+// q = A p, pq = p.q.  CTA of RVE_SPMV_WARPS (=2) warps per window.  The CTA first stages the p entries
+// its window needs (own rows: one coalesced copy; halo rows: list-driven gather) in shared memory.
+// Then every lane owns one row of a SELL-32 slice and each warp walks the slices w, w+2, w+4, w+6 of the
+// window: rows are sorted by length inside a window (2 long vertex slices, 6 short mid-edge slices), so
+// both warps get the same number of slots — no warp idles at a barrier.  Per slot: one coalesced 2-byte
+// column load, two coalesced LDG.128 of the 2x2 block and K LDS.128 gathers from the tile; the loads of
+// the next slot pair (also across a slice boundary) are in flight while the current pair is multiplied.
+// No cross-lane reduction; q leaves through shared memory so the global store is coalesced.
+#define RVE_SPMV_WARPS 2
+#define RVE_SPMV_THREADS (32 * RVE_SPMV_WARPS)
 template <int K>
-__global__ void __launch_bounds__(RVE_WIN)
+__global__ void __launch_bounds__(RVE_SPMV_THREADS)
 k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __restrict__ p,
        double2* __restrict__ q, const int* __restrict__ active, double* part, int* cnt, double* sc) {
-    extern __shared__ double2 s_tile[];           // [(n + nhalo) * K] p-tile, then [RVE_WIN * K] q staging
+    extern __shared__ double2 s_tile[];           // [(n + nhalo) * K] p-tile
+    __shared__ unsigned s_g0[RVE_WIN / 32 + 1];
     const int win = blockIdx.x;
     const int sys = wt.win_sys[win];
     if (!active[sys]) return;
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
     const int h0 = wt.win_halo0[win], nh = wt.win_halo0[win + 1] - h0;
-    // software pipeline over slot pairs: the loads of the next pair are in flight while the current
-    // pair is multiplied; the first pair is requested before the p-tile is staged
-    const int slice = wt.win_slice0[win] + wv;
-    unsigned g0 = 0, g1 = 0;
-    if (wv * 32 < n) { g0 = sl.slice_ptr[slice]; g1 = sl.slice_ptr[slice + 1]; }
-    const uint16_t* cp = sl.scol + (size_t)g0 * 32 + lane;
-    const double2* vp = bval + (size_t)g0 * 64 + lane;
-    const int ng = (int)(g1 - g0);
-    int c0 = 0, c1 = 0;
-    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0;
-    if (0 < ng) { c0 = cp[0]; a0 = vp[0]; a1 = vp[32]; }
-    if (1 < ng) { c1 = cp[32]; b0 = vp[64]; b1 = vp[96]; }
+    const int nsl = (n + 31) >> 5;
+    if (tid <= nsl) s_g0[tid] = sl.slice_ptr[wt.win_slice0[win] + tid];
     {
         const double2* src = p + (size_t)row0 * K;
-        for (int e = tid; e < n * K; e += RVE_WIN) s_tile[e] = src[e];
+        for (int e = tid; e < n * K; e += RVE_SPMV_THREADS) s_tile[e] = src[e];
         double2* dst = s_tile + n * K;
-        for (int e = tid; e < nh * K; e += RVE_WIN) {
+        for (int e = tid; e < nh * K; e += RVE_SPMV_THREADS) {
             const int hr = sl.halo[h0 + e / K];
             dst[e] = p[(size_t)hr * K + (e % K)];
         }
     }
     __syncthreads();
+    __shared__ double2 s_wq[RVE_SPMV_WARPS][32 * K];
+    const uint16_t* cp = sl.scol + lane;
+    const double2* vp = bval + lane;
+    double dot[K];
     double2 y[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) y[k] = make_double2(0.0, 0.0);
-    for (int j = 0; j < ng; j += 2) {
+    for (int k = 0; k < K; ++k) { dot[k] = 0.0; y[k] = make_double2(0.0, 0.0); }
+    // current pair
+    int s = wv, j = 0;
+    int c0 = 0, c1 = 0;
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0;
+    if (s < nsl) {
+        const size_t g = s_g0[s];
+        const int ng = (int)(s_g0[s + 1] - s_g0[s]);
+        c0 = cp[g * 32]; a0 = vp[g * 64]; a1 = vp[g * 64 + 32];
+        if (1 < ng) { c1 = cp[(g + 1) * 32]; b0 = vp[(g + 1) * 64]; b1 = vp[(g + 1) * 64 + 32]; }
+    }
+    while (s < nsl) {
+        // position of the next pair (possibly in the warp's next slice) and its loads
+        int ns = s, nj = j + 2;
+        if (nj >= (int)(s_g0[s + 1] - s_g0[s])) { ns = s + RVE_SPMV_WARPS; nj = 0; }
         int nc0 = 0, nc1 = 0;
         double2 na0 = make_double2(0.0, 0.0), na1 = na0, nb0 = na0, nb1 = na0;
-        if (j + 2 < ng) { nc0 = cp[(size_t)(j + 2) * 32]; na0 = vp[(size_t)(j + 2) * 64]; na1 = vp[(size_t)(j + 2) * 64 + 32]; }
-        if (j + 3 < ng) { nc1 = cp[(size_t)(j + 3) * 32]; nb0 = vp[(size_t)(j + 3) * 64]; nb1 = vp[(size_t)(j + 3) * 64 + 32]; }
-        // a pair past the end of the slice carries zero blocks against column 0 of the tile
+        if (ns < nsl) {
+            const size_t g = (size_t)s_g0[ns] + nj;
+            const int rem = (int)(s_g0[ns + 1] - s_g0[ns]) - nj;
+            nc0 = cp[g * 32]; na0 = vp[g * 64]; na1 = vp[g * 64 + 32];
+            if (1 < rem) { nc1 = cp[(g + 1) * 32]; nb0 = vp[(g + 1) * 64]; nb1 = vp[(g + 1) * 64 + 32]; }
+        }
+        // a missing second slot carries zero blocks against column 0 of the tile
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const double2 xa = s_tile[c0 * K + k], xb = s_tile[c1 * K + k];
             y[k].x += a0.x * xa.x + a0.y * xa.y; y[k].y += a1.x * xa.x + a1.y * xa.y;
             y[k].x += b0.x * xb.x + b0.y * xb.y; y[k].y += b1.x * xb.x + b1.y * xb.y;
         }
-        c0 = nc0; c1 = nc1; a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
-    }
-    // dot with the own p entries, q through shared memory
-    double2* s_q = s_tile + (size_t)(n + nh) * K;
-    double dot[K];
+        if (ns != s) {                              // slice finished: rows s*32 + lane
+            const int rl = s * 32 + lane;
+            if (rl < n) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) dot[k] = 0.0;
-    if (tid < n) {
+                for (int k = 0; k < K; ++k) {
+                    const double2 pv = s_tile[rl * K + k];
+                    dot[k] += y[k].x * pv.x + y[k].y * pv.y;
+                }
+            }
+            // the 32 rows of the slice leave through a per-warp staging line: coalesced 512-byte stores
+            __syncwarp();
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const double2 pv = s_tile[tid * K + k];
-            dot[k] = y[k].x * pv.x + y[k].y * pv.y;
-            s_q[tid * K + k] = y[k];
+            for (int k = 0; k < K; ++k) s_wq[wv][lane * K + k] = y[k];
+            __syncwarp();
+            {
+                double2* dst = q + ((size_t)row0 + s * 32) * K;
+                const int lim = (min(n - s * 32, 32)) * K;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int e = lane + 32 * k;
+                    if (e < lim) dst[e] = s_wq[wv][e];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) y[k] = make_double2(0.0, 0.0);
         }
+        s = ns; j = nj; c0 = nc0; c1 = nc1; a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
     }
-    __shared__ double s_dot[8][4];
+    __shared__ double s_dot[RVE_SPMV_WARPS][4];
     __shared__ double s_out[4][1];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -506,20 +536,16 @@ k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __re
         if (lane == 0) s_dot[wv][k] = v;
     }
     __syncthreads();
-    {
-        double2* dst = q + (size_t)row0 * K;
-        for (int e = tid; e < n * K; e += RVE_WIN) dst[e] = s_q[e];
-    }
     double my = 0.0;
     if (tid < K)
-        for (int i = 0; i < 8; ++i) my += s_dot[i][tid];
+        for (int i = 0; i < RVE_SPMV_WARPS; ++i) my += s_dot[i][tid];
     const int w0 = wt.sys_win0[sys], w1 = wt.sys_win0[sys + 1];
     if (last_block_sum<1>(part, cnt, sys, win, w0, w1, my, s_out)) {
         if (tid < K) {
-            double* s = sc + ((size_t)sys * 4 + tid) * SC_N;
+            double* s_ = sc + ((size_t)sys * 4 + tid) * SC_N;
             const double pq = s_out[tid][0];
-            s[SC_PQ] = pq;
-            s[SC_ALPHA] = (pq > 0.0) ? s[SC_RZ] / pq : 0.0;
+            s_[SC_PQ] = pq;
+            s_[SC_ALPHA] = (pq > 0.0) ? s_[SC_RZ] / pq : 0.0;
         }
     }
 }
@@ -1084,12 +1110,17 @@ k_rhs(int n_elem, int K, const int* __restrict__ elem_node, const unsigned char*
     __shared__ double s_mat[8];
     if (threadIdx.x < 8) s_mat[threadIdx.x] = mat.v[threadIdx.x];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (e >= n_elem) return;
-    const int sys = elem_sys[e];
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    const int e = blockIdx.x * (blockDim.x >> 5) + wv;
+    __shared__ double s_m2[8][3];
+    __shared__ int s_sys[8];
+    const bool valid = e < n_elem;
+    const int sys = valid ? elem_sys[e] : -1;
+    if (lane == 0) { s_sys[wv] = sys; s_m2[wv][0] = s_m2[wv][1] = s_m2[wv][2] = 0.0; }
     int node = 0, row = -1, bnd = -1;
-    double px = 0, py = 0;
+    double px = 0, py = 0, lam = 0, mu = 0;
+    TriGeom g;
+    if (valid) {
     if (lane < 6) {
         node = elem_node[(size_t)e * 6 + lane];
         row = node_row[node];
@@ -1100,10 +1131,9 @@ k_rhs(int n_elem, int K, const int* __restrict__ elem_node, const unsigned char*
     double x0 = __shfl_sync(0xffffffffu, px, 0), y0 = __shfl_sync(0xffffffffu, py, 0);
     double x1 = __shfl_sync(0xffffffffu, px, 1), y1 = __shfl_sync(0xffffffffu, py, 1);
     double x2 = __shfl_sync(0xffffffffu, px, 2), y2 = __shfl_sync(0xffffffffu, py, 2);
-    TriGeom g;
     tri_geom(x0, y0, x1, y1, x2, y2, g);
     const int reg = elem_reg[e];
-    const double lam = s_mat[2 * reg], mu = s_mat[2 * reg + 1];
+    lam = s_mat[2 * reg]; mu = s_mat[2 * reg + 1];
     {
         double gx = 0, gy = 0;
         if (lane < 6) p2_grad_int(g, lane, gx, gy);
@@ -1121,9 +1151,29 @@ k_rhs(int n_elem, int K, const int* __restrict__ elem_node, const unsigned char*
             double m2 = (lane < 6 && row >= 0) ? f0 * f0 + f1 * f1 : 0.0;
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
-            if (lane == 0) atomicAdd(sc + ((size_t)sys * 4 + k) * SC_N + SC_BREF, m2);
+            if (lane == 0) s_m2[wv][k] = m2;
         }
     }
+    }
+    // reference magnitude: one atomic per CTA and rhs when its 8 elements belong to one system
+    __syncthreads();
+    if (threadIdx.x < 3 * 8) {
+        const int w2 = threadIdx.x / 3, k = threadIdx.x % 3;
+        bool same = true;
+        for (int i = 1; i < 8; ++i) same = same && (s_sys[i] == s_sys[0] || s_sys[i] < 0);
+        if (k < K) {
+            if (same) {
+                if (w2 == 0 && s_sys[0] >= 0) {
+                    double t = 0.0;
+                    for (int i = 0; i < 8; ++i) t += s_m2[i][k];
+                    atomicAdd(sc + ((size_t)s_sys[0] * 4 + k) * SC_N + SC_BREF, t);
+                }
+            } else if (s_sys[w2] >= 0) {
+                atomicAdd(sc + ((size_t)s_sys[w2] * 4 + k) * SC_N + SC_BREF, s_m2[w2][k]);
+            }
+        }
+    }
+    if (!valid) return;
     const unsigned anyb = __ballot_sync(0xffffffffu, bnd >= 0);
     if (anyb == 0) return;
     int a = 0, bb = 0;
@@ -1311,50 +1361,70 @@ __global__ void k_nodal_field(long long n_nodes, int K, int NL, const int* __res
 //   [0..1] int u~ (L), [2..5] int grad u~ (L), [6..8] int sigma(u~) (L: 00,11,01), [9..11] same over all regions
 #define ACC_PER_SYS (6 + 16 * RVE_MAX_RHS)
 
+// add v from every lane to *addr: one atomic per warp when all lanes target the same system
+__device__ __forceinline__ void warp_acc(double v, double* addr, bool uniform, bool valid) {
+    if (uniform) {
+        v = warp_sum(v);
+        if ((threadIdx.x & 31) == 0) atomicAdd(addr, v);
+    } else if (valid) {
+        atomicAdd(addr, v);
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_epi_elements(int n_elem, int NL, const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
                const int* __restrict__ elem_sys, const double* __restrict__ node_xy,
                const double* __restrict__ U, double* __restrict__ acc, Mat8 mat) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_elem) return;
-    const int sys = elem_sys[e];
+    const bool valid = e < n_elem;
+    const int sys0 = __shfl_sync(0xffffffffu, valid ? elem_sys[e] : -1, 0);
+    if (sys0 < 0) return;                               // whole warp past the end
+    const int sys = valid ? elem_sys[e] : sys0;
+    const bool uniform = __all_sync(0xffffffffu, sys == sys0);
     int nd[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) nd[k] = elem_node[(size_t)e * 6 + k];
+    for (int k = 0; k < 6; ++k) nd[k] = valid ? elem_node[(size_t)e * 6 + k] : 0;
     TriGeom g;
-    tri_geom(node_xy[2 * (size_t)nd[0]], node_xy[2 * (size_t)nd[0] + 1], node_xy[2 * (size_t)nd[1]],
-             node_xy[2 * (size_t)nd[1] + 1], node_xy[2 * (size_t)nd[2]], node_xy[2 * (size_t)nd[2] + 1], g);
-    const int reg = elem_reg[e];
+    g.area = 0.0;
+    int reg = 0;
+    double cxa = 0.0, cya = 0.0;
+    if (valid) {
+        tri_geom(node_xy[2 * (size_t)nd[0]], node_xy[2 * (size_t)nd[0] + 1], node_xy[2 * (size_t)nd[1]],
+                 node_xy[2 * (size_t)nd[1] + 1], node_xy[2 * (size_t)nd[2]], node_xy[2 * (size_t)nd[2] + 1], g);
+        reg = elem_reg[e];
+        cxa = g.area * (node_xy[2 * (size_t)nd[0]] + node_xy[2 * (size_t)nd[1]] + node_xy[2 * (size_t)nd[2]]) / 3.0;
+        cya = g.area * (node_xy[2 * (size_t)nd[0] + 1] + node_xy[2 * (size_t)nd[1] + 1] + node_xy[2 * (size_t)nd[2] + 1]) / 3.0;
+    }
     const double lam = mat.v[2 * reg], mu = mat.v[2 * reg + 1];
     double* A = acc + (size_t)sys * ACC_PER_SYS;
-    atomicAdd(A + reg, g.area);
-    const bool inL = reg < 2;
-    if (inL) {
-        const double cx = (node_xy[2 * (size_t)nd[0]] + node_xy[2 * (size_t)nd[1]] + node_xy[2 * (size_t)nd[2]]) / 3.0;
-        const double cy = (node_xy[2 * (size_t)nd[0] + 1] + node_xy[2 * (size_t)nd[1] + 1] + node_xy[2 * (size_t)nd[2] + 1]) / 3.0;
-        atomicAdd(A + 4, cx * g.area); atomicAdd(A + 5, cy * g.area);
-    }
+    const bool inL = valid && reg < 2;
+#pragma unroll
+    for (int rg = 0; rg < 4; ++rg) warp_acc((valid && reg == rg) ? g.area : 0.0, A + rg, uniform, valid && reg == rg);
+    warp_acc(inL ? cxa : 0.0, A + 4, uniform, inL);
+    warp_acc(inL ? cya : 0.0, A + 5, uniform, inL);
     double gx[6], gy[6];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) p2_grad_int(g, a, gx[a], gy[a]);
+    for (int a = 0; a < 6; ++a) { gx[a] = 0.0; gy[a] = 0.0; if (valid) p2_grad_int(g, a, gx[a], gy[a]); }
     for (int l = 0; l < NL; ++l) {
         double G00 = 0, G01 = 0, G10 = 0, G11 = 0, ui0 = 0, ui1 = 0;
+        if (valid) {
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            const double u0 = U[((size_t)nd[a] * NL + l) * 2], u1 = U[((size_t)nd[a] * NL + l) * 2 + 1];
-            G00 += u0 * gx[a]; G01 += u0 * gy[a]; G10 += u1 * gx[a]; G11 += u1 * gy[a];
-            if (a >= 3) { ui0 += u0; ui1 += u1; }
+            for (int a = 0; a < 6; ++a) {
+                const double u0 = U[((size_t)nd[a] * NL + l) * 2], u1 = U[((size_t)nd[a] * NL + l) * 2 + 1];
+                G00 += u0 * gx[a]; G01 += u0 * gy[a]; G10 += u1 * gx[a]; G11 += u1 * gy[a];
+                if (a >= 3) { ui0 += u0; ui1 += u1; }
+            }
         }
         ui0 *= g.area / 3.0; ui1 *= g.area / 3.0;
         const double tr = G00 + G11;
         const double s00 = lam * tr + 2 * mu * G00, s11 = lam * tr + 2 * mu * G11, s01 = mu * (G01 + G10);
         double* Al = A + 6 + 16 * l;
-        if (inL) {
-            atomicAdd(Al + 0, ui0); atomicAdd(Al + 1, ui1);
-            atomicAdd(Al + 2, G00); atomicAdd(Al + 3, G01); atomicAdd(Al + 4, G10); atomicAdd(Al + 5, G11);
-            atomicAdd(Al + 6, s00); atomicAdd(Al + 7, s11); atomicAdd(Al + 8, s01);
-        }
-        atomicAdd(Al + 9, s00); atomicAdd(Al + 10, s11); atomicAdd(Al + 11, s01);
+        const double vL[9] = {ui0, ui1, G00, G01, G10, G11, s00, s11, s01};
+#pragma unroll
+        for (int q = 0; q < 9; ++q) warp_acc(inL ? vL[q] : 0.0, Al + q, uniform, inL);
+        warp_acc(valid ? s00 : 0.0, Al + 9, uniform, valid);
+        warp_acc(valid ? s11 : 0.0, Al + 10, uniform, valid);
+        warp_acc(valid ? s01 : 0.0, Al + 11, uniform, valid);
     }
 }
 

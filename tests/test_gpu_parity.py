@@ -325,3 +325,62 @@ def test_config1_against_committed_goldens():
                 got = snap[key][0, k].ravel()
                 assert np.abs(got - ref).max() < 1e-8 * max(np.abs(ref).max(), 1e-3), (model, key, lab)
         b.close()
+
+
+def test_ragged_batch_and_refined_mesh(coarse_reduced_meshes):
+    """one batch mixing mesh resolutions (lcar 0.1, 2/30 and the 'refined' 1/30 of BASELINE config 5): every
+    system must match its own oracle solve."""
+    from deepbnd_b200.batch import RVEBatch
+    from deepbnd_b200.mesh.rve_mesher import buildRVEmesh_arrays
+    from oracle.rve_oracle import OracleRVE
+    from conftest import synthetic_param
+    par = synthetic_param(3, seed=21)
+    meshes = [coarse_reduced_meshes[0], buildRVEmesh_arrays(par[1].copy(), size="reduced"),
+              buildRVEmesh_arrays(par[2].copy(), size="reduced", lcar=1.0 / 30.0)]
+    sizes = [len(m[1]) for m in meshes]
+    assert sizes[2] > 3 * sizes[1] > 3 * sizes[0]
+    b = RVEBatch().set_meshes(meshes, PARAM, model="per").assemble()
+    status, iters = b.solve(np.broadcast_to(EPS3, (3, 3, 3)).copy(), rtol=1e-11, maxit=6000)
+    assert (status == 0).all()
+    C = b.tangent()
+    for s in range(3):
+        Co = OracleRVE(*meshes[s], param=PARAM, model="per").compute_tangent()
+        assert np.abs(C[s] - Co).max() < 1e-8 * np.abs(Co).max(), (s, np.abs(C[s] - Co).max())
+    b.close()
+
+
+def test_error_codes_and_state_machine(coarse_reduced_meshes):
+    """the C-ABI reports misuse through status codes + rve_last_error, never by crashing or falling back."""
+    from deepbnd_b200.batch import RVEBatch
+    from deepbnd_b200 import _lib as L
+    b = RVEBatch()
+    with pytest.raises(L.RVEError) as ei:
+        b.assemble()                                                   # before set_batch
+    assert ei.value.code == -3
+    m = coarse_reduced_meshes[0]
+    with pytest.raises(L.RVEError) as ei:
+        b.set_meshes([m], PARAM, model="lin").solve(EPS3[None].copy())  # solve before assemble
+    assert ei.value.code == -3
+    b.assemble()
+    with pytest.raises(L.RVEError) as ei:
+        b.solve(EPS3[None].copy(), uD=np.zeros((1, 3, 162)))           # uD on a non-dnn batch
+    assert ei.value.code == -1
+    with pytest.raises(L.RVEError) as ei:
+        b.tangent()                                                    # epilogue before solve
+    assert ei.value.code == -3
+    bad = (m[0], np.vstack([m[1], [[0, 1, 10 ** 6]]]).astype(np.int32), np.append(m[2], 0).astype(np.int32))
+    with pytest.raises(L.RVEError) as ei:
+        b.set_meshes([bad], PARAM, model="lin")                        # vertex id out of range
+    assert ei.value.code == -4
+    shifted = (m[0] * 1.5, m[1], m[2])
+    with pytest.raises(L.RVEError) as ei:
+        b.set_meshes([m, shifted], PARAM, model="lin")                 # different box sizes in one batch
+    assert ei.value.code == -4
+    # maxit too small: RVE_E_NOCONV with per-system status, partial result still retrievable
+    b.set_meshes([m], PARAM, model="lin").assemble()
+    status, iters = b.solve(EPS3[None].copy(), maxit=3, raise_on_noconv=False)
+    assert status[0] == 1 and iters[0] == 3
+    with pytest.raises(L.RVEError) as ei:
+        b.solve(EPS3[None].copy(), maxit=3)
+    assert ei.value.code == -5
+    b.close()
