@@ -99,6 +99,10 @@ struct rve_batch_s {
     DBuf<unsigned char> elem_reg;
     DBuf<unsigned> slice_ptr, cn_beg;
     DBuf<uint16_t> scol, cn_ent;
+    DBuf<unsigned> d_row_ptr, adjf_ptr;
+    DBuf<int> adjf, csr_col, win_nhalo, sym_cnt;
+    std::vector<long long> adjf_base;
+    int max_words = 0;
     DBuf<RowInfo> rowinfo;
     DBuf<double> lvA[RVE_MAXLEV], lvD[RVE_MAXLEV], lvR[RVE_MAXLEV], lvX[RVE_MAXLEV], lvT[RVE_MAXLEV];
     DBuf<float4> lvA4[RVE_MAXLEV], lvH4[RVE_MAXLEV];
@@ -150,7 +154,7 @@ static cudaError_t upload(DBuf<T>& d, const std::vector<T>& v, cudaStream_t s) {
 static WinTab win_tab(rve_batch_s* h) {
     WinTab wt;
     wt.win_sys = h->win_sys.p; wt.win_row0 = h->win_row0.p; wt.win_n = h->win_n.p; wt.win_slice0 = h->win_slice0.p;
-    wt.win_halo0 = h->win_halo0.p; wt.win_cn0 = h->win_cn0.p; wt.sys_win0 = h->sys_win0.p; wt.row_base = h->d_row_base.p;
+    wt.win_halo0 = h->win_halo0.p; wt.win_nhalo = h->win_nhalo.p; wt.win_cn0 = h->win_cn0.p; wt.sys_win0 = h->sys_win0.p; wt.row_base = h->d_row_base.p;
     return wt;
 }
 
@@ -292,8 +296,11 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     P.model = model; P.vref_nb = vref_nb; P.vref_box_given = vref_box != nullptr;
     for (int k = 0; k < 4; ++k) P.vref_box[k] = vref_box ? vref_box[k] : 0.0;
     P.ncx = pick_nc(Lx, ext); P.ncy = pick_nc(Ly, ext);
+    P.lite = true;   // block columns, halo lists and SELL columns are built on the GPU below
     h->ncx = P.ncx; h->ncy = P.ncy;
+    auto tp1 = std::chrono::steady_clock::now();
     parallel_for(n_sys, [&](int s) { sym_pass2(S[s], P); });
+    auto tp2 = std::chrono::steady_clock::now();
     for (int s = 0; s < n_sys; ++s)
         if (!S[s].err.empty()) FAIL(RVE_E_MESH, "system " + std::to_string(s) + ": " + S[s].err);
     for (int k = 0; k < 4; ++k) h->vref_box[k] = vref_box ? vref_box[k] : S[0].box[k];
@@ -301,32 +308,31 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     // prefix sums
     h->node_base.assign(n_sys + 1, 0); h->elem_base.assign(n_sys + 1, 0); h->row_base.assign(n_sys + 1, 0);
     h->bnd_base.assign(n_sys + 1, 0); h->bedge_base.assign(n_sys + 1, 0); h->blk_base.assign(n_sys + 1, 0);
-    h->win_base.assign(n_sys + 1, 0); h->slice_base.assign(n_sys + 1, 0); h->halo_base.assign(n_sys + 1, 0);
+    h->win_base.assign(n_sys + 1, 0); h->slice_base.assign(n_sys + 1, 0); h->adjf_base.assign(n_sys + 1, 0);
     h->cn_base.assign(n_sys + 1, 0); h->grp_base.assign(n_sys + 1, 0); h->ent_base.assign(n_sys + 1, 0);
-    h->max_tile = 0; h->max_cn = 0;
+    h->max_tile = 0; h->max_cn = 0; h->max_words = 0;
     for (int s = 0; s < n_sys; ++s) {
         long long nn = (long long)h->node_base[s] + S[s].nn, ne = (long long)h->elem_base[s] + S[s].nt;
         long long nr = (long long)h->row_base[s] + S[s].na;
-        long long nb = h->blk_base[s] + (long long)S[s].bcol.size();
+        long long nb = h->blk_base[s] + (long long)S[s].nblocks;
         long long ng = h->grp_base[s] + (long long)S[s].slice_ptr.back();
-        long long nh = (long long)h->halo_base[s] + (long long)S[s].halo.size();
+        long long nh = h->adjf_base[s] + (long long)S[s].adjf.size();
         long long nent = h->ent_base[s] + (long long)S[s].cn_ent.size();
         if (nn > 2000000000LL || ne > 2000000000LL || nr * 4 > 2000000000LL || ng > 4000000000LL || nh > 2000000000LL ||
             nent > 4000000000LL)
             FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
         h->node_base[s + 1] = (int)nn; h->elem_base[s + 1] = (int)ne; h->row_base[s + 1] = (int)nr;
         h->bnd_base[s + 1] = h->bnd_base[s] + S[s].nb; h->bedge_base[s + 1] = h->bedge_base[s] + S[s].nbe;
-        h->blk_base[s + 1] = nb; h->grp_base[s + 1] = ng; h->halo_base[s + 1] = (int)nh; h->ent_base[s + 1] = nent;
+        h->blk_base[s + 1] = nb; h->grp_base[s + 1] = ng; h->adjf_base[s + 1] = nh; h->ent_base[s + 1] = nent;
         h->win_base[s + 1] = h->win_base[s] + S[s].nwin;
         h->slice_base[s + 1] = h->slice_base[s] + (int)S[s].slice_ptr.size() - 1;
         h->cn_base[s + 1] = h->cn_base[s] + (int)S[s].cn_node.size();
-        h->max_tile = std::max(h->max_tile, S[s].max_tile); h->max_cn = std::max(h->max_cn, S[s].max_cn);
+        h->max_cn = std::max(h->max_cn, S[s].max_cn); h->max_words = std::max(h->max_words, (S[s].na + 31) / 32);
     }
     h->N = h->node_base[n_sys]; h->E = h->elem_base[n_sys]; h->R = h->row_base[n_sys];
     h->NB = h->blk_base[n_sys]; h->NBN = h->bnd_base[n_sys]; h->NBE = h->bedge_base[n_sys];
     h->NG = h->grp_base[n_sys]; h->n_win = h->win_base[n_sys];
     const int n_win = h->n_win, n_slice = h->slice_base[n_sys], n_cn = h->cn_base[n_sys];
-    if ((size_t)(h->max_tile + RVE_WIN) * 3 * sizeof(double2) > 200 * 1024) FAIL(RVE_E_MESH, "window halo too large for shared memory");
 
     // flatten (parallel over systems) straight into the pinned staging arena
     const size_t nvs = (size_t)n_sys * h->nvref;
@@ -337,8 +343,8 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         add(2 * h->N, 8); add(4 * (size_t)n_sys, 8); add(n_bnds, 8); add(2 * h->NBE, 8); add(2 * nvs, 8);
         add(h->N, 4); add(h->N, 4); add(h->N, 4); add(6 * h->E, 4); add(h->E, 4); add(h->NBN, 4); add(h->NBN, 4);
         add(3 * h->NBE, 4); add(nvs, 4); for (int k = 0; k < 4; ++k) add(n_win, 4);
-        add(n_win + 1, 4); add(n_win + 1, 4); add(h->halo_base[n_sys], 4); add(n_cn, 4); add(h->E, 1);
-        add(n_slice + 1, 4); add(n_cn + 1, 4); add((size_t)h->NG * 32, 2); add(h->ent_base[n_sys], 2); add(h->R, sizeof(RowInfo));
+        add(n_win + 1, 4); add(h->adjf_base[n_sys], 4); add(n_cn, 4); add(h->E, 1); add(h->R + 1, 4); add(h->R + 1, 4);
+        add(n_slice + 1, 4); add(n_cn + 1, 4); add(h->ent_base[n_sys], 2); add(h->R, sizeof(RowInfo));
         CU(cudaStreamSynchronize(h->stream));          // the previous batch's copies out of the arena are done
         CU(h->arena.reserve(bytes));
     }
@@ -349,11 +355,12 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
               elem_node = AR.take<int>(6 * h->E), elem_sys = AR.take<int>(h->E), bnd_sys = AR.take<int>(h->NBN),
               bnd_node = AR.take<int>(h->NBN), bedge = AR.take<int>(3 * h->NBE), samp_elem = AR.take<int>(nvs),
               win_sys = AR.take<int>(n_win), win_row0 = AR.take<int>(n_win), win_n = AR.take<int>(n_win),
-              win_slice0 = AR.take<int>(n_win), win_halo0 = AR.take<int>(n_win + 1), win_cn0 = AR.take<int>(n_win + 1),
-              halo = AR.take<int>(h->halo_base[n_sys]), cn_node = AR.take<int>(n_cn);
+              win_slice0 = AR.take<int>(n_win), win_cn0 = AR.take<int>(n_win + 1),
+              adjf = AR.take<int>(h->adjf_base[n_sys]), cn_node = AR.take<int>(n_cn);
     Span<unsigned char> elem_reg = AR.take<unsigned char>(h->E);
-    Span<unsigned> slice_ptr = AR.take<unsigned>(n_slice + 1), cn_beg = AR.take<unsigned>(n_cn + 1);
-    Span<uint16_t> scol = AR.take<uint16_t>((size_t)h->NG * 32), cn_ent = AR.take<uint16_t>(h->ent_base[n_sys]);
+    Span<unsigned> slice_ptr = AR.take<unsigned>(n_slice + 1), cn_beg = AR.take<unsigned>(n_cn + 1),
+                   row_ptr = AR.take<unsigned>(h->R + 1), adjf_ptr = AR.take<unsigned>(h->R + 1);
+    Span<uint16_t> cn_ent = AR.take<uint16_t>(h->ent_base[n_sys]);
     Span<RowInfo> rowinfo = AR.take<RowInfo>(h->R);
     parallel_for(n_sys, [&](int s) {
         const SysSym& Y = S[s];
@@ -370,17 +377,21 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
             elem_reg[eb0 + t] = Y.reg[t]; elem_sys[eb0 + t] = s;
         }
         for (int r = 0; r < Y.na; ++r) rowinfo[(size_t)rb0 + r] = Y.rowinfo[r];
-        const int w0 = h->win_base[s], sl0 = h->slice_base[s], hb0 = h->halo_base[s], cb0 = h->cn_base[s];
+        const int w0 = h->win_base[s], sl0 = h->slice_base[s], cb0 = h->cn_base[s];
         for (int w = 0; w < Y.nwin; ++w) {
             win_sys[w0 + w] = s; win_row0[w0 + w] = rb0 + w * RVE_WIN; win_n[w0 + w] = Y.win_n[w];
-            win_slice0[w0 + w] = sl0 + Y.win_slice0[w]; win_halo0[w0 + w] = hb0 + Y.win_halo0[w];
+            win_slice0[w0 + w] = sl0 + Y.win_slice0[w];
             win_cn0[w0 + w] = cb0 + Y.win_cn0[w];
         }
-        if (s == n_sys - 1) { win_halo0[n_win] = h->halo_base[n_sys]; win_cn0[n_win] = n_cn; }
+        if (s == n_sys - 1) win_cn0[n_win] = n_cn;
         for (size_t k = 0; k + 1 < Y.slice_ptr.size(); ++k) slice_ptr[sl0 + k] = (unsigned)(h->grp_base[s] + Y.slice_ptr[k]);
         if (s == n_sys - 1) slice_ptr[n_slice] = (unsigned)h->NG;
-        std::copy(Y.scol.begin(), Y.scol.end(), scol.begin() + (size_t)h->grp_base[s] * 32);
-        for (size_t k = 0; k < Y.halo.size(); ++k) halo[hb0 + k] = rb0 + Y.halo[k];
+        for (int r = 0; r < Y.na; ++r) {
+            row_ptr[(size_t)rb0 + r] = (unsigned)(h->blk_base[s] + Y.row_ptr[r]);
+            adjf_ptr[(size_t)rb0 + r] = (unsigned)(h->adjf_base[s] + Y.adjf_ptr[r]);
+        }
+        if (s == n_sys - 1) { row_ptr[h->R] = (unsigned)h->NB; adjf_ptr[h->R] = (unsigned)h->adjf_base[n_sys]; }
+        for (size_t k = 0; k < Y.adjf.size(); ++k) adjf[h->adjf_base[s] + k] = eb0 + Y.adjf[k];
         for (size_t k = 0; k < Y.cn_node.size(); ++k) { cn_node[cb0 + k] = Y.cn_node[k]; cn_beg[cb0 + k] = (unsigned)(h->ent_base[s] + Y.cn_beg[k]); }
         if (s == n_sys - 1) cn_beg[n_cn] = (unsigned)h->ent_base[n_sys];
         std::copy(Y.cn_ent.begin(), Y.cn_ent.end(), cn_ent.begin() + h->ent_base[s]);
@@ -403,6 +414,10 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     });
     auto t1 = std::chrono::steady_clock::now();
     h->t_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (std::getenv("RVE_DEBUG_TIMING"))
+        fprintf(stderr, "[rve_set_batch] n_sys %d: pass1 %.1f ms, pass2 %.1f ms, prefix+flatten %.1f ms\n", n_sys,
+                std::chrono::duration<double, std::milli>(tp1 - t0).count(), std::chrono::duration<double, std::milli>(tp2 - tp1).count(),
+                std::chrono::duration<double, std::milli>(t1 - tp2).count());
 
     cudaStream_t st = h->stream;
     UPL(h->node_xy, node_xy); UPL(h->box, box);
@@ -413,8 +428,8 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     UPL(h->bnd_s, bnd_s); UPL(h->bedge, bedge); UPL(h->bedge_nl, bedge_nl);
     UPL(h->d_bedge_base, h->bedge_base); UPL(h->samp_elem, samp_elem); UPL(h->samp_lam, samp_lam);
     UPL(h->win_sys, win_sys); UPL(h->win_row0, win_row0); UPL(h->win_n, win_n); UPL(h->win_slice0, win_slice0);
-    UPL(h->win_halo0, win_halo0); UPL(h->win_cn0, win_cn0); UPL(h->sys_win0, h->win_base);
-    UPL(h->slice_ptr, slice_ptr); UPL(h->scol, scol); UPL(h->halo, halo); UPL(h->cn_node, cn_node);
+    UPL(h->win_cn0, win_cn0); UPL(h->sys_win0, h->win_base);
+    UPL(h->slice_ptr, slice_ptr); UPL(h->cn_node, cn_node); UPL(h->d_row_ptr, row_ptr); UPL(h->adjf_ptr, adjf_ptr); UPL(h->adjf, adjf);
     UPL(h->cn_beg, cn_beg); UPL(h->cn_ent, cn_ent); UPL(h->rowinfo, rowinfo);
     std::vector<double> vb(h->vref_box, h->vref_box + 4);
     UPL(h->d_vbox, vb);
@@ -448,7 +463,31 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     LV.L = L;
     CU(h->cpart.alloc((size_t)n_sys * ((LV.g[0].G + 255) / 256) * 4));
     if (n_sys > 65535) FAIL(RVE_E_ARG, "more than 65535 systems in one batch: split it");
+    // device half of the symbolic phase: block columns, halo lists, SELL columns
+    const long long halo_cap = h->R + h->R / 2 + 4096;
+    if (halo_cap > 2000000000LL) FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
+    CU(h->csr_col.alloc((size_t)h->NB)); CU(h->halo.alloc((size_t)halo_cap)); CU(h->scol.alloc((size_t)h->NG * 32));
+    CU(h->win_halo0.alloc(n_win)); CU(h->win_nhalo.alloc(n_win)); CU(h->sym_cnt.alloc(4));
+    CU(cudaMemsetAsync(h->sym_cnt.p, 0, 4 * sizeof(int), st));
+    {
+        WinTab wt = win_tab(h);
+        k_sym_cols<<<n_win, RVE_WIN, 0, st>>>(wt, h->d_row_ptr.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->node_row.p,
+                                               h->csr_col.p, h->sym_cnt.p);
+        const size_t sm = 2 * (size_t)h->max_words * sizeof(unsigned);
+        if (sm > 200 * 1024) FAIL(RVE_E_MESH, "system too large for the halo bitmap in shared memory");
+        CU(cudaFuncSetAttribute(k_sym_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_sym_window<<<n_win, RVE_WIN, sm, st>>>(wt, h->win_halo0.p, h->win_nhalo.p, h->d_row_ptr.p, h->csr_col.p, h->slice_ptr.p,
+                                                  h->scol.p, h->halo.p, (int)halo_cap, h->sym_cnt.p);
+        h->launches += 2;
+    }
+    int scnt[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (scnt[2] == 2) FAIL(RVE_E_MESH, "device pattern build: row length mismatch");
+    if (scnt[2] == 3) FAIL(RVE_E_MESH, "device pattern build: halo list overflow");
+    h->max_tile = scnt[1];
+    if ((size_t)h->max_tile * 3 * sizeof(double2) > 200 * 1024) FAIL(RVE_E_MESH, "window halo too large for shared memory");
     auto t2 = std::chrono::steady_clock::now();
     h->t_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
     h->have_batch = true;
@@ -499,7 +538,7 @@ int rve_get_sizes(rve_handle_t h, int32_t sys, int64_t* n_nodes, int64_t* n_rows
     if (!h->have_batch || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_ARG, "bad system index");
     if (n_nodes) *n_nodes = h->sym[sys].nn;
     if (n_rows) *n_rows = h->sym[sys].na;
-    if (n_blocks) *n_blocks = (int64_t)h->sym[sys].bcol.size();
+    if (n_blocks) *n_blocks = (int64_t)h->sym[sys].nblocks;
     if (n_elems) *n_elems = h->sym[sys].nt;
     return 0;
 }
@@ -511,6 +550,9 @@ int rve_get_csr(rve_handle_t h, int32_t sys, int32_t* rowptr, int32_t* col, doub
     const size_t ng = Y.slice_ptr.back();
     std::vector<double> bv(128 * ng);
     CU(cudaMemcpy(bv.data(), h->bval.p + 128 * (size_t)h->grp_base[sys], bv.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<int> cc(Y.nblocks);            // block columns as found on the device (global rows)
+    CU(cudaMemcpy(cc.data(), h->csr_col.p + (size_t)h->blk_base[sys], cc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    const int rb0 = h->row_base[sys];
     // SELL slot j of a row holds the j-th (sorted) CSR column of that row
     int64_t pos = 0;
     for (int r = 0; r < Y.na; ++r) {
@@ -520,7 +562,7 @@ int rve_get_csr(rve_handle_t h, int32_t sys, int32_t* rowptr, int32_t* col, doub
             rowptr[2 * r + c] = (int32_t)pos;
             for (unsigned k = Y.row_ptr[r]; k < Y.row_ptr[r + 1]; ++k) {
                 const size_t g = g0 + (k - Y.row_ptr[r]);
-                for (int d = 0; d < 2; ++d) { col[pos] = 2 * Y.bcol[k] + d; val[pos] = bv[128 * g + 64 * c + 2 * lane + d]; ++pos; }
+                for (int d = 0; d < 2; ++d) { col[pos] = 2 * (cc[k] - rb0) + d; val[pos] = bv[128 * g + 64 * c + 2 * lane + d]; ++pos; }
             }
         }
     }
@@ -723,7 +765,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     // algorithmic SpMV bytes of the solve: sum over systems of iters * B_spmv(K)
     double bytes = 0;
     for (int s = 0; s < n_sys; ++s) {
-        const double n = 2.0 * h->sym[s].na, nnz = 4.0 * (double)h->sym[s].bcol.size();
+        const double n = 2.0 * h->sym[s].na, nnz = 4.0 * (double)h->sym[s].nblocks;
         bytes += hit[s] * (12.0 * nnz + 4.0 * (n + 1) + 16.0 * n * K);
     }
     h->c_cnt[1] = bytes;

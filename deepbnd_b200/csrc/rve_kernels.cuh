@@ -54,7 +54,8 @@ struct WinTab {
     const int* win_row0;     // global first row
     const int* win_n;        // rows in the window (<= RVE_WIN)
     const int* win_slice0;   // global first slice (ceil(n/32) slices)
-    const int* win_halo0;    // [n_win+1] offsets into halo
+    const int* win_halo0;    // [n_win] offset of the window's halo list (segments are claimed on the device)
+    const int* win_nhalo;    // [n_win] halo rows of the window
     const int* win_cn0;      // [n_win+1] offsets into cn_node / cn_beg
     const int* sys_win0;     // [n_sys+1]
     const int* row_base;     // [n_sys+1] first global row of a system
@@ -113,6 +114,115 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// (0) device half of the symbolic phase.  The host sends, per row, its length and the elements around
+//     it; the GPU finds the block columns (k_sym_cols) and, per window, the halo list and the
+//     window-local 16-bit SELL columns (k_sym_window: shared-memory bitmap over the rows of the system,
+//     popcount prefix = rank of a halo row; halo segments are claimed with one atomic per window).
+// ---------------------------------------------------------------------------------------------
+// counters: [0] halo entries used, [1] max rows of a p-tile (own + halo), [2] error code
+__global__ void __launch_bounds__(RVE_WIN)
+k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __restrict__ adjf_ptr,
+           const int* __restrict__ adjf, const int* __restrict__ elem_node, const int* __restrict__ node_row,
+           int* __restrict__ csr_col, int* counters) {
+    const int w = blockIdx.x, t = threadIdx.x;
+    if (t >= wt.win_n[w]) return;
+    const int r = wt.win_row0[w] + t;
+    const unsigned o = row_ptr[r];
+    const int len = (int)(row_ptr[r + 1] - o);
+    int* cols = csr_col + o;                     // unique rows in discovery order (same order as the host path)
+    int cnt = 0;
+    for (unsigned i = adjf_ptr[r]; i < adjf_ptr[r + 1]; ++i) {
+        const int* en = elem_node + 6 * (size_t)adjf[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int c = node_row[en[k]];
+            if (c < 0) continue;
+            bool found = false;
+            for (int j = 0; j < cnt; ++j) found = found || (cols[j] == c);
+            if (!found) { if (cnt < len) cols[cnt] = c; ++cnt; }
+        }
+    }
+    if (cnt != len) atomicExch(counters + 2, 2);
+}
+
+__global__ void __launch_bounds__(RVE_WIN)
+k_sym_window(WinTab wt, int* __restrict__ win_halo0, int* __restrict__ win_nhalo, const unsigned* __restrict__ row_ptr,
+             const int* __restrict__ csr_col, const unsigned* __restrict__ slice_ptr, uint16_t* __restrict__ scol,
+             int* __restrict__ halo, int halo_cap, int* counters) {
+    extern __shared__ unsigned s_bm[];           // [words] bitmap of halo rows, then [words] popcount prefix
+    __shared__ int s_scan[RVE_WIN];
+    __shared__ int s_h0;
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const int sys = wt.win_sys[w];
+    const int rb0 = wt.row_base[sys], na = wt.row_base[sys + 1] - rb0;
+    const int words = (na + 31) >> 5;
+    unsigned* s_pre = s_bm + words;
+    const int r0 = wt.win_row0[w], n = wt.win_n[w], r0l = r0 - rb0;
+    for (int i = tid; i < words; i += RVE_WIN) s_bm[i] = 0u;
+    __syncthreads();
+    unsigned o = 0; int len = 0;
+    if (tid < n) {
+        o = row_ptr[r0 + tid]; len = (int)(row_ptr[r0 + tid + 1] - o);
+        for (int j = 0; j < len; ++j) {
+            const int c = csr_col[o + j] - rb0;
+            if (c < r0l || c >= r0l + n) atomicOr(&s_bm[c >> 5], 1u << (c & 31));
+        }
+    }
+    __syncthreads();
+    // exclusive popcount prefix over the words: contiguous span per thread, block scan of the span sums
+    const int wpt = (words + RVE_WIN - 1) / RVE_WIN;
+    const int wa = min(words, tid * wpt), wb = min(words, wa + wpt);
+    int sum = 0;
+    for (int i = wa; i < wb; ++i) sum += __popc(s_bm[i]);
+    s_scan[tid] = sum;
+    __syncthreads();
+    for (int d = 1; d < RVE_WIN; d <<= 1) {
+        const int v = tid >= d ? s_scan[tid - d] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    int run = s_scan[tid] - sum;                  // exclusive
+    for (int i = wa; i < wb; ++i) { s_pre[i] = (unsigned)run; run += __popc(s_bm[i]); }
+    const int nh = s_scan[RVE_WIN - 1];
+    if (tid == 0) {
+        int h0 = atomicAdd(counters, nh);
+        atomicMax(counters + 1, n + nh);
+        if (h0 + nh > halo_cap || n + nh > 65535) { atomicExch(counters + 2, 3); h0 = -1; }
+        s_h0 = h0;
+        win_halo0[w] = h0 < 0 ? 0 : h0;
+        win_nhalo[w] = h0 < 0 ? 0 : nh;
+    }
+    __syncthreads();
+    const int h0 = s_h0;
+    if (h0 < 0) return;
+    for (int i = tid; i < words; i += RVE_WIN) {
+        unsigned bits = s_bm[i];
+        int pos = h0 + (int)s_pre[i];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            halo[pos++] = rb0 + i * 32 + b;
+            bits &= bits - 1;
+        }
+    }
+    const int nsl = (n + 31) >> 5;
+    if (tid < nsl * 32) {
+        const int slice = wt.win_slice0[w] + (tid >> 5), lane = tid & 31;
+        const unsigned g0 = slice_ptr[slice];
+        const int width = (int)(slice_ptr[slice + 1] - g0);
+        uint16_t* sc = scol + (size_t)g0 * 32 + lane;
+        for (int j = 0; j < len; ++j) {
+            const int c = csr_col[o + j] - rb0;
+            const int lc = (c >= r0l && c < r0l + n) ? c - r0l
+                                                     : n + (int)s_pre[c >> 5] + __popc(s_bm[c >> 5] & ((1u << (c & 31)) - 1u));
+            sc[(size_t)j * 32] = (uint16_t)lc;
+        }
+        const uint16_t self = (uint16_t)(tid < n ? tid : 0);     // padding: zero block against a valid tile entry
+        for (int j = len; j < width; ++j) sc[(size_t)j * 32] = self;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // (1) numeric assembly: warp per element, 21 lanes compute the upper-triangular 2x2 blocks and
 //     scatter them (and their transposes) with fp64 atomics into the SELL block storage.
 //     Connectivity / coordinates are staged through warp shuffles, the material table lives in
@@ -126,7 +236,7 @@ __device__ __forceinline__ long long sell_find(const WinTab& wt, const Sell& sl,
     if (rb >= r0 && rb < r0 + n) {
         lc = rb - r0;
     } else {
-        int lo = wt.win_halo0[w], hi = wt.win_halo0[w + 1];
+        int lo = wt.win_halo0[w], hi = lo + wt.win_nhalo[w];
         const int h0 = lo;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -451,7 +561,7 @@ k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __re
     if (!active[sys]) return;
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
-    const int h0 = wt.win_halo0[win], nh = wt.win_halo0[win + 1] - h0;
+    const int h0 = wt.win_halo0[win], nh = wt.win_nhalo[win];
     const int nsl = (n + 31) >> 5;
     if (tid <= nsl) s_g0[tid] = sl.slice_ptr[wt.win_slice0[win] + tid];
     {
@@ -760,7 +870,7 @@ k_vc_down1(Levels LV, const int* __restrict__ active) {
 // levels >= 2: one CTA per system.  Restricts t1, runs the rest of the V-cycle, prolongs the level-2
 // correction into x1.
 template <int K>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 k_vc_mid(Levels LV, const int* __restrict__ active) {
     const int sys = blockIdx.x;
     if (!active[sys]) return;

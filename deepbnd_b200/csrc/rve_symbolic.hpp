@@ -51,6 +51,10 @@ struct SysSym {
     std::vector<unsigned> cn_beg;    // [sum ncn + 1] offsets into cn_ent
     std::vector<uint16_t> cn_ent;    // (row_in_window << 2) | corner
     std::vector<RowInfo> rowinfo;    // [na] bilinear weights + window-local coarse slots
+    // inputs of the device-side pattern build (lite mode): elements around every row, in final row order
+    std::vector<unsigned> adjf_ptr;  // [na+1]
+    std::vector<int> adjf;           // local element ids
+    size_t nblocks = 0;              // number of 2x2 blocks of the system
     std::vector<int> bnd_node;       // [nb]
     std::vector<double> bnd_s;       // [nb][2] Vref perimeter parameters of the end vertices
     std::vector<int> bedge;          // [nbe][3] boundary edges (a,b,m), outward normal to the right
@@ -68,6 +72,7 @@ struct SymParams {
     int vref_nb;         // 0: none
     bool vref_box_given;
     double vref_box[4];
+    bool lite = false;   // true: the block columns, halo lists and SELL column fill are built on the GPU
 };
 
 // pass 1: everything that does not depend on the level-1 grid
@@ -318,20 +323,32 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
     for (int r = 0; r < na; ++r) S.row_node[r] = pnode[oldid[r]];
     S.node_row.resize(nn);
     for (int n = 0; n < nn; ++n) S.node_row[n] = nrow0[n] < 0 ? -1 : newid[nrow0[n]];
-    // CSR pattern directly in the final numbering (columns in discovery order) — kept on the host for accessors/tests
+    // CSR row pointer in the final numbering; in lite mode the columns themselves are found on the GPU
+    // (k_sym_cols) from the element lists around each row, otherwise here (accessors, CPU tests)
     S.row_ptr.assign(na + 1, 0);
     for (int r = 0; r < na; ++r) S.row_ptr[r + 1] = S.row_ptr[r] + (unsigned)len0[oldid[r]];
-    S.bcol.resize(S.row_ptr[na]);
-    std::fill(mark.begin(), mark.end(), -1);
-    for (int r = 0; r < na; ++r) {
-        const int o = oldid[r];
-        int* dst = &S.bcol[S.row_ptr[r]];
-        int cnt = 0;
-        for (int i = adj_ptr[o]; i < adj_ptr[o + 1]; ++i) {
-            const int* er = &erow[6 * (size_t)adj[i]];
-            for (int k = 0; k < 6; ++k) {
-                const int c = er[k];
-                if (c >= 0 && mark[c] != r) { mark[c] = r; dst[cnt++] = newid[c]; }
+    S.nblocks = S.row_ptr[na];
+    S.bcol.clear();
+    S.adjf_ptr.clear(); S.adjf.clear();
+    if (P.lite) {
+        S.adjf_ptr.assign(na + 1, 0u);
+        for (int r = 0; r < na; ++r) S.adjf_ptr[r + 1] = S.adjf_ptr[r] + (unsigned)(adj_ptr[oldid[r] + 1] - adj_ptr[oldid[r]]);
+        S.adjf.resize(S.adjf_ptr[na]);
+        for (int r = 0; r < na; ++r)
+            std::copy(adj.begin() + adj_ptr[oldid[r]], adj.begin() + adj_ptr[oldid[r] + 1], S.adjf.begin() + S.adjf_ptr[r]);
+    } else {
+        S.bcol.resize(S.row_ptr[na]);
+        std::fill(mark.begin(), mark.end(), -1);
+        for (int r = 0; r < na; ++r) {
+            const int o = oldid[r];
+            int* dst = &S.bcol[S.row_ptr[r]];
+            int cnt = 0;
+            for (int i = adj_ptr[o]; i < adj_ptr[o + 1]; ++i) {
+                const int* er = &erow[6 * (size_t)adj[i]];
+                for (int k = 0; k < 6; ++k) {
+                    const int c = er[k];
+                    if (c >= 0 && mark[c] != r) { mark[c] = r; dst[cnt++] = newid[c]; }
+                }
             }
         }
     }
@@ -339,7 +356,7 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
     S.win_n.assign(nwin, 0); S.win_slice0.assign(nwin + 1, 0); S.win_halo0.assign(nwin + 1, 0); S.win_cn0.assign(nwin + 1, 0);
     S.slice_ptr.assign(1, 0u);
     S.scol.clear(); S.halo.clear(); S.cn_node.clear(); S.cn_beg.assign(1, 0u); S.cn_ent.clear();
-    S.scol.reserve((size_t)S.bcol.size() + S.bcol.size() / 6);
+    if (!P.lite) S.scol.reserve((size_t)S.bcol.size() + S.bcol.size() / 6);
     S.rowinfo.resize(na);
     S.max_tile = 0; S.max_cn = 0;
     const int nxg = ncx + 1;
@@ -355,6 +372,16 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
     for (int w = 0; w < nwin; ++w) {
         const int r0 = w * RVE_WIN, r1 = std::min(na, r0 + RVE_WIN), wn = r1 - r0;
         S.win_n[w] = wn;
+        const int nsl = (wn + 31) / 32;
+        if (P.lite) {
+            // only the slice widths: the device fills halo lists and SELL columns (k_sym_window)
+            for (int sl = 0; sl < nsl; ++sl) {
+                const int a0 = r0 + 32 * sl, a1 = std::min(r1, a0 + 32);
+                int width = 0;
+                for (int r = a0; r < a1; ++r) width = std::max(width, (int)(S.row_ptr[r + 1] - S.row_ptr[r]));
+                S.slice_ptr.push_back(S.slice_ptr.back() + (unsigned)width);
+            }
+        } else {
         hal.clear();
         for (unsigned k = S.row_ptr[r0]; k < S.row_ptr[r1]; ++k) {
             const int c = S.bcol[k];
@@ -366,7 +393,6 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
         S.max_tile = std::max(S.max_tile, wn + (int)hal.size());
         S.halo.insert(S.halo.end(), hal.begin(), hal.end());
         S.win_halo0[w + 1] = (int)S.halo.size();
-        const int nsl = (wn + 31) / 32;
         for (int sl = 0; sl < nsl; ++sl) {
             const int a0 = r0 + 32 * sl, a1 = std::min(r1, a0 + 32);
             int width = 0;
@@ -388,6 +414,7 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
             S.slice_ptr.push_back(S.slice_ptr.back() + (unsigned)width);
         }
         for (size_t k = 0; k < hal.size(); ++k) hpos[hal[k]] = -1;
+        }
         S.win_slice0[w + 1] = S.win_slice0[w] + nsl;
         // coarse nodes touched by the window and the (row, corner) lists of each of them
         cns.clear();
