@@ -101,6 +101,7 @@ struct rve_batch_s {
     DBuf<uint16_t> scol, cn_ent;
     DBuf<unsigned> d_row_ptr, adjf_ptr;
     DBuf<int> adjf, csr_col, win_nhalo, sym_cnt;
+    DBuf<unsigned char> emap;
     std::vector<long long> adjf_base;
     int max_words = 0;
     DBuf<RowInfo> rowinfo;
@@ -466,13 +467,13 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     // device half of the symbolic phase: block columns, halo lists, SELL columns
     const long long halo_cap = h->R + h->R / 2 + 4096;
     if (halo_cap > 2000000000LL) FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
-    CU(h->csr_col.alloc((size_t)h->NB)); CU(h->halo.alloc((size_t)halo_cap)); CU(h->scol.alloc((size_t)h->NG * 32));
+    CU(h->csr_col.alloc((size_t)h->NB)); CU(h->emap.alloc(36 * (size_t)h->E)); CU(h->halo.alloc((size_t)halo_cap)); CU(h->scol.alloc((size_t)h->NG * 32));
     CU(h->win_halo0.alloc(n_win)); CU(h->win_nhalo.alloc(n_win)); CU(h->sym_cnt.alloc(4));
     CU(cudaMemsetAsync(h->sym_cnt.p, 0, 4 * sizeof(int), st));
     {
         WinTab wt = win_tab(h);
         k_sym_cols<<<n_win, RVE_WIN, 0, st>>>(wt, h->d_row_ptr.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->node_row.p,
-                                               h->csr_col.p, h->sym_cnt.p);
+                                               h->csr_col.p, h->emap.p, h->sym_cnt.p);
         const size_t sm = 2 * (size_t)h->max_words * sizeof(unsigned);
         if (sm > 200 * 1024) FAIL(RVE_E_MESH, "system too large for the halo bitmap in shared memory");
         CU(cudaFuncSetAttribute(k_sym_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -503,7 +504,7 @@ int rve_assemble(rve_handle_t h) {
     CU(cudaMemsetAsync(h->wmean.p, 0, h->wmean.n * sizeof(double), st));
     CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), st));
     k_assemble<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
-                                               h->node_row.p, win_tab(h), sell_tab(h), h->bval.p, h->wmean.p, h->mat);
+                                               h->node_row.p, win_tab(h), sell_tab(h), h->emap.p, h->bval.p, h->wmean.p, h->mat);
     k_dinv<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), sell_tab(h), h->bval.p, h->dinv.p);
     CU(cudaEventRecord(h->ev[1], st));
     // two-level preconditioner: Galerkin hierarchy

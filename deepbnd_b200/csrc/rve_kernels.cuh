@@ -123,7 +123,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(RVE_WIN)
 k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __restrict__ adjf_ptr,
            const int* __restrict__ adjf, const int* __restrict__ elem_node, const int* __restrict__ node_row,
-           int* __restrict__ csr_col, int* counters) {
+           int* __restrict__ csr_col, unsigned char* __restrict__ emap, int* counters) {
     const int w = blockIdx.x, t = threadIdx.x;
     if (t >= wt.win_n[w]) return;
     const int r = wt.win_row0[w] + t;
@@ -132,14 +132,22 @@ k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __re
     int* cols = csr_col + o;                     // unique rows in discovery order (same order as the host path)
     int cnt = 0;
     for (unsigned i = adjf_ptr[r]; i < adjf_ptr[r + 1]; ++i) {
-        const int* en = elem_node + 6 * (size_t)adjf[i];
+        const int e = adjf[i];
+        const int* en = elem_node + 6 * (size_t)e;
+        int rows[6], a = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { rows[k] = node_row[en[k]]; if (rows[k] == r) a = k; }
+        // emap[e][a][k] = SELL slot of block (row of local node a, row of local node k): k_assemble scatters
+        // without searching
+        unsigned char* em = emap + (size_t)e * 36 + a * 6;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            const int c = node_row[en[k]];
-            if (c < 0) continue;
-            bool found = false;
-            for (int j = 0; j < cnt; ++j) found = found || (cols[j] == c);
-            if (!found) { if (cnt < len) cols[cnt] = c; ++cnt; }
+            const int c = rows[k];
+            if (c < 0) { em[k] = 0xff; continue; }
+            int j = 0;
+            while (j < cnt && j < len && cols[j] != c) ++j;
+            if (j == cnt) { if (cnt < len) cols[cnt] = c; ++cnt; }
+            em[k] = (unsigned char)j;
         }
     }
     if (cnt != len) atomicExch(counters + 2, 2);
@@ -258,7 +266,8 @@ __device__ __forceinline__ size_t sell_val0(long long e) { return (size_t)(e >> 
 __global__ void __launch_bounds__(256)
 k_assemble(int n_elem, const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
            const int* __restrict__ elem_sys, const double* __restrict__ node_xy, const int* __restrict__ node_row,
-           WinTab wt, Sell sl, double* __restrict__ bval, double* __restrict__ wmean, Mat8 mat) {
+           WinTab wt, Sell sl, const unsigned char* __restrict__ emap, double* __restrict__ bval,
+           double* __restrict__ wmean, Mat8 mat) {
     __shared__ double s_mat[8];
     if (threadIdx.x < 8) s_mat[threadIdx.x] = mat.v[threadIdx.x];
     __syncthreads();
@@ -288,24 +297,18 @@ k_assemble(int n_elem, const int* __restrict__ elem_node, const unsigned char* _
     if (lane < 21 && ra >= 0 && rb >= 0) {
         double K[4];
         p2_stiff_block(g, a, b, lam, mu, K);
-        const long long e0 = sell_find(wt, sl, sys, ra, rb);
-        if (e0 >= 0) {
-            double* d = bval + sell_val0(e0);
+        const int rbase = wt.row_base[sys], w0 = wt.sys_win0[sys];
+        {
+            const int rl = (ra - rbase) % RVE_WIN, slice = wt.win_slice0[w0 + (ra - rbase) / RVE_WIN] + (rl >> 5);
+            const size_t g0 = (size_t)sl.slice_ptr[slice] + emap[(size_t)e * 36 + a * 6 + b];
+            double* d = bval + g0 * 128 + 2 * (rl & 31);
             atomicAdd(d + 0, K[0]); atomicAdd(d + 1, K[1]); atomicAdd(d + 64, K[2]); atomicAdd(d + 65, K[3]);
         }
-        if (ra != rb) {   // (two local nodes can share a row only under the periodic map: then a==b terms add up)
-            const long long e1 = sell_find(wt, sl, sys, rb, ra);
-            if (e1 >= 0) {
-                double* dt = bval + sell_val0(e1);
-                atomicAdd(dt + 0, K[0]); atomicAdd(dt + 1, K[2]); atomicAdd(dt + 64, K[1]); atomicAdd(dt + 65, K[3]);
-            }
-        } else if (a != b) {
-            // distinct local nodes mapped to the same row: the transposed block lands on the same entry
-            const long long e1 = e0;
-            if (e1 >= 0) {
-                double* dt = bval + sell_val0(e1);
-                atomicAdd(dt + 0, K[0]); atomicAdd(dt + 1, K[2]); atomicAdd(dt + 64, K[1]); atomicAdd(dt + 65, K[3]);
-            }
+        if (a != b) {   // transposed block in the row of local node b
+            const int rl = (rb - rbase) % RVE_WIN, slice = wt.win_slice0[w0 + (rb - rbase) / RVE_WIN] + (rl >> 5);
+            const size_t g0 = (size_t)sl.slice_ptr[slice] + emap[(size_t)e * 36 + b * 6 + a];
+            double* dt = bval + g0 * 128 + 2 * (rl & 31);
+            atomicAdd(dt + 0, K[0]); atomicAdd(dt + 1, K[2]); atomicAdd(dt + 64, K[1]); atomicAdd(dt + 65, K[3]);
         }
     }
     // int phi_a dx: A/3 for the mid-edge functions (mean-value constraint of 'per' / 'MR')
