@@ -232,37 +232,11 @@ k_sym_window(WinTab wt, int* __restrict__ win_halo0, int* __restrict__ win_nhalo
 
 // ---------------------------------------------------------------------------------------------
 // (1) numeric assembly: warp per element, 21 lanes compute the upper-triangular 2x2 blocks and
-//     scatter them (and their transposes) with fp64 atomics into the SELL block storage.
+//     scatter them (and their transposes) with fp64 atomics into the SELL block storage; the slot of
+//     every (local node a, local node b) block comes from the element map written by k_sym_cols.
 //     Connectivity / coordinates are staged through warp shuffles, the material table lives in
 //     shared memory.  Replaces mp.block_assemble(a) (micro_model.py:60).
 // ---------------------------------------------------------------------------------------------
-// entry index (group*32 + lane) of block (ra, rb), both global rows of system sys
-__device__ __forceinline__ long long sell_find(const WinTab& wt, const Sell& sl, int sys, int ra, int rb) {
-    const int w = wt.sys_win0[sys] + (ra - wt.row_base[sys]) / RVE_WIN;
-    const int r0 = wt.win_row0[w], n = wt.win_n[w];
-    int lc;
-    if (rb >= r0 && rb < r0 + n) {
-        lc = rb - r0;
-    } else {
-        int lo = wt.win_halo0[w], hi = lo + wt.win_nhalo[w];
-        const int h0 = lo;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (sl.halo[mid] < rb) lo = mid + 1; else hi = mid;
-        }
-        lc = n + (lo - h0);
-    }
-    const int rl = ra - r0, lane = rl & 31;
-    const int slice = wt.win_slice0[w] + (rl >> 5);
-    const unsigned g0 = sl.slice_ptr[slice], g1 = sl.slice_ptr[slice + 1];
-    for (unsigned g = g0; g < g1; ++g)
-        if (sl.scol[(size_t)g * 32 + lane] == lc) return (long long)g * 32 + lane;
-    return -1;  // cannot happen for a pattern built from the same mesh
-}
-
-// doubles of entry e=(g,lane): K00,K01 at 128 g + 2 lane, K10,K11 at 128 g + 64 + 2 lane
-__device__ __forceinline__ size_t sell_val0(long long e) { return (size_t)(e >> 5) * 128 + 2 * (size_t)(e & 31); }
-
 __global__ void __launch_bounds__(256)
 k_assemble(int n_elem, const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
            const int* __restrict__ elem_sys, const double* __restrict__ node_xy, const int* __restrict__ node_row,
@@ -513,7 +487,7 @@ template <int NQ>
 __device__ __forceinline__ bool last_block_sum(double* part, int* cnt, int sys, int win, int c0, int c1,
                                                double my, double (*s_out)[NQ]) {
     __shared__ int s_last;
-    __shared__ double s_red[256];
+    __shared__ double s_red[RVE_WIN * 3];
     const int tid = threadIdx.x;
     // only the publishing threads fence (a fence by every thread would make the whole CTA wait for
     // its x/r/q stores to land)
@@ -666,15 +640,20 @@ k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __re
 // x += alpha p ; r -= alpha q ; partial rr and r.Dinv r ; restriction of the new residual to the
 // level-1 grid (rc += Z^T r, per-window partial sums then one RED per touched coarse value);
 // convergence test by the last CTA of the system.  Thread = one (row, rhs) pair, flat and coalesced.
+// elements (row, rhs) per thread of the vector kernels: measured best is 2 for K = 2 (256-thread CTAs) and
+// 1 for K = 1, 3 (256 / 768-thread CTAs); all of a thread's loads are issued before the first use
+#define RVE_EPT(K) ((K) == 2 ? 2 : 1)
+#define RVE_VEC_THREADS(K) (RVE_WIN * (K) / RVE_EPT(K))
+
 template <int K>
-__global__ void __launch_bounds__(RVE_WIN)
+__global__ void __launch_bounds__(RVE_VEC_THREADS(K), (K == 1 ? 5 : (K == 2 ? 4 : 2)))
 k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q, double2* __restrict__ x,
          double2* __restrict__ r, const float4* __restrict__ dinv32, const RowInfo* __restrict__ rowinfo,
          const int* __restrict__ cn_node, const unsigned* __restrict__ cn_beg, const uint16_t* __restrict__ cn_ent,
          double* __restrict__ rc1, int G, int* active, double* part, int* cnt, double* sc, int init, int iter,
          double rtol2, int precond, int* iters, int* n_active) {
     extern __shared__ double2 s_r[];              // [n*K] new residual, then float2 s_st[n], uint16 s_ent[4n]
-    constexpr int TPB = (RVE_WIN / K) * K;        // active threads: a thread keeps its rhs index
+    constexpr int EPT = RVE_EPT(K), TPB = RVE_VEC_THREADS(K);   // TPB % K == 0: a thread keeps its rhs index
     const int win = blockIdx.x;
     const int sys = wt.win_sys[win];
     if (!active[sys]) return;
@@ -685,21 +664,13 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
     uint16_t* s_ent = (uint16_t*)(s_st + RVE_WIN);
     const int cn0 = wt.win_cn0[win], ncn = wt.win_cn0[win + 1] - cn0;
     unsigned ent0 = 0, nent = 0;
-    if (precond) {
-        ent0 = cn_beg[cn0]; nent = cn_beg[cn0 + ncn] - ent0;
-        for (unsigned e = tid; e < nent; e += RVE_WIN) s_ent[e] = cn_ent[ent0 + e];
-        if (tid < n) { const RowInfo ri = rowinfo[row0 + tid]; s_st[tid] = make_float2(ri.s, ri.t); }
-    }
-    const double alpha = sc[((size_t)sys * 4 + k) * SC_N + SC_ALPHA];
     double rr = 0.0, rdr = 0.0;
-    if (tid < TPB) {
-        // all loads of the thread's (row, rhs) pairs are issued before the first use
-        constexpr int NIT = (RVE_WIN * K + TPB - 1) / TPB;
+    {
         const size_t base = (size_t)row0 * K;
-        double2 rv[NIT], pv[NIT], qv[NIT], xv[NIT];
-        float4 dv[NIT];
+        double2 rv[EPT], pv[EPT], qv[EPT], xv[EPT];
+        float4 dv[EPT];
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
+        for (int it = 0; it < EPT; ++it) {
             const int e = tid + it * TPB;
             if (e < n * K) {
                 rv[it] = r[base + e];
@@ -707,8 +678,14 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
                 if (!init) { pv[it] = p[base + e]; qv[it] = q[base + e]; xv[it] = x[base + e]; }
             }
         }
+        if (precond) {
+            ent0 = cn_beg[cn0]; nent = cn_beg[cn0 + ncn] - ent0;
+            for (unsigned t = tid; t < nent; t += TPB) s_ent[t] = cn_ent[ent0 + t];
+            for (int t = tid; t < n; t += TPB) { const RowInfo ri = rowinfo[row0 + t]; s_st[t] = make_float2(ri.s, ri.t); }
+        }
+        const double alpha = sc[((size_t)sys * 4 + k) * SC_N + SC_ALPHA];
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
+        for (int it = 0; it < EPT; ++it) {
             const int e = tid + it * TPB;
             if (e < n * K) {
                 double2 rw = rv[it];
@@ -725,7 +702,7 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
             }
         }
     }
-    __shared__ double s_a[RVE_WIN], s_b[RVE_WIN];
+    __shared__ double s_a[TPB], s_b[TPB];
     __shared__ double s_fin[8];
     __shared__ double s_out[4][2];
     s_a[tid] = rr; s_b[tid] = rdr;
@@ -743,7 +720,7 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
     // restriction: 4 threads per (coarse node of the window, rhs) split the node's (row, corner) list;
     // weights from the staged (s,t)
     if (precond) {
-        for (int t = tid; t < ((ncn * K * 4 + 31) & ~31); t += RVE_WIN) {
+        for (int t = tid; t < ((ncn * K * 4 + 31) & ~31); t += TPB) {
             const int task = t >> 2, sub = t & 3;
             double a0 = 0.0, a1 = 0.0;
             int jn = 0, kk = 0;
@@ -1088,45 +1065,41 @@ k_vc_up1(Levels LV, const int* __restrict__ active, double* sc, double* part, in
 // p = Dinv r + Z xc1 + beta p     (thread = one (row, rhs) pair; the level-1 values the window
 // touches are staged in shared memory)
 template <int K>
-__global__ void __launch_bounds__(RVE_WIN)
+__global__ void __launch_bounds__(RVE_VEC_THREADS(K), (K == 1 ? 5 : (K == 2 ? 4 : 2)))
 k_direction(WinTab wt, double2* __restrict__ p, const double2* __restrict__ r, const float4* __restrict__ dinv32,
             const RowInfo* __restrict__ rowinfo, const int* __restrict__ cn_node, const double2* __restrict__ xc1,
             int G, const int* __restrict__ active, const double* __restrict__ sc, int precond) {
     extern __shared__ double2 s_xc[];             // [ncn*K]
-    constexpr int TPB = (RVE_WIN / K) * K;
+    constexpr int EPT = RVE_EPT(K), TPB = RVE_VEC_THREADS(K);
     const int win = blockIdx.x;
     const int sys = wt.win_sys[win];
     if (!active[sys]) return;
     const int tid = threadIdx.x;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
     const int k = tid % K;
-    const double beta = sc[((size_t)sys * 4 + k) * SC_N + SC_BETA];
     const size_t base = (size_t)row0 * K;
-    constexpr int NIT = (RVE_WIN * K + TPB - 1) / TPB;
-    double2 rv[NIT], pv[NIT];
-    float4 dv[NIT];
-    RowInfo ri[NIT];
     // the streaming loads do not depend on the staged coarse values: request them first
-    if (tid < TPB) {
+    double2 rv[EPT], pv[EPT];
+    float4 dv[EPT];
+    RowInfo ri[EPT];
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int e = tid + it * TPB;
-            if (e < n * K) {
-                rv[it] = r[base + e]; pv[it] = p[base + e];
-                dv[it] = dinv32[row0 + e / K];
-                if (precond) ri[it] = rowinfo[row0 + e / K];
-            }
+    for (int it = 0; it < EPT; ++it) {
+        const int e = tid + it * TPB;
+        if (e < n * K) {
+            rv[it] = r[base + e]; pv[it] = p[base + e];
+            dv[it] = dinv32[row0 + e / K];
+            if (precond) ri[it] = rowinfo[row0 + e / K];
         }
     }
+    const double beta = sc[((size_t)sys * 4 + k) * SC_N + SC_BETA];
     if (precond) {
         const int cn0 = wt.win_cn0[win], ncn = wt.win_cn0[win + 1] - cn0;
-        for (int t = tid; t < ncn * K; t += RVE_WIN)
+        for (int t = tid; t < ncn * K; t += TPB)
             s_xc[t] = xc1[((size_t)sys * G + cn_node[cn0 + t / K]) * K + (t % K)];
         __syncthreads();
     }
-    if (tid >= TPB) return;
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
+    for (int it = 0; it < EPT; ++it) {
         const int e = tid + it * TPB;
         if (e < n * K) {
             const float4 d = dv[it];
