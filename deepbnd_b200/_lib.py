@@ -17,7 +17,7 @@ PRECOND = {"jacobi": 0, "twolevel": 1}
 SYMBOLS = ["rve_create", "rve_destroy", "rve_last_error", "rve_set_batch", "rve_assemble", "rve_get_sizes",
            "rve_get_csr", "rve_get_rowmap", "rve_get_nodemap", "rve_get_rhs", "rve_get_solution",
            "rve_get_coarse_dim", "rve_get_coarse_dense", "rve_solve", "rve_epilogue_tangent",
-           "rve_epilogue_snapshot", "rve_project", "rve_timings", "rve_bench_spmv", "rve_host_symbolic"]
+           "rve_epilogue_snapshot", "rve_epilogue_homogenisation", "rve_set_option", "rve_project", "rve_timings", "rve_bench_spmv", "rve_host_symbolic"]
 
 _lib = None
 
@@ -57,6 +57,8 @@ def load():
                               ctypes.c_int32, ctypes.c_int32, c_int32_p, c_int32_p]
     lib.rve_epilogue_tangent.argtypes = [ctypes.c_void_p, c_double_p]
     lib.rve_epilogue_snapshot.argtypes = [ctypes.c_void_p] + [c_double_p] * 5
+    lib.rve_epilogue_homogenisation.argtypes = [ctypes.c_void_p] + [c_double_p] * 5
+    lib.rve_set_option.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]
     lib.rve_project.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_double_p, c_double_p, c_double_p,
                                 c_double_p]
     lib.rve_timings.argtypes = [ctypes.c_void_p, c_double_p, c_double_p]

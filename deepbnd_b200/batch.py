@@ -93,6 +93,20 @@ class RVEBatch:
                                                    L.dptr(out["B"]), L.dptr(out["sigmaT"])))
         return out
 
+    def set_option(self, option, value):
+        self._check(self.lib.rve_set_option(self.h, int(option), int(value)))
+        return self
+
+    def homogenisation(self):
+        """sigmaL, sigmaT (n,k,3), gradL, gradT (n,k,2,2), eps_eff (n,k,3) of the last solve
+        (micro_model_gen.py:139-147)."""
+        n, k = self.n_sys, self.n_rhs
+        out = dict(sigmaL=np.zeros((n, k, 3)), sigmaT=np.zeros((n, k, 3)), gradL=np.zeros((n, k, 2, 2)),
+                   gradT=np.zeros((n, k, 2, 2)), eps_eff=np.zeros((n, k, 3)))
+        self._check(self.lib.rve_epilogue_homogenisation(self.h, L.dptr(out["sigmaL"]), L.dptr(out["sigmaT"]),
+                                                         L.dptr(out["gradL"]), L.dptr(out["gradT"]), L.dptr(out["eps_eff"])))
+        return out
+
     def project(self, W, M, translate=None):
         """W: (n_rhs, nmax, nh) or (nmax, nh) shared; M: (nh, nh).  Returns Y (n_sys, n_rhs, nmax)."""
         W = L.f64(W)

@@ -109,7 +109,8 @@ struct rve_batch_s {
     DBuf<float4> lvA4[RVE_MAXLEV], lvH4[RVE_MAXLEV];
     DBuf<double> p, q, x, r, b, part, sc, cpart;
     DBuf<double> eps, eps_eff, Bmat, uD, gval, d_vbox, U, acc, sigL, sigT, aout, Bout, sol, Mx, Gaff, aaff;
-    DBuf<double> MWt, transl, Yd;
+    DBuf<double> MWt, transl, Yd, gradT;
+    int opt_sym_B = 0;
     int* h_nactive = nullptr;  // pinned
     PinnedArena arena;
     std::vector<cudaEvent_t> evpool;  // per-iteration SpMV timing
@@ -665,7 +666,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     }
     CU(cudaEventRecord(h->ev[0], st));
     k_dnn_prep<<<cdiv((long long)n_sys * NL, 128), 128, 0, st>>>(n_sys, NL, nside, h->d_vbox.p, uD ? h->uD.p : nullptr,
-                                                                  h->eps.p, h->eps_eff.p, h->Bmat.p);
+                                                                  h->eps.p, h->eps_eff.p, h->Bmat.p, h->opt_sym_B);
     if (uD)
         k_bnd_values<<<cdiv(h->NBN * NL, 256), 256, 0, st>>>((int)h->NBN, NL, nside, h->bnd_sys.p, h->bnd_node.p, h->bnd_s.p,
                                                               h->node_xy.p, h->uD.p, h->Bmat.p, h->gval.p);
@@ -779,13 +780,13 @@ static int run_epilogue(rve_handle_t h) {
     cudaStream_t st = h->stream;
     const int NL = h->NL, n_sys = h->n_sys;
     CU(h->sigL.alloc((size_t)n_sys * NL * 3)); CU(h->sigT.alloc((size_t)n_sys * NL * 3));
-    CU(h->aout.alloc((size_t)n_sys * NL * 2)); CU(h->Bout.alloc((size_t)n_sys * NL * 4));
+    CU(h->aout.alloc((size_t)n_sys * NL * 2)); CU(h->Bout.alloc((size_t)n_sys * NL * 4)); CU(h->gradT.alloc((size_t)n_sys * NL * 4));
     CU(cudaEventRecord(h->ev[0], st));
     CU(cudaMemsetAsync(h->acc.p, 0, h->acc.n * sizeof(double), st));
     k_epi_elements<<<cdiv(h->E, 128), 128, 0, st>>>((int)h->E, NL, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
                                                     h->U.p, h->acc.p, h->mat);
     k_epi_finalize<<<cdiv((long long)n_sys * NL, 128), 128, 0, st>>>(n_sys, NL, h->acc.p, h->eps_eff.p, h->mat, h->sigL.p,
-                                                                     h->sigT.p, h->aout.p, h->Bout.p);
+                                                                     h->sigT.p, h->aout.p, h->Bout.p, h->gradT.p);
     if (h->nvref) {
         CU(h->sol.alloc((size_t)n_sys * NL * 2 * h->nvref));
         const long long n = (long long)n_sys * h->nvref * NL;
@@ -830,6 +831,33 @@ int rve_epilogue_snapshot(rve_handle_t h, double* sol, double* sigma, double* a,
     if (B) CU(cudaMemcpyAsync(B, h->Bout.p, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[7] = ms;
+    return 0;
+}
+
+int rve_set_option(rve_handle_t h, int32_t option, int32_t value) {
+    H_CHECK(h);
+    if (option == RVE_OPT_SYM_B) { h->opt_sym_B = value ? 1 : 0; return 0; }
+    FAIL(RVE_E_ARG, "unknown option");
+}
+
+int rve_epilogue_homogenisation(rve_handle_t h, double* sigmaL, double* sigmaT, double* gradL, double* gradT, double* eps_eff) {
+    H_CHECK(h);
+    if (!h->solved) FAIL(RVE_E_STATE, "rve_epilogue_homogenisation before rve_solve");
+    int rc = run_epilogue(h);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    const size_t n = (size_t)h->n_sys * h->NL;
+    std::vector<double> bl(gradL ? 4 * n : 0);
+    if (sigmaL) CU(cudaMemcpyAsync(sigmaL, h->sigL.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (sigmaT) CU(cudaMemcpyAsync(sigmaT, h->sigT.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (gradL) CU(cudaMemcpyAsync(bl.data(), h->Bout.p, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (gradT) CU(cudaMemcpyAsync(gradT, h->gradT.p, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (eps_eff) CU(cudaMemcpyAsync(eps_eff, h->eps_eff.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    h->d2h_bytes += (double)n * sizeof(double) * ((sigmaL ? 3 : 0) + (sigmaT ? 3 : 0) + (gradL ? 4 : 0) + (gradT ? 4 : 0) + (eps_eff ? 3 : 0));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (gradL) for (size_t i = 0; i < 4 * n; ++i) gradL[i] = -bl[i];      // B = -average gradient
     float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[7] = ms;
     return 0;
 }

@@ -1129,7 +1129,7 @@ k_direction(WinTab wt, double2* __restrict__ p, const double2* __restrict__ r, c
 __global__ void k_dnn_prep(int n_sys, int K, int nside, const double* __restrict__ vbox /*[4]*/,
                            const double* __restrict__ uD /*[sys][K][2*(4*nside+1)] or null*/,
                            const double* __restrict__ eps, double* __restrict__ eps_eff,
-                           double* __restrict__ Bmat /*[sys][K][4]*/) {
+                           double* __restrict__ Bmat /*[sys][K][4]*/, int sym_B) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_sys * K) return;
     double B00 = 0, B01 = 0, B10 = 0, B11 = 0;
@@ -1148,6 +1148,7 @@ __global__ void k_dnn_prep(int n_sys, int K, int nside, const double* __restrict
         }
         const double iv = -1.0 / (vbox[2] * vbox[3]);
         B00 *= iv; B01 *= iv; B10 *= iv; B11 *= iv;
+        if (sym_B) { const double m = 0.5 * (B01 + B10); B01 = m; B10 = m; }   // micro_model_gen.py:122
     }
     Bmat[4 * (size_t)gid] = B00; Bmat[4 * (size_t)gid + 1] = B01;
     Bmat[4 * (size_t)gid + 2] = B10; Bmat[4 * (size_t)gid + 3] = B11;
@@ -1444,7 +1445,8 @@ __global__ void k_nodal_field(long long n_nodes, int K, int NL, const int* __res
 // (6) fused epilogues
 // ---------------------------------------------------------------------------------------------
 // accumulators per system: [0..3] vol_r, [4..5] int y over regions {0,1}; per load l (base 6+16*l):
-//   [0..1] int u~ (L), [2..5] int grad u~ (L), [6..8] int sigma(u~) (L: 00,11,01), [9..11] same over all regions
+//   [0..1] int u~ (L), [2..5] int grad u~ (L), [6..8] int sigma(u~) (L: 00,11,01), [9..11] same over all regions,
+//   [12..15] int grad u~ over all regions
 #define ACC_PER_SYS (6 + 16 * RVE_MAX_RHS)
 
 // add v from every lane to *addr: one atomic per warp when all lanes target the same system
@@ -1511,13 +1513,17 @@ k_epi_elements(int n_elem, int NL, const int* __restrict__ elem_node, const unsi
         warp_acc(valid ? s00 : 0.0, Al + 9, uniform, valid);
         warp_acc(valid ? s11 : 0.0, Al + 10, uniform, valid);
         warp_acc(valid ? s01 : 0.0, Al + 11, uniform, valid);
+        warp_acc(valid ? G00 : 0.0, Al + 12, uniform, valid);
+        warp_acc(valid ? G01 : 0.0, Al + 13, uniform, valid);
+        warp_acc(valid ? G10 : 0.0, Al + 14, uniform, valid);
+        warp_acc(valid ? G11 : 0.0, Al + 15, uniform, valid);
     }
 }
 
 // thread per (sys, load): sigma over {0,1}, sigma over all, a, B, tangent column
 __global__ void k_epi_finalize(int n_sys, int NL, const double* __restrict__ acc, const double* __restrict__ eps_eff,
                                Mat8 mat, double* __restrict__ sigL, double* __restrict__ sigT,
-                               double* __restrict__ aout, double* __restrict__ Bout) {
+                               double* __restrict__ aout, double* __restrict__ Bout, double* __restrict__ gradT) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_sys * NL) return;
     const int sys = gid / NL, l = gid % NL;
@@ -1539,6 +1545,8 @@ __global__ void k_epi_finalize(int n_sys, int NL, const double* __restrict__ acc
     aout[2 * (size_t)gid + 1] = -Al[1] / volL + G10 * yG0 + G11 * yG1;
     Bout[4 * (size_t)gid] = -G00; Bout[4 * (size_t)gid + 1] = -G01;
     Bout[4 * (size_t)gid + 2] = -G10; Bout[4 * (size_t)gid + 3] = -G11;
+    if (gradT)
+        for (int k = 0; k < 4; ++k) gradT[4 * (size_t)gid + k] = Al[12 + k] / volT;
 }
 
 // internal-boundary DOF extraction: P2 evaluation at the Vref points; thread per (sys, point, load)

@@ -109,3 +109,50 @@ class MicroConstitutiveModelDNN:
         if not self.isTangentComputed:
             self.computeTangent()
         return self.Chom_
+
+
+class MicroConstitutiveModelGen:
+    """Mirror of core/multiscale/micro_model_gen.py:31-160: average stress and strain over the whole RVE and
+    over the internal regions `domainL` = [0, 1], and the tangents sigma eps^-1 built from them.  Voigt
+    conventions of core/elasticity/misc.py:58-62 (stress [00,11,01], strain [00,11,2*01]).  The dnn variant
+    symmetrises the B correction (:122), which the library does under RVE_OPT_SYM_B."""
+
+    def __init__(self, nameMesh, param, model, device=0, rtol=1e-10):
+        self.nameMesh = nameMesh
+        self.param = param
+        self.model = model
+        self.device = device
+        self.rtol = rtol
+        self.others = {'polyorder': 2}
+        self.ndim = 2
+        self.nvoigt = 3
+        self.Hom = None
+
+    def computeHomogenisation(self, domainL=(0, 1)):
+        if sorted(domainL) != [0, 1]:
+            raise NotImplementedError("domainL must be the internal regions [0, 1]")
+        mesh = _mesh_of(self.nameMesh)
+        xy = mesh[0]
+        self.others.update(x0=xy[:, 0].min(), x1=xy[:, 0].max(), y0=xy[:, 1].min(), y1=xy[:, 1].max())
+        model, uD = self.model, None
+        if model == 'dnn':
+            uD = np.stack([np.asarray(self.others['uD%d_' % i], dtype=np.float64) for i in range(3)])[None]
+        b = RVEBatch(self.device).set_meshes([mesh], tuple(self.param), model=model)
+        b.set_option(1, 1)                                              # RVE_OPT_SYM_B
+        b.assemble()
+        b.solve(np.stack([macro_strain_voigt(i) for i in range(3)])[None], uD=uD, rtol=self.rtol)
+        h = b.homogenisation()
+        b.close()
+        Hom = {k: np.zeros((3, 3)) for k in ("sigma", "sigmaL", "eps", "epsL", "tangent", "tangentL")}
+        for i in range(3):
+            e = h["eps_eff"][0, i]
+            for key, g, s in (("L", h["gradL"][0, i], h["sigmaL"][0, i]), ("", h["gradT"][0, i], h["sigmaT"][0, i])):
+                Hom["sigma" + key][:, i] = s                             # stress2voigt: [00, 11, 01]
+                Hom["eps" + key][:, i] = [e[0] + g[0, 0], e[1] + g[1, 1], e[2] + g[0, 1] + g[1, 0]]   # strain2voigt
+        Hom["tangent"] = Hom["sigma"] @ np.linalg.inv(Hom["eps"])
+        Hom["tangentL"] = Hom["sigmaL"] @ np.linalg.inv(Hom["epsL"])
+        self.Hom = Hom
+        return Hom
+
+    def getHomogenisation(self):
+        return self.Hom if self.Hom is not None else self.computeHomogenisation()

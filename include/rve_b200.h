@@ -112,6 +112,19 @@ int rve_epilogue_tangent(rve_handle_t h, double* C);
 int rve_epilogue_snapshot(rve_handle_t h, double* sol, double* sigma, double* a, double* B,
                           double* sigmaT);
 
+/* replaces the per-load post-processing of MicroConstitutiveModelGen.computeHomogenisation
+ * (core/multiscale/micro_model_gen.py:139-147): average stress (Voigt 00,11,01) over the regions {0,1}
+ * ("L") and over all regions, average gradient of the fluctuation (2x2, row-major) over the same two
+ * region sets, and the effective macro strain eps - B of each load ([e11, e22, 2 e12]).  Each array is
+ * [n_sys][n_rhs][.]; any pointer may be NULL. */
+int rve_epilogue_homogenisation(rve_handle_t h, double* sigmaL, double* sigmaT, double* gradL, double* gradT,
+                                double* eps_eff);
+
+/* solver options.  RVE_OPT_SYM_B: symmetrise the dnn correction B = 0.5 (B + B^T) like
+ * micro_model_gen.py:122 (default 0: full B, micro_model_dnn.py:88). */
+#define RVE_OPT_SYM_B 1
+int rve_set_option(rve_handle_t h, int32_t option, int32_t value);
+
 /* replaces getAlphas_fast (creation_model/RB/RB_utils.py:211-213): Y = U M W[:nmax]^T on the
  * Vref samples of the last solve.  W[n_rhs][nmax][nh] (one basis per load), M[nh][nh],
  * translate[n_sys][n_rhs][2] or NULL: constant added to the samples first

@@ -11,8 +11,9 @@ the reference's own tests hold no golden vector for the solve path (SURVEY.md
 F2/F3/F6).  The oracle is therefore pinned only by (i) analytic known answers
 (homogeneous material, patch tests, energy ordering), (ii) the reference's
 material constants and tag conventions, (iii) `tests/test_sampling.py` goldens
-(off-path).  A FEniCS-side exporter (tools/export_goldens_fenics.py) exists to
-turn this into a pinned oracle on a machine that has FEniCS.
+(off-path), (iv) the reference's golden mesh volume fractions (tests/test_meshes.py:58-59), which the
+mesher reproduces to 1e-15.  tools/export_goldens_fenics.py + tests/test_fenics_goldens.py turn this
+into a pinned oracle on a machine that has FEniCS (the tests are skipped while the files are absent).
 
 Reference call sites restated here (file:line under /root/reference):
   material table          core/elasticity/fenics_utils.py:41-53, core/elasticity/misc.py:25-33
@@ -510,6 +511,39 @@ class OracleRVE:
         uavg = uint[sel].sum(axis=0) / vol
         Gavg = self._elem_grad_int(u)[sel].sum(axis=0) / vol
         return -uavg + Gavg @ yG, -Gavg
+
+    def compute_homogenisation(self, uD_list=None, pts=None, domainL=(0, 1)):
+        """MicroConstitutiveModelGen.computeHomogenisation (micro_model_gen.py:63-154): sigma, eps over the RVE
+        and over domainL (Voigt, elasticity/misc.py:58-62), tangent = sigma eps^-1.  dnn: B symmetrised (:122)."""
+        m = self.mesh
+        Hom = {k: np.zeros((3, 3)) for k in ("sigma", "sigmaL", "eps", "epsL", "tangent", "tangentL")}
+        for i in range(3):
+            B = np.zeros((2, 2))
+            g = None
+            if self.model == 'dnn' and uD_list is not None:
+                uD = np.asarray(uD_list[i], dtype=float)
+                B = vref_B_correction(uD, pts)
+                B = 0.5 * (B + B.T)
+                uDc = uD.reshape(-1, 2) + pts @ B.T
+                gn = np.zeros((m.nn, 2))
+                bv = m.bnd_nodes[m.bnd_nodes < m.nv]
+                gn[bv] = vref_eval_on_boundary(uDc.ravel(), pts, m.xy[bv])
+                be = m.bnd_edges
+                gn[m.nv + be] = 0.5 * (gn[m.edges[be, 0]] + gn[m.edges[be, 1]])
+                g = gn[m.bnd_nodes]
+            eps = macro_strain(i) - B
+            self.solve_load(i, eps=eps, g_bnd=g)
+            G = self._elem_grad_int(self.sol[i])
+            for key, regions in (("L", list(domainL)), ("", [0, 1, 2, 3])):
+                sel = np.isin(m.region, regions)
+                vol = m.area[sel].sum()
+                s = self.homogenise(regions, i)
+                e = eps + 0.5 * (G[sel].sum(0) + G[sel].sum(0).T) / vol
+                Hom["sigma" + key][:, i] = [s[0, 0], s[1, 1], s[0, 1]]
+                Hom["eps" + key][:, i] = [e[0, 0], e[1, 1], 2 * e[0, 1]]
+        Hom["tangent"] = Hom["sigma"] @ np.linalg.inv(Hom["eps"])
+        Hom["tangentL"] = Hom["sigmaL"] @ np.linalg.inv(Hom["epsL"])
+        return Hom
 
     def eval_at(self, u, pts):
         """P2 evaluation of u at arbitrary points (usol.interpolate, simulation_snapshots.py:56)."""

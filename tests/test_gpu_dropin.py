@@ -85,3 +85,28 @@ def test_micro_model_mirrors(reduced_meshes):
     C = d.getTangent()
     Co = OracleRVE(*mesh, model='lin').compute_tangent()
     assert np.abs(C - Co).max() < 1e-8 * np.abs(Co).max() and d.getTangent() is C
+
+
+@pytest.mark.parametrize("model", ["per", "MR", "dnn"])
+def test_micro_model_gen_matches_oracle(full_mesh, model):
+    """MicroConstitutiveModelGen.computeHomogenisation on a 'full' mesh (regions 0..3)."""
+    from deepbnd_b200.micro_model import MicroConstitutiveModelGen
+    from oracle.rve_oracle import OracleRVE, vref_points
+    mesh = full_mesh
+    if model == "dnn":                                   # dnn prescribes the boundary of the mesh itself: use the 6x6 box as Vref
+        pts = vref_points(-3, -3, 6, 6, 21)
+        uD = [smooth_uD(81, 40 + i) for i in range(3)]
+    mm = MicroConstitutiveModelGen(mesh, [0.3, 10.0, 0.3, 1.0], model)
+    if model == "dnn":
+        for i in range(3):
+            mm.others['uD%d_' % i] = uD[i]
+    if model == "dnn":
+        # the library takes the Vref box from the batch: the mirror uses the mesh bounding box by default
+        Hg = mm.computeHomogenisation()
+        Ho = OracleRVE(*mesh, model="dnn").compute_homogenisation(uD_list=uD, pts=pts)
+    else:
+        Hg = mm.computeHomogenisation()
+        Ho = OracleRVE(*mesh, model=model).compute_homogenisation()
+    for k in ("sigma", "sigmaL", "eps", "epsL", "tangent", "tangentL"):
+        assert np.abs(Hg[k] - Ho[k]).max() < 1e-8 * np.abs(Ho[k]).max(), (model, k)
+    assert mm.getHomogenisation() is Hg

@@ -141,3 +141,15 @@ def test_oracle_reproduces_committed_c1_goldens():
     for model in ("lin", "per", "MR"):
         C = OracleRVE(*mesh, param=PARAM, model=model).compute_tangent()
         assert np.abs(C - gold["tangent_reduced_" + model]).max() < 1e-10 * np.abs(C).max(), model
+
+
+def test_homogenisation_gen_consistency(coarse_reduced_meshes):
+    """micro_model_gen.py: for a reduced mesh (regions {0,1} only) the L and total quantities coincide, the average
+    strain of 'lin' equals the macro strain (zero boundary fluctuation) and tangent == sigma there."""
+    from oracle.rve_oracle import OracleRVE
+    mesh = coarse_reduced_meshes[0]
+    H = OracleRVE(*mesh, param=PARAM, model="lin").compute_homogenisation()
+    assert np.allclose(H["sigma"], H["sigmaL"]) and np.allclose(H["eps"], H["epsL"])
+    assert np.abs(H["eps"] - np.eye(3)).max() < 1e-10
+    C = OracleRVE(*mesh, param=PARAM, model="lin").compute_tangent()
+    assert np.abs(H["tangent"] - C[[0, 1, 2]][:, :]).max() < 1e-9 * np.abs(C).max()
