@@ -202,14 +202,32 @@ static void launch_update(rve_batch_s* h, const PcgArgs& a, int init, int iter, 
                                                    h->sc.p, init, iter, a.rtol2, a.precond, h->d_iters.p, h->n_active.p);
 }
 
-// coarse V-cycle: level 1 as two grid-wide kernels (thread per coarse node), levels >= 2 in one CTA per system
+// coarse V-cycle: the large levels (always level 1) as grid-wide kernels (thread per coarse node), the small
+// ones in one CTA per system (k_vc_mid)
 template <int K>
 static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStream_t st) {
-    const int G = a.LV.g[0].G;
-    const dim3 grid((unsigned)((G + 255) / 256), (unsigned)a.n_sys);
-    k_vc_down1<K><<<grid, 256, 0, st>>>(a.LV, h->active.p);
-    if (a.LV.L > 1) k_vc_mid<K><<<a.n_sys, a.LV.g[1].G <= 128 ? 128 : 256, 0, st>>>(a.LV, h->active.p);
-    k_vc_up1<K><<<grid, 256, 0, st>>>(a.LV, h->active.p, h->sc.p, h->cpart.p, h->cnt.p, first);
+    const Levels& LV = a.LV;
+    int W = 1;                                         // number of wide levels; the coarsest level stays in k_vc_mid
+    while (W < LV.L - 1 && LV.g[W].G >= RVE_WIDE_NODES) ++W;
+    auto grid = [&](int l) { return dim3((unsigned)((LV.g[l].G + 255) / 256), (unsigned)a.n_sys); };
+    k_vc_down1<K><<<grid(0), 256, 0, st>>>(LV, 0, h->active.p);
+    for (int l = 1; l < W; ++l) {
+        k_vc_restrict<K><<<grid(l), 256, 0, st>>>(LV, l, h->active.p);
+        k_vc_down1<K><<<grid(l), 256, 0, st>>>(LV, l, h->active.p);
+    }
+    int nk = 2 + 2 * (W - 1);
+    if (LV.L > 1) {
+        const int Gm = LV.g[W].G;
+        k_vc_mid<K><<<a.n_sys, Gm <= 128 ? 128 : (Gm <= 256 ? 256 : 320), 0, st>>>(LV, W, h->active.p);
+        for (int l = W - 1; l >= 0; --l) {
+            const double* src = (l + 1 == W) ? LV.xc[W] : LV.tc[l + 1];
+            k_vc_prolong<K><<<grid(l), 256, 0, st>>>(LV, l, src, h->active.p);
+            if (l > 0) k_vc_upl<K><<<grid(l), 256, 0, st>>>(LV, l, h->active.p);
+        }
+        nk += 1 + W + (W - 1);
+    }
+    k_vc_up1<K><<<grid(0), 256, 0, st>>>(LV, h->active.p, h->sc.p, h->cpart.p, h->cnt.p, first);
+    h->launches += nk;
 }
 
 template <int K>
@@ -727,7 +745,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
             K_DISPATCH(K, UPD_);
 #undef UPD_
             ++launched;
-            h->launches += precond ? (LV.L > 1 ? 6 : 5) : 3;
+            h->launches += 3;
         }
         CU(cudaMemcpyAsync(h->h_nactive, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

@@ -820,25 +820,25 @@ __device__ __forceinline__ void stencil_apply(const Grid& g, const float4* __res
         }
 }
 
-// level-1 down: x1 = om Dinv rc ; t1 = rc - H rc.   thread per (sys, node), grid (ceil(G/256), n_sys)
+// wide level l, down: x_l = om Dinv rc_l ; t_l = rc_l - H rc_l.   thread per (sys, node), grid (ceil(G_l/256), n_sys)
 template <int K>
 __global__ void __launch_bounds__(256)
-k_vc_down1(Levels LV, const int* __restrict__ active) {
+k_vc_down1(Levels LV, int l, const int* __restrict__ active) {
     const int sys = blockIdx.y;
     if (!active[sys]) return;
-    const Grid g = LV.g[0];
+    const Grid g = LV.g[l];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= g.G) return;
-    const double2* rc = (const double2*)LV.rc[0] + (size_t)sys * g.G * K;
-    double2* xc = (double2*)LV.xc[0] + (size_t)sys * g.G * K;
-    double2* tc = (double2*)LV.tc[0] + (size_t)sys * g.G * K;
-    const double* d = LV.dinv[0] + ((size_t)sys * g.G + idx) * 4;
+    const double2* rc = (const double2*)LV.rc[l] + (size_t)sys * g.G * K;
+    double2* xc = (double2*)LV.xc[l] + (size_t)sys * g.G * K;
+    double2* tc = (double2*)LV.tc[l] + (size_t)sys * g.G * K;
+    const double* d = LV.dinv[l] + ((size_t)sys * g.G + idx) * 4;
     const double om = RVE_OMEGA;
     const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
     double2 acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
-    stencil_apply<K>(g, LV.H4[0] + (size_t)sys * 25 * g.G, rc, idx % g.nx, idx / g.nx, acc);
+    stencil_apply<K>(g, LV.H4[l] + (size_t)sys * 25 * g.G, rc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const double2 rv = rc[(size_t)idx * K + k];
@@ -847,16 +847,16 @@ k_vc_down1(Levels LV, const int* __restrict__ active) {
     }
 }
 
-// levels >= 2: one CTA per system.  Restricts t1, runs the rest of the V-cycle, prolongs the level-2
-// correction into x1.
+// levels >= l0 (the small ones): one CTA per system.  Restricts t_{l0-1}, runs the rest of the V-cycle down to
+// the coarsest level and back up to level l0 (post-smoothed result in xc[l0]).
 template <int K>
-__global__ void __launch_bounds__(256, 4)
-k_vc_mid(Levels LV, const int* __restrict__ active) {
+__global__ void __launch_bounds__(320, 3)
+k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
     const int sys = blockIdx.x;
     if (!active[sys]) return;
     const int nth = blockDim.x, tid = threadIdx.x;
     const double om = RVE_OMEGA;
-    for (int l = 1; l < LV.L; ++l) {
+    for (int l = l0; l < LV.L; ++l) {
         const Grid g = LV.g[l], gf = LV.g[l - 1];
         const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
         double2* rc = (double2*)LV.rc[l] + (size_t)sys * g.G * K;
@@ -943,8 +943,8 @@ k_vc_mid(Levels LV, const int* __restrict__ active) {
             __syncthreads();
         }
     }
-    // up sweep: x_l += P x_{l+1}, then (for l >= 1) post-smoothing; level 0 is post-smoothed by k_vc_up1
-    for (int l = LV.L - 2; l >= 0; --l) {
+    // up sweep: x_l += P x_{l+1}, then post-smoothing, for the levels this kernel owns
+    for (int l = LV.L - 2; l >= l0; --l) {
         const Grid g = LV.g[l], gc = LV.g[l + 1];
         double2* xc = (double2*)LV.xc[l] + (size_t)sys * g.G * K;
         const double2* xcc = (const double2*)LV.xc[l + 1] + (size_t)sys * gc.G * K;
@@ -971,7 +971,6 @@ k_vc_mid(Levels LV, const int* __restrict__ active) {
             for (int k = 0; k < K; ++k) xc[(size_t)idx * K + k] = acc[k];
         }
         __syncthreads();
-        if (l == 0) break;
         const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
         const float4* A4 = LV.A4[l] + (size_t)sys * 25 * g.G;
         const double2* rc = (const double2*)LV.rc[l] + (size_t)sys * g.G * K;
@@ -1000,6 +999,106 @@ k_vc_mid(Levels LV, const int* __restrict__ active) {
             }
         }
         __syncthreads();
+    }
+}
+
+// Large coarse levels (>= RVE_WIDE_NODES nodes; always level 1) run as grid-wide kernels, thread per (system,
+// node), grid (ceil(G_l/256), n_sys): restriction, pre-smoothing + residual, prolongation, post-smoothing.
+#define RVE_WIDE_NODES 1024
+
+// rc_l = P^T t_{l-1} (full weighting; t vanishes outside the coarse space)
+template <int K>
+__global__ void __launch_bounds__(256)
+k_vc_restrict(Levels LV, int l, const int* __restrict__ active) {
+    const int sys = blockIdx.y;
+    if (!active[sys]) return;
+    const Grid g = LV.g[l], gf = LV.g[l - 1];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.G) return;
+    const double2* tf = (const double2*)LV.tc[l - 1] + (size_t)sys * gf.G * K;
+    double2* rc = (double2*)LV.rc[l] + (size_t)sys * g.G * K;
+    const int I = idx % g.nx, J = idx / g.nx;
+    double2 acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+    if (grid_valid(g, I, J)) {
+#pragma unroll
+        for (int aj = -1; aj <= 1; ++aj)
+#pragma unroll
+            for (int ai = -1; ai <= 1; ++ai) {
+                int nf;
+                if (!grid_node_fast(gf, 2 * I + ai, 2 * J + aj, nf)) continue;
+                const double wgt = (ai ? 0.5 : 1.0) * (aj ? 0.5 : 1.0);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const double2 tv = tf[(size_t)nf * K + k];
+                    acc[k].x += wgt * tv.x; acc[k].y += wgt * tv.y;
+                }
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) rc[(size_t)idx * K + k] = acc[k];
+}
+
+// x_l += P src_{l+1}   (src = the post-smoothed correction of the next coarser level)
+template <int K>
+__global__ void __launch_bounds__(256)
+k_vc_prolong(Levels LV, int l, const double* __restrict__ src, const int* __restrict__ active) {
+    const int sys = blockIdx.y;
+    if (!active[sys]) return;
+    const Grid g = LV.g[l], gc = LV.g[l + 1];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.G) return;
+    const int i = idx % g.nx, j = idx / g.nx;
+    if (!grid_valid(g, i, j)) return;
+    double2* xc = (double2*)LV.xc[l] + (size_t)sys * g.G * K;
+    const double2* xcc = (const double2*)src + (size_t)sys * gc.G * K;
+    const int I0 = i >> 1, J0 = j >> 1;
+    const int ni = (i & 1) ? 2 : 1, nj = (j & 1) ? 2 : 1;
+    const double wgt = ((i & 1) ? 0.5 : 1.0) * ((j & 1) ? 0.5 : 1.0);
+    double2 acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = xc[(size_t)idx * K + k];
+    for (int bj = 0; bj < nj; ++bj)
+        for (int bi = 0; bi < ni; ++bi) {
+            int nc;
+            if (!grid_node_fast(gc, I0 + bi, J0 + bj, nc)) continue;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double2 v = xcc[(size_t)nc * K + k];
+                acc[k].x += wgt * v.x; acc[k].y += wgt * v.y;
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < K; ++k) xc[(size_t)idx * K + k] = acc[k];
+}
+
+// post-smoothing of a wide level l >= 1: tc_l = x_l + om Dinv (rc_l - A x_l)
+template <int K>
+__global__ void __launch_bounds__(256)
+k_vc_upl(Levels LV, int l, const int* __restrict__ active) {
+    const int sys = blockIdx.y;
+    if (!active[sys]) return;
+    const Grid g = LV.g[l];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.G) return;
+    const double2* rc = (const double2*)LV.rc[l] + (size_t)sys * g.G * K;
+    const double2* xc = (const double2*)LV.xc[l] + (size_t)sys * g.G * K;
+    double2* zc = (double2*)LV.tc[l] + (size_t)sys * g.G * K;
+    const double* d = LV.dinv[l] + ((size_t)sys * g.G + idx) * 4;
+    const double om = RVE_OMEGA;
+    const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
+    double2 acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+    stencil_apply<K>(g, LV.A4[l] + (size_t)sys * 25 * g.G, xc, idx % g.nx, idx / g.nx, acc);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double2 rv = rc[(size_t)idx * K + k];
+        const double t0 = rv.x - acc[k].x, t1 = rv.y - acc[k].y;
+        double2 xv = xc[(size_t)idx * K + k];
+        xv.x += d0 * t0 + d1 * t1; xv.y += d2 * t0 + d3 * t1;
+        zc[(size_t)idx * K + k] = xv;
     }
 }
 
