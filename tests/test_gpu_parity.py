@@ -384,3 +384,27 @@ def test_error_codes_and_state_machine(coarse_reduced_meshes):
         b.solve(EPS3[None].copy(), maxit=3)
     assert ei.value.code == -5
     b.close()
+
+
+@pytest.mark.parametrize("model", ["lin", "per", "MR"])
+def test_single_load_and_no_vref(coarse_reduced_meshes, model):
+    """n_rhs = 1 (the K = 1 instantiation of the PCG kernels; MR still solves its 3 traction problems) and a batch
+    without a Vref space (vref_nb = 0): nodal field and sigma of the shear load against the oracle."""
+    from deepbnd_b200.batch import RVEBatch
+    from oracle.rve_oracle import OracleRVE
+    meshes = coarse_reduced_meshes[:3]
+    b = RVEBatch().set_meshes(meshes, PARAM, model=model, vref_nb=0).assemble()
+    eps = np.broadcast_to(np.array([[0.0, 0.0, 1.0]]), (3, 1, 3)).copy()
+    status, iters = b.solve(eps, rtol=1e-11, maxit=6000)
+    assert (status == 0).all()
+    snap = b.snapshot()
+    assert snap["sol"] is None
+    for s in range(3):
+        o = OracleRVE(*meshes[s], param=PARAM, model=model)
+        o.solve_load(2)
+        uo = o.sol[2].reshape(-1, 2)
+        U = b.solution(s)[:, 0, :]
+        assert np.linalg.norm(U - uo) < 1e-8 * np.linalg.norm(uo), (model, s)
+        sig = o.homogenise([0, 1], 2).flatten()[[0, 3, 2]]
+        assert np.abs(snap["sigma"][s, 0] - sig).max() < 1e-8 * np.abs(sig).max()
+    b.close()
