@@ -692,6 +692,9 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     CU(cudaMemsetAsync(h->sc.p, 0, h->sc.n * sizeof(double), st));
     if (h->model == RVE_MODEL_MR)
         k_rhs_mr<<<cdiv(h->NBE, 256), 256, 0, st>>>((int)h->NBE, h->bedge.p, h->bedge_nl.p, h->node_row.p, h->b.p);
+    else if (!uD)
+        k_rhs_load<<<cdiv(h->E, 40), 256, 0, st>>>((int)h->E, K, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
+                                                   h->node_row.p, h->eps_eff.p, h->b.p, h->sc.p, h->mat);
     else
         k_rhs<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, K, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
                                               h->node_row.p, h->node_bnd.p, h->eps_eff.p, uD ? h->gval.p : nullptr, h->b.p, h->sc.p, h->mat);

@@ -385,12 +385,17 @@ k_galerkin1(int n_elem, const int* __restrict__ elem_node, const unsigned char* 
     }
     __syncwarp();
     double* Asys = A1 + (size_t)sys * 100 * g1.G;
-    for (int idx = lane; idx < 81; idx += 32) {
-        const int I = idx / 9, J = idx % 9;
-        double wI = 0, wJ = 0;
+    // coarse nodes of the 3x3 window that carry weight (4 for an element inside one cell, up to 9): only their
+    // pairs are formed, one pair per lane
+    double wsum = 0.0;
+    if (lane < 9) {
 #pragma unroll
-        for (int a = 0; a < 6; ++a) { wI += s_W[w][a][I]; wJ += s_W[w][a][J]; }
-        if (wI == 0.0 || wJ == 0.0) continue;
+        for (int a = 0; a < 6; ++a) wsum += s_W[w][a][lane];
+    }
+    const unsigned am = __ballot_sync(0xffffffffu, lane < 9 && wsum != 0.0);
+    const int na = __popc(am);
+    for (int pr = lane; pr < na * na; pr += 32) {
+        const int I = __fns(am, 0, pr / na + 1), J = __fns(am, 0, pr % na + 1);
         int Ii = imin + I % 3, Ij = jmin + I / 3, Ji = imin + J % 3, Jj = jmin + J / 3;
         int nI, nJ;
         if (!grid_node(g1, Ii, Ij, nI) || !grid_node(g1, Ji, Jj, nJ)) continue;
@@ -1382,6 +1387,59 @@ k_rhs(int n_elem, int K, const int* __restrict__ elem_node, const unsigned char*
                 atomicAdd(b + ((size_t)rb * K + k) * 2, -(Kb[0] * g0 + Kb[2] * g1));
                 atomicAdd(b + ((size_t)rb * K + k) * 2 + 1, -(Kb[1] * g0 + Kb[3] * g1));
             }
+        }
+    }
+}
+
+// Load vector without Dirichlet data (lin with zero fluctuation, per): b = -int B^T D eps in closed form per node.
+// Thread per (element, node): 5 elements per warp, no idle element lanes.
+__global__ void __launch_bounds__(256)
+k_rhs_load(int n_elem, int K, const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
+           const int* __restrict__ elem_sys, const double* __restrict__ node_xy, const int* __restrict__ node_row,
+           const double* __restrict__ eps_eff, double* __restrict__ b, double* __restrict__ sc, Mat8 mat) {
+    __shared__ double s_mat[8];
+    if (threadIdx.x < 8) s_mat[threadIdx.x] = mat.v[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    const int slot = lane / 6, a = lane - 6 * slot;
+    const long long e = ((long long)blockIdx.x * 8 + wv) * 5 + slot;
+    const bool valid = lane < 30 && e < n_elem;
+    const int sys0 = __shfl_sync(0xffffffffu, valid ? elem_sys[e] : -1, 0);
+    if (sys0 < 0) return;                                   // whole warp past the end
+    const int sys = valid ? elem_sys[e] : sys0;
+    const bool uniform = __all_sync(0xffffffffu, sys == sys0);
+    double gx = 0.0, gy = 0.0, lam = 0.0, mu = 0.0;
+    int row = -1;
+    if (valid) {
+        const int* en = elem_node + 6 * (size_t)e;
+        const int n0 = en[0], n1 = en[1], n2 = en[2];
+        TriGeom g;
+        tri_geom(node_xy[2 * (size_t)n0], node_xy[2 * (size_t)n0 + 1], node_xy[2 * (size_t)n1], node_xy[2 * (size_t)n1 + 1],
+                 node_xy[2 * (size_t)n2], node_xy[2 * (size_t)n2 + 1], g);
+        p2_grad_int(g, a, gx, gy);
+        row = node_row[en[a]];
+        const int reg = elem_reg[e];
+        lam = s_mat[2 * reg]; mu = s_mat[2 * reg + 1];
+    }
+    for (int k = 0; k < K; ++k) {
+        const double* ev = eps_eff + 3 * ((size_t)sys * K + k);
+        const double s00 = (lam + 2 * mu) * ev[0] + lam * ev[1];
+        const double s11 = lam * ev[0] + (lam + 2 * mu) * ev[1];
+        const double s01 = mu * ev[2];
+        const double f0 = -(s00 * gx + s01 * gy), f1 = -(s01 * gx + s11 * gy);
+        double m2 = 0.0;
+        if (row >= 0) {
+            atomicAdd(b + ((size_t)row * K + k) * 2, f0);
+            atomicAdd(b + ((size_t)row * K + k) * 2 + 1, f1);
+            m2 = f0 * f0 + f1 * f1;
+        }
+        // reference magnitude of the load before cancellation (absolute convergence floor)
+        double* dst = sc + ((size_t)sys * 4 + k) * SC_N + SC_BREF;
+        if (uniform) {
+            m2 = warp_sum(m2);
+            if (lane == 0) atomicAdd(dst, m2);
+        } else if (row >= 0) {
+            atomicAdd(dst, m2);
         }
     }
 }
