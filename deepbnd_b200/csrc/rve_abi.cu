@@ -2,6 +2,7 @@
 // Host side: batch set-up, uploads, the PCG driver loop, epilogue downloads.  No torch types, no
 // CPU fallback: every entry point fails with RVE_E_CUDA if the device is unusable.
 #include <cuda_runtime.h>
+#include <malloc.h>
 
 #include <chrono>
 #include <cstdio>
@@ -257,6 +258,15 @@ int rve_create(int device, rve_handle_t* out) {
     }
     if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return RVE_E_ARG; }
     if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return RVE_E_CUDA; }
+    // the symbolic phase allocates and frees several MB of work vectors per RVE on every call: keep freed
+    // memory in the process heap (no mmap/munmap round trips, no page faults on re-use)
+    static bool heap_tuned = false;
+    if (!heap_tuned) {
+        mallopt(M_MMAP_THRESHOLD, 1 << 30);
+        mallopt(M_TRIM_THRESHOLD, 1 << 30);
+        mallopt(M_TOP_PAD, 64 << 20);
+        heap_tuned = true;
+    }
     rve_batch_s* h = new rve_batch_s();
     h->device = device;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -297,8 +307,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     h->n_sys = n_sys; h->model = model; h->vref_nb = vref_nb;
     h->nvref = vref_nb > 0 ? 4 * (vref_nb - 1) + 1 : 0;
     for (int k = 0; k < 8; ++k) h->mat.v[k] = mat[k];
-    h->sym.clear();
-    h->sym.resize(n_sys);
+    h->sym.resize(n_sys);                      // keeps the vectors (and their capacity) of earlier batches
     std::vector<SysSym>& S = h->sym;
     parallel_for(n_sys, [&](int s) {
         sym_pass1(S[s], xy + 2 * vert_off[s], tri + 3 * tri_off[s], region + tri_off[s],

@@ -77,6 +77,8 @@ struct SymParams {
 
 // pass 1: everything that does not depend on the level-1 grid
 static void sym_pass1(SysSym& S, const double* xy, const int* tri, const int* region, int nv, int nt) {
+    // S may be a re-used object of an earlier batch (its vectors keep their capacity): reset the appended lists
+    S.err.clear(); S.bedge.clear(); S.bedge_nl.clear(); S.bnd_node.clear();
     S.nv = nv; S.nt = nt;
     S.tri.assign(tri, tri + 3 * (size_t)nt);
     int rmin = 1 << 30;

@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""End-to-end example of the drop-in chain on synthetic data (one GPU):
+
+  paramRVEdataset.hd5  --buildSnapshots-->  snapshots_0.hd5  --build_inout (ops 0-3)-->  Wbasis.hd5, XY.hd5
+  paramRVEdataset.hd5  --predictTangents (lin / per / MR)-->  tangents_<model>.hd5
+
+  python examples/run_pipeline.py [out_dir] [n_snapshots] [n_tangents]
+
+File names and dataset layouts are the reference's (creation_model/dataset/simulation_snapshots.py,
+creation_model/RB/build_inout.py, creation_model/prediction/tangents_prediction.py)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    out = sys.argv[1] if len(sys.argv) > 1 else "pipeline_out"
+    ns = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    nt = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+    os.makedirs(os.path.join(out, "meshes"), exist_ok=True)
+    from conftest import synthetic_param
+    import deepbnd_b200.wrapper_h5py as myhd
+    from deepbnd_b200.simulation_snapshots import buildSnapshots
+    from deepbnd_b200.tangents_prediction import predictTangents
+    import deepbnd_b200.build_inout as bio
+
+    param = [0.3, 10.0, 0.3, 1.0]
+    p_snap, p_tan = os.path.join(out, "paramRVEdataset.hd5"), os.path.join(out, "paramRVEdataset_tangents.hd5")
+    myhd.savehd5(p_snap, synthetic_param(ns, seed=13), 'param', 'w')
+    myhd.savehd5(p_tan, synthetic_param(nt, seed=2), 'param', 'w')
+
+    t = time.perf_counter()
+    snaps = os.path.join(out, "snapshots_0.hd5")
+    buildSnapshots(param, ["", p_snap, snaps, os.path.join(out, "meshes", "mesh_temp_0.xdmf")], 'per', True, 0, 1, None,
+                   device=0, batch_size=256)
+    print("snapshots: %d full RVEs in %.1f s (meshing included)" % (ns, time.perf_counter() - t))
+
+    Nmax = min(160, ns - 2)
+    wb, yl, xy = (os.path.join(out, n) for n in ("Wbasis.hd5", "Y.h5", "XY.hd5"))
+    bio.translateSolution(snaps)
+    bio.computingBasis(snaps, wb, Nmax)
+    bio.extractAlpha(snaps, wb, Nmax, yl)
+    bio.createXY(p_snap, yl, xy)
+    print("RB stage: sig_A[:4] =", myhd.loadhd5(wb, 'sig_A')[:4], " XY:", myhd.loadhd5(xy, 'Y_A').shape)
+
+    for model in ("lin", "per", "MR"):
+        t = time.perf_counter()
+        tf = os.path.join(out, "tangents_%s.hd5" % model)
+        predictTangents(0, 1, model, ["", p_tan, tf, "", os.path.join(out, "meshes", "mesh_micro_{0}_{1}.xdmf")],
+                        model == "lin", 'reduced', device=0)
+        C = myhd.loadhd5(tf, 'tangent')
+        print("tangents %-3s: %d reduced RVEs in %.1f s; mean C11 = %.5f" % (model, nt, time.perf_counter() - t, C[:, 0, 0].mean()))
+
+
+if __name__ == "__main__":
+    main()
