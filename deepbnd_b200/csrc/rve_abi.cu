@@ -262,7 +262,7 @@ int rve_create(int device, rve_handle_t* out) {
     // memory in the process heap (no mmap/munmap round trips, no page faults on re-use)
     static bool heap_tuned = false;
     if (!heap_tuned) {
-        mallopt(M_MMAP_THRESHOLD, 1 << 30);
+        mallopt(M_MMAP_THRESHOLD, 32 << 20);   // glibc's upper limit for the threshold
         mallopt(M_TRIM_THRESHOLD, 1 << 30);
         mallopt(M_TOP_PAD, 64 << 20);
         heap_tuned = true;

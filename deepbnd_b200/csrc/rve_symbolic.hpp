@@ -363,13 +363,13 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
     S.max_tile = 0; S.max_cn = 0;
     const int nxg = ncx + 1;
     auto cnode = [&](int i, int j) -> int {   // same validity rules as grid_node() on the device
-        if (P.model == RVE_MODEL_PER) { i = ((i % ncx) + ncx) % ncx; j = ((j % ncy) + ncy) % ncy; return j * nxg + i; }
+        if (P.model == RVE_MODEL_PER) { if (i >= ncx) i -= ncx; if (j >= ncy) j -= ncy; return j * nxg + i; }   // i in [0, ncx], j in [0, ncy]
         const int lo = (P.model == RVE_MODEL_MR) ? 0 : 1, hix = (P.model == RVE_MODEL_MR) ? ncx : ncx - 1,
                   hiy = (P.model == RVE_MODEL_MR) ? ncy : ncy - 1;
         if (i < lo || i > hix || j < lo || j > hiy) return -1;
         return j * nxg + i;
     };
-    std::vector<int> hal, cns, hpos(na, -1), cpos((size_t)nxg * (ncy + 1), -1), ccount, cfill;
+    std::vector<int> hal, cns, hpos(P.lite ? 0 : na, -1), cpos((size_t)nxg * (ncy + 1), -1), ccount, cfill;
     std::vector<int> corner(4 * (size_t)RVE_WIN);
     for (int w = 0; w < nwin; ++w) {
         const int r0 = w * RVE_WIN, r1 = std::min(na, r0 + RVE_WIN), wn = r1 - r0;
