@@ -3,7 +3,9 @@ snapshots.hd5: (0) translateSolution, (1) computingBasis -> Wbasis.hd5, (2) extr
 Same file/dataset names; the dolfin pieces (Vref functions, the ds mass matrix) are replaced by their closed
 forms on the library's Vref order (deepbnd_b200/vref.py).  The dense algebra (SVD of the ns x 162 snapshot
 matrix, the projections) runs in fp64 through torch on the GPU when one is present, on the CPU otherwise —
-library calls, this stage is not part of the hand-written hot path."""
+library calls, this stage is not part of the hand-written hot path.  The device is "cuda"
+unless the caller asks for "cpu" explicitly (module attribute DEVICE or the `device` arguments): there is no
+silent fallback."""
 import os
 
 import numpy as np
@@ -13,9 +15,15 @@ from .simulation_snapshots import vref_box_from_mesh
 from .vref import vref_mass, vref_points
 
 
-def _dev():
+DEVICE = "cuda"
+
+
+def _dev(device=None):
     import torch
-    return torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+    d = torch.device(device or DEVICE)
+    if d.type == "cuda" and not torch.cuda.is_available():
+        raise RuntimeError("deepbnd_b200.build_inout: no CUDA device (pass device='cpu' explicitly to run the RB algebra on the host)")
+    return d
 
 
 def getMassMatrix(nameMeshRefBnd=None):
@@ -31,11 +39,11 @@ def translateSolution(nameSnaps, nameMeshRefBnd=None):
         myhd.addDataset(nameSnaps, trans, 'solutions_trans_partial_%s' % load_flag)
 
 
-def computingBasis_svd(Isol, M, Nmax):
+def computingBasis_svd(Isol, M, Nmax, device=None):
     """RB_utils.computingBasis_svd (:134-157): Msqrt from the SVD of M, thin SVD of Isol Msqrt,
     Wbasis[i] = (U[:, i] / sig[i])^T Isol; returns (Wbasis (Nmax, Nh), sig**2)."""
     import torch
-    dev = _dev()
+    dev = _dev(device)
     UM, SM, VMT = np.linalg.svd(M)
     Msqrt = (UM[:, :len(SM)] * np.sqrt(SM)) @ VMT
     I = torch.from_numpy(np.ascontiguousarray(Isol)).to(dev)
@@ -44,36 +52,36 @@ def computingBasis_svd(Isol, M, Nmax):
     return W.cpu().numpy(), (sig ** 2).cpu().numpy()
 
 
-def computingBasis(nameSnaps, nameWbasis, Nmax, Nh=None, nameMeshRefBnd=None):
+def computingBasis(nameSnaps, nameWbasis, Nmax, Nh=None, nameMeshRefBnd=None, device=None):
     if os.path.exists(nameWbasis):
         os.remove(nameWbasis)
     M = getMassMatrix(nameMeshRefBnd)
     out = {'massMat': M}
     for load_flag in ['A', 'S']:
         Isol = myhd.loadhd5(nameSnaps, 'solutions_trans_partial_%s' % load_flag)
-        W, sig2 = computingBasis_svd(Isol, M, Nmax)
+        W, sig2 = computingBasis_svd(Isol, M, Nmax, device)
         out['Wbasis_%s' % load_flag] = W
         out['sig_%s' % load_flag] = sig2[:Nmax]
     labels = ['Wbasis_A', 'Wbasis_S', 'sig_A', 'sig_S', 'massMat']
     myhd.savehd5(nameWbasis, [out[l] for l in labels], labels, 'w')
 
 
-def getAlphas_fast(Wbasis_M, Isol, Nmax):
+def getAlphas_fast(Wbasis_M, Isol, Nmax, device=None):
     """RB_utils.getAlphas_fast (:211-213): Isol M Wbasis[:Nmax]^T."""
     import torch
-    dev = _dev()
+    dev = _dev(device)
     W, M = Wbasis_M
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     return (t(Isol) @ t(M) @ t(W[:Nmax]).T).cpu().numpy()
 
 
-def extractAlpha(nameSnaps, nameWbasis, Nmax, nameYlist):
+def extractAlpha(nameSnaps, nameWbasis, Nmax, nameYlist, device=None):
     if os.path.exists(nameYlist):
         os.remove(nameYlist)
     for load_flag in ['A', 'S']:
         Wbasis_M = myhd.loadhd5(nameWbasis, ['Wbasis_%s' % load_flag, 'massMat'])
         Isol = myhd.loadhd5(nameSnaps, 'solutions_trans_partial_%s' % load_flag)
-        Ylist = getAlphas_fast(Wbasis_M, Isol, Nmax)
+        Ylist = getAlphas_fast(Wbasis_M, Isol, Nmax, device)
         if os.path.exists(nameYlist):
             myhd.addDataset(nameYlist, Ylist, 'Ylist_%s' % load_flag)
         else:

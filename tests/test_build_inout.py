@@ -26,7 +26,7 @@ def _fake_snapshots(path, ns=300, seed=0):
     return data
 
 
-def test_build_inout_pipeline_matches_numpy_restatement(tmp_path):
+def test_build_inout_pipeline_matches_numpy_restatement(tmp_path, device="cpu"):
     import deepbnd_b200.wrapper_h5py as myhd
     import deepbnd_b200.build_inout as bio
     from oracle import rb_oracle
@@ -37,8 +37,8 @@ def test_build_inout_pipeline_matches_numpy_restatement(tmp_path):
     myhd.savehd5(pr, np.random.RandomState(1).rand(ns, 36, 5), 'param', 'w')
     Nmax = 60
     bio.translateSolution(snaps)
-    bio.computingBasis(snaps, wb, Nmax)
-    bio.extractAlpha(snaps, wb, Nmax, yl)
+    bio.computingBasis(snaps, wb, Nmax, device=device)
+    bio.extractAlpha(snaps, wb, Nmax, yl, device=device)
     bio.createXY(pr, yl, xy)
     M = vref_mass(vref_points(-1, -1, 2, 2, 21))
     assert np.abs(myhd.loadhd5(wb, 'massMat') - M).max() < 1e-15
@@ -69,4 +69,13 @@ def test_build_inout_pipeline_matches_numpy_restatement(tmp_path):
 def test_build_inout_pipeline_on_the_gpu(tmp_path):
     import torch
     assert torch.cuda.is_available()
-    test_build_inout_pipeline_matches_numpy_restatement(tmp_path)
+    test_build_inout_pipeline_matches_numpy_restatement(tmp_path, device="cuda")
+
+
+def test_build_inout_has_no_silent_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import deepbnd_b200.build_inout as bio
+    with pytest.raises(RuntimeError):
+        bio.getAlphas_fast((np.eye(4), np.eye(4)), np.ones((2, 4)), 2)
