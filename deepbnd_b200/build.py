@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "rve_abi.cu")
 DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("rve_kernels.cuh", "rve_math.cuh", "rve_symbolic.hpp")] + \
        [os.path.join(HERE, "..", "include", "rve_b200.h")]
-LIB = os.path.join(HERE, "lib", "librve_b200.so")
+LIB = os.environ.get("DEEPBND_RVE_LIB") or os.path.join(HERE, "lib", "librve_b200.so")   # override: kernel-variant experiments
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-pthread", "-shared"]

@@ -197,7 +197,7 @@ static void launch_spmv(rve_batch_s* h, const PcgArgs& a, const double* p, doubl
 
 template <int K>
 static void launch_update(rve_batch_s* h, const PcgArgs& a, int init, int iter, cudaStream_t st) {
-    k_update<K><<<a.n_win, RVE_VEC_THREADS(K), a.sm_upd, st>>>(a.wt, (const double2*)h->p.p, (const double2*)h->q.p, (double2*)h->x.p,
+    k_update<K><<<a.n_win, RVE_UPD_THREADS(K), a.sm_upd, st>>>(a.wt, (const double2*)h->p.p, (const double2*)h->q.p, (double2*)h->x.p,
                                                    (double2*)h->r.p, h->dinv.p, h->rowinfo.p, h->cn_node.p, h->cn_beg.p,
                                                    h->cn_ent.p, a.LV.rc[0], a.LV.g[0].G, h->active.p, h->part.p, h->cnt.p,
                                                    h->sc.p, init, iter, a.rtol2, a.precond, h->d_iters.p, h->n_active.p);
@@ -233,7 +233,7 @@ static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStrea
 
 template <int K>
 static void launch_direction(rve_batch_s* h, const PcgArgs& a, cudaStream_t st) {
-    k_direction<K><<<a.n_win, RVE_VEC_THREADS(K), a.sm_dir, st>>>(a.wt, (double2*)h->p.p, (const double2*)h->r.p, h->dinv.p, h->rowinfo.p,
+    k_direction<K><<<a.n_win, RVE_DIR_THREADS(K), a.sm_dir, st>>>(a.wt, (double2*)h->p.p, (const double2*)h->r.p, h->dinv.p, h->rowinfo.p,
                                                       h->cn_node.p, (const double2*)a.LV.tc[0], a.LV.g[0].G, h->active.p,
                                                       h->sc.p, a.precond);
 }

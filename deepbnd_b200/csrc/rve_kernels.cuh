@@ -647,18 +647,24 @@ k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __re
 // convergence test by the last CTA of the system.  Thread = one (row, rhs) pair, flat and coalesced.
 // elements (row, rhs) per thread of the vector kernels: measured best is 2 for K = 2 (256-thread CTAs) and
 // 1 for K = 1, 3 (256 / 768-thread CTAs); all of a thread's loads are issued before the first use
-#define RVE_EPT(K) ((K) == 2 ? 2 : 1)
-#define RVE_VEC_THREADS(K) (RVE_WIN * (K) / RVE_EPT(K))
+#ifndef RVE_EPT_UPD
+#define RVE_EPT_UPD(K) ((K) == 2 ? 2 : 1)
+#endif
+#ifndef RVE_EPT_DIR
+#define RVE_EPT_DIR(K) ((K) == 2 ? 2 : 1)
+#endif
+#define RVE_UPD_THREADS(K) (RVE_WIN * (K) / RVE_EPT_UPD(K))
+#define RVE_DIR_THREADS(K) (RVE_WIN * (K) / RVE_EPT_DIR(K))
 
 template <int K>
-__global__ void __launch_bounds__(RVE_VEC_THREADS(K), (K == 1 ? 5 : (K == 2 ? 4 : 2)))
+__global__ void __launch_bounds__(RVE_UPD_THREADS(K), (K == 1 ? 5 : (RVE_UPD_THREADS(K) <= 256 ? 4 : 2)))
 k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q, double2* __restrict__ x,
          double2* __restrict__ r, const float4* __restrict__ dinv32, const RowInfo* __restrict__ rowinfo,
          const int* __restrict__ cn_node, const unsigned* __restrict__ cn_beg, const uint16_t* __restrict__ cn_ent,
          double* __restrict__ rc1, int G, int* active, double* part, int* cnt, double* sc, int init, int iter,
          double rtol2, int precond, int* iters, int* n_active) {
     extern __shared__ double2 s_r[];              // [n*K] new residual, then float2 s_st[n], uint16 s_ent[4n]
-    constexpr int EPT = RVE_EPT(K), TPB = RVE_VEC_THREADS(K);   // TPB % K == 0: a thread keeps its rhs index
+    constexpr int EPT = RVE_EPT_UPD(K), TPB = RVE_UPD_THREADS(K);   // TPB % K == 0: a thread keeps its rhs index
     const int win = blockIdx.x;
     const int sys = wt.win_sys[win];
     if (!active[sys]) return;
@@ -1169,12 +1175,12 @@ k_vc_up1(Levels LV, const int* __restrict__ active, double* sc, double* part, in
 // p = Dinv r + Z xc1 + beta p     (thread = one (row, rhs) pair; the level-1 values the window
 // touches are staged in shared memory)
 template <int K>
-__global__ void __launch_bounds__(RVE_VEC_THREADS(K), (K == 1 ? 5 : (K == 2 ? 4 : 2)))
+__global__ void __launch_bounds__(RVE_DIR_THREADS(K), (K == 1 ? 5 : (RVE_DIR_THREADS(K) <= 256 ? 4 : 2)))
 k_direction(WinTab wt, double2* __restrict__ p, const double2* __restrict__ r, const float4* __restrict__ dinv32,
             const RowInfo* __restrict__ rowinfo, const int* __restrict__ cn_node, const double2* __restrict__ xc1,
             int G, const int* __restrict__ active, const double* __restrict__ sc, int precond) {
     extern __shared__ double2 s_xc[];             // [ncn*K]
-    constexpr int EPT = RVE_EPT(K), TPB = RVE_VEC_THREADS(K);
+    constexpr int EPT = RVE_EPT_DIR(K), TPB = RVE_DIR_THREADS(K);
     const int win = blockIdx.x;
     const int sys = wt.win_sys[win];
     if (!active[sys]) return;
