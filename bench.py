@@ -185,7 +185,9 @@ def main():
     ncpu = os.cpu_count() or 1
     nproc_local = max(1, ncpu // max(1, world))
     if world > 1:                                   # ranks share the host cores of the box
-        os.environ.setdefault("RVE_HOST_THREADS", str(max(1, ncpu // world - 1)))
+        os.environ.setdefault("RVE_HOST_THREADS", str(max(1, ncpu // world)))
+        if ncpu // world < 8:
+            os.environ.setdefault("RVE_BLOCKING_SYNC", "1")   # few cores per rank: the kernel-feeding thread sleeps while it waits
     from conftest import synthetic_param, smooth_uD
 
     if args.impl == "reference":

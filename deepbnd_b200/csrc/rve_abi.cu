@@ -78,6 +78,7 @@ struct rve_batch_s {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_block = nullptr;   // cudaEventBlockingSync
     // host-side batch description
     int n_sys = 0, model = 0, vref_nb = 0, nvref = 0;
     bool have_batch = false, assembled = false, solved = false;
@@ -135,6 +136,17 @@ struct rve_batch_s {
     } while (0)
 
 #define FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
+
+// wait for the handle's stream
+static cudaError_t stream_wait(rve_batch_s* h) {
+    // RVE_BLOCKING_SYNC=1: sleep instead of spinning (a few % slower per wait, but it frees a core per rank when
+    // several ranks share few host cores); default: spin
+    static const bool blocking = [] { const char* e = std::getenv("RVE_BLOCKING_SYNC"); return e && e[0] == '1'; }();
+    if (!blocking) return cudaStreamSynchronize(h->stream);
+    cudaError_t e = cudaEventRecord(h->ev_block, h->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(h->ev_block);
+}
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -273,6 +285,7 @@ int rve_create(int device, rve_handle_t* out) {
         g_create_err = cudaGetErrorString(e); delete h; return RVE_E_CUDA;
     }
     for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+    cudaEventCreateWithFlags(&h->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
     cudaMallocHost((void**)&h->h_nactive, sizeof(int));
     memset(&h->LV, 0, sizeof(Levels));
     *out = h;
@@ -284,6 +297,7 @@ int rve_destroy(rve_handle_t h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->ev_block) cudaEventDestroy(h->ev_block);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
     h->arena.release();
@@ -374,7 +388,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         add(3 * h->NBE, 4); add(nvs, 4); for (int k = 0; k < 4; ++k) add(n_win, 4);
         add(n_win + 1, 4); add(h->adjf_base[n_sys], 4); add(n_cn, 4); add(h->E, 1); add(h->R + 1, 4); add(h->R + 1, 4);
         add(n_slice + 1, 4); add(n_cn + 1, 4); add(h->ent_base[n_sys], 2); add(h->R, sizeof(RowInfo));
-        CU(cudaStreamSynchronize(h->stream));          // the previous batch's copies out of the arena are done
+        CU(stream_wait(h));          // the previous batch's copies out of the arena are done
         CU(h->arena.reserve(bytes));
     }
     PinnedArena& AR = h->arena;
@@ -511,7 +525,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     }
     int scnt[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(h));
     CU(cudaGetLastError());
     if (scnt[2] == 2) FAIL(RVE_E_MESH, "device pattern build: row length mismatch");
     if (scnt[2] == 3) FAIL(RVE_E_MESH, "device pattern build: halo list overflow");
@@ -553,7 +567,7 @@ int rve_assemble(rve_handle_t h) {
     CU(cudaEventRecord(h->ev[2], st));
     int flag = 0;
     CU(cudaMemcpyAsync(&flag, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(h));
     CU(cudaGetLastError());
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[2] = ms;
@@ -760,7 +774,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
             h->launches += 3;
         }
         CU(cudaMemcpyAsync(h->h_nactive, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CU(stream_wait(h));
         if (*h->h_nactive <= 0) break;
     }
     CU(cudaEventRecord(h->ev[2], st));
@@ -774,7 +788,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     std::vector<int> hit(n_sys), hact(n_sys);
     CU(cudaMemcpyAsync(hit.data(), h->d_iters.p, n_sys * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(hact.data(), h->active.p, n_sys * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(h));
     CU(cudaGetLastError());
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[4] = ms;
@@ -836,7 +850,7 @@ int rve_epilogue_tangent(rve_handle_t h, double* C) {
     std::vector<double> s((size_t)h->n_sys * 9);
     CU(cudaMemcpyAsync(s.data(), h->sigL.p, s.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     h->d2h_bytes += (double)s.size() * sizeof(double);
-    CU(cudaStreamSynchronize(h->stream));
+    CU(stream_wait(h));
     CU(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[7] = ms;
     for (int sys = 0; sys < h->n_sys; ++sys)
@@ -859,7 +873,7 @@ int rve_epilogue_snapshot(rve_handle_t h, double* sol, double* sigma, double* a,
     if (sigmaT) CU(cudaMemcpyAsync(sigmaT, h->sigT.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (a) CU(cudaMemcpyAsync(a, h->aout.p, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (B) CU(cudaMemcpyAsync(B, h->Bout.p, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(h));
     CU(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[7] = ms;
     return 0;
@@ -885,7 +899,7 @@ int rve_epilogue_homogenisation(rve_handle_t h, double* sigmaL, double* sigmaT, 
     if (gradT) CU(cudaMemcpyAsync(gradT, h->gradT.p, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (eps_eff) CU(cudaMemcpyAsync(eps_eff, h->eps_eff.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     h->d2h_bytes += (double)n * sizeof(double) * ((sigmaL ? 3 : 0) + (sigmaT ? 3 : 0) + (gradL ? 4 : 0) + (gradT ? 4 : 0) + (eps_eff ? 3 : 0));
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(h));
     CU(cudaGetLastError());
     if (gradL) for (size_t i = 0; i < 4 * n; ++i) gradL[i] = -bl[i];      // B = -average gradient
     float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->t_ms[7] = ms;
@@ -921,7 +935,7 @@ int rve_project(rve_handle_t h, int32_t nmax, int32_t nh, const double* W, const
     CU(cudaMemcpyAsync(Y, h->Yd.p, n * nmax * sizeof(double), cudaMemcpyDeviceToHost, st));
     h->d2h_bytes += (double)n * nmax * sizeof(double);
     h->h2d_bytes += (translate ? (double)n * 2 * sizeof(double) : 0.0);
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(h));
     CU(cudaGetLastError());
     return 0;
 }
@@ -963,7 +977,7 @@ int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_l
     for (int i = 0; i < reps; ++i) K_DISPATCH(K, SPMV_);
 #undef SPMV_
     CU(cudaEventRecord(h->ev[1], st));
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(h));
     CU(cudaGetLastError());
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
