@@ -102,7 +102,7 @@ struct rve_batch_s {
     DBuf<unsigned> slice_ptr, cn_beg;
     DBuf<uint16_t> scol, cn_ent;
     DBuf<unsigned> d_row_ptr, adjf_ptr;
-    DBuf<int> adjf, csr_col, win_nhalo, sym_cnt;
+    DBuf<int> adjf, csr_col, win_nhalo, win_ncn, row_node, sym_cnt;
     DBuf<unsigned char> emap;
     std::vector<long long> adjf_base;
     int max_words = 0;
@@ -169,7 +169,7 @@ static cudaError_t upload(DBuf<T>& d, const std::vector<T>& v, cudaStream_t s) {
 static WinTab win_tab(rve_batch_s* h) {
     WinTab wt;
     wt.win_sys = h->win_sys.p; wt.win_row0 = h->win_row0.p; wt.win_n = h->win_n.p; wt.win_slice0 = h->win_slice0.p;
-    wt.win_halo0 = h->win_halo0.p; wt.win_nhalo = h->win_nhalo.p; wt.win_cn0 = h->win_cn0.p; wt.sys_win0 = h->sys_win0.p; wt.row_base = h->d_row_base.p;
+    wt.win_halo0 = h->win_halo0.p; wt.win_nhalo = h->win_nhalo.p; wt.win_cn0 = h->win_cn0.p; wt.win_ncn = h->win_ncn.p; wt.sys_win0 = h->sys_win0.p; wt.row_base = h->d_row_base.p;
     return wt;
 }
 
@@ -360,22 +360,19 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         long long nb = h->blk_base[s] + (long long)S[s].nblocks;
         long long ng = h->grp_base[s] + (long long)S[s].slice_ptr.back();
         long long nh = h->adjf_base[s] + (long long)S[s].adjf.size();
-        long long nent = h->ent_base[s] + (long long)S[s].cn_ent.size();
-        if (nn > 2000000000LL || ne > 2000000000LL || nr * 4 > 2000000000LL || ng > 4000000000LL || nh > 2000000000LL ||
-            nent > 4000000000LL)
+        if (nn > 2000000000LL || ne > 2000000000LL || nr * 4 > 2000000000LL || ng > 4000000000LL || nh > 2000000000LL )
             FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
         h->node_base[s + 1] = (int)nn; h->elem_base[s + 1] = (int)ne; h->row_base[s + 1] = (int)nr;
         h->bnd_base[s + 1] = h->bnd_base[s] + S[s].nb; h->bedge_base[s + 1] = h->bedge_base[s] + S[s].nbe;
-        h->blk_base[s + 1] = nb; h->grp_base[s + 1] = ng; h->adjf_base[s + 1] = nh; h->ent_base[s + 1] = nent;
+        h->blk_base[s + 1] = nb; h->grp_base[s + 1] = ng; h->adjf_base[s + 1] = nh;
         h->win_base[s + 1] = h->win_base[s] + S[s].nwin;
         h->slice_base[s + 1] = h->slice_base[s] + (int)S[s].slice_ptr.size() - 1;
-        h->cn_base[s + 1] = h->cn_base[s] + (int)S[s].cn_node.size();
-        h->max_cn = std::max(h->max_cn, S[s].max_cn); h->max_words = std::max(h->max_words, (S[s].na + 31) / 32);
+        h->max_words = std::max(h->max_words, (S[s].na + 31) / 32);
     }
     h->N = h->node_base[n_sys]; h->E = h->elem_base[n_sys]; h->R = h->row_base[n_sys];
     h->NB = h->blk_base[n_sys]; h->NBN = h->bnd_base[n_sys]; h->NBE = h->bedge_base[n_sys];
     h->NG = h->grp_base[n_sys]; h->n_win = h->win_base[n_sys];
-    const int n_win = h->n_win, n_slice = h->slice_base[n_sys], n_cn = h->cn_base[n_sys];
+    const int n_win = h->n_win, n_slice = h->slice_base[n_sys];
 
     // flatten (parallel over systems) straight into the pinned staging arena
     const size_t nvs = (size_t)n_sys * h->nvref;
@@ -386,8 +383,8 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         add(2 * h->N, 8); add(4 * (size_t)n_sys, 8); add(n_bnds, 8); add(2 * h->NBE, 8); add(2 * nvs, 8);
         add(h->N, 4); add(h->N, 4); add(h->N, 4); add(6 * h->E, 4); add(h->E, 4); add(h->NBN, 4); add(h->NBN, 4);
         add(3 * h->NBE, 4); add(nvs, 4); for (int k = 0; k < 4; ++k) add(n_win, 4);
-        add(n_win + 1, 4); add(h->adjf_base[n_sys], 4); add(n_cn, 4); add(h->E, 1); add(h->R + 1, 4); add(h->R + 1, 4);
-        add(n_slice + 1, 4); add(n_cn + 1, 4); add(h->ent_base[n_sys], 2); add(h->R, sizeof(RowInfo));
+        add(h->adjf_base[n_sys], 4); add(h->R, 4); add(h->E, 1); add(h->R + 1, 4); add(h->R + 1, 4);
+        add(n_slice + 1, 4);
         CU(stream_wait(h));          // the previous batch's copies out of the arena are done
         CU(h->arena.reserve(bytes));
     }
@@ -398,13 +395,11 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
               elem_node = AR.take<int>(6 * h->E), elem_sys = AR.take<int>(h->E), bnd_sys = AR.take<int>(h->NBN),
               bnd_node = AR.take<int>(h->NBN), bedge = AR.take<int>(3 * h->NBE), samp_elem = AR.take<int>(nvs),
               win_sys = AR.take<int>(n_win), win_row0 = AR.take<int>(n_win), win_n = AR.take<int>(n_win),
-              win_slice0 = AR.take<int>(n_win), win_cn0 = AR.take<int>(n_win + 1),
-              adjf = AR.take<int>(h->adjf_base[n_sys]), cn_node = AR.take<int>(n_cn);
+              win_slice0 = AR.take<int>(n_win), row_node = AR.take<int>(h->R),
+              adjf = AR.take<int>(h->adjf_base[n_sys]);
     Span<unsigned char> elem_reg = AR.take<unsigned char>(h->E);
-    Span<unsigned> slice_ptr = AR.take<unsigned>(n_slice + 1), cn_beg = AR.take<unsigned>(n_cn + 1),
+    Span<unsigned> slice_ptr = AR.take<unsigned>(n_slice + 1),
                    row_ptr = AR.take<unsigned>(h->R + 1), adjf_ptr = AR.take<unsigned>(h->R + 1);
-    Span<uint16_t> cn_ent = AR.take<uint16_t>(h->ent_base[n_sys]);
-    Span<RowInfo> rowinfo = AR.take<RowInfo>(h->R);
     parallel_for(n_sys, [&](int s) {
         const SysSym& Y = S[s];
         const int nb0 = h->node_base[s], eb0 = h->elem_base[s], rb0 = h->row_base[s];
@@ -419,14 +414,12 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
             for (int k = 0; k < 6; ++k) elem_node[6 * ((size_t)eb0 + t) + k] = nb0 + Y.elem_node[6 * t + k];
             elem_reg[eb0 + t] = Y.reg[t]; elem_sys[eb0 + t] = s;
         }
-        for (int r = 0; r < Y.na; ++r) rowinfo[(size_t)rb0 + r] = Y.rowinfo[r];
-        const int w0 = h->win_base[s], sl0 = h->slice_base[s], cb0 = h->cn_base[s];
+        for (int r = 0; r < Y.na; ++r) row_node[(size_t)rb0 + r] = nb0 + Y.row_node[r];
+        const int w0 = h->win_base[s], sl0 = h->slice_base[s];
         for (int w = 0; w < Y.nwin; ++w) {
             win_sys[w0 + w] = s; win_row0[w0 + w] = rb0 + w * RVE_WIN; win_n[w0 + w] = Y.win_n[w];
             win_slice0[w0 + w] = sl0 + Y.win_slice0[w];
-            win_cn0[w0 + w] = cb0 + Y.win_cn0[w];
         }
-        if (s == n_sys - 1) win_cn0[n_win] = n_cn;
         for (size_t k = 0; k + 1 < Y.slice_ptr.size(); ++k) slice_ptr[sl0 + k] = (unsigned)(h->grp_base[s] + Y.slice_ptr[k]);
         if (s == n_sys - 1) slice_ptr[n_slice] = (unsigned)h->NG;
         for (int r = 0; r < Y.na; ++r) {
@@ -435,9 +428,6 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         }
         if (s == n_sys - 1) { row_ptr[h->R] = (unsigned)h->NB; adjf_ptr[h->R] = (unsigned)h->adjf_base[n_sys]; }
         for (size_t k = 0; k < Y.adjf.size(); ++k) adjf[h->adjf_base[s] + k] = eb0 + Y.adjf[k];
-        for (size_t k = 0; k < Y.cn_node.size(); ++k) { cn_node[cb0 + k] = Y.cn_node[k]; cn_beg[cb0 + k] = (unsigned)(h->ent_base[s] + Y.cn_beg[k]); }
-        if (s == n_sys - 1) cn_beg[n_cn] = (unsigned)h->ent_base[n_sys];
-        std::copy(Y.cn_ent.begin(), Y.cn_ent.end(), cn_ent.begin() + h->ent_base[s]);
         for (int i = 0; i < Y.nb; ++i) {
             bnd_sys[h->bnd_base[s] + i] = s; bnd_node[h->bnd_base[s] + i] = nb0 + Y.bnd_node[i];
             if (model == RVE_MODEL_DNN) {
@@ -471,9 +461,8 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     UPL(h->bnd_s, bnd_s); UPL(h->bedge, bedge); UPL(h->bedge_nl, bedge_nl);
     UPL(h->d_bedge_base, h->bedge_base); UPL(h->samp_elem, samp_elem); UPL(h->samp_lam, samp_lam);
     UPL(h->win_sys, win_sys); UPL(h->win_row0, win_row0); UPL(h->win_n, win_n); UPL(h->win_slice0, win_slice0);
-    UPL(h->win_cn0, win_cn0); UPL(h->sys_win0, h->win_base);
-    UPL(h->slice_ptr, slice_ptr); UPL(h->cn_node, cn_node); UPL(h->d_row_ptr, row_ptr); UPL(h->adjf_ptr, adjf_ptr); UPL(h->adjf, adjf);
-    UPL(h->cn_beg, cn_beg); UPL(h->cn_ent, cn_ent); UPL(h->rowinfo, rowinfo);
+    UPL(h->sys_win0, h->win_base); UPL(h->row_node, row_node);
+    UPL(h->slice_ptr, slice_ptr); UPL(h->d_row_ptr, row_ptr); UPL(h->adjf_ptr, adjf_ptr); UPL(h->adjf, adjf);
     std::vector<double> vb(h->vref_box, h->vref_box + 4);
     UPL(h->d_vbox, vb);
     CU(h->bval.alloc(128 * (size_t)h->NG)); CU(h->dinv.alloc((size_t)h->R)); CU(h->wmean.alloc(h->R));
@@ -510,8 +499,11 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     const long long halo_cap = h->R + h->R / 2 + 4096;
     if (halo_cap > 2000000000LL) FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
     CU(h->csr_col.alloc((size_t)h->NB)); CU(h->emap.alloc(36 * (size_t)h->E)); CU(h->halo.alloc((size_t)halo_cap)); CU(h->scol.alloc((size_t)h->NG * 32));
-    CU(h->win_halo0.alloc(n_win)); CU(h->win_nhalo.alloc(n_win)); CU(h->sym_cnt.alloc(4));
-    CU(cudaMemsetAsync(h->sym_cnt.p, 0, 4 * sizeof(int), st));
+    CU(h->win_halo0.alloc(n_win)); CU(h->win_nhalo.alloc(n_win)); CU(h->sym_cnt.alloc(8));
+    CU(cudaMemsetAsync(h->sym_cnt.p, 0, 8 * sizeof(int), st));
+    const long long cn_cap = h->R + (long long)n_win + 4096;      // level-1 nodes touched per window are far fewer than its rows
+    CU(h->win_cn0.alloc(n_win)); CU(h->win_ncn.alloc(n_win)); CU(h->cn_node.alloc((size_t)cn_cap)); CU(h->cn_beg.alloc((size_t)cn_cap));
+    CU(h->cn_ent.alloc(4 * (size_t)h->R)); CU(h->rowinfo.alloc((size_t)h->R));
     {
         WinTab wt = win_tab(h);
         k_sym_cols<<<n_win, RVE_WIN, 0, st>>>(wt, h->d_row_ptr.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->node_row.p,
@@ -521,15 +513,21 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         CU(cudaFuncSetAttribute(k_sym_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         k_sym_window<<<n_win, RVE_WIN, sm, st>>>(wt, h->win_halo0.p, h->win_nhalo.p, h->d_row_ptr.p, h->csr_col.p, h->slice_ptr.p,
                                                   h->scol.p, h->halo.p, (int)halo_cap, h->sym_cnt.p);
-        h->launches += 2;
+        const size_t smc = 2 * (size_t)((LV.g[0].G + 31) / 32) * sizeof(unsigned);
+        if (smc > 150 * 1024) FAIL(RVE_E_MESH, "level-1 grid too large for the coarse-node bitmap in shared memory");
+        CU(cudaFuncSetAttribute(k_sym_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+        k_sym_coarse<<<n_win, RVE_WIN, smc, st>>>(wt, h->win_cn0.p, h->win_ncn.p, h->row_node.p, h->node_xy.p, h->box.p, LV.g[0],
+                                                  model, h->rowinfo.p, h->cn_node.p, h->cn_beg.p, h->cn_ent.p, (int)cn_cap, h->sym_cnt.p);
+        h->launches += 3;
     }
-    int scnt[4] = {0, 0, 0, 0};
-    CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    int scnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(stream_wait(h));
     CU(cudaGetLastError());
     if (scnt[2] == 2) FAIL(RVE_E_MESH, "device pattern build: row length mismatch");
     if (scnt[2] == 3) FAIL(RVE_E_MESH, "device pattern build: halo list overflow");
-    h->max_tile = scnt[1];
+    if (scnt[2] == 4) FAIL(RVE_E_MESH, "device pattern build: coarse-node list overflow");
+    h->max_tile = scnt[1]; h->max_cn = scnt[5];
     if ((size_t)h->max_tile * 3 * sizeof(double2) > 200 * 1024) FAIL(RVE_E_MESH, "window halo too large for shared memory");
     auto t2 = std::chrono::steady_clock::now();
     h->t_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();

@@ -56,7 +56,8 @@ struct WinTab {
     const int* win_slice0;   // global first slice (ceil(n/32) slices)
     const int* win_halo0;    // [n_win] offset of the window's halo list (segments are claimed on the device)
     const int* win_nhalo;    // [n_win] halo rows of the window
-    const int* win_cn0;      // [n_win+1] offsets into cn_node / cn_beg
+    const int* win_cn0;      // [n_win] offset of the window's coarse-node list (claimed on the device; ncn + 1 slots)
+    const int* win_ncn;      // [n_win] level-1 nodes the window touches
     const int* sys_win0;     // [n_sys+1]
     const int* row_base;     // [n_sys+1] first global row of a system
 };
@@ -227,6 +228,126 @@ k_sym_window(WinTab wt, int* __restrict__ win_halo0, int* __restrict__ win_nhalo
         }
         const uint16_t self = (uint16_t)(tid < n ? tid : 0);     // padding: zero block against a valid tile entry
         for (int j = len; j < width; ++j) sc[(size_t)j * 32] = self;
+    }
+}
+
+// Restriction / prolongation data of a window (fine rows <-> level-1 grid): bilinear position (s,t) of every row in
+// its coarse cell, the sorted list of level-1 nodes the window touches (bitmap + popcount ranks, like the halo), the
+// window-local slot of the 4 corners of every row, and per coarse node the (row, corner) pairs restricting to it
+// (counting sort in shared memory, each list then ordered so that the summation order is reproducible).
+// counters: [3] coarse-node slots used, [4] list entries used, [5] max nodes of a window
+__global__ void __launch_bounds__(RVE_WIN)
+k_sym_coarse(WinTab wt, int* __restrict__ win_cn0, int* __restrict__ win_ncn, const int* __restrict__ row_node,
+             const double* __restrict__ node_xy, const double* __restrict__ box, Grid g1, int model,
+             RowInfo* __restrict__ rowinfo, int* __restrict__ cn_node, unsigned* __restrict__ cn_beg,
+             uint16_t* __restrict__ cn_ent, int cn_cap, int* counters) {
+    extern __shared__ unsigned s_bm[];           // [words] bitmap of touched level-1 nodes, then [words] popcount prefix
+    __shared__ int s_scan[RVE_WIN];
+    __shared__ int s_base[2];
+    __shared__ int s_cnt[4 * RVE_WIN + 1];       // per-slot counts / offsets (ncn <= 4 * rows)
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const int sys = wt.win_sys[w];
+    const int words = (g1.G + 31) >> 5;
+    unsigned* s_pre = s_bm + words;
+    const int r0 = wt.win_row0[w], n = wt.win_n[w];
+    for (int i = tid; i < words; i += RVE_WIN) s_bm[i] = 0u;
+    for (int i = tid; i <= 4 * RVE_WIN; i += RVE_WIN) s_cnt[i] = 0;
+    __syncthreads();
+    int nd[4] = {-1, -1, -1, -1};
+    float fs = 0.f, ft = 0.f;
+    if (tid < n) {
+        const int node = row_node[r0 + tid];
+        int ci, cj; double s, t;
+        coarse_cell(node_xy[2 * (size_t)node], node_xy[2 * (size_t)node + 1], box[4 * sys], box[4 * sys + 1],
+                    g1.ncx / box[4 * sys + 2], g1.ncy / box[4 * sys + 3], g1.ncx, g1.ncy, ci, cj, s, t);
+        fs = (float)s; ft = (float)t;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int idx;
+            if (grid_node_fast(g1, ci + (c & 1), cj + (c >> 1), idx)) { nd[c] = idx; atomicOr(&s_bm[idx >> 5], 1u << (idx & 31)); }
+        }
+    }
+    __syncthreads();
+    const int wpt = (words + RVE_WIN - 1) / RVE_WIN;
+    const int wa = min(words, tid * wpt), wb = min(words, wa + wpt);
+    int sum = 0;
+    for (int i = wa; i < wb; ++i) sum += __popc(s_bm[i]);
+    s_scan[tid] = sum;
+    __syncthreads();
+    for (int d = 1; d < RVE_WIN; d <<= 1) {
+        const int v = tid >= d ? s_scan[tid - d] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    int run = s_scan[tid] - sum;
+    for (int i = wa; i < wb; ++i) { s_pre[i] = (unsigned)run; run += __popc(s_bm[i]); }
+    const int ncn = s_scan[RVE_WIN - 1];
+    __syncthreads();
+    // slots of the corners, per-slot counts
+    int slot[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        slot[c] = -1;
+        if (nd[c] >= 0) {
+            slot[c] = (int)s_pre[nd[c] >> 5] + __popc(s_bm[nd[c] >> 5] & ((1u << (nd[c] & 31)) - 1u));
+            atomicAdd(&s_cnt[slot[c] + 1], 1);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {                               // exclusive offsets (ncn is ~50-250)
+        for (int j = 0; j < ncn; ++j) s_cnt[j + 1] += s_cnt[j];
+        const int nent = s_cnt[ncn];
+        int c0 = atomicAdd(counters + 3, ncn + 1);
+        int e0 = atomicAdd(counters + 4, nent);
+        atomicMax(counters + 5, ncn);
+        if (c0 + ncn + 1 > cn_cap) { atomicExch(counters + 2, 4); c0 = -1; }
+        s_base[0] = c0; s_base[1] = e0;
+        win_cn0[w] = c0 < 0 ? 0 : c0;
+        win_ncn[w] = c0 < 0 ? 0 : ncn;
+    }
+    __syncthreads();
+    const int c0 = s_base[0], e0 = s_base[1];
+    if (c0 < 0) return;
+    for (int i = tid; i < words; i += RVE_WIN) {
+        unsigned bits = s_bm[i];
+        int pos = c0 + (int)s_pre[i];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            cn_node[pos++] = i * 32 + b;
+            bits &= bits - 1;
+        }
+    }
+    for (int j = tid; j <= ncn; j += RVE_WIN) cn_beg[c0 + j] = (unsigned)(e0 + s_cnt[j]);
+    __syncthreads();
+    // fill: position inside a list by atomics on a second counter array (re-using s_scan is too small: use s_pre space? no —
+    // lists are ordered afterwards, so the fill order does not matter)
+    __shared__ int s_fill[4 * RVE_WIN];
+    for (int j = tid; j < ncn; j += RVE_WIN) s_fill[j] = 0;
+    __syncthreads();
+    if (tid < n) {
+        RowInfo ri;
+        ri.s = fs; ri.t = ft;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            ri.slot[c] = slot[c] < 0 ? (uint16_t)0xffffu : (uint16_t)slot[c];
+            if (slot[c] >= 0) {
+                const int pos = atomicAdd(&s_fill[slot[c]], 1);
+                cn_ent[(size_t)e0 + s_cnt[slot[c]] + pos] = (uint16_t)((tid << 2) | c);
+            }
+        }
+        rowinfo[r0 + tid] = ri;
+    }
+    __syncthreads();
+    for (int j = tid; j < ncn; j += RVE_WIN) {     // order every list: reproducible summation order in the restriction
+        uint16_t* L = cn_ent + (size_t)e0 + s_cnt[j];
+        const int len = s_cnt[j + 1] - s_cnt[j];
+        for (int i = 1; i < len; ++i) {
+            const uint16_t v = L[i];
+            int k = i - 1;
+            while (k >= 0 && L[k] > v) { L[k + 1] = L[k]; --k; }
+            L[k + 1] = v;
+        }
     }
 }
 
@@ -673,7 +794,7 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
     const int k = tid % K;
     float2* s_st = (float2*)(s_r + (size_t)RVE_WIN * K);
     uint16_t* s_ent = (uint16_t*)(s_st + RVE_WIN);
-    const int cn0 = wt.win_cn0[win], ncn = wt.win_cn0[win + 1] - cn0;
+    const int cn0 = wt.win_cn0[win], ncn = wt.win_ncn[win];
     unsigned ent0 = 0, nent = 0;
     double rr = 0.0, rdr = 0.0;
     {
@@ -1203,7 +1324,7 @@ k_direction(WinTab wt, double2* __restrict__ p, const double2* __restrict__ r, c
     }
     const double beta = sc[((size_t)sys * 4 + k) * SC_N + SC_BETA];
     if (precond) {
-        const int cn0 = wt.win_cn0[win], ncn = wt.win_cn0[win + 1] - cn0;
+        const int cn0 = wt.win_cn0[win], ncn = wt.win_ncn[win];
         for (int t = tid; t < ncn * K; t += TPB)
             s_xc[t] = xc1[((size_t)sys * G + cn_node[cn0 + t / K]) * K + (t % K)];
         __syncthreads();

@@ -359,7 +359,7 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
     S.slice_ptr.assign(1, 0u);
     S.scol.clear(); S.halo.clear(); S.cn_node.clear(); S.cn_beg.assign(1, 0u); S.cn_ent.clear();
     if (!P.lite) S.scol.reserve((size_t)S.bcol.size() + S.bcol.size() / 6);
-    S.rowinfo.resize(na);
+    S.rowinfo.resize(P.lite ? 0 : na);
     S.max_tile = 0; S.max_cn = 0;
     const int nxg = ncx + 1;
     auto cnode = [&](int i, int j) -> int {   // same validity rules as grid_node() on the device
@@ -418,6 +418,7 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
         for (size_t k = 0; k < hal.size(); ++k) hpos[hal[k]] = -1;
         }
         S.win_slice0[w + 1] = S.win_slice0[w] + nsl;
+        if (P.lite) { S.win_cn0[w + 1] = 0; continue; }   // restriction lists are built on the GPU (k_sym_coarse)
         // coarse nodes touched by the window and the (row, corner) lists of each of them
         cns.clear();
         for (int r = r0; r < r1; ++r) {
