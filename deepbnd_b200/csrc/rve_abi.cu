@@ -103,7 +103,9 @@ struct rve_batch_s {
     DBuf<uint16_t> scol, cn_ent;
     DBuf<unsigned> d_row_ptr, adjf_ptr;
     DBuf<int> adjf, csr_col, win_nhalo, win_ncn, row_node, sym_cnt;
-    DBuf<unsigned char> emap;
+    DBuf<unsigned char> emap, rlen;
+    DBuf<int> sys_blocks;
+    std::vector<long long> true_blocks;   // per system, found by the device pattern build
     std::vector<long long> adjf_base;
     int max_words = 0;
     DBuf<RowInfo> rowinfo;
@@ -498,7 +500,8 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     // device half of the symbolic phase: block columns, halo lists, SELL columns
     const long long halo_cap = h->R + h->R / 2 + 4096;
     if (halo_cap > 2000000000LL) FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
-    CU(h->csr_col.alloc((size_t)h->NB)); CU(h->emap.alloc(36 * (size_t)h->E)); CU(h->halo.alloc((size_t)halo_cap)); CU(h->scol.alloc((size_t)h->NG * 32));
+    CU(h->csr_col.alloc((size_t)h->NB)); CU(h->emap.alloc(36 * (size_t)h->E)); CU(h->rlen.alloc((size_t)h->R));
+    CU(h->sys_blocks.alloc(n_sys)); CU(cudaMemsetAsync(h->sys_blocks.p, 0, n_sys * sizeof(int), st)); CU(h->halo.alloc((size_t)halo_cap)); CU(h->scol.alloc((size_t)h->NG * 32));
     CU(h->win_halo0.alloc(n_win)); CU(h->win_nhalo.alloc(n_win)); CU(h->sym_cnt.alloc(8));
     CU(cudaMemsetAsync(h->sym_cnt.p, 0, 8 * sizeof(int), st));
     const long long cn_cap = h->R + (long long)n_win + 4096;      // level-1 nodes touched per window are far fewer than its rows
@@ -507,11 +510,11 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     {
         WinTab wt = win_tab(h);
         k_sym_cols<<<n_win, RVE_WIN, 0, st>>>(wt, h->d_row_ptr.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->node_row.p,
-                                               h->csr_col.p, h->emap.p, h->sym_cnt.p);
+                                               h->csr_col.p, h->rlen.p, h->emap.p, h->sys_blocks.p, h->sym_cnt.p);
         const size_t sm = 2 * (size_t)h->max_words * sizeof(unsigned);
         if (sm > 200 * 1024) FAIL(RVE_E_MESH, "system too large for the halo bitmap in shared memory");
         CU(cudaFuncSetAttribute(k_sym_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_sym_window<<<n_win, RVE_WIN, sm, st>>>(wt, h->win_halo0.p, h->win_nhalo.p, h->d_row_ptr.p, h->csr_col.p, h->slice_ptr.p,
+        k_sym_window<<<n_win, RVE_WIN, sm, st>>>(wt, h->win_halo0.p, h->win_nhalo.p, h->d_row_ptr.p, h->rlen.p, h->csr_col.p, h->slice_ptr.p,
                                                   h->scol.p, h->halo.p, (int)halo_cap, h->sym_cnt.p);
         const size_t smc = 2 * (size_t)((LV.g[0].G + 31) / 32) * sizeof(unsigned);
         if (smc > 150 * 1024) FAIL(RVE_E_MESH, "level-1 grid too large for the coarse-node bitmap in shared memory");
@@ -522,9 +525,12 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     }
     int scnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    std::vector<int> sb(n_sys);
+    CU(cudaMemcpyAsync(sb.data(), h->sys_blocks.p, n_sys * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(stream_wait(h));
     CU(cudaGetLastError());
-    if (scnt[2] == 2) FAIL(RVE_E_MESH, "device pattern build: row length mismatch");
+    if (scnt[2] == 2) FAIL(RVE_E_MESH, "device pattern build: a row has more blocks than its element fan allows (non-manifold vertex?)");
+    h->true_blocks.assign(sb.begin(), sb.end());
     if (scnt[2] == 3) FAIL(RVE_E_MESH, "device pattern build: halo list overflow");
     if (scnt[2] == 4) FAIL(RVE_E_MESH, "device pattern build: coarse-node list overflow");
     h->max_tile = scnt[1]; h->max_cn = scnt[5];
@@ -579,7 +585,7 @@ int rve_get_sizes(rve_handle_t h, int32_t sys, int64_t* n_nodes, int64_t* n_rows
     if (!h->have_batch || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_ARG, "bad system index");
     if (n_nodes) *n_nodes = h->sym[sys].nn;
     if (n_rows) *n_rows = h->sym[sys].na;
-    if (n_blocks) *n_blocks = (int64_t)h->sym[sys].nblocks;
+    if (n_blocks) *n_blocks = (int64_t)h->true_blocks[sys];
     if (n_elems) *n_elems = h->sym[sys].nt;
     return 0;
 }
@@ -591,17 +597,19 @@ int rve_get_csr(rve_handle_t h, int32_t sys, int32_t* rowptr, int32_t* col, doub
     const size_t ng = Y.slice_ptr.back();
     std::vector<double> bv(128 * ng);
     CU(cudaMemcpy(bv.data(), h->bval.p + 128 * (size_t)h->grp_base[sys], bv.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    std::vector<int> cc(Y.nblocks);            // block columns as found on the device (global rows)
+    std::vector<int> cc(Y.nblocks);            // block columns as found on the device (global rows), capacity layout
     CU(cudaMemcpy(cc.data(), h->csr_col.p + (size_t)h->blk_base[sys], cc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<unsigned char> rl(Y.na);       // true row lengths
+    CU(cudaMemcpy(rl.data(), h->rlen.p + (size_t)h->row_base[sys], rl.size(), cudaMemcpyDeviceToHost));
     const int rb0 = h->row_base[sys];
-    // SELL slot j of a row holds the j-th (sorted) CSR column of that row
+    // SELL slot j of a row holds the j-th column the device found for that row
     int64_t pos = 0;
     for (int r = 0; r < Y.na; ++r) {
-        const int w = r / RVE_WIN, rl = r % RVE_WIN, lane = rl & 31;
-        const size_t g0 = Y.slice_ptr[Y.win_slice0[w] + (rl >> 5)];
+        const int w = r / RVE_WIN, rlw = r % RVE_WIN, lane = rlw & 31;
+        const size_t g0 = Y.slice_ptr[Y.win_slice0[w] + (rlw >> 5)];
         for (int c = 0; c < 2; ++c) {
             rowptr[2 * r + c] = (int32_t)pos;
-            for (unsigned k = Y.row_ptr[r]; k < Y.row_ptr[r + 1]; ++k) {
+            for (unsigned k = Y.row_ptr[r]; k < Y.row_ptr[r] + rl[r]; ++k) {
                 const size_t g = g0 + (k - Y.row_ptr[r]);
                 for (int d = 0; d < 2; ++d) { col[pos] = 2 * (cc[k] - rb0) + d; val[pos] = bv[128 * g + 64 * c + 2 * lane + d]; ++pos; }
             }
@@ -809,7 +817,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     // algorithmic SpMV bytes of the solve: sum over systems of iters * B_spmv(K)
     double bytes = 0;
     for (int s = 0; s < n_sys; ++s) {
-        const double n = 2.0 * h->sym[s].na, nnz = 4.0 * (double)h->sym[s].nblocks;
+        const double n = 2.0 * h->sym[s].na, nnz = 4.0 * (double)h->true_blocks[s];
         bytes += hit[s] * (12.0 * nnz + 4.0 * (n + 1) + 16.0 * n * K);
     }
     h->c_cnt[1] = bytes;

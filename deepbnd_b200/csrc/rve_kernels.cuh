@@ -124,39 +124,54 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(RVE_WIN)
 k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __restrict__ adjf_ptr,
            const int* __restrict__ adjf, const int* __restrict__ elem_node, const int* __restrict__ node_row,
-           int* __restrict__ csr_col, unsigned char* __restrict__ emap, int* counters) {
+           int* __restrict__ csr_col, unsigned char* __restrict__ rlen, unsigned char* __restrict__ emap,
+           int* __restrict__ sys_blocks, int* counters) {
     const int w = blockIdx.x, t = threadIdx.x;
-    if (t >= wt.win_n[w]) return;
-    const int r = wt.win_row0[w] + t;
-    const unsigned o = row_ptr[r];
-    const int len = (int)(row_ptr[r + 1] - o);
-    int* cols = csr_col + o;                     // unique rows in discovery order (same order as the host path)
     int cnt = 0;
-    for (unsigned i = adjf_ptr[r]; i < adjf_ptr[r + 1]; ++i) {
-        const int e = adjf[i];
-        const int* en = elem_node + 6 * (size_t)e;
-        int rows[6], a = 0;
+    if (t < wt.win_n[w]) {
+        const int r = wt.win_row0[w] + t;
+        const unsigned o = row_ptr[r];
+        const int cap = (int)(row_ptr[r + 1] - o);   // capacity of the row (>= its true length)
+        int* cols = csr_col + o;                     // unique rows in discovery order (same order as the host path)
+        for (unsigned i = adjf_ptr[r]; i < adjf_ptr[r + 1]; ++i) {
+            const int e = adjf[i];
+            const int* en = elem_node + 6 * (size_t)e;
+            int rows[6], a = 0;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { rows[k] = node_row[en[k]]; if (rows[k] == r) a = k; }
-        // emap[e][a][k] = SELL slot of block (row of local node a, row of local node k): k_assemble scatters
-        // without searching
-        unsigned char* em = emap + (size_t)e * 36 + a * 6;
+            for (int k = 0; k < 6; ++k) { rows[k] = node_row[en[k]]; if (rows[k] == r) a = k; }
+            // emap[e][a][k] = SELL slot of block (row of local node a, row of local node k): k_assemble scatters
+            // without searching
+            unsigned char* em = emap + (size_t)e * 36 + a * 6;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const int c = rows[k];
-            if (c < 0) { em[k] = 0xff; continue; }
-            int j = 0;
-            while (j < cnt && j < len && cols[j] != c) ++j;
-            if (j == cnt) { if (cnt < len) cols[cnt] = c; ++cnt; }
-            em[k] = (unsigned char)j;
+            for (int k = 0; k < 6; ++k) {
+                const int c = rows[k];
+                if (c < 0) { em[k] = 0xff; continue; }
+                int j = 0;
+                while (j < cnt && j < cap && cols[j] != c) ++j;
+                if (j == cnt) { if (cnt < cap) cols[cnt] = c; ++cnt; }
+                em[k] = (unsigned char)j;
+            }
         }
+        if (cnt > cap) { atomicExch(counters + 2, 2); cnt = cap; }
+        rlen[r] = (unsigned char)cnt;
     }
-    if (cnt != len) atomicExch(counters + 2, 2);
+    // true number of blocks of the system (one atomic per window)
+    __shared__ int s_w[RVE_WIN / 32];
+    int v = cnt;
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+    if ((t & 31) == 0) s_w[t >> 5] = v;
+    __syncthreads();
+    if (t == 0) {
+        int tot = 0;
+        for (int i = 0; i < RVE_WIN / 32; ++i) tot += s_w[i];
+        atomicAdd(sys_blocks + wt.win_sys[w], tot);
+    }
 }
 
 __global__ void __launch_bounds__(RVE_WIN)
 k_sym_window(WinTab wt, int* __restrict__ win_halo0, int* __restrict__ win_nhalo, const unsigned* __restrict__ row_ptr,
-             const int* __restrict__ csr_col, const unsigned* __restrict__ slice_ptr, uint16_t* __restrict__ scol,
+             const unsigned char* __restrict__ rlen, const int* __restrict__ csr_col, const unsigned* __restrict__ slice_ptr, uint16_t* __restrict__ scol,
              int* __restrict__ halo, int halo_cap, int* counters) {
     extern __shared__ unsigned s_bm[];           // [words] bitmap of halo rows, then [words] popcount prefix
     __shared__ int s_scan[RVE_WIN];
@@ -171,7 +186,7 @@ k_sym_window(WinTab wt, int* __restrict__ win_halo0, int* __restrict__ win_nhalo
     __syncthreads();
     unsigned o = 0; int len = 0;
     if (tid < n) {
-        o = row_ptr[r0 + tid]; len = (int)(row_ptr[r0 + tid + 1] - o);
+        o = row_ptr[r0 + tid]; len = rlen[r0 + tid];
         for (int j = 0; j < len; ++j) {
             const int c = csr_col[o + j] - rb0;
             if (c < r0l || c >= r0l + n) atomicOr(&s_bm[c >> 5], 1u << (c & 31));
