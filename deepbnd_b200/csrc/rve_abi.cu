@@ -989,7 +989,9 @@ int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_l
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
     if (ms_per_launch) *ms_per_launch = ms / reps;
     if (alg_bytes_per_launch) {
-        const double n = 2.0 * (double)h->R, nnz = 4.0 * (double)h->NB;
+        double blocks = 0;
+        for (long long tb : h->true_blocks) blocks += (double)tb;          // true blocks (NB counts row capacities)
+        const double n = 2.0 * (double)h->R, nnz = 4.0 * blocks;
         *alg_bytes_per_launch = 12.0 * nnz + 4.0 * (n + n_sys) + 16.0 * n * K;
     }
     return 0;

@@ -408,3 +408,17 @@ def test_single_load_and_no_vref(coarse_reduced_meshes, model):
         sig = o.homogenise([0, 1], 2).flatten()[[0, 3, 2]]
         assert np.abs(snap["sigma"][s, 0] - sig).max() < 1e-8 * np.abs(sig).max()
     b.close()
+
+
+def test_spmv_microbenchmark_entry(coarse_reduced_meshes):
+    """rve_bench_spmv runs the production SpMV kernel for 1..3 right-hand sides and reports the CSR-accounted bytes."""
+    from deepbnd_b200.batch import RVEBatch
+    b = RVEBatch().set_meshes(coarse_reduced_meshes, PARAM, model="per").assemble()
+    nrow = sum(b.sizes(s)["n_rows"] for s in range(len(coarse_reduced_meshes)))
+    nblk = sum(b.sizes(s)["n_blocks"] for s in range(len(coarse_reduced_meshes)))
+    for k in (1, 2, 3):
+        ms, by = b.bench_spmv(n_rhs=k, reps=5)
+        assert ms > 0
+        n, nnz = 2 * nrow, 4 * nblk
+        assert by == pytest.approx(12.0 * nnz + 4.0 * (n + len(coarse_reduced_meshes)) + 16.0 * n * k)
+    b.close()
