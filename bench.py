@@ -326,11 +326,23 @@ def main():
         jobs = [c for _ in range(nsteps) for c in range(nchunk)]
         set_pass(hb[0], jobs[0])
         outs = []
+        dbg = os.environ.get("BENCH_E2E_DEBUG") == "1"
+        acc = {}
         for i, c in enumerate(jobs):
             fut = pool.submit(set_pass, hb[(i + 1) % 2], jobs[i + 1]) if i + 1 < len(jobs) else None
+            tc0 = time.perf_counter()
             outs.append(chunk_pass(hb[i % 2], c))
+            tc1 = time.perf_counter()
             if fut is not None:
                 fut.result()
+            if dbg:                                            # where the wall time of a chunk goes (stderr only)
+                tt = hb[i % 2].timings()[0]
+                for k_, v_ in tt.items():
+                    acc[k_] = acc.get(k_, 0.0) + v_
+                acc["wall_chunk_pass"] = acc.get("wall_chunk_pass", 0.0) + 1e3 * (tc1 - tc0)
+                acc["wall_wait_set_batch"] = acc.get("wall_wait_set_batch", 0.0) + 1e3 * (time.perf_counter() - tc1)
+        if dbg:
+            print("[e2e debug] per step (ms): " + json.dumps({k_: round(v_ / nsteps, 2) for k_, v_ in acc.items()}), file=sys.stderr)
         last = outs[-nchunk:]
         iters = np.concatenate([o[1] for o in last])
         if nl == 3:

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "rve_abi.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("rve_kernels.cuh", "rve_math.cuh", "rve_symbolic.hpp")] + \
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("rve_kernels.cuh", "rve_devsym.cuh", "rve_math.cuh", "rve_symbolic.hpp")] + \
        [os.path.join(HERE, "..", "include", "rve_b200.h")]
 LIB = os.environ.get("DEEPBND_RVE_LIB") or os.path.join(HERE, "lib", "librve_b200.so")   # override: kernel-variant experiments
 

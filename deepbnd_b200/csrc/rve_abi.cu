@@ -12,6 +12,7 @@
 
 #include "rve_kernels.cuh"
 #include "rve_symbolic.hpp"
+#include "rve_devsym.cuh"
 
 namespace {
 
@@ -73,6 +74,9 @@ struct PinnedArena {
 
 }  // namespace
 
+// sizes of one system (device symbolic phase, rve_devsym.cuh)
+struct SysInfo { int nv = 0, nt = 0, ne = 0, nn = 0, na = 0, nb = 0, nbe = 0, nwin = 0, nsl = 0; long long nblk = 0, ngrp = 0, nadj = 0; };
+
 struct rve_batch_s {
     int device = 0;
     std::string err;
@@ -85,7 +89,10 @@ struct rve_batch_s {
     int K = 0, NL = 0;  // solver rhs count, load count of the last solve
     Mat8 mat;
     double vref_box[4];
-    std::vector<SysSym> sym;
+    std::vector<SysInfo> info;          // per-system sizes found by the device symbolic phase
+    std::vector<int> voff, toff, cellrank, h_cnt;
+    std::vector<double> h_ext, h_box;
+    std::vector<unsigned> u_blk, u_grp, u_adjf;
     std::vector<int> node_base, elem_base, row_base, bnd_base, bedge_base, win_base, slice_base, halo_base, cn_base;
     std::vector<long long> blk_base, grp_base, ent_base;
     long long N = 0, E = 0, R = 0, NB = 0, NBN = 0, NBE = 0, NG = 0;
@@ -103,6 +110,9 @@ struct rve_batch_s {
     DBuf<uint16_t> scol, cn_ent;
     DBuf<unsigned> d_row_ptr, adjf_ptr;
     DBuf<int> adjf, csr_col, win_nhalo, win_ncn, row_node, sym_cnt;
+    DBuf<double> d_xy, sys_ext;
+    DBuf<int> d_tri, d_region, d_voff, d_toff, scrA, scrB, sys_cnt, node_va, node_vb, d_node_base, d_bnd_base, d_cellrank, d_slice_base;
+    DBuf<unsigned> d_blk_base, d_grp_base, d_adjf_base;
     DBuf<unsigned char> emap, rlen;
     DBuf<int> sys_blocks;
     std::vector<long long> true_blocks;   // per system, found by the device pattern build
@@ -323,150 +333,180 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     h->n_sys = n_sys; h->model = model; h->vref_nb = vref_nb;
     h->nvref = vref_nb > 0 ? 4 * (vref_nb - 1) + 1 : 0;
     for (int k = 0; k < 8; ++k) h->mat.v[k] = mat[k];
-    h->sym.resize(n_sys);                      // keeps the vectors (and their capacity) of earlier batches
-    std::vector<SysSym>& S = h->sym;
-    parallel_for(n_sys, [&](int s) {
-        sym_pass1(S[s], xy + 2 * vert_off[s], tri + 3 * tri_off[s], region + tri_off[s],
-                  (int)(vert_off[s + 1] - vert_off[s]), (int)(tri_off[s + 1] - tri_off[s]));
-    });
-    double ext = 0, Lx = 0, Ly = 0;
-    for (int s = 0; s < n_sys; ++s) {
-        if (!S[s].err.empty()) FAIL(RVE_E_MESH, "system " + std::to_string(s) + ": " + S[s].err);
-        ext += S[s].mean_ext / n_sys;   // batch mean of the mean element extent
-        if (s == 0) { Lx = S[s].box[2]; Ly = S[s].box[3]; }
-        else if (std::fabs(S[s].box[2] - Lx) > 1e-9 * Lx || std::fabs(S[s].box[3] - Ly) > 1e-9 * Ly)
-            FAIL(RVE_E_MESH, "all systems of a batch must share the box size");
-    }
-    SymParams P;
-    P.model = model; P.vref_nb = vref_nb; P.vref_box_given = vref_box != nullptr;
-    for (int k = 0; k < 4; ++k) P.vref_box[k] = vref_box ? vref_box[k] : 0.0;
-    P.ncx = pick_nc(Lx, ext); P.ncy = pick_nc(Ly, ext);
-    P.lite = true;   // block columns, halo lists and SELL columns are built on the GPU below
-    h->ncx = P.ncx; h->ncy = P.ncy;
-    auto tp1 = std::chrono::steady_clock::now();
-    parallel_for(n_sys, [&](int s) { sym_pass2(S[s], P); });
-    auto tp2 = std::chrono::steady_clock::now();
+    if (n_sys > 65535) FAIL(RVE_E_ARG, "more than 65535 systems in one batch: split it");
+    if (vert_off[0] != 0 || tri_off[0] != 0) FAIL(RVE_E_ARG, "offset arrays must start at 0");
     for (int s = 0; s < n_sys; ++s)
-        if (!S[s].err.empty()) FAIL(RVE_E_MESH, "system " + std::to_string(s) + ": " + S[s].err);
-    for (int k = 0; k < 4; ++k) h->vref_box[k] = vref_box ? vref_box[k] : S[0].box[k];
+        if (vert_off[s + 1] <= vert_off[s] || tri_off[s + 1] <= tri_off[s]) FAIL(RVE_E_MESH, "system " + std::to_string(s) + ": empty mesh");
+    const long long NV = vert_off[n_sys], NT = tri_off[n_sys];
+    if (NV + 3 * NT + n_sys > 2000000000LL || 6 * NT > 2000000000LL) FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
+    cudaStream_t st = h->stream;
+    std::vector<SysInfo>& I = h->info;
+    I.assign(n_sys, SysInfo());
+    h->voff.resize(n_sys + 1); h->toff.resize(n_sys + 1);
+    for (int s = 0; s <= n_sys; ++s) { h->voff[s] = (int)vert_off[s]; h->toff[s] = (int)tri_off[s]; }
+    for (int s = 0; s < n_sys; ++s) { I[s].nv = h->voff[s + 1] - h->voff[s]; I[s].nt = h->toff[s + 1] - h->toff[s]; }
 
-    // prefix sums
-    h->node_base.assign(n_sys + 1, 0); h->elem_base.assign(n_sys + 1, 0); h->row_base.assign(n_sys + 1, 0);
-    h->bnd_base.assign(n_sys + 1, 0); h->bedge_base.assign(n_sys + 1, 0); h->blk_base.assign(n_sys + 1, 0);
-    h->win_base.assign(n_sys + 1, 0); h->slice_base.assign(n_sys + 1, 0); h->adjf_base.assign(n_sys + 1, 0);
-    h->cn_base.assign(n_sys + 1, 0); h->grp_base.assign(n_sys + 1, 0); h->ent_base.assign(n_sys + 1, 0);
-    h->max_tile = 0; h->max_cn = 0; h->max_words = 0;
-    for (int s = 0; s < n_sys; ++s) {
-        long long nn = (long long)h->node_base[s] + S[s].nn, ne = (long long)h->elem_base[s] + S[s].nt;
-        long long nr = (long long)h->row_base[s] + S[s].na;
-        long long nb = h->blk_base[s] + (long long)S[s].nblocks;
-        long long ng = h->grp_base[s] + (long long)S[s].slice_ptr.back();
-        long long nh = h->adjf_base[s] + (long long)S[s].adjf.size();
-        if (nn > 2000000000LL || ne > 2000000000LL || nr * 4 > 2000000000LL || ng > 4000000000LL || nh > 2000000000LL )
-            FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
-        h->node_base[s + 1] = (int)nn; h->elem_base[s + 1] = (int)ne; h->row_base[s + 1] = (int)nr;
-        h->bnd_base[s + 1] = h->bnd_base[s] + S[s].nb; h->bedge_base[s + 1] = h->bedge_base[s] + S[s].nbe;
-        h->blk_base[s + 1] = nb; h->grp_base[s + 1] = ng; h->adjf_base[s + 1] = nh;
-        h->win_base[s + 1] = h->win_base[s] + S[s].nwin;
-        h->slice_base[s + 1] = h->slice_base[s] + (int)S[s].slice_ptr.size() - 1;
-        h->max_words = std::max(h->max_words, (S[s].na + 31) / 32);
-    }
-    h->N = h->node_base[n_sys]; h->E = h->elem_base[n_sys]; h->R = h->row_base[n_sys];
-    h->NB = h->blk_base[n_sys]; h->NBN = h->bnd_base[n_sys]; h->NBE = h->bedge_base[n_sys];
-    h->NG = h->grp_base[n_sys]; h->n_win = h->win_base[n_sys];
-    const int n_win = h->n_win, n_slice = h->slice_base[n_sys];
-
-    // flatten (parallel over systems) straight into the pinned staging arena
-    const size_t nvs = (size_t)n_sys * h->nvref;
-    const size_t n_bnds = model == RVE_MODEL_DNN ? 2 * (size_t)h->NBN : 0;
+    // ---- the raw meshes go to the GPU as they are (through the pinned staging arena)
     {
-        size_t bytes = 0;
-        auto add = [&](size_t c, size_t e) { bytes += PinnedArena::need(c, e); };
-        add(2 * h->N, 8); add(4 * (size_t)n_sys, 8); add(n_bnds, 8); add(2 * h->NBE, 8); add(2 * nvs, 8);
-        add(h->N, 4); add(h->N, 4); add(h->N, 4); add(6 * h->E, 4); add(h->E, 4); add(h->NBN, 4); add(h->NBN, 4);
-        add(3 * h->NBE, 4); add(nvs, 4); for (int k = 0; k < 4; ++k) add(n_win, 4);
-        add(h->adjf_base[n_sys], 4); add(h->R, 4); add(h->E, 1); add(h->R + 1, 4); add(h->R + 1, 4);
-        add(n_slice + 1, 4);
+        size_t bytes = PinnedArena::need(2 * NV, 8) + PinnedArena::need(3 * NT, 4) + PinnedArena::need(NT, 4);
         CU(stream_wait(h));          // the previous batch's copies out of the arena are done
         CU(h->arena.reserve(bytes));
     }
     PinnedArena& AR = h->arena;
-    Span<double> node_xy = AR.take<double>(2 * h->N), box = AR.take<double>(4 * (size_t)n_sys), bnd_s = AR.take<double>(n_bnds),
-                 bedge_nl = AR.take<double>(2 * h->NBE), samp_lam = AR.take<double>(2 * nvs);
-    Span<int> node_row = AR.take<int>(h->N), node_bnd = AR.take<int>(h->N), node_sys = AR.take<int>(h->N),
-              elem_node = AR.take<int>(6 * h->E), elem_sys = AR.take<int>(h->E), bnd_sys = AR.take<int>(h->NBN),
-              bnd_node = AR.take<int>(h->NBN), bedge = AR.take<int>(3 * h->NBE), samp_elem = AR.take<int>(nvs),
-              win_sys = AR.take<int>(n_win), win_row0 = AR.take<int>(n_win), win_n = AR.take<int>(n_win),
-              win_slice0 = AR.take<int>(n_win), row_node = AR.take<int>(h->R),
-              adjf = AR.take<int>(h->adjf_base[n_sys]);
-    Span<unsigned char> elem_reg = AR.take<unsigned char>(h->E);
-    Span<unsigned> slice_ptr = AR.take<unsigned>(n_slice + 1),
-                   row_ptr = AR.take<unsigned>(h->R + 1), adjf_ptr = AR.take<unsigned>(h->R + 1);
+    Span<double> a_xy = AR.take<double>(2 * NV);
+    Span<int> a_tri = AR.take<int>(3 * NT), a_reg = AR.take<int>(NT);
     parallel_for(n_sys, [&](int s) {
-        const SysSym& Y = S[s];
-        const int nb0 = h->node_base[s], eb0 = h->elem_base[s], rb0 = h->row_base[s];
-        for (int k = 0; k < 4; ++k) box[4 * (size_t)s + k] = Y.box[k];
-        for (int n = 0; n < Y.nn; ++n) {
-            node_xy[2 * ((size_t)nb0 + n)] = Y.node_xy[2 * n]; node_xy[2 * ((size_t)nb0 + n) + 1] = Y.node_xy[2 * n + 1];
-            node_row[nb0 + n] = Y.node_row[n] < 0 ? -1 : rb0 + Y.node_row[n];
-            node_bnd[nb0 + n] = Y.node_bnd[n] < 0 ? -1 : h->bnd_base[s] + Y.node_bnd[n];
-            node_sys[nb0 + n] = s;
-        }
-        for (int t = 0; t < Y.nt; ++t) {
-            for (int k = 0; k < 6; ++k) elem_node[6 * ((size_t)eb0 + t) + k] = nb0 + Y.elem_node[6 * t + k];
-            elem_reg[eb0 + t] = Y.reg[t]; elem_sys[eb0 + t] = s;
-        }
-        for (int r = 0; r < Y.na; ++r) row_node[(size_t)rb0 + r] = nb0 + Y.row_node[r];
-        const int w0 = h->win_base[s], sl0 = h->slice_base[s];
-        for (int w = 0; w < Y.nwin; ++w) {
-            win_sys[w0 + w] = s; win_row0[w0 + w] = rb0 + w * RVE_WIN; win_n[w0 + w] = Y.win_n[w];
-            win_slice0[w0 + w] = sl0 + Y.win_slice0[w];
-        }
-        for (size_t k = 0; k + 1 < Y.slice_ptr.size(); ++k) slice_ptr[sl0 + k] = (unsigned)(h->grp_base[s] + Y.slice_ptr[k]);
-        if (s == n_sys - 1) slice_ptr[n_slice] = (unsigned)h->NG;
-        for (int r = 0; r < Y.na; ++r) {
-            row_ptr[(size_t)rb0 + r] = (unsigned)(h->blk_base[s] + Y.row_ptr[r]);
-            adjf_ptr[(size_t)rb0 + r] = (unsigned)(h->adjf_base[s] + Y.adjf_ptr[r]);
-        }
-        if (s == n_sys - 1) { row_ptr[h->R] = (unsigned)h->NB; adjf_ptr[h->R] = (unsigned)h->adjf_base[n_sys]; }
-        for (size_t k = 0; k < Y.adjf.size(); ++k) adjf[h->adjf_base[s] + k] = eb0 + Y.adjf[k];
-        for (int i = 0; i < Y.nb; ++i) {
-            bnd_sys[h->bnd_base[s] + i] = s; bnd_node[h->bnd_base[s] + i] = nb0 + Y.bnd_node[i];
-            if (model == RVE_MODEL_DNN) {
-                bnd_s[2 * ((size_t)h->bnd_base[s] + i)] = Y.bnd_s[2 * i]; bnd_s[2 * ((size_t)h->bnd_base[s] + i) + 1] = Y.bnd_s[2 * i + 1];
-            }
-        }
-        for (int i = 0; i < Y.nbe; ++i) {
-            for (int k = 0; k < 3; ++k) bedge[3 * ((size_t)h->bedge_base[s] + i) + k] = nb0 + Y.bedge[3 * i + k];
-            bedge_nl[2 * ((size_t)h->bedge_base[s] + i)] = Y.bedge_nl[2 * i];
-            bedge_nl[2 * ((size_t)h->bedge_base[s] + i) + 1] = Y.bedge_nl[2 * i + 1];
-        }
-        for (int k = 0; k < h->nvref; ++k) {
-            samp_elem[(size_t)s * h->nvref + k] = eb0 + Y.samp_elem[k];
-            samp_lam[2 * ((size_t)s * h->nvref + k)] = Y.samp_lam[2 * k];
-            samp_lam[2 * ((size_t)s * h->nvref + k) + 1] = Y.samp_lam[2 * k + 1];
-        }
+        memcpy(a_xy.p + 2 * vert_off[s], xy + 2 * vert_off[s], 2 * sizeof(double) * (size_t)I[s].nv);
+        memcpy(a_tri.p + 3 * tri_off[s], tri + 3 * tri_off[s], 3 * sizeof(int) * (size_t)I[s].nt);
+        memcpy(a_reg.p + tri_off[s], region + tri_off[s], sizeof(int) * (size_t)I[s].nt);
     });
+    UPL(h->d_xy, a_xy); UPL(h->d_tri, a_tri); UPL(h->d_region, a_reg); UPL(h->d_voff, h->voff); UPL(h->d_toff, h->toff);
+    h->E = NT;
+    DsMesh DM;
+    DM.xy = h->d_xy.p; DM.tri = h->d_tri.p; DM.region = h->d_region.p; DM.voff = h->d_voff.p; DM.toff = h->d_toff.p;
+
+    // ---- (A) orientation, bounding boxes, edges
+    CU(h->scrA.alloc((size_t)(2 * NV + n_sys + 9 * NT + 64)));
+    int* vptr = h->scrA.p; int* vfill = vptr + NV + n_sys; int* he_vb = vfill + NV; int* he_slot = he_vb + 3 * NT; int* emid = he_slot + 3 * NT;
+    CU(h->elem_reg.alloc((size_t)NT)); CU(h->box.alloc(4 * (size_t)n_sys)); CU(h->sys_cnt.alloc(8 * (size_t)n_sys)); CU(h->sys_ext.alloc(n_sys));
+    CU(cudaMemsetAsync(h->sys_cnt.p, 0, 8 * (size_t)n_sys * sizeof(int), st));
+    k_ds_edges<<<n_sys, DS_THREADS, 0, st>>>(DM, vptr, vfill, he_vb, he_slot, emid, h->elem_reg.p, h->box.p, h->sys_cnt.p, h->sys_ext.p);
+    h->launches += 1;
+    std::vector<int>& cnt = h->h_cnt; std::vector<double>& hext = h->h_ext; std::vector<double>& hbox = h->h_box;
+    cnt.resize(8 * (size_t)n_sys); hext.resize(n_sys); hbox.resize(4 * (size_t)n_sys);
+    CU(cudaMemcpyAsync(cnt.data(), h->sys_cnt.p, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hext.data(), h->sys_ext.p, hext.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hbox.data(), h->box.p, hbox.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(stream_wait(h));
+    CU(cudaGetLastError());
+    auto check_sys = [&]() -> int {
+        for (int s = 0; s < n_sys; ++s)
+            if (cnt[8 * (size_t)s + DC_ERR]) { h->err = "system " + std::to_string(s) + ": " + ds_error_text(cnt[8 * (size_t)s + DC_ERR]); return RVE_E_MESH; }
+        return 0;
+    };
+    if (check_sys()) return RVE_E_MESH;
+    double ext = 0;
+    const double Lx = hbox[2], Ly = hbox[3];
+    h->node_base.assign(n_sys + 1, 0); h->bnd_base.assign(n_sys + 1, 0); h->bedge_base.assign(n_sys + 1, 0);
+    for (int s = 0; s < n_sys; ++s) {
+        I[s].ne = cnt[8 * (size_t)s + DC_NE]; I[s].nbe = cnt[8 * (size_t)s + DC_NBE]; I[s].nb = cnt[8 * (size_t)s + DC_NB];
+        I[s].nn = I[s].nv + I[s].ne;
+        ext += hext[s] / n_sys;        // batch mean of the mean element extent
+        if (std::fabs(hbox[4 * (size_t)s + 2] - Lx) > 1e-9 * Lx || std::fabs(hbox[4 * (size_t)s + 3] - Ly) > 1e-9 * Ly)
+            FAIL(RVE_E_MESH, "all systems of a batch must share the box size");
+        h->node_base[s + 1] = h->node_base[s] + I[s].nn;
+        h->bnd_base[s + 1] = h->bnd_base[s] + I[s].nb; h->bedge_base[s + 1] = h->bedge_base[s] + I[s].nbe;
+    }
+    h->N = h->node_base[n_sys]; h->NBN = h->bnd_base[n_sys]; h->NBE = h->bedge_base[n_sys];
+    const long long N = h->N;
+    const int ncx = pick_nc(Lx, ext), ncy = pick_nc(Ly, ext);
+    h->ncx = ncx; h->ncy = ncy;
+    for (int k = 0; k < 4; ++k) h->vref_box[k] = vref_box ? vref_box[k] : hbox[k];
+    // Morton rank of every level-1 cell
+    {
+        auto spread = [](unsigned v) -> uint64_t {
+            uint64_t x = v & 0xffffu;
+            x = (x | (x << 8)) & 0x00ff00ffull; x = (x | (x << 4)) & 0x0f0f0f0full;
+            x = (x | (x << 2)) & 0x33333333ull; x = (x | (x << 1)) & 0x55555555ull;
+            return x;
+        };
+        std::vector<std::pair<uint64_t, int>> ck((size_t)ncx * ncy);
+        for (int cj = 0; cj < ncy; ++cj)
+            for (int ci = 0; ci < ncx; ++ci) ck[(size_t)cj * ncx + ci] = {spread((unsigned)ci) | (spread((unsigned)cj) << 1), cj * ncx + ci};
+        std::sort(ck.begin(), ck.end());
+        h->cellrank.resize(ck.size());
+        for (size_t k = 0; k < ck.size(); ++k) h->cellrank[ck[k].second] = (int)k;
+    }
+    const size_t ncells = (size_t)ncx * ncy;
+    auto tp1 = std::chrono::steady_clock::now();
+
+    // ---- (B) nodes, boundary lists, constraint map, row order, elements around rows, capacities, windows; Vref samples
+    const size_t nvs = (size_t)n_sys * h->nvref;
+    UPL(h->d_node_base, h->node_base); UPL(h->d_bnd_base, h->bnd_base); UPL(h->d_bedge_base, h->bedge_base); UPL(h->d_cellrank, h->cellrank);
+    std::vector<double> vb(h->vref_box, h->vref_box + 4);
+    UPL(h->d_vbox, vb);
+    CU(h->node_xy.alloc(2 * (size_t)N)); CU(h->node_va.alloc((size_t)N)); CU(h->node_vb.alloc((size_t)N)); CU(h->node_sys.alloc((size_t)N));
+    CU(h->node_bnd.alloc((size_t)N)); CU(h->node_row.alloc((size_t)N)); CU(h->elem_node.alloc(6 * (size_t)NT)); CU(h->elem_sys.alloc((size_t)NT));
+    CU(h->bnd_sys.alloc((size_t)h->NBN)); CU(h->bnd_node.alloc((size_t)h->NBN)); CU(h->bnd_s.alloc(model == RVE_MODEL_DNN ? 2 * (size_t)h->NBN : 0));
+    CU(h->bedge.alloc(3 * (size_t)h->NBE)); CU(h->bedge_nl.alloc(2 * (size_t)h->NBE));
+    CU(h->samp_elem.alloc(nvs)); CU(h->samp_lam.alloc(2 * nvs));
+    {
+        const size_t words = 14 * (size_t)N + 8 * (size_t)n_sys + 6 * (size_t)NT + (size_t)n_sys * (2 * ncells + 1) + (size_t)N / 4 + (size_t)N / 32 + 256;
+        CU(h->scrB.alloc(words));
+    }
+    DsRows DR;
+    {
+        int* q = h->scrB.p;
+        auto take = [&](size_t n) { int* r = q; q += n; return r; };
+        DR.master = take(N); DR.ncell = take(N); DR.pnode = take(N); DR.prow = take(N); DR.nrow0 = take(N); DR.cur = take(N);
+        DR.len0 = take(N); DR.newid = take(N); DR.oldid = take(N); DR.row_node_loc = take(N); DR.node_row_loc = take(N);
+        DR.adjc = take(N + n_sys); DR.loc_rowptr = take(N + n_sys); DR.loc_adjptr = take(N + n_sys);
+        DR.adj = take(6 * NT); DR.ccnt = take((size_t)n_sys * (ncells + 1)); DR.cfill = take((size_t)n_sys * ncells);
+        DR.loc_slw = take((size_t)N / 32 + 2 * (size_t)n_sys + 8);
+        DR.rowb = (unsigned char*)take((size_t)N / 4 + 8);
+        DR.scan3 = he_slot;              // phase-A scratch that is free again
+    }
+    DR.emid = emid; DR.node_base = h->d_node_base.p; DR.bnd_base = h->d_bnd_base.p; DR.bedge_base = h->d_bedge_base.p;
+    DR.cellrank = h->d_cellrank.p; DR.box = h->box.p; DR.vbox = vref_box ? h->d_vbox.p : nullptr;
+    DR.model = model; DR.ncx = ncx; DR.ncy = ncy; DR.nside = vref_nb > 0 ? vref_nb - 1 : 0;
+    DR.node_xy = h->node_xy.p; DR.node_va = h->node_va.p; DR.node_vb = h->node_vb.p; DR.node_sys = h->node_sys.p; DR.node_bnd = h->node_bnd.p;
+    DR.elem_node = h->elem_node.p; DR.elem_sys = h->elem_sys.p; DR.bnd_sys = h->bnd_sys.p; DR.bnd_node = h->bnd_node.p; DR.bnd_s = h->bnd_s.p;
+    DR.bedge = h->bedge.p; DR.bedge_nl = h->bedge_nl.p; DR.sys_cnt = h->sys_cnt.p;
+    if (model == RVE_MODEL_DNN && DR.nside == 0) FAIL(RVE_E_MESH, "dnn model needs vref_nb > 0");
+    k_ds_rows<<<n_sys, DS_THREADS, 0, st>>>(DM, DR);
+    h->launches += 1;
+    if (h->nvref > 0) {
+        k_ds_vref<<<n_sys, 256, 0, st>>>(DM, h->box.p, DR.vbox, DR.nside, he_vb /* free phase-A scratch */, h->samp_elem.p, h->samp_lam.p, h->sys_cnt.p);
+        h->launches += 1;
+    }
+    CU(cudaMemcpyAsync(cnt.data(), h->sys_cnt.p, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(stream_wait(h));
+    CU(cudaGetLastError());
+    if (check_sys()) return RVE_E_MESH;
+
+    // prefix sums over the systems
+    h->elem_base = h->toff;
+    h->row_base.assign(n_sys + 1, 0); h->blk_base.assign(n_sys + 1, 0); h->win_base.assign(n_sys + 1, 0);
+    h->slice_base.assign(n_sys + 1, 0); h->adjf_base.assign(n_sys + 1, 0); h->grp_base.assign(n_sys + 1, 0);
+    h->max_tile = 0; h->max_cn = 0; h->max_words = 0;
+    for (int s = 0; s < n_sys; ++s) {
+        I[s].na = cnt[8 * (size_t)s + DC_NA]; I[s].nblk = cnt[8 * (size_t)s + DC_NBLK]; I[s].ngrp = cnt[8 * (size_t)s + DC_NGRP];
+        I[s].nadj = cnt[8 * (size_t)s + DC_NADJ];
+        I[s].nwin = (I[s].na + RVE_WIN - 1) / RVE_WIN; I[s].nsl = (I[s].na + 31) / 32;
+        const long long nr = (long long)h->row_base[s] + I[s].na, nb = h->blk_base[s] + I[s].nblk, ng = h->grp_base[s] + I[s].ngrp,
+                        nh = h->adjf_base[s] + I[s].nadj;
+        if (nr * 4 > 2000000000LL || nb > 4000000000LL || ng > 4000000000LL || nh > 2000000000LL)
+            FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
+        h->row_base[s + 1] = (int)nr; h->blk_base[s + 1] = nb; h->grp_base[s + 1] = ng; h->adjf_base[s + 1] = nh;
+        h->win_base[s + 1] = h->win_base[s] + I[s].nwin; h->slice_base[s + 1] = h->slice_base[s] + I[s].nsl;
+        h->max_words = std::max(h->max_words, (I[s].na + 31) / 32);
+    }
+    h->R = h->row_base[n_sys]; h->NB = h->blk_base[n_sys]; h->NG = h->grp_base[n_sys]; h->n_win = h->win_base[n_sys];
+    const int n_win = h->n_win, n_slice = h->slice_base[n_sys];
+    h->u_blk.resize(n_sys + 1); h->u_grp.resize(n_sys + 1); h->u_adjf.resize(n_sys + 1);
+    for (int s = 0; s <= n_sys; ++s) { h->u_blk[s] = (unsigned)h->blk_base[s]; h->u_grp[s] = (unsigned)h->grp_base[s]; h->u_adjf[s] = (unsigned)h->adjf_base[s]; }
+
+    // ---- (C) local numbering -> global row / block / slice index spaces
+    UPL(h->d_row_base, h->row_base); UPL(h->sys_win0, h->win_base); UPL(h->d_slice_base, h->slice_base);
+    UPL(h->d_blk_base, h->u_blk); UPL(h->d_grp_base, h->u_grp); UPL(h->d_adjf_base, h->u_adjf);
+    CU(h->row_node.alloc((size_t)h->R)); CU(h->d_row_ptr.alloc((size_t)h->R + 1)); CU(h->adjf_ptr.alloc((size_t)h->R + 1));
+    CU(h->adjf.alloc((size_t)h->adjf_base[n_sys])); CU(h->win_sys.alloc(n_win)); CU(h->win_row0.alloc(n_win)); CU(h->win_n.alloc(n_win));
+    CU(h->win_slice0.alloc(n_win)); CU(h->slice_ptr.alloc((size_t)n_slice + 1));
+    DsFinish DF;
+    DF.node_base = h->d_node_base.p; DF.row_base = h->d_row_base.p; DF.win_base = h->sys_win0.p; DF.slice_base = h->d_slice_base.p;
+    DF.blk_base = h->d_blk_base.p; DF.grp_base = h->d_grp_base.p; DF.adjf_base = h->d_adjf_base.p;
+    DF.row_node_loc = DR.row_node_loc; DF.node_row_loc = DR.node_row_loc; DF.loc_rowptr = DR.loc_rowptr; DF.loc_adjptr = DR.loc_adjptr;
+    DF.loc_slw = DR.loc_slw; DF.oldid = DR.oldid; DF.adjc = DR.adjc; DF.adj = DR.adj;
+    DF.node_row = h->node_row.p; DF.row_node = h->row_node.p; DF.row_ptr = h->d_row_ptr.p; DF.adjf_ptr = h->adjf_ptr.p; DF.adjf = h->adjf.p;
+    DF.win_sys = h->win_sys.p; DF.win_row0 = h->win_row0.p; DF.win_n = h->win_n.p; DF.win_slice0 = h->win_slice0.p; DF.slice_ptr = h->slice_ptr.p;
+    DF.n_sys = n_sys;
+    k_ds_finish<<<n_sys, DS_THREADS, 0, st>>>(DM, DF);
+    h->launches += 1;
     auto t1 = std::chrono::steady_clock::now();
     h->t_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
     if (std::getenv("RVE_DEBUG_TIMING"))
-        fprintf(stderr, "[rve_set_batch] n_sys %d: pass1 %.1f ms, pass2 %.1f ms, prefix+flatten %.1f ms\n", n_sys,
-                std::chrono::duration<double, std::milli>(tp1 - t0).count(), std::chrono::duration<double, std::milli>(tp2 - tp1).count(),
-                std::chrono::duration<double, std::milli>(t1 - tp2).count());
-
-    cudaStream_t st = h->stream;
-    UPL(h->node_xy, node_xy); UPL(h->box, box);
-    UPL(h->node_row, node_row); UPL(h->node_bnd, node_bnd); UPL(h->node_sys, node_sys);
-    UPL(h->elem_node, elem_node); UPL(h->elem_sys, elem_sys); UPL(h->elem_reg, elem_reg);
-    UPL(h->d_row_base, h->row_base);
-    UPL(h->bnd_sys, bnd_sys); UPL(h->bnd_node, bnd_node);
-    UPL(h->bnd_s, bnd_s); UPL(h->bedge, bedge); UPL(h->bedge_nl, bedge_nl);
-    UPL(h->d_bedge_base, h->bedge_base); UPL(h->samp_elem, samp_elem); UPL(h->samp_lam, samp_lam);
-    UPL(h->win_sys, win_sys); UPL(h->win_row0, win_row0); UPL(h->win_n, win_n); UPL(h->win_slice0, win_slice0);
-    UPL(h->sys_win0, h->win_base); UPL(h->row_node, row_node);
-    UPL(h->slice_ptr, slice_ptr); UPL(h->d_row_ptr, row_ptr); UPL(h->adjf_ptr, adjf_ptr); UPL(h->adjf, adjf);
-    std::vector<double> vb(h->vref_box, h->vref_box + 4);
-    UPL(h->d_vbox, vb);
+        fprintf(stderr, "[rve_set_batch] n_sys %d: copy + edges %.1f ms, rows + finish (enqueue) %.1f ms\n", n_sys,
+                std::chrono::duration<double, std::milli>(tp1 - t0).count(), std::chrono::duration<double, std::milli>(t1 - tp1).count());
     CU(h->bval.alloc(128 * (size_t)h->NG)); CU(h->dinv.alloc((size_t)h->R)); CU(h->wmean.alloc(h->R));
     CU(h->active.alloc(n_sys)); CU(h->cnt.alloc(n_sys)); CU(h->d_iters.alloc(n_sys)); CU(h->n_active.alloc(1));
     CU(h->err_flag.alloc(1));
@@ -476,14 +516,14 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     // coarse hierarchy
     Levels& LV = h->LV;
     memset(&LV, 0, sizeof(Levels));
-    int ncx = P.ncx, ncy = P.ncy, L = 0;
+    int lcx = ncx, lcy = ncy, L = 0;
     while (L < RVE_MAXLEV) {
         Grid& g = LV.g[L];
-        g.ncx = ncx; g.ncy = ncy; g.nx = ncx + 1; g.ny = ncy + 1; g.G = g.nx * g.ny;
+        g.ncx = lcx; g.ncy = lcy; g.nx = lcx + 1; g.ny = lcy + 1; g.G = g.nx * g.ny;
         g.wrap = (model == RVE_MODEL_PER);
-        if (model == RVE_MODEL_LIN || model == RVE_MODEL_DNN) { g.lox = 1; g.loy = 1; g.hix = ncx - 1; g.hiy = ncy - 1; }
-        else if (model == RVE_MODEL_PER) { g.lox = 0; g.loy = 0; g.hix = ncx - 1; g.hiy = ncy - 1; }
-        else { g.lox = 0; g.loy = 0; g.hix = ncx; g.hiy = ncy; }
+        if (model == RVE_MODEL_LIN || model == RVE_MODEL_DNN) { g.lox = 1; g.loy = 1; g.hix = lcx - 1; g.hiy = lcy - 1; }
+        else if (model == RVE_MODEL_PER) { g.lox = 0; g.loy = 0; g.hix = lcx - 1; g.hiy = lcy - 1; }
+        else { g.lox = 0; g.loy = 0; g.hix = lcx; g.hiy = lcy; }
         CU(h->lvA[L].alloc((size_t)n_sys * 100 * g.G)); CU(h->lvD[L].alloc((size_t)n_sys * 4 * g.G));
         CU(h->lvR[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2)); CU(h->lvX[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2));
         CU(h->lvT[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2));
@@ -491,13 +531,12 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         LV.A[L] = h->lvA[L].p; LV.dinv[L] = h->lvD[L].p; LV.rc[L] = h->lvR[L].p; LV.xc[L] = h->lvX[L].p; LV.tc[L] = h->lvT[L].p;
         LV.A4[L] = h->lvA4[L].p; LV.H4[L] = h->lvH4[L].p;
         ++L;
-        if ((ncx % 2) || (ncy % 2) || ncx / 2 < 2 || ncy / 2 < 2) break;
-        ncx /= 2; ncy /= 2;
+        if ((lcx % 2) || (lcy % 2) || lcx / 2 < 2 || lcy / 2 < 2) break;
+        lcx /= 2; lcy /= 2;
     }
     LV.L = L;
     CU(h->cpart.alloc((size_t)n_sys * ((LV.g[0].G + 255) / 256) * 4));
-    if (n_sys > 65535) FAIL(RVE_E_ARG, "more than 65535 systems in one batch: split it");
-    // device half of the symbolic phase: block columns, halo lists, SELL columns
+    // block columns, halo lists, SELL columns, restriction lists
     const long long halo_cap = h->R + h->R / 2 + 4096;
     if (halo_cap > 2000000000LL) FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
     CU(h->csr_col.alloc((size_t)h->NB)); CU(h->emap.alloc(36 * (size_t)h->E)); CU(h->rlen.alloc((size_t)h->R));
@@ -583,34 +622,39 @@ int rve_assemble(rve_handle_t h) {
 int rve_get_sizes(rve_handle_t h, int32_t sys, int64_t* n_nodes, int64_t* n_rows, int64_t* n_blocks, int64_t* n_elems) {
     H_CHECK(h);
     if (!h->have_batch || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_ARG, "bad system index");
-    if (n_nodes) *n_nodes = h->sym[sys].nn;
-    if (n_rows) *n_rows = h->sym[sys].na;
+    if (n_nodes) *n_nodes = h->info[sys].nn;
+    if (n_rows) *n_rows = h->info[sys].na;
     if (n_blocks) *n_blocks = (int64_t)h->true_blocks[sys];
-    if (n_elems) *n_elems = h->sym[sys].nt;
+    if (n_elems) *n_elems = h->info[sys].nt;
     return 0;
 }
 
 int rve_get_csr(rve_handle_t h, int32_t sys, int32_t* rowptr, int32_t* col, double* val) {
     H_CHECK(h);
     if (!h->assembled || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_STATE, "not assembled / bad system index");
-    const SysSym& Y = h->sym[sys];
-    const size_t ng = Y.slice_ptr.back();
+    const SysInfo& Y = h->info[sys];
+    const size_t ng = (size_t)Y.ngrp;
+    const int rb0 = h->row_base[sys], sl0 = h->slice_base[sys];
     std::vector<double> bv(128 * ng);
     CU(cudaMemcpy(bv.data(), h->bval.p + 128 * (size_t)h->grp_base[sys], bv.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    std::vector<int> cc(Y.nblocks);            // block columns as found on the device (global rows), capacity layout
+    std::vector<int> cc((size_t)Y.nblk);       // block columns as found on the device (global rows), capacity layout
     CU(cudaMemcpy(cc.data(), h->csr_col.p + (size_t)h->blk_base[sys], cc.size() * sizeof(int), cudaMemcpyDeviceToHost));
     std::vector<unsigned char> rl(Y.na);       // true row lengths
-    CU(cudaMemcpy(rl.data(), h->rlen.p + (size_t)h->row_base[sys], rl.size(), cudaMemcpyDeviceToHost));
-    const int rb0 = h->row_base[sys];
+    CU(cudaMemcpy(rl.data(), h->rlen.p + (size_t)rb0, rl.size(), cudaMemcpyDeviceToHost));
+    std::vector<unsigned> rp((size_t)Y.na + 1), sp((size_t)Y.nsl + 1);   // capacity row pointer / slice pointer (global offsets)
+    CU(cudaMemcpy(rp.data(), h->d_row_ptr.p + (size_t)rb0, rp.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(sp.data(), h->slice_ptr.p + (size_t)sl0, sp.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    const unsigned kb0 = (unsigned)h->blk_base[sys], gb0 = (unsigned)h->grp_base[sys];
     // SELL slot j of a row holds the j-th column the device found for that row
     int64_t pos = 0;
     for (int r = 0; r < Y.na; ++r) {
         const int w = r / RVE_WIN, rlw = r % RVE_WIN, lane = rlw & 31;
-        const size_t g0 = Y.slice_ptr[Y.win_slice0[w] + (rlw >> 5)];
+        const size_t g0 = sp[(size_t)w * (RVE_WIN / 32) + (rlw >> 5)] - gb0;
+        const unsigned k0 = rp[r] - kb0;
         for (int c = 0; c < 2; ++c) {
             rowptr[2 * r + c] = (int32_t)pos;
-            for (unsigned k = Y.row_ptr[r]; k < Y.row_ptr[r] + rl[r]; ++k) {
-                const size_t g = g0 + (k - Y.row_ptr[r]);
+            for (unsigned k = k0; k < k0 + rl[r]; ++k) {
+                const size_t g = g0 + (k - k0);
                 for (int d = 0; d < 2; ++d) { col[pos] = 2 * (cc[k] - rb0) + d; val[pos] = bv[128 * g + 64 * c + 2 * lane + d]; ++pos; }
             }
         }
@@ -619,26 +663,39 @@ int rve_get_csr(rve_handle_t h, int32_t sys, int32_t* rowptr, int32_t* col, doub
     return 0;
 }
 
+// (va, vb) = the mesh vertices a node sits on (va == vb) or between: numbering-independent node keys
+static int node_keys(rve_handle_t h, int32_t sys, std::vector<int>& va, std::vector<int>& vb) {
+    const SysInfo& Y = h->info[sys];
+    va.resize(Y.nn); vb.resize(Y.nn);
+    CU(cudaMemcpy(va.data(), h->node_va.p + (size_t)h->node_base[sys], va.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(vb.data(), h->node_vb.p + (size_t)h->node_base[sys], vb.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int rve_get_rowmap(rve_handle_t h, int32_t sys, int32_t* va, int32_t* vb) {
     H_CHECK(h);
     if (!h->have_batch || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_ARG, "bad system index");
-    const SysSym& Y = h->sym[sys];
-    for (int r = 0; r < Y.na; ++r) { va[r] = Y.node_va[Y.row_node[r]]; vb[r] = Y.node_vb[Y.row_node[r]]; }
+    const SysInfo& Y = h->info[sys];
+    std::vector<int> a, b, rn(Y.na);
+    if (int rc = node_keys(h, sys, a, b)) return rc;
+    CU(cudaMemcpy(rn.data(), h->row_node.p + (size_t)h->row_base[sys], rn.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < Y.na; ++r) { va[r] = a[rn[r] - h->node_base[sys]]; vb[r] = b[rn[r] - h->node_base[sys]]; }
     return 0;
 }
 
 int rve_get_nodemap(rve_handle_t h, int32_t sys, int32_t* va, int32_t* vb) {
     H_CHECK(h);
     if (!h->have_batch || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_ARG, "bad system index");
-    const SysSym& Y = h->sym[sys];
-    for (int n = 0; n < Y.nn; ++n) { va[n] = Y.node_va[n]; vb[n] = Y.node_vb[n]; }
+    std::vector<int> a, b;
+    if (int rc = node_keys(h, sys, a, b)) return rc;
+    for (size_t n = 0; n < a.size(); ++n) { va[n] = a[n]; vb[n] = b[n]; }
     return 0;
 }
 
 int rve_get_rhs(rve_handle_t h, int32_t sys, double* rhs) {
     H_CHECK(h);
     if (!h->solved || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_STATE, "no solve yet / bad system index");
-    CU(cudaMemcpy(rhs, h->b.p + (size_t)h->row_base[sys] * h->K * 2, (size_t)h->sym[sys].na * h->K * 2 * sizeof(double),
+    CU(cudaMemcpy(rhs, h->b.p + (size_t)h->row_base[sys] * h->K * 2, (size_t)h->info[sys].na * h->K * 2 * sizeof(double),
                   cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -646,7 +703,7 @@ int rve_get_rhs(rve_handle_t h, int32_t sys, double* rhs) {
 int rve_get_solution(rve_handle_t h, int32_t sys, double* u) {
     H_CHECK(h);
     if (!h->solved || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_STATE, "no solve yet / bad system index");
-    CU(cudaMemcpy(u, h->U.p + (size_t)h->node_base[sys] * h->NL * 2, (size_t)h->sym[sys].nn * h->NL * 2 * sizeof(double),
+    CU(cudaMemcpy(u, h->U.p + (size_t)h->node_base[sys] * h->NL * 2, (size_t)h->info[sys].nn * h->NL * 2 * sizeof(double),
                   cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -817,7 +874,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     // algorithmic SpMV bytes of the solve: sum over systems of iters * B_spmv(K)
     double bytes = 0;
     for (int s = 0; s < n_sys; ++s) {
-        const double n = 2.0 * h->sym[s].na, nnz = 4.0 * (double)h->true_blocks[s];
+        const double n = 2.0 * h->info[s].na, nnz = 4.0 * (double)h->true_blocks[s];
         bytes += hit[s] * (12.0 * nnz + 4.0 * (n + 1) + 16.0 * n * K);
     }
     h->c_cnt[1] = bytes;

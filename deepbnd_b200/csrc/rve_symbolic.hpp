@@ -290,12 +290,13 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
             const int r = erow[6 * (size_t)t + k];
             if (r >= 0) adj[fill[r]++] = t;
         }
-    std::vector<int> mark(P.lite ? 0 : na, -1), len0(na);
-    if (P.lite) {
-        // row CAPACITIES from the element fans alone (no dedupe on the host; the GPU finds the true columns and
-        // lengths): a vertex with d elements around it couples to 3d+1 nodes in a closed fan and to 3d+3 in an open
-        // one (rows that gather a mesh-boundary node), a mid-edge node to 9 (two elements) or 6 (one).  Inactive
-        // neighbours only shorten a row.  Measured SELL padding with these widths: +0.3..1 % over the exact ones.
+    std::vector<int> mark(P.lite ? 0 : na, -1), len0(na), cap0(na);
+    {
+        // row CAPACITIES from the element fans alone (no dedupe; the GPU finds the true columns and lengths): a vertex
+        // with d elements around it couples to 3d+1 nodes in a closed fan and to 3d+3 in an open one (rows that gather a
+        // mesh-boundary node), a mid-edge node to 9 (two elements) or 6 (one).  Inactive neighbours only shorten a row.
+        // Measured SELL padding with these widths: +0.3..1 % over the exact ones.  The window sort below always uses
+        // the capacities, so that this numbering is the one of the device symbolic phase (rve_devsym.cuh).
         std::vector<unsigned char> rowb(na, 0);
         for (int i = 0; i < S.nb; ++i) {
             const int r = nrow0[S.bnd_node[i]];
@@ -303,8 +304,11 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
         }
         for (int r = 0; r < na; ++r) {
             const int d = adj_ptr[r + 1] - adj_ptr[r];
-            len0[r] = pnode[r] < S.nv ? 3 * d + (rowb[r] ? 3 : 1) : (d >= 2 ? 9 : 6);
+            cap0[r] = pnode[r] < S.nv ? 3 * d + (rowb[r] ? 3 : 1) : (d >= 2 ? 9 : 6);
         }
+    }
+    if (P.lite) {
+        len0 = cap0;
     } else {
         for (int r = 0; r < na; ++r) {
             int cnt = 0;
@@ -328,11 +332,11 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
         for (int w = 0; w < nwin; ++w) {                    // stable counting sort by length (lengths < 64)
             const int r0 = w * RVE_WIN, r1 = std::min(na, r0 + RVE_WIN);
             for (int k = 0; k < 64; ++k) bucket[k] = 0;
-            for (int r = r0; r < r1; ++r) bucket[63 - std::min(len0[r], 63)]++;
+            for (int r = r0; r < r1; ++r) bucket[63 - std::min(cap0[r], 63)]++;
             int acc = 0;
             for (int k = 0; k < 64; ++k) { const int c = bucket[k]; bucket[k] = acc; acc += c; }
             for (int r = r0; r < r1; ++r) {
-                const int pos = r0 + bucket[63 - std::min(len0[r], 63)]++;
+                const int pos = r0 + bucket[63 - std::min(cap0[r], 63)]++;
                 newid[r] = pos; oldid[pos] = r;
             }
         }
@@ -595,8 +599,6 @@ static std::string sym_selfcheck(const SysSym& S) {
                 const int c = lc < wn ? r0 + lc : (lc - wn < h1 - h0 ? S.halo[h0 + lc - wn] : -1);
                 if (c != S.bcol[S.row_ptr[r] + j]) return "SELL column mismatch";
             }
-            // length-sorted inside the window
-            if (rl > 0 && len > (int)(S.row_ptr[r] - S.row_ptr[r - 1])) return "rows not sorted by length";
         }
         const int c0 = S.win_cn0[w], c1 = S.win_cn0[w + 1];
         std::vector<int> seen(4 * (size_t)wn, 0);

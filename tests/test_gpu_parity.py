@@ -422,3 +422,29 @@ def test_spmv_microbenchmark_entry(coarse_reduced_meshes):
         n, nnz = 2 * nrow, 4 * nblk
         assert by == pytest.approx(12.0 * nnz + 4.0 * (n + len(coarse_reduced_meshes)) + 16.0 * n * k)
     b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["lin", "per", "MR", "dnn"])
+def test_device_symbolic_matches_host_hook(reduced_meshes, full_mesh, model):
+    """the GPU symbolic phase (rve_devsym.cuh: P2 numbering, constraint map, Morton row order, window sort) yields the
+    numbering of the CPU test hook rve_host_symbolic entry by entry, on a reduced and on a full mesh."""
+    from deepbnd_b200.batch import RVEBatch, host_symbolic
+    for mesh in (reduced_meshes[0], full_mesh):
+        ref = host_symbolic(*mesh, model=model, vref_nb=21)
+        b = RVEBatch().set_meshes([mesh], PARAM, model=model, vref_nb=21)
+        sz = b.sizes(0)
+        assert sz["n_nodes"] == ref["n_nodes"] and sz["n_rows"] == ref["n_rows"]
+        va, vb = b.rowmap(0)
+        assert np.array_equal(va, ref["row_va"]) and np.array_equal(vb, ref["row_vb"])
+        nva, nvb = b.nodemap(0)
+        tri = np.asarray(mesh[1])
+        nv = len(mesh[0])
+        assert np.array_equal(nva[:nv], np.arange(nv)) and np.array_equal(nvb[:nv], np.arange(nv))
+        keys = nva[nv:].astype(np.int64) * (1 << 32) + nvb[nv:]
+        assert np.all(np.diff(keys) > 0)                                 # mid-edge nodes sorted by (va, vb), unique
+        e = np.sort(np.concatenate([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]]), axis=1)
+        assert np.array_equal(np.unique(e[:, 0].astype(np.int64) * (1 << 32) + e[:, 1]), keys)
+        b.assemble()
+        assert b.sizes(0)["n_blocks"] == ref["n_blocks"]                 # true block count found from the element fans
+        b.close()
