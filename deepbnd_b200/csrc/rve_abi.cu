@@ -128,6 +128,7 @@ struct rve_batch_s {
     int* h_nactive = nullptr;  // pinned
     PinnedArena arena;
     std::vector<cudaEvent_t> evpool;  // per-iteration SpMV timing
+    std::vector<cudaEvent_t> evdbg;   // RVE_KTIME diagnostics
     double launches = 0;              // kernels launched since rve_create
     double h2d_bytes = 0, d2h_bytes = 0;  // host<->device traffic since rve_create
     double t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -311,6 +312,7 @@ int rve_destroy(rve_handle_t h) {
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->ev_block) cudaEventDestroy(h->ev_block);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->evdbg) cudaEventDestroy(e);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
     h->arena.release();
     cudaStream_t s = h->stream;
@@ -815,13 +817,21 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
         return h->evpool[i];
     };
     *h->h_nactive = n_sys;
+    // RVE_KTIME=1: per-iteration time of the V-cycle, direction, SpMV and update kernels (stderr; diagnostics only)
+    static const bool ktime = [] { const char* e = std::getenv("RVE_KTIME"); return e && e[0] == '1'; }();
+    auto dbg_event = [&](size_t i) -> cudaEvent_t {
+        while (h->evdbg.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); h->evdbg.push_back(e); }
+        return h->evdbg[i];
+    };
     while (it < maxit) {
         for (int k = 0; k < CHECK && it < maxit; ++k, ++it) {
+            if (ktime) cudaEventRecord(dbg_event(3 * (size_t)it), st);
             if (precond) {
 #define VC_(KK) launch_vcycle<KK>(h, pa, it == 0, st)
                 K_DISPATCH(K, VC_);
 #undef VC_
             }
+            if (ktime) cudaEventRecord(dbg_event(3 * (size_t)it + 1), st);
 #define DIR_(KK) launch_direction<KK>(h, pa, st)
             K_DISPATCH(K, DIR_);
 #undef DIR_
@@ -833,6 +843,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
 #define UPD_(KK) launch_update<KK>(h, pa, 0, it, st)
             K_DISPATCH(K, UPD_);
 #undef UPD_
+            if (ktime) cudaEventRecord(dbg_event(3 * (size_t)it + 2), st);
             ++launched;
             h->launches += 3;
         }
@@ -859,6 +870,16 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     double spmv_ms = 0;
     for (int i = 0; i < launched; ++i) { cudaEventElapsedTime(&ms, h->evpool[2 * i], h->evpool[2 * i + 1]); spmv_ms += ms; }
     h->t_ms[6] = spmv_ms;
+    if (ktime && launched > 0) {
+        double tv = 0, td = 0, tu = 0;
+        for (int i = 0; i < launched; ++i) {
+            cudaEventElapsedTime(&ms, h->evdbg[3 * i], h->evdbg[3 * i + 1]); tv += ms;
+            cudaEventElapsedTime(&ms, h->evdbg[3 * i + 1], h->evpool[2 * i]); td += ms;
+            cudaEventElapsedTime(&ms, h->evpool[2 * i + 1], h->evdbg[3 * i + 2]); tu += ms;
+        }
+        fprintf(stderr, "[rve_solve] n_sys %d K %d its %d: per iteration (us) vcycle %.1f direction %.1f spmv %.1f update %.1f\n", n_sys, K,
+                launched, 1e3 * tv / launched, 1e3 * td / launched, 1e3 * spmv_ms / launched, 1e3 * tu / launched);
+    }
     cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->c_cnt[5] = ms;  // constraint post-processing + nodal field
     h->launches += 2;
     bool allconv = true;

@@ -475,8 +475,9 @@ k_ds_rows(DsMesh M, DsRows A) {
         if (r >= 0) adj[adjc[r] + atomicAdd(&cur[r], 1)] = q / 6;
     }
     __syncthreads();
-    // row CAPACITIES from the element fans (rve_symbolic.hpp, lite mode): a vertex with d elements couples to 3d+1
-    // nodes in a closed fan, 3d+3 in an open one, a mid-edge node to 9 or 6; the true columns come from k_sym_cols
+    // row CAPACITIES from the element fans: a vertex with d elements couples to 3d+1 nodes in a closed fan, 3d+3 in an
+    // open one (rows that gather a mesh-boundary node), a mid-edge node to 9 or 6; inactive neighbours only shorten a
+    // row.  The true columns and lengths come from k_sym_cols; SELL padding with these widths is +0.3..1 %
     for (int r = tid; r < na; r += nth) {
         const int d = adjc[r + 1] - adjc[r];
         ds_isort(adj + adjc[r], d);

@@ -1,11 +1,15 @@
-// rve_symbolic.hpp — host-side symbolic phase of rve_set_batch (multi-threaded over systems).
+// rve_symbolic.hpp — CPU restatement of the symbolic phase, used ONLY by the test hook rve_host_symbolic
+// (the product runs this phase on the GPU: rve_devsym.cuh + k_sym_cols / k_sym_window / k_sym_coarse).
 //
-// For every RVE mesh: P2 numbering (vertices, then edges sorted by (va,vb) — the same order
+// For one RVE mesh: P2 numbering (vertices, then edges sorted by (va,vb) — the same order
 // numpy.unique gives the oracle), boundary detection, the constraint map of the BC model
 // (Dirichlet elimination for lin/dnn, periodic master map for per, identity for MR), active
-// block rows ordered by level-1 coarse cell, node-block CSR pattern, Vref sample location.
-// This replaces what dolfin's DofMap / multiphenics' BlockDofMap / PeriodicBoundary build
+// block rows ordered by level-1 coarse cell, node-block CSR pattern, windows / SELL slices / halo and
+// restriction lists, Vref sample location — the device layout, checked for consistency by sym_selfcheck.
+// The CPU tests compare it with the oracle's pattern, the GPU tests compare the device numbering with it.
+// Mirrors what dolfin's DofMap / multiphenics' BlockDofMap / PeriodicBoundary build
 // behind listMultiscaleModels[model](mesh, ...) (core/multiscale/micro_model.py:56-57).
+// Also holds the shared constants (RVE_WIN, RowInfo), the level-1 grid rule (pick_nc) and parallel_for.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -51,9 +55,6 @@ struct SysSym {
     std::vector<unsigned> cn_beg;    // [sum ncn + 1] offsets into cn_ent
     std::vector<uint16_t> cn_ent;    // (row_in_window << 2) | corner
     std::vector<RowInfo> rowinfo;    // [na] bilinear weights + window-local coarse slots
-    // inputs of the device-side pattern build (lite mode): elements around every row, in final row order
-    std::vector<unsigned> adjf_ptr;  // [na+1]
-    std::vector<int> adjf;           // local element ids
     size_t nblocks = 0;              // number of 2x2 blocks of the system
     std::vector<int> bnd_node;       // [nb]
     std::vector<double> bnd_s;       // [nb][2] Vref perimeter parameters of the end vertices
@@ -72,7 +73,6 @@ struct SymParams {
     int vref_nb;         // 0: none
     bool vref_box_given;
     double vref_box[4];
-    bool lite = false;   // true: the block columns, halo lists and SELL column fill are built on the GPU
 };
 
 // pass 1: everything that does not depend on the level-1 grid
@@ -290,7 +290,7 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
             const int r = erow[6 * (size_t)t + k];
             if (r >= 0) adj[fill[r]++] = t;
         }
-    std::vector<int> mark(P.lite ? 0 : na, -1), len0(na), cap0(na);
+    std::vector<int> mark(na, -1), len0(na), cap0(na);
     {
         // row CAPACITIES from the element fans alone (no dedupe; the GPU finds the true columns and lengths): a vertex
         // with d elements around it couples to 3d+1 nodes in a closed fan and to 3d+3 in an open one (rows that gather a
@@ -307,20 +307,16 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
             cap0[r] = pnode[r] < S.nv ? 3 * d + (rowb[r] ? 3 : 1) : (d >= 2 ? 9 : 6);
         }
     }
-    if (P.lite) {
-        len0 = cap0;
-    } else {
-        for (int r = 0; r < na; ++r) {
-            int cnt = 0;
-            for (int i = adj_ptr[r]; i < adj_ptr[r + 1]; ++i) {
-                const int* er = &erow[6 * (size_t)adj[i]];
-                for (int k = 0; k < 6; ++k) {
-                    const int c = er[k];
-                    if (c >= 0 && mark[c] != r) { mark[c] = r; ++cnt; }
-                }
+    for (int r = 0; r < na; ++r) {       // exact row lengths by a marker-array dedupe over the adjacent elements
+        int cnt = 0;
+        for (int i = adj_ptr[r]; i < adj_ptr[r + 1]; ++i) {
+            const int* er = &erow[6 * (size_t)adj[i]];
+            for (int k = 0; k < 6; ++k) {
+                const int c = er[k];
+                if (c >= 0 && mark[c] != r) { mark[c] = r; ++cnt; }
             }
-            len0[r] = cnt;
         }
+        len0[r] = cnt;
     }
     // windows of RVE_WIN consecutive rows; inside a window rows are sorted by descending length so
     // that the 32-row SELL slices are nearly uniform (vertex rows ~19 blocks, mid-edge rows ~9)
@@ -345,32 +341,21 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
     for (int r = 0; r < na; ++r) S.row_node[r] = pnode[oldid[r]];
     S.node_row.resize(nn);
     for (int n = 0; n < nn; ++n) S.node_row[n] = nrow0[n] < 0 ? -1 : newid[nrow0[n]];
-    // CSR row pointer in the final numbering (lite mode: from the row capacities; the columns and true lengths are
-    // found on the GPU by k_sym_cols from the element lists around each row), otherwise exact (accessors, CPU tests)
+    // CSR row pointer and block columns in the final numbering
     S.row_ptr.assign(na + 1, 0);
     for (int r = 0; r < na; ++r) S.row_ptr[r + 1] = S.row_ptr[r] + (unsigned)len0[oldid[r]];
     S.nblocks = S.row_ptr[na];
-    S.bcol.clear();
-    S.adjf_ptr.clear(); S.adjf.clear();
-    if (P.lite) {
-        S.adjf_ptr.assign(na + 1, 0u);
-        for (int r = 0; r < na; ++r) S.adjf_ptr[r + 1] = S.adjf_ptr[r] + (unsigned)(adj_ptr[oldid[r] + 1] - adj_ptr[oldid[r]]);
-        S.adjf.resize(S.adjf_ptr[na]);
-        for (int r = 0; r < na; ++r)
-            std::copy(adj.begin() + adj_ptr[oldid[r]], adj.begin() + adj_ptr[oldid[r] + 1], S.adjf.begin() + S.adjf_ptr[r]);
-    } else {
-        S.bcol.resize(S.row_ptr[na]);
-        std::fill(mark.begin(), mark.end(), -1);
-        for (int r = 0; r < na; ++r) {
-            const int o = oldid[r];
-            int* dst = &S.bcol[S.row_ptr[r]];
-            int cnt = 0;
-            for (int i = adj_ptr[o]; i < adj_ptr[o + 1]; ++i) {
-                const int* er = &erow[6 * (size_t)adj[i]];
-                for (int k = 0; k < 6; ++k) {
-                    const int c = er[k];
-                    if (c >= 0 && mark[c] != r) { mark[c] = r; dst[cnt++] = newid[c]; }
-                }
+    S.bcol.resize(S.row_ptr[na]);
+    std::fill(mark.begin(), mark.end(), -1);
+    for (int r = 0; r < na; ++r) {
+        const int o = oldid[r];
+        int* dst = &S.bcol[S.row_ptr[r]];
+        int cnt = 0;
+        for (int i = adj_ptr[o]; i < adj_ptr[o + 1]; ++i) {
+            const int* er = &erow[6 * (size_t)adj[i]];
+            for (int k = 0; k < 6; ++k) {
+                const int c = er[k];
+                if (c >= 0 && mark[c] != r) { mark[c] = r; dst[cnt++] = newid[c]; }
             }
         }
     }
@@ -378,8 +363,8 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
     S.win_n.assign(nwin, 0); S.win_slice0.assign(nwin + 1, 0); S.win_halo0.assign(nwin + 1, 0); S.win_cn0.assign(nwin + 1, 0);
     S.slice_ptr.assign(1, 0u);
     S.scol.clear(); S.halo.clear(); S.cn_node.clear(); S.cn_beg.assign(1, 0u); S.cn_ent.clear();
-    if (!P.lite) S.scol.reserve((size_t)S.bcol.size() + S.bcol.size() / 6);
-    S.rowinfo.resize(P.lite ? 0 : na);
+    S.scol.reserve((size_t)S.bcol.size() + S.bcol.size() / 6);
+    S.rowinfo.resize(na);
     S.max_tile = 0; S.max_cn = 0;
     const int nxg = ncx + 1;
     auto cnode = [&](int i, int j) -> int {   // same validity rules as grid_node() on the device
@@ -389,21 +374,12 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
         if (i < lo || i > hix || j < lo || j > hiy) return -1;
         return j * nxg + i;
     };
-    std::vector<int> hal, cns, hpos(P.lite ? 0 : na, -1), cpos((size_t)nxg * (ncy + 1), -1), ccount, cfill;
+    std::vector<int> hal, cns, hpos(na, -1), cpos((size_t)nxg * (ncy + 1), -1), ccount, cfill;
     std::vector<int> corner(4 * (size_t)RVE_WIN);
     for (int w = 0; w < nwin; ++w) {
         const int r0 = w * RVE_WIN, r1 = std::min(na, r0 + RVE_WIN), wn = r1 - r0;
         S.win_n[w] = wn;
         const int nsl = (wn + 31) / 32;
-        if (P.lite) {
-            // only the slice widths: the device fills halo lists and SELL columns (k_sym_window)
-            for (int sl = 0; sl < nsl; ++sl) {
-                const int a0 = r0 + 32 * sl, a1 = std::min(r1, a0 + 32);
-                int width = 0;
-                for (int r = a0; r < a1; ++r) width = std::max(width, (int)(S.row_ptr[r + 1] - S.row_ptr[r]));
-                S.slice_ptr.push_back(S.slice_ptr.back() + (unsigned)width);
-            }
-        } else {
         hal.clear();
         for (unsigned k = S.row_ptr[r0]; k < S.row_ptr[r1]; ++k) {
             const int c = S.bcol[k];
@@ -436,9 +412,7 @@ static void sym_pass2(SysSym& S, const SymParams& P) {
             S.slice_ptr.push_back(S.slice_ptr.back() + (unsigned)width);
         }
         for (size_t k = 0; k < hal.size(); ++k) hpos[hal[k]] = -1;
-        }
         S.win_slice0[w + 1] = S.win_slice0[w] + nsl;
-        if (P.lite) { S.win_cn0[w + 1] = 0; continue; }   // restriction lists are built on the GPU (k_sym_coarse)
         // coarse nodes touched by the window and the (row, corner) lists of each of them
         cns.clear();
         for (int r = r0; r < r1; ++r) {
