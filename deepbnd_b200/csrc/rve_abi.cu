@@ -119,7 +119,8 @@ struct rve_batch_s {
     std::vector<long long> adjf_base;
     int max_words = 0;
     DBuf<RowInfo> rowinfo;
-    DBuf<double> lvA[RVE_MAXLEV], lvD[RVE_MAXLEV], lvR[RVE_MAXLEV], lvX[RVE_MAXLEV], lvT[RVE_MAXLEV];
+    DBuf<double> lvA[RVE_MAXLEV], lvD[RVE_MAXLEV];
+    DBuf<float> lvR[RVE_MAXLEV], lvX[RVE_MAXLEV], lvT[RVE_MAXLEV];   // V-cycle vectors (fp32)
     DBuf<float4> lvA4[RVE_MAXLEV], lvH4[RVE_MAXLEV];
     DBuf<double> p, q, x, r, b, part, sc, cpart;
     DBuf<double> eps, eps_eff, Bmat, uD, gval, d_vbox, U, acc, sigL, sigT, aout, Bout, sol, Mx, Gaff, aaff;
@@ -246,7 +247,7 @@ static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStrea
         const int Gm = LV.g[W].G;
         k_vc_mid<K><<<a.n_sys, Gm <= 128 ? 128 : (Gm <= 256 ? 256 : 320), 0, st>>>(LV, W, h->active.p);
         for (int l = W - 1; l >= 0; --l) {
-            const double* src = (l + 1 == W) ? LV.xc[W] : LV.tc[l + 1];
+            const float* src = (l + 1 == W) ? LV.xc[W] : LV.tc[l + 1];
             k_vc_prolong<K><<<grid(l), 256, 0, st>>>(LV, l, src, h->active.p);
             if (l > 0) k_vc_upl<K><<<grid(l), 256, 0, st>>>(LV, l, h->active.p);
         }
@@ -259,7 +260,7 @@ static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStrea
 template <int K>
 static void launch_direction(rve_batch_s* h, const PcgArgs& a, cudaStream_t st) {
     k_direction<K><<<a.n_win, RVE_DIR_THREADS(K), a.sm_dir, st>>>(a.wt, (double2*)h->p.p, (const double2*)h->r.p, h->dinv.p, h->rowinfo.p,
-                                                      h->cn_node.p, (const double2*)a.LV.tc[0], a.LV.g[0].G, h->active.p,
+                                                      h->cn_node.p, (const cvec*)a.LV.tc[0], a.LV.g[0].G, h->active.p,
                                                       h->sc.p, a.precond);
 }
 
@@ -805,7 +806,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     K_DISPATCH(K, ATTR_);
 #undef ATTR_
     const Levels& LV = pa.LV;
-    CU(cudaMemsetAsync(LV.rc[0], 0, h->lvR[0].n * sizeof(double), st));
+    CU(cudaMemsetAsync(LV.rc[0], 0, h->lvR[0].n * sizeof(float), st));
 #define UPD0_(KK) launch_update<KK>(h, pa, 1, -1, st)
     K_DISPATCH(K, UPD0_);
 #undef UPD0_

@@ -36,15 +36,17 @@ struct Grid {
     int wrap;                // periodic wrap
 };
 
+typedef float2 cvec;   // one rhs of a coarse node
+
 struct Levels {
     int L;          // number of coarse levels
     int K;          // rhs count
     Grid g[RVE_MAXLEV];
     double* A[RVE_MAXLEV];      // [n_sys][25][4][G]
     double* dinv[RVE_MAXLEV];   // [n_sys][G][4]
-    double* rc[RVE_MAXLEV];     // [n_sys][G][K][2]
-    double* xc[RVE_MAXLEV];
-    double* tc[RVE_MAXLEV];
+    float* rc[RVE_MAXLEV];      // [n_sys][G][K][2]  the V-cycle runs in fp32 (preconditioner arithmetic only)
+    float* xc[RVE_MAXLEV];
+    float* tc[RVE_MAXLEV];
     float4* A4[RVE_MAXLEV];     // [n_sys][25][G] fp32 copy of A (a00,a01,a10,a11): preconditioner arithmetic only
     float4* H4[RVE_MAXLEV];     // [n_sys][25][G] A_ij * (omega Dinv_j): residual after the first Jacobi step
 };
@@ -797,7 +799,7 @@ __global__ void __launch_bounds__(RVE_UPD_THREADS(K), (K == 1 ? 5 : (RVE_UPD_THR
 k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q, double2* __restrict__ x,
          double2* __restrict__ r, const float4* __restrict__ dinv32, const RowInfo* __restrict__ rowinfo,
          const int* __restrict__ cn_node, const unsigned* __restrict__ cn_beg, const uint16_t* __restrict__ cn_ent,
-         double* __restrict__ rc1, int G, int* active, double* part, int* cnt, double* sc, int init, int iter,
+         float* __restrict__ rc1, int G, int* active, double* part, int* cnt, double* sc, int init, int iter,
          double rtol2, int precond, int* iters, int* n_active) {
     extern __shared__ double2 s_r[];              // [n*K] new residual, then float2 s_st[n], uint16 s_ent[4n]
     constexpr int EPT = RVE_EPT_UPD(K), TPB = RVE_UPD_THREADS(K);   // TPB % K == 0: a thread keeps its rhs index
@@ -864,30 +866,43 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
         acc = warp_sum(acc);
         if (lane == 0) s_fin[wv] = acc;
     }
-    // restriction: 4 threads per (coarse node of the window, rhs) split the node's (row, corner) list;
-    // weights from the staged (s,t)
+    // restriction: 4 threads per coarse node of the window split the node's (row, corner) list, all rhs at once;
+    // weights from the staged (s,t); one vector RED (8 / 16 bytes) per node into the fp32 level-1 residual
     if (precond) {
-        for (int t = tid; t < ((ncn * K * 4 + 31) & ~31); t += TPB) {
-            const int task = t >> 2, sub = t & 3;
-            double a0 = 0.0, a1 = 0.0;
-            int jn = 0, kk = 0;
-            if (task < ncn * K) {
-                jn = task / K; kk = task % K;
+        for (int t = tid; t < ((ncn * 4 + 31) & ~31); t += TPB) {
+            const int jn = t >> 2, sub = t & 3;
+            double a[K][2];
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) { a[kk][0] = 0.0; a[kk][1] = 0.0; }
+            if (jn < ncn) {
                 const unsigned b0 = cn_beg[cn0 + jn] - ent0, b1 = cn_beg[cn0 + jn + 1] - ent0;
                 for (unsigned e = b0 + sub; e < b1; e += 4) {
                     const int en = s_ent[e];
                     const int rl = en >> 2, c = en & 3;
                     const float2 st = s_st[rl];
                     const double wgt = (double)((c & 1) ? st.x : 1.0f - st.x) * (double)((c & 2) ? st.y : 1.0f - st.y);
-                    const double2 v = s_r[rl * K + kk];
-                    a0 += wgt * v.x; a1 += wgt * v.y;
+#pragma unroll
+                    for (int kk = 0; kk < K; ++kk) {
+                        const double2 v = s_r[rl * K + kk];
+                        a[kk][0] += wgt * v.x; a[kk][1] += wgt * v.y;
+                    }
                 }
             }
-            a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-            a0 += __shfl_xor_sync(0xffffffffu, a0, 2); a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-            if (task < ncn * K && sub == 0) {
-                double* d = rc1 + (((size_t)sys * G + cn_node[cn0 + jn]) * K + kk) * 2;
-                atomicAdd(d, a0); atomicAdd(d + 1, a1);
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    a[kk][c] += __shfl_xor_sync(0xffffffffu, a[kk][c], 1);
+                    a[kk][c] += __shfl_xor_sync(0xffffffffu, a[kk][c], 2);
+                }
+            if (jn < ncn && sub == 0) {
+                float* d = rc1 + ((size_t)sys * G + cn_node[cn0 + jn]) * K * 2;
+                if (K == 2) {
+                    atomicAdd((float4*)d, make_float4((float)a[0][0], (float)a[0][1], (float)a[K - 1][0], (float)a[K - 1][1]));
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < K; ++kk) atomicAdd((float2*)d + kk, make_float2((float)a[kk][0], (float)a[kk][1]));
+                }
             }
         }
     }
@@ -948,7 +963,7 @@ __global__ void k_coarse_pack(int n_sys, Grid g, const double* __restrict__ A, c
 // space are zero by construction, so their x is read from the node itself.
 template <int K>
 __device__ __forceinline__ void stencil_apply(const Grid& g, const float4* __restrict__ S4,
-                                              const double2* __restrict__ x, int i, int j, double2* out) {
+                                              const cvec* __restrict__ x, int i, int j, cvec* out) {
     const int idx = j * g.nx + i;
 #pragma unroll
     for (int dj = -2; dj <= 2; ++dj)
@@ -957,12 +972,12 @@ __device__ __forceinline__ void stencil_apply(const Grid& g, const float4* __res
             int nb;
             if (!grid_node_fast(g, i + di, j + dj, nb)) nb = idx;
             const float4 a = S4[(size_t)((dj + 2) * 5 + (di + 2)) * g.G + idx];
-            const double2* xn = x + (size_t)nb * K;
+            const cvec* xn = x + (size_t)nb * K;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double2 xv = xn[k];
-                out[k].x += (double)a.x * xv.x + (double)a.y * xv.y;
-                out[k].y += (double)a.z * xv.x + (double)a.w * xv.y;
+                const cvec xv = xn[k];
+                out[k].x += a.x * xv.x + a.y * xv.y;
+                out[k].y += a.z * xv.x + a.w * xv.y;
             }
         }
 }
@@ -976,21 +991,21 @@ k_vc_down1(Levels LV, int l, const int* __restrict__ active) {
     const Grid g = LV.g[l];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= g.G) return;
-    const double2* rc = (const double2*)LV.rc[l] + (size_t)sys * g.G * K;
-    double2* xc = (double2*)LV.xc[l] + (size_t)sys * g.G * K;
-    double2* tc = (double2*)LV.tc[l] + (size_t)sys * g.G * K;
+    const cvec* rc = (const cvec*)LV.rc[l] + (size_t)sys * g.G * K;
+    cvec* xc = (cvec*)LV.xc[l] + (size_t)sys * g.G * K;
+    cvec* tc = (cvec*)LV.tc[l] + (size_t)sys * g.G * K;
     const double* d = LV.dinv[l] + ((size_t)sys * g.G + idx) * 4;
-    const double om = RVE_OMEGA;
-    const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
-    double2 acc[K];
+    const float om = (float)RVE_OMEGA;
+    const float d0 = om * (float)d[0], d1 = om * (float)d[1], d2 = om * (float)d[2], d3 = om * (float)d[3];
+    cvec acc[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+    for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
     stencil_apply<K>(g, LV.H4[l] + (size_t)sys * 25 * g.G, rc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const double2 rv = rc[(size_t)idx * K + k];
-        xc[(size_t)idx * K + k] = make_double2(d0 * rv.x + d1 * rv.y, d2 * rv.x + d3 * rv.y);
-        tc[(size_t)idx * K + k] = make_double2(rv.x - acc[k].x, rv.y - acc[k].y);
+        const cvec rv = rc[(size_t)idx * K + k];
+        xc[(size_t)idx * K + k] = make_float2(d0 * rv.x + d1 * rv.y, d2 * rv.x + d3 * rv.y);
+        tc[(size_t)idx * K + k] = make_float2(rv.x - acc[k].x, rv.y - acc[k].y);
     }
 }
 
@@ -1002,20 +1017,20 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
     const int sys = blockIdx.x;
     if (!active[sys]) return;
     const int nth = blockDim.x, tid = threadIdx.x;
-    const double om = RVE_OMEGA;
+    const float om = (float)RVE_OMEGA;
     for (int l = l0; l < LV.L; ++l) {
         const Grid g = LV.g[l], gf = LV.g[l - 1];
         const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
-        double2* rc = (double2*)LV.rc[l] + (size_t)sys * g.G * K;
-        double2* xc = (double2*)LV.xc[l] + (size_t)sys * g.G * K;
-        double2* tc = (double2*)LV.tc[l] + (size_t)sys * g.G * K;
-        const double2* tf = (const double2*)LV.tc[l - 1] + (size_t)sys * gf.G * K;
+        cvec* rc = (cvec*)LV.rc[l] + (size_t)sys * g.G * K;
+        cvec* xc = (cvec*)LV.xc[l] + (size_t)sys * g.G * K;
+        cvec* tc = (cvec*)LV.tc[l] + (size_t)sys * g.G * K;
+        const cvec* tf = (const cvec*)LV.tc[l - 1] + (size_t)sys * gf.G * K;
         // rc_l = P^T t_{l-1} (full weighting; t vanishes outside the coarse space)
         for (int idx = tid; idx < g.G; idx += nth) {
             const int I = idx % g.nx, J = idx / g.nx;
-            double2 acc[K];
+            cvec acc[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+            for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
             if (grid_valid(g, I, J)) {
 #pragma unroll
                 for (int aj = -1; aj <= 1; ++aj)
@@ -1023,10 +1038,10 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
                     for (int ai = -1; ai <= 1; ++ai) {
                         int nf;
                         if (!grid_node_fast(gf, 2 * I + ai, 2 * J + aj, nf)) continue;
-                        const double wgt = (ai ? 0.5 : 1.0) * (aj ? 0.5 : 1.0);
+                        const float wgt = (ai ? 0.5f : 1.0f) * (aj ? 0.5f : 1.0f);
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
-                            const double2 tv = tf[(size_t)nf * K + k];
+                            const cvec tv = tf[(size_t)nf * K + k];
                             acc[k].x += wgt * tv.x; acc[k].y += wgt * tv.y;
                         }
                     }
@@ -1039,16 +1054,16 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
         const float4* H4 = LV.H4[l] + (size_t)sys * 25 * g.G;
         for (int idx = tid; idx < g.G; idx += nth) {
             const double* d = Di + 4 * (size_t)idx;
-            const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
-            double2 acc[K];
+            const float d0 = om * (float)d[0], d1 = om * (float)d[1], d2 = om * (float)d[2], d3 = om * (float)d[3];
+            cvec acc[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+            for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
             stencil_apply<K>(g, H4, rc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double2 rv = rc[(size_t)idx * K + k];
-                xc[(size_t)idx * K + k] = make_double2(d0 * rv.x + d1 * rv.y, d2 * rv.x + d3 * rv.y);
-                tc[(size_t)idx * K + k] = make_double2(rv.x - acc[k].x, rv.y - acc[k].y);
+                const cvec rv = rc[(size_t)idx * K + k];
+                xc[(size_t)idx * K + k] = make_float2(d0 * rv.x + d1 * rv.y, d2 * rv.x + d3 * rv.y);
+                tc[(size_t)idx * K + k] = make_float2(rv.x - acc[k].x, rv.y - acc[k].y);
             }
         }
         __syncthreads();
@@ -1059,17 +1074,17 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
         const Grid g = LV.g[l];
         const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
         const float4* A4 = LV.A4[l] + (size_t)sys * 25 * g.G;
-        const double2* rc = (const double2*)LV.rc[l] + (size_t)sys * g.G * K;
-        double2* xc = (double2*)LV.xc[l] + (size_t)sys * g.G * K;
-        double2* tc = (double2*)LV.tc[l] + (size_t)sys * g.G * K;
+        const cvec* rc = (const cvec*)LV.rc[l] + (size_t)sys * g.G * K;
+        cvec* xc = (cvec*)LV.xc[l] + (size_t)sys * g.G * K;
+        cvec* tc = (cvec*)LV.tc[l] + (size_t)sys * g.G * K;
         for (int sw = 0; sw < 2; ++sw) {
             for (int idx = tid; idx < g.G; idx += nth) {
                 const double* d = Di + 4 * (size_t)idx;
-                const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
+                const float d0 = om * (float)d[0], d1 = om * (float)d[1], d2 = om * (float)d[2], d3 = om * (float)d[3];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const double2 tv = tc[(size_t)idx * K + k];
-                    double2 xv = xc[(size_t)idx * K + k];
+                    const cvec tv = tc[(size_t)idx * K + k];
+                    cvec xv = xc[(size_t)idx * K + k];
                     xv.x += d0 * tv.x + d1 * tv.y; xv.y += d2 * tv.x + d3 * tv.y;
                     xc[(size_t)idx * K + k] = xv;
                 }
@@ -1077,14 +1092,14 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
             __syncthreads();
             if (sw == 1) break;
             for (int idx = tid; idx < g.G; idx += nth) {
-                double2 acc[K];
+                cvec acc[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+                for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
                 stencil_apply<K>(g, A4, xc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const double2 rv = rc[(size_t)idx * K + k];
-                    tc[(size_t)idx * K + k] = make_double2(rv.x - acc[k].x, rv.y - acc[k].y);
+                    const cvec rv = rc[(size_t)idx * K + k];
+                    tc[(size_t)idx * K + k] = make_float2(rv.x - acc[k].x, rv.y - acc[k].y);
                 }
             }
             __syncthreads();
@@ -1093,15 +1108,15 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
     // up sweep: x_l += P x_{l+1}, then post-smoothing, for the levels this kernel owns
     for (int l = LV.L - 2; l >= l0; --l) {
         const Grid g = LV.g[l], gc = LV.g[l + 1];
-        double2* xc = (double2*)LV.xc[l] + (size_t)sys * g.G * K;
-        const double2* xcc = (const double2*)LV.xc[l + 1] + (size_t)sys * gc.G * K;
+        cvec* xc = (cvec*)LV.xc[l] + (size_t)sys * g.G * K;
+        const cvec* xcc = (const cvec*)LV.xc[l + 1] + (size_t)sys * gc.G * K;
         for (int idx = tid; idx < g.G; idx += nth) {
             const int i = idx % g.nx, j = idx / g.nx;
             if (!grid_valid(g, i, j)) continue;
             const int I0 = i >> 1, J0 = j >> 1;
             const int ni = (i & 1) ? 2 : 1, nj = (j & 1) ? 2 : 1;
-            const double wgt = ((i & 1) ? 0.5 : 1.0) * ((j & 1) ? 0.5 : 1.0);
-            double2 acc[K];
+            const float wgt = ((i & 1) ? 0.5f : 1.0f) * ((j & 1) ? 0.5f : 1.0f);
+            cvec acc[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) acc[k] = xc[(size_t)idx * K + k];
             for (int bj = 0; bj < nj; ++bj)
@@ -1110,7 +1125,7 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
                     if (!grid_node_fast(gc, I0 + bi, J0 + bj, nc)) continue;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        const double2 v = xcc[(size_t)nc * K + k];
+                        const cvec v = xcc[(size_t)nc * K + k];
                         acc[k].x += wgt * v.x; acc[k].y += wgt * v.y;
                     }
                 }
@@ -1120,27 +1135,27 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
         __syncthreads();
         const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
         const float4* A4 = LV.A4[l] + (size_t)sys * 25 * g.G;
-        const double2* rc = (const double2*)LV.rc[l] + (size_t)sys * g.G * K;
-        double2* tc = (double2*)LV.tc[l] + (size_t)sys * g.G * K;
+        const cvec* rc = (const cvec*)LV.rc[l] + (size_t)sys * g.G * K;
+        cvec* tc = (cvec*)LV.tc[l] + (size_t)sys * g.G * K;
         for (int idx = tid; idx < g.G; idx += nth) {
-            double2 acc[K];
+            cvec acc[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+            for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
             stencil_apply<K>(g, A4, xc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double2 rv = rc[(size_t)idx * K + k];
-                tc[(size_t)idx * K + k] = make_double2(rv.x - acc[k].x, rv.y - acc[k].y);
+                const cvec rv = rc[(size_t)idx * K + k];
+                tc[(size_t)idx * K + k] = make_float2(rv.x - acc[k].x, rv.y - acc[k].y);
             }
         }
         __syncthreads();
         for (int idx = tid; idx < g.G; idx += nth) {
             const double* d = Di + 4 * (size_t)idx;
-            const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
+            const float d0 = om * (float)d[0], d1 = om * (float)d[1], d2 = om * (float)d[2], d3 = om * (float)d[3];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double2 tv = tc[(size_t)idx * K + k];
-                double2 xv = xc[(size_t)idx * K + k];
+                const cvec tv = tc[(size_t)idx * K + k];
+                cvec xv = xc[(size_t)idx * K + k];
                 xv.x += d0 * tv.x + d1 * tv.y; xv.y += d2 * tv.x + d3 * tv.y;
                 xc[(size_t)idx * K + k] = xv;
             }
@@ -1162,12 +1177,12 @@ k_vc_restrict(Levels LV, int l, const int* __restrict__ active) {
     const Grid g = LV.g[l], gf = LV.g[l - 1];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= g.G) return;
-    const double2* tf = (const double2*)LV.tc[l - 1] + (size_t)sys * gf.G * K;
-    double2* rc = (double2*)LV.rc[l] + (size_t)sys * g.G * K;
+    const cvec* tf = (const cvec*)LV.tc[l - 1] + (size_t)sys * gf.G * K;
+    cvec* rc = (cvec*)LV.rc[l] + (size_t)sys * g.G * K;
     const int I = idx % g.nx, J = idx / g.nx;
-    double2 acc[K];
+    cvec acc[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+    for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
     if (grid_valid(g, I, J)) {
 #pragma unroll
         for (int aj = -1; aj <= 1; ++aj)
@@ -1175,10 +1190,10 @@ k_vc_restrict(Levels LV, int l, const int* __restrict__ active) {
             for (int ai = -1; ai <= 1; ++ai) {
                 int nf;
                 if (!grid_node_fast(gf, 2 * I + ai, 2 * J + aj, nf)) continue;
-                const double wgt = (ai ? 0.5 : 1.0) * (aj ? 0.5 : 1.0);
+                const float wgt = (ai ? 0.5f : 1.0f) * (aj ? 0.5f : 1.0f);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const double2 tv = tf[(size_t)nf * K + k];
+                    const cvec tv = tf[(size_t)nf * K + k];
                     acc[k].x += wgt * tv.x; acc[k].y += wgt * tv.y;
                 }
             }
@@ -1190,7 +1205,7 @@ k_vc_restrict(Levels LV, int l, const int* __restrict__ active) {
 // x_l += P src_{l+1}   (src = the post-smoothed correction of the next coarser level)
 template <int K>
 __global__ void __launch_bounds__(256)
-k_vc_prolong(Levels LV, int l, const double* __restrict__ src, const int* __restrict__ active) {
+k_vc_prolong(Levels LV, int l, const float* __restrict__ src, const int* __restrict__ active) {
     const int sys = blockIdx.y;
     if (!active[sys]) return;
     const Grid g = LV.g[l], gc = LV.g[l + 1];
@@ -1198,12 +1213,12 @@ k_vc_prolong(Levels LV, int l, const double* __restrict__ src, const int* __rest
     if (idx >= g.G) return;
     const int i = idx % g.nx, j = idx / g.nx;
     if (!grid_valid(g, i, j)) return;
-    double2* xc = (double2*)LV.xc[l] + (size_t)sys * g.G * K;
-    const double2* xcc = (const double2*)src + (size_t)sys * gc.G * K;
+    cvec* xc = (cvec*)LV.xc[l] + (size_t)sys * g.G * K;
+    const cvec* xcc = (const cvec*)src + (size_t)sys * gc.G * K;
     const int I0 = i >> 1, J0 = j >> 1;
     const int ni = (i & 1) ? 2 : 1, nj = (j & 1) ? 2 : 1;
-    const double wgt = ((i & 1) ? 0.5 : 1.0) * ((j & 1) ? 0.5 : 1.0);
-    double2 acc[K];
+    const float wgt = ((i & 1) ? 0.5f : 1.0f) * ((j & 1) ? 0.5f : 1.0f);
+    cvec acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = xc[(size_t)idx * K + k];
     for (int bj = 0; bj < nj; ++bj)
@@ -1212,7 +1227,7 @@ k_vc_prolong(Levels LV, int l, const double* __restrict__ src, const int* __rest
             if (!grid_node_fast(gc, I0 + bi, J0 + bj, nc)) continue;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double2 v = xcc[(size_t)nc * K + k];
+                const cvec v = xcc[(size_t)nc * K + k];
                 acc[k].x += wgt * v.x; acc[k].y += wgt * v.y;
             }
         }
@@ -1229,21 +1244,21 @@ k_vc_upl(Levels LV, int l, const int* __restrict__ active) {
     const Grid g = LV.g[l];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= g.G) return;
-    const double2* rc = (const double2*)LV.rc[l] + (size_t)sys * g.G * K;
-    const double2* xc = (const double2*)LV.xc[l] + (size_t)sys * g.G * K;
-    double2* zc = (double2*)LV.tc[l] + (size_t)sys * g.G * K;
+    const cvec* rc = (const cvec*)LV.rc[l] + (size_t)sys * g.G * K;
+    const cvec* xc = (const cvec*)LV.xc[l] + (size_t)sys * g.G * K;
+    cvec* zc = (cvec*)LV.tc[l] + (size_t)sys * g.G * K;
     const double* d = LV.dinv[l] + ((size_t)sys * g.G + idx) * 4;
-    const double om = RVE_OMEGA;
-    const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
-    double2 acc[K];
+    const float om = (float)RVE_OMEGA;
+    const float d0 = om * (float)d[0], d1 = om * (float)d[1], d2 = om * (float)d[2], d3 = om * (float)d[3];
+    cvec acc[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+    for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
     stencil_apply<K>(g, LV.A4[l] + (size_t)sys * 25 * g.G, xc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const double2 rv = rc[(size_t)idx * K + k];
-        const double t0 = rv.x - acc[k].x, t1 = rv.y - acc[k].y;
-        double2 xv = xc[(size_t)idx * K + k];
+        const cvec rv = rc[(size_t)idx * K + k];
+        const float t0 = rv.x - acc[k].x, t1 = rv.y - acc[k].y;
+        cvec xv = xc[(size_t)idx * K + k];
         xv.x += d0 * t0 + d1 * t1; xv.y += d2 * t0 + d3 * t1;
         zc[(size_t)idx * K + k] = xv;
     }
@@ -1263,25 +1278,25 @@ k_vc_up1(Levels LV, const int* __restrict__ active, double* sc, double* part, in
 #pragma unroll
     for (int k = 0; k < K; ++k) dot[k] = 0.0;
     if (idx < g.G) {
-        double2* rc = (double2*)LV.rc[0] + (size_t)sys * g.G * K;
-        const double2* xc = (const double2*)LV.xc[0] + (size_t)sys * g.G * K;
-        double2* zc = (double2*)LV.tc[0] + (size_t)sys * g.G * K;
+        cvec* rc = (cvec*)LV.rc[0] + (size_t)sys * g.G * K;
+        const cvec* xc = (const cvec*)LV.xc[0] + (size_t)sys * g.G * K;
+        cvec* zc = (cvec*)LV.tc[0] + (size_t)sys * g.G * K;
         const double* d = LV.dinv[0] + ((size_t)sys * g.G + idx) * 4;
-        const double om = RVE_OMEGA;
-        const double d0 = om * d[0], d1 = om * d[1], d2 = om * d[2], d3 = om * d[3];
-        double2 acc[K];
+        const float om = (float)RVE_OMEGA;
+        const float d0 = om * (float)d[0], d1 = om * (float)d[1], d2 = om * (float)d[2], d3 = om * (float)d[3];
+        cvec acc[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+        for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
         stencil_apply<K>(g, LV.A4[0] + (size_t)sys * 25 * g.G, xc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const double2 rv = rc[(size_t)idx * K + k];
-            const double t0 = rv.x - acc[k].x, t1 = rv.y - acc[k].y;
-            double2 xv = xc[(size_t)idx * K + k];
+            const cvec rv = rc[(size_t)idx * K + k];
+            const float t0 = rv.x - acc[k].x, t1 = rv.y - acc[k].y;
+            cvec xv = xc[(size_t)idx * K + k];
             xv.x += d0 * t0 + d1 * t1; xv.y += d2 * t0 + d3 * t1;
             zc[(size_t)idx * K + k] = xv;
-            dot[k] = rv.x * xv.x + rv.y * xv.y;
-            rc[(size_t)idx * K + k] = make_double2(0.0, 0.0);
+            dot[k] = (double)rv.x * (double)xv.x + (double)rv.y * (double)xv.y;
+            rc[(size_t)idx * K + k] = make_float2(0.f, 0.f);
         }
     }
     __shared__ double s_dot[8][4];
@@ -1313,7 +1328,7 @@ k_vc_up1(Levels LV, const int* __restrict__ active, double* sc, double* part, in
 template <int K>
 __global__ void __launch_bounds__(RVE_DIR_THREADS(K), (K == 1 ? 5 : (RVE_DIR_THREADS(K) <= 256 ? 4 : 2)))
 k_direction(WinTab wt, double2* __restrict__ p, const double2* __restrict__ r, const float4* __restrict__ dinv32,
-            const RowInfo* __restrict__ rowinfo, const int* __restrict__ cn_node, const double2* __restrict__ xc1,
+            const RowInfo* __restrict__ rowinfo, const int* __restrict__ cn_node, const cvec* __restrict__ xc1,
             int G, const int* __restrict__ active, const double* __restrict__ sc, int precond) {
     extern __shared__ double2 s_xc[];             // [ncn*K]
     constexpr int EPT = RVE_EPT_DIR(K), TPB = RVE_DIR_THREADS(K);
@@ -1341,7 +1356,10 @@ k_direction(WinTab wt, double2* __restrict__ p, const double2* __restrict__ r, c
     if (precond) {
         const int cn0 = wt.win_cn0[win], ncn = wt.win_ncn[win];
         for (int t = tid; t < ncn * K; t += TPB)
-            s_xc[t] = xc1[((size_t)sys * G + cn_node[cn0 + t / K]) * K + (t % K)];
+        {
+            const cvec v = xc1[((size_t)sys * G + cn_node[cn0 + t / K]) * K + (t % K)];
+            s_xc[t] = make_double2((double)v.x, (double)v.y);
+        }
         __syncthreads();
     }
 #pragma unroll
