@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(DS_THREADS)
 k_ds_rows(DsMesh M, DsRows A) {
     __shared__ int s_w[33];
     __shared__ int s_err;
-    __shared__ int s_key[4][RVE_WIN];
+    __shared__ int s_hist[4][8][64], s_tot[4][64], s_pre[4][64];   // window sort
     const int s = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     if (A.sys_cnt[8 * s + DC_ERR]) return;
     const int v0 = M.voff[s], nv = M.voff[s + 1] - v0, t0 = M.toff[s], nt = M.toff[s + 1] - t0;
@@ -488,21 +488,39 @@ k_ds_rows(DsMesh M, DsRows A) {
     __syncthreads();
     if (s_err) { if (tid == 0) A.sys_cnt[8 * s + DC_ERR] = s_err; return; }
     // ---- windows of RVE_WIN preliminary rows, each stably sorted by descending capacity (4 windows per pass)
+    // (stable counting sort on the 64 possible keys: per-warp histograms by __match_any, prefix over keys and warps)
     const int nwin = (na + RVE_WIN - 1) / RVE_WIN;
-    const int grp = tid / RVE_WIN, i = tid % RVE_WIN;
+    const int grp = tid / RVE_WIN, i = tid % RVE_WIN, wvg = i >> 5, lane = tid & 31;
     for (int w0 = 0; w0 < nwin; w0 += nth / RVE_WIN) {
         const int w = w0 + grp;
         const int r0 = w * RVE_WIN;
         const int wn = w < nwin ? min(RVE_WIN, na - r0) : 0;
-        const int key = i < wn ? 63 - len0[r0 + i] : 64;
-        s_key[grp][i] = key;
+        const bool valid = i < wn;
+        const int key = valid ? 63 - len0[r0 + i] : 64;
+        for (int q = tid; q < 4 * 8 * 64; q += nth) (&s_hist[0][0][0])[q] = 0;
         __syncthreads();
-        if (i < wn) {
-            int pos = 0;
-            for (int j = 0; j < wn; ++j) {
-                const int kj = s_key[grp][j];
-                pos += (kj < key) || (kj == key && j < i);
-            }
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) s_hist[grp][wvg][key] = __popc(peers);
+        __syncthreads();
+        if (i < 64) {
+            int tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) tot += s_hist[grp][q][i];
+            s_tot[grp][i] = tot;
+        }
+        __syncthreads();
+        if (i < 32) {            // exclusive prefix over the 64 keys: two per lane
+            const int t0k = s_tot[grp][2 * i], t1k = s_tot[grp][2 * i + 1];
+            int inc = t0k + t1k;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            s_pre[grp][2 * i] = inc - t0k - t1k; s_pre[grp][2 * i + 1] = inc - t1k;
+        }
+        __syncthreads();
+        if (valid) {
+            int pos = s_pre[grp][key] + rank;
+            for (int q = 0; q < wvg; ++q) pos += s_hist[grp][q][key];
             newid[r0 + i] = r0 + pos; oldid[r0 + pos] = r0 + i;
         }
         __syncthreads();

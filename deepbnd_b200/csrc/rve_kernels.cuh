@@ -337,9 +337,10 @@ k_sym_coarse(WinTab wt, int* __restrict__ win_cn0, int* __restrict__ win_ncn, co
     }
     for (int j = tid; j <= ncn; j += RVE_WIN) cn_beg[c0 + j] = (unsigned)(e0 + s_cnt[j]);
     __syncthreads();
-    // fill: position inside a list by atomics on a second counter array (re-using s_scan is too small: use s_pre space? no —
-    // lists are ordered afterwards, so the fill order does not matter)
+    // fill in shared memory (position inside a list by atomics on a second counter array), order every list there
+    // (reproducible summation order in the restriction), then write the window's entries out in one coalesced pass
     __shared__ int s_fill[4 * RVE_WIN];
+    __shared__ uint16_t s_entl[4 * RVE_WIN];
     for (int j = tid; j < ncn; j += RVE_WIN) s_fill[j] = 0;
     __syncthreads();
     if (tid < n) {
@@ -350,14 +351,14 @@ k_sym_coarse(WinTab wt, int* __restrict__ win_cn0, int* __restrict__ win_ncn, co
             ri.slot[c] = slot[c] < 0 ? (uint16_t)0xffffu : (uint16_t)slot[c];
             if (slot[c] >= 0) {
                 const int pos = atomicAdd(&s_fill[slot[c]], 1);
-                cn_ent[(size_t)e0 + s_cnt[slot[c]] + pos] = (uint16_t)((tid << 2) | c);
+                s_entl[s_cnt[slot[c]] + pos] = (uint16_t)((tid << 2) | c);
             }
         }
         rowinfo[r0 + tid] = ri;
     }
     __syncthreads();
-    for (int j = tid; j < ncn; j += RVE_WIN) {     // order every list: reproducible summation order in the restriction
-        uint16_t* L = cn_ent + (size_t)e0 + s_cnt[j];
+    for (int j = tid; j < ncn; j += RVE_WIN) {
+        uint16_t* L = s_entl + s_cnt[j];
         const int len = s_cnt[j + 1] - s_cnt[j];
         for (int i = 1; i < len; ++i) {
             const uint16_t v = L[i];
@@ -366,6 +367,9 @@ k_sym_coarse(WinTab wt, int* __restrict__ win_cn0, int* __restrict__ win_ncn, co
             L[k + 1] = v;
         }
     }
+    __syncthreads();
+    const int nent = s_cnt[ncn];
+    for (int i = tid; i < nent; i += RVE_WIN) cn_ent[(size_t)e0 + i] = s_entl[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -793,9 +797,15 @@ k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __re
 #endif
 #define RVE_UPD_THREADS(K) (RVE_WIN * (K) / RVE_EPT_UPD(K))
 #define RVE_DIR_THREADS(K) (RVE_WIN * (K) / RVE_EPT_DIR(K))
+#ifndef RVE_UPD_MINB
+#define RVE_UPD_MINB(K) ((K) == 1 ? 5 : (RVE_UPD_THREADS(K) <= 256 ? 4 : 2))
+#endif
+#ifndef RVE_DIR_MINB
+#define RVE_DIR_MINB(K) ((K) == 1 ? 5 : (RVE_DIR_THREADS(K) <= 256 ? 4 : 2))
+#endif
 
 template <int K>
-__global__ void __launch_bounds__(RVE_UPD_THREADS(K), (K == 1 ? 5 : (RVE_UPD_THREADS(K) <= 256 ? 4 : 2)))
+__global__ void __launch_bounds__(RVE_UPD_THREADS(K), RVE_UPD_MINB(K))
 k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q, double2* __restrict__ x,
          double2* __restrict__ r, const float4* __restrict__ dinv32, const RowInfo* __restrict__ rowinfo,
          const int* __restrict__ cn_node, const unsigned* __restrict__ cn_beg, const uint16_t* __restrict__ cn_ent,
@@ -1326,7 +1336,7 @@ k_vc_up1(Levels LV, const int* __restrict__ active, double* sc, double* part, in
 // p = Dinv r + Z xc1 + beta p     (thread = one (row, rhs) pair; the level-1 values the window
 // touches are staged in shared memory)
 template <int K>
-__global__ void __launch_bounds__(RVE_DIR_THREADS(K), (K == 1 ? 5 : (RVE_DIR_THREADS(K) <= 256 ? 4 : 2)))
+__global__ void __launch_bounds__(RVE_DIR_THREADS(K), RVE_DIR_MINB(K))
 k_direction(WinTab wt, double2* __restrict__ p, const double2* __restrict__ r, const float4* __restrict__ dinv32,
             const RowInfo* __restrict__ rowinfo, const int* __restrict__ cn_node, const cvec* __restrict__ xc1,
             int G, const int* __restrict__ active, const double* __restrict__ sc, int precond) {
