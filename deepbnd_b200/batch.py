@@ -189,28 +189,45 @@ class RVEBatch:
 
 
 class DoubleBuffer:
-    """Two handles on one GPU: `prepare(job, handle)` (meshing, symbolic phase, H2D — host bound) of job
-    i+1 runs on a second host thread while `consume(job, handle, prepared)` (device work, D2H) of job i
-    runs on the caller's thread.  ctypes releases the GIL during the library calls."""
+    """Two handles on one GPU, one host worker thread each.  Worker k takes jobs k, k+2, ... and runs
+    `prepare(job, handle)` (meshing on the host; H2D + symbolic phase on the GPU) and `solve(job, handle, prepared)`
+    (assemble, PCG, epilogues, D2H) back to back; the kernels of the two handles interleave on the GPU, so the host
+    gaps of one worker (meshing, result copies, synchronisation points) and the tails of its kernels are filled by
+    the other.  `store(job, result)` runs on the caller's thread in job order (file writes stay serial and ordered).
+    ctypes releases the GIL during the library calls."""
 
     def __init__(self, device=0):
-        from concurrent.futures import ThreadPoolExecutor
         self.h = [RVEBatch(device), RVEBatch(device)]
-        self.pool = ThreadPoolExecutor(max_workers=1)
 
-    def run(self, jobs, prepare, consume):
+    def run(self, jobs, prepare, solve, store=None):
+        import threading
+        from concurrent.futures import Future
         jobs = list(jobs)
-        if not jobs:
-            return
-        fut = self.pool.submit(prepare, jobs[0], self.h[0])
-        for i, job in enumerate(jobs):
-            prepared = fut.result()
-            if i + 1 < len(jobs):
-                fut = self.pool.submit(prepare, jobs[i + 1], self.h[(i + 1) % 2])
-            consume(job, self.h[i % 2], prepared)
+        futs = [Future() for _ in jobs]
+
+        def worker(k):
+            for i in range(k, len(jobs), 2):
+                try:
+                    futs[i].set_result(solve(jobs[i], self.h[k], prepare(jobs[i], self.h[k])))
+                except BaseException as e:   # noqa: BLE001 - handed to the caller's thread
+                    for j in range(i, len(jobs), 2):
+                        futs[j].set_exception(e)
+                    return
+
+        threads = [threading.Thread(target=worker, args=(k,), daemon=True) for k in range(min(2, len(jobs)))]
+        for t in threads:
+            t.start()
+        results = []
+        try:
+            for job, fut in zip(jobs, futs):
+                res = fut.result()
+                results.append(store(job, res) if store is not None else res)
+        finally:
+            for t in threads:
+                t.join()
+        return results
 
     def close(self):
-        self.pool.shutdown(wait=True)
         for b in self.h:
             b.close()
 

@@ -67,13 +67,24 @@ def get_meshes(paramRVEdata, meshnames, size, createMesh, nproc=None):
 def solve_snapshot_batch(rows, batch, datasets, rtol=1e-10):
     """Batch twin of solve_snapshot (reference :42-64) on a batch already set on the GPU: fills rows `rows`
     of the 11 datasets."""
-    ids, sol_S, sigma_S, a_S, B_S, sigmaT_S, sol_A, sigma_A, a_A, B_A, sigmaT_A = datasets
     start = timer()
+    out = _solve_snapshots(batch, rtol)
+    _store_snapshots(rows, out, datasets)
+    print("batch of", batch.n_sys, "snapshots concluded in ", timer() - start)
+    return out
+
+
+def _solve_snapshots(batch, rtol):
+    """loads S (Voigt 2) and A (Voigt 0) like the reference's loop `for j_voigt, sol, ... in zip([2, 0], ...)` (:52)"""
     batch.assemble()
     n = batch.n_sys
     eps = np.broadcast_to(np.stack([macro_strain_voigt(2), macro_strain_voigt(0)]), (n, 2, 3)).copy()
     batch.solve(eps, rtol=rtol)
-    out = batch.snapshot()
+    return batch.snapshot()
+
+
+def _store_snapshots(rows, out, datasets):
+    ids, sol_S, sigma_S, a_S, B_S, sigmaT_S, sol_A, sigma_A, a_A, B_A, sigmaT_A = datasets
     for k, (sol, sigma, a, B, sigmaT) in enumerate(((sol_S, sigma_S, a_S, B_S, sigmaT_S),
                                                      (sol_A, sigma_A, a_A, B_A, sigmaT_A))):
         sol[rows, :] = out["sol"][:, k]
@@ -81,8 +92,6 @@ def solve_snapshot_batch(rows, batch, datasets, rtol=1e-10):
         a[rows, :] = out["a"][:, k]
         B[rows, :, :] = out["B"][:, k]
         sigmaT[rows, :] = out["sigmaT"][:, k]
-    print("batch of", n, "snapshots concluded in ", timer() - start)
-    return out
 
 
 def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs, comm_self=None,
@@ -109,14 +118,17 @@ def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs
         meshes = get_meshes(paramRVEdata[rows], names, 'full', createMesh, nproc)
         batch.set_meshes(meshes, tuple(paramMaterial), model=opModel, vref_nb=nb, vref_box=box)
 
-    def consume(rows, batch, _):
+    def solve(rows, batch, _):
+        print("Solving snapshots", int(ids_run[rows[0]]), "..", int(ids_run[rows[-1]]))
+        return _solve_snapshots(batch, rtol)
+
+    def store(rows, out):
         ids[rows] = ids_run[rows]
-        print("Solving snapshots", int(ids[rows[0]]), "..", int(ids[rows[-1]]))
-        solve_snapshot_batch(rows, batch, snapshots, rtol)
+        _store_snapshots(rows, out, snapshots)
         fsnaps.flush()
 
     db = DoubleBuffer(run if device is None else device)
-    db.run([np.arange(b0, min(nrun, b0 + batch_size)) for b0 in range(0, nrun, batch_size)], prepare, consume)
+    db.run([np.arange(b0, min(nrun, b0 + batch_size)) for b0 in range(0, nrun, batch_size)], prepare, solve, store)
     db.close()
     fsnaps.close()
 

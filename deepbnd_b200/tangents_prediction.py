@@ -51,18 +51,21 @@ def predictTangents(num, num_runs, modelBnd, namefiles, createMesh, meshSize, de
         meshes = get_meshes(paramRVEdata[rows], names, meshSize, createMesh, nproc)
         batch.set_meshes(meshes, tuple(param), model=modelBnd, vref_nb=nb, vref_box=box)
 
-    def consume(rows, batch, _):
-        Iid[rows] = ids[rows]
+    def solve(rows, batch, _):
         print(run, rows[0], rows[-1], ids[rows[0]])
         batch.assemble()
         batch.solve(np.broadcast_to(eps3, (len(rows), 3, 3)).copy(), uD=uD_all[rows] if modelBnd == 'dnn' else None, rtol=rtol)
-        Itangent[rows, :, :] = batch.tangent()
+        return batch.tangent()
+
+    def store(rows, tangents):
+        Iid[rows] = ids[rows]
+        Itangent[rows, :, :] = tangents
         Icenter[rows, :] = centers[rows, :]
         f.flush()
         sys.stdout.flush()
 
     db = DoubleBuffer(run if device is None else device)
-    db.run([np.arange(b0, min(ns, b0 + batch_size)) for b0 in range(0, ns, batch_size)], prepare, consume)
+    db.run([np.arange(b0, min(ns, b0 + batch_size)) for b0 in range(0, ns, batch_size)], prepare, solve, store)
     db.close()
     f.close()
     print("tangents of", ns, "RVEs concluded in", timer() - start)

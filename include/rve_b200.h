@@ -133,7 +133,7 @@ int rve_project(rve_handle_t h, int32_t nmax, int32_t nh, const double* W, const
                 const double* translate, double* Y);
 
 /* CUDA-event phase timings of the last calls (ms) and traffic counters:
- *   t[0] symbolic(host) t[1] upload t[2] assemble t[3] precond set-up t[4] rhs t[5] pcg total
+ *   t[0] H2D + symbolic phase up to the global numbering t[1] pattern / halo / restriction lists t[2] assemble t[3] precond set-up t[4] rhs t[5] pcg total
  *   t[6] spmv kernels total t[7] epilogue;   c[0] spmv launches c[1] algorithmic spmv bytes (B_spmv(k))
  *   c[2] pcg iterations launched c[3] sum of per-system iterations c[4] kernels launched since
  *   rve_create c[5] constraint post-processing ms c[6]/c[7] host->device / device->host bytes since
