@@ -198,13 +198,29 @@ static size_t smem_spmv(rve_batch_s* h, int K) { return (size_t)h->max_tile * K 
 static size_t smem_update(int K) { return (size_t)RVE_WIN * K * sizeof(double2) + RVE_WIN * sizeof(float2) + 4 * RVE_WIN * sizeof(uint16_t); }
 static size_t smem_direction(rve_batch_s* h, int K) { return (size_t)h->max_cn * K * sizeof(double2); }
 
-template <int K>
-static cudaError_t pcg_attrs(rve_batch_s* h) {
-    cudaError_t e = cudaFuncSetAttribute(k_spmv<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_spmv(h, K));
+// Opt-in dynamic shared memory of the kernels that size their tiles at run time.  The attribute belongs to the
+// FUNCTION (shared by every handle and host thread of the process), so it is raised once, to the device limit
+// minus the kernel's static shared memory; the launches then ask for what their batch needs.  (Setting it per
+// batch would let one handle shrink the limit under a concurrent solve of another handle.)
+template <class F>
+static cudaError_t raise_smem_limit(F* kernel, int optin) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, (const void*)kernel);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_update<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_update(K));
+    return cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
+
+static cudaError_t raise_smem_limits(int device) {
+    int optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_direction<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_direction(h, K));
+#define RAISE_(f) if ((e = raise_smem_limit(f, optin)) != cudaSuccess) return e
+    RAISE_(k_spmv<1>); RAISE_(k_spmv<2>); RAISE_(k_spmv<3>);
+    RAISE_(k_update<1>); RAISE_(k_update<2>); RAISE_(k_update<3>);
+    RAISE_(k_direction<1>); RAISE_(k_direction<2>); RAISE_(k_direction<3>);
+    RAISE_(k_sym_window); RAISE_(k_sym_coarse);
+#undef RAISE_
+    return cudaSuccess;
 }
 
 struct PcgArgs {
@@ -293,6 +309,7 @@ int rve_create(int device, rve_handle_t* out) {
         mallopt(M_TOP_PAD, 64 << 20);
         heap_tuned = true;
     }
+    if ((e = raise_smem_limits(device)) != cudaSuccess) { g_create_err = std::string("shared-memory opt-in: ") + cudaGetErrorString(e); return RVE_E_CUDA; }
     rve_batch_s* h = new rve_batch_s();
     h->device = device;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -555,12 +572,10 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
                                                h->csr_col.p, h->rlen.p, h->emap.p, h->sys_blocks.p, h->sym_cnt.p);
         const size_t sm = 2 * (size_t)h->max_words * sizeof(unsigned);
         if (sm > 200 * 1024) FAIL(RVE_E_MESH, "system too large for the halo bitmap in shared memory");
-        CU(cudaFuncSetAttribute(k_sym_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         k_sym_window<<<n_win, RVE_WIN, sm, st>>>(wt, h->win_halo0.p, h->win_nhalo.p, h->d_row_ptr.p, h->rlen.p, h->csr_col.p, h->slice_ptr.p,
                                                   h->scol.p, h->halo.p, (int)halo_cap, h->sym_cnt.p);
         const size_t smc = 2 * (size_t)((LV.g[0].G + 31) / 32) * sizeof(unsigned);
         if (smc > 150 * 1024) FAIL(RVE_E_MESH, "level-1 grid too large for the coarse-node bitmap in shared memory");
-        CU(cudaFuncSetAttribute(k_sym_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
         k_sym_coarse<<<n_win, RVE_WIN, smc, st>>>(wt, h->win_cn0.p, h->win_ncn.p, h->row_node.p, h->node_xy.p, h->box.p, LV.g[0],
                                                   model, h->rowinfo.p, h->cn_node.p, h->cn_beg.p, h->cn_ent.p, (int)cn_cap, h->sym_cnt.p);
         h->launches += 3;
@@ -802,9 +817,6 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     pa.wt = win_tab(h); pa.sl = sell_tab(h); pa.LV = h->LV; pa.LV.K = K;
     pa.n_win = h->n_win; pa.n_sys = n_sys; pa.K = K; pa.precond = precond; pa.rtol2 = rtol * rtol;
     pa.sm_spmv = smem_spmv(h, K); pa.sm_upd = smem_update(K); pa.sm_dir = smem_direction(h, K);
-#define ATTR_(KK) CU(pcg_attrs<KK>(h))
-    K_DISPATCH(K, ATTR_);
-#undef ATTR_
     const Levels& LV = pa.LV;
     CU(cudaMemsetAsync(LV.rc[0], 0, h->lvR[0].n * sizeof(float), st));
 #define UPD0_(KK) launch_update<KK>(h, pa, 1, -1, st)
@@ -1053,9 +1065,6 @@ int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_l
     PcgArgs pa;
     pa.wt = win_tab(h); pa.sl = sell_tab(h); pa.LV = h->LV; pa.n_win = h->n_win; pa.n_sys = n_sys; pa.K = K;
     pa.precond = 0; pa.rtol2 = 0; pa.sm_spmv = smem_spmv(h, K); pa.sm_upd = smem_update(K); pa.sm_dir = smem_direction(h, K);
-#define ATTR_(KK) CU(pcg_attrs<KK>(h))
-    K_DISPATCH(K, ATTR_);
-#undef ATTR_
 #define SPMV_(KK) launch_spmv<KK>(h, pa, p.p, q.p, active.p, part.p, cnt.p, sc.p, st)
     for (int wu = 0; wu < 3; ++wu) K_DISPATCH(K, SPMV_);
     CU(cudaEventRecord(h->ev[0], st));

@@ -448,3 +448,43 @@ def test_device_symbolic_matches_host_hook(reduced_meshes, full_mesh, model):
         b.assemble()
         assert b.sizes(0)["n_blocks"] == ref["n_blocks"]                 # true block count found from the element fans
         b.close()
+
+
+def test_two_handles_solve_concurrently(reduced_meshes, full_mesh):
+    """two handles driven from two host threads at once (what DoubleBuffer and bench.py's e2e loop do), with batches
+    whose shared-memory tiles differ: same results as the sequential runs, no launch failure."""
+    import threading
+    from deepbnd_b200.batch import RVEBatch
+    eps2 = np.stack([EPS3[2], EPS3[0]])
+    jobs = [([full_mesh] * 3, "per"), (list(reduced_meshes[:4]), "lin")]
+
+    def run(meshes, model, reps, out):
+        b = RVEBatch()
+        for _ in range(reps):
+            b.set_meshes(meshes, PARAM, model=model, vref_nb=21).assemble()
+            b.solve(np.broadcast_to(eps2, (len(meshes), 2, 3)).copy())
+            out.append(b.snapshot()["sol"].copy())
+        b.close()
+
+    ref = [[], []]
+    for k, (meshes, model) in enumerate(jobs):
+        run(meshes, model, 1, ref[k])
+    got = [[], []]
+    errs = []
+
+    def guarded(k):
+        try:
+            run(jobs[k][0], jobs[k][1], 4, got[k])
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=guarded, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for k in range(2):
+        scale = np.abs(ref[k][0]).max()
+        for sol in got[k]:
+            assert np.abs(sol - ref[k][0]).max() <= 1e-8 * scale
