@@ -615,6 +615,7 @@ int rve_assemble(rve_handle_t h) {
     for (int l = 0; l < LV.L; ++l) CU(cudaMemsetAsync(LV.A[l], 0, h->lvA[l].n * sizeof(double), st));
     k_galerkin1<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
                                                 h->node_row.p, h->box.p, LV.g[0], LV.A[0], h->mat, h->err_flag.p);
+    k_galerkin_mirror<<<cdiv((long long)h->n_sys * 12 * LV.g[0].G, 256), 256, 0, st>>>(h->n_sys, LV.g[0], LV.A[0]);
     for (int l = 0; l + 1 < LV.L; ++l) {
         long long n = (long long)h->n_sys * LV.g[l + 1].G * 25;
         k_galerkin_coarse<<<cdiv(n, 256), 256, 0, st>>>(h->n_sys, LV.g[l], LV.g[l + 1], LV.A[l], LV.A[l + 1]);
@@ -624,7 +625,7 @@ int rve_assemble(rve_handle_t h) {
         k_coarse_dinv<<<cdiv(n, 256), 256, 0, st>>>(h->n_sys, LV.g[l], LV.A[l], LV.dinv[l]);
         k_coarse_pack<<<cdiv(25 * n, 256), 256, 0, st>>>(h->n_sys, LV.g[l], LV.A[l], LV.dinv[l], LV.A4[l], LV.H4[l]);
     }
-    h->launches += 3 + (LV.L - 1) + 2 * LV.L;
+    h->launches += 4 + (LV.L - 1) + 2 * LV.L;
     CU(cudaEventRecord(h->ev[2], st));
     int flag = 0;
     CU(cudaMemcpyAsync(&flag, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -451,9 +451,14 @@ k_dinv(WinTab wt, Sell sl, const double* __restrict__ bval, float4* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// (2) level-1 Galerkin operator A1 = Z^T A Z, element by element: warp per element, K_e and the
-//     bilinear weights staged in shared memory, 9x9 window of coarse nodes, atomics into the
-//     25-slot stencil arrays.
+// (2) level-1 Galerkin operator A1 = Z^T A Z, element by element, warp per element.  The element stiffness is never
+//     formed: with the bilinear weights W[a][I] of the element's 6 nodes on its 3x3 window of coarse nodes, the
+//     coarse basis function of node I restricted to the element has the gradient gI(q) = sum_a W[a][I] grad phi_a(q)
+//     at the 3 quadrature points, and the 2x2 block of the pair (I, J) is
+//        sum_q w [ lam gI (x) gJ + mu gJ (x) gI + mu (gI . gJ) I ]
+//     (p2_stiff_block with the coarse gradients in place of the P2 ones).  A1 is symmetric: only the blocks with
+//     offset (dj > 0) or (dj == 0, di >= 0) are accumulated (atomics into the 25-slot stencil arrays),
+//     k_galerkin_mirror fills the other 12 slots with the transposes.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_galerkin1(int n_elem, const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
@@ -461,8 +466,8 @@ k_galerkin1(int n_elem, const int* __restrict__ elem_node, const unsigned char* 
             const int* __restrict__ node_row, const double* __restrict__ box, Grid g1,
             double* __restrict__ A1, Mat8 mat, int* __restrict__ err_flag) {
     __shared__ double s_mat[8];
-    __shared__ double s_K[8][36][4];
     __shared__ double s_W[8][6][9];
+    __shared__ double s_G[8][3][9][2];          // coarse gradients gI(q)
     if (threadIdx.x < 8) s_mat[threadIdx.x] = mat.v[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -484,18 +489,6 @@ k_galerkin1(int n_elem, const int* __restrict__ elem_node, const unsigned char* 
     tri_geom(x0, y0, x1, y1, x2, y2, g);
     const int reg = elem_reg[e];
     const double lam = s_mat[2 * reg], mu = s_mat[2 * reg + 1];
-    if (lane < 21) {
-        int a, b;
-        pair_ab(lane, a, b);
-        double K[4];
-        p2_stiff_block(g, a, b, lam, mu, K);
-        s_K[w][a * 6 + b][0] = K[0]; s_K[w][a * 6 + b][1] = K[1];
-        s_K[w][a * 6 + b][2] = K[2]; s_K[w][a * 6 + b][3] = K[3];
-        if (a != b) {
-            s_K[w][b * 6 + a][0] = K[0]; s_K[w][b * 6 + a][1] = K[2];
-            s_K[w][b * 6 + a][2] = K[1]; s_K[w][b * 6 + a][3] = K[3];
-        }
-    }
     // coarse cell of every node
     const double bx0 = box[4 * sys], by0 = box[4 * sys + 1];
     const double invHx = g1.ncx / box[4 * sys + 2], invHy = g1.ncy / box[4 * sys + 3];
@@ -526,38 +519,61 @@ k_galerkin1(int n_elem, const int* __restrict__ elem_node, const unsigned char* 
         }
     }
     __syncwarp();
-    double* Asys = A1 + (size_t)sys * 100 * g1.G;
-    // coarse nodes of the 3x3 window that carry weight (4 for an element inside one cell, up to 9): only their
-    // pairs are formed, one pair per lane
+    // gI(q) for the 9 window nodes x 3 quadrature points (27 lanes); window nodes that carry weight
     double wsum = 0.0;
-    if (lane < 9) {
+    if (lane < 27) {
+        const int I = lane % 9, q = lane / 9;
+        double gx = 0.0, gy = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) wsum += s_W[w][a][lane];
+        for (int a = 0; a < 6; ++a) {
+            const double wa = s_W[w][a][I];
+            double ax, ay;
+            p2_grad(g, q, a, ax, ay);
+            gx += wa * ax; gy += wa * ay;
+            wsum += wa;
+        }
+        s_G[w][q][I][0] = gx; s_G[w][q][I][1] = gy;
     }
+    __syncwarp();
+    double* Asys = A1 + (size_t)sys * 100 * g1.G;
     const unsigned am = __ballot_sync(0xffffffffu, lane < 9 && wsum != 0.0);
     const int na = __popc(am);
+    const double wq = g.area * (1.0 / 3.0);
+    // one pair of weighted window nodes per lane (4 nodes for an element inside one cell, up to 9)
     for (int pr = lane; pr < na * na; pr += 32) {
         const int I = __fns(am, 0, pr / na + 1), J = __fns(am, 0, pr % na + 1);
         int Ii = imin + I % 3, Ij = jmin + I / 3, Ji = imin + J % 3, Jj = jmin + J / 3;
+        if (Jj < Ij || (Jj == Ij && Ji < Ii)) continue;     // lower half: k_galerkin_mirror
         int nI, nJ;
         if (!grid_node(g1, Ii, Ij, nI) || !grid_node(g1, Ji, Jj, nJ)) continue;
-        double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-        for (int a = 0; a < 6; ++a) {
-            double wa = s_W[w][a][I];
-            if (wa == 0.0) continue;
-            for (int b = 0; b < 6; ++b) {
-                double wb = s_W[w][b][J];
-                if (wb == 0.0) continue;
-                double ww = wa * wb;
-                const double* k4 = s_K[w][a * 6 + b];
-                acc0 += ww * k4[0]; acc1 += ww * k4[1]; acc2 += ww * k4[2]; acc3 += ww * k4[3];
-            }
+        double G00 = 0, G01 = 0, G10 = 0, G11 = 0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double ix = s_G[w][q][I][0], iy = s_G[w][q][I][1], jx = s_G[w][q][J][0], jy = s_G[w][q][J][1];
+            G00 += ix * jx; G01 += ix * jy; G10 += iy * jx; G11 += iy * jy;
         }
+        G00 *= wq; G01 *= wq; G10 *= wq; G11 *= wq;
+        const double tr = G00 + G11;
         const int slot = (Jj - Ij + 2) * 5 + (Ji - Ii + 2);
         double* d = Asys + (size_t)slot * 4 * g1.G + nI;
-        atomicAdd(d, acc0); atomicAdd(d + g1.G, acc1);
-        atomicAdd(d + 2 * (size_t)g1.G, acc2); atomicAdd(d + 3 * (size_t)g1.G, acc3);
+        atomicAdd(d, lam * G00 + mu * G00 + mu * tr); atomicAdd(d + g1.G, lam * G01 + mu * G10);
+        atomicAdd(d + 2 * (size_t)g1.G, lam * G10 + mu * G01); atomicAdd(d + 3 * (size_t)g1.G, lam * G11 + mu * G11 + mu * tr);
     }
+}
+
+// lower half of the level-1 stencils from the upper half: A[n][-d] = A[n - d][d]^T.  thread per (sys, lower slot, node)
+__global__ void k_galerkin_mirror(int n_sys, Grid g, double* __restrict__ A) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n_sys * 12 * g.G) return;
+    const int idx = (int)(gid % g.G), slot = (int)((gid / g.G) % 12), sys = (int)(gid / ((long long)12 * g.G));
+    const int di = slot % 5 - 2, dj = slot / 5 - 2;        // slots 0..11: dj < 0, or dj == 0 and di < 0
+    const int i = idx % g.nx, j = idx / g.nx;
+    int m;
+    if (!grid_valid(g, i, j) || !grid_node(g, i + di, j + dj, m)) return;
+    double* As = A + (size_t)sys * 100 * g.G;
+    const double* src = As + (size_t)(24 - slot) * 4 * g.G + m;
+    double* dst = As + (size_t)slot * 4 * g.G + idx;
+    dst[0] = src[0]; dst[g.G] = src[2 * (size_t)g.G]; dst[2 * (size_t)g.G] = src[g.G]; dst[3 * (size_t)g.G] = src[3 * (size_t)g.G];
 }
 
 // level l -> l+1 Galerkin (stencil collapse with bilinear P), gather form: thread per (sys, I, slot)
