@@ -603,11 +603,9 @@ int rve_assemble(rve_handle_t h) {
     if (!h->have_batch) FAIL(RVE_E_STATE, "rve_assemble before rve_set_batch");
     cudaStream_t st = h->stream;
     CU(cudaEventRecord(h->ev[0], st));
-    CU(cudaMemsetAsync(h->bval.p, 0, h->bval.n * sizeof(double), st));
-    CU(cudaMemsetAsync(h->wmean.p, 0, h->wmean.n * sizeof(double), st));
     CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), st));
-    k_assemble<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
-                                               h->node_row.p, win_tab(h), sell_tab(h), h->emap.p, h->bval.p, h->wmean.p, h->mat);
+    k_assemble<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), sell_tab(h), h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->elem_reg.p,
+                                              h->node_xy.p, h->node_row.p, h->emap.p, h->bval.p, h->wmean.p, h->mat);
     k_dinv<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), sell_tab(h), h->bval.p, h->dinv.p);
     CU(cudaEventRecord(h->ev[1], st));
     // two-level preconditioner: Galerkin hierarchy

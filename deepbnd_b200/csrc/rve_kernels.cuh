@@ -373,62 +373,87 @@ k_sym_coarse(WinTab wt, int* __restrict__ win_cn0, int* __restrict__ win_ncn, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// (1) numeric assembly: warp per element, 21 lanes compute the upper-triangular 2x2 blocks and
-//     scatter them (and their transposes) with fp64 atomics into the SELL block storage; the slot of
-//     every (local node a, local node b) block comes from the element map written by k_sym_cols.
-//     Connectivity / coordinates are staged through warp shuffles, the material table lives in
-//     shared memory.  Replaces mp.block_assemble(a) (micro_model.py:60).
+// (1) numeric assembly, row-wise: thread per block row (CTA per window, warp per 32-row SELL slice).  A thread
+//     zeroes the slots of its row, walks the elements around the row (adjf), computes the 6 blocks K_e[a][0..5] of
+//     its own local node a (closed-form P2, branch-free gradient table) and adds them into the SELL slots named
+//     by the element map of k_sym_cols.  One writer per row: no atomics, no memset of the 128-byte groups, the
+//     matrix leaves the L2 once (the element-wise scatter with fp64 atomics it replaces moved 3x the bytes).
+//     Also int phi_a dx per row (mean-value constraint of 'per' / 'MR').  Replaces mp.block_assemble(a)
+//     (micro_model.py:60).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_assemble(int n_elem, const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
-           const int* __restrict__ elem_sys, const double* __restrict__ node_xy, const int* __restrict__ node_row,
-           WinTab wt, Sell sl, const unsigned char* __restrict__ emap, double* __restrict__ bval,
-           double* __restrict__ wmean, Mat8 mat) {
+// grad phi_a at quadrature point q = sum_i c[q][a][i] grad lambda_i  (points (1/2,1/2,0), (0,1/2,1/2), (1/2,0,1/2))
+__constant__ double c_p2grad[3][6][3] = {
+    {{1, 0, 0}, {0, 1, 0}, {0, 0, -1}, {2, 2, 0}, {0, 0, 2}, {0, 0, 2}},
+    {{-1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {2, 0, 0}, {0, 2, 2}, {2, 0, 0}},
+    {{1, 0, 0}, {0, -1, 0}, {0, 0, 1}, {0, 2, 0}, {0, 2, 0}, {2, 0, 2}}};
+
+__global__ void __launch_bounds__(RVE_WIN, 3)
+k_assemble(WinTab wt, Sell sl, const unsigned* __restrict__ adjf_ptr, const int* __restrict__ adjf,
+           const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
+           const double* __restrict__ node_xy, const int* __restrict__ node_row,
+           const unsigned char* __restrict__ emap, double* __restrict__ bval, double* __restrict__ wmean, Mat8 mat) {
     __shared__ double s_mat[8];
+    __shared__ double s_c[3][6][3];                     // the table in shared memory: lanes index it with different a
     if (threadIdx.x < 8) s_mat[threadIdx.x] = mat.v[threadIdx.x];
+    if (threadIdx.x < 54) (&s_c[0][0][0])[threadIdx.x] = (&c_p2grad[0][0][0])[threadIdx.x];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (e >= n_elem) return;
-    const int sys = elem_sys[e];
-    int node = 0, row = -1;
-    double px = 0, py = 0;
-    if (lane < 6) {
-        node = elem_node[(size_t)e * 6 + lane];
-        row = node_row[node];
-        px = node_xy[2 * (size_t)node];
-        py = node_xy[2 * (size_t)node + 1];
+    const int w = blockIdx.x, t = threadIdx.x, lane = t & 31;
+    const int n = wt.win_n[w];
+    if ((t >> 5) >= ((n + 31) >> 5)) return;            // no such slice in this window
+    const int slice = wt.win_slice0[w] + (t >> 5);
+    const size_t g0 = sl.slice_ptr[slice];
+    const int width = (int)(sl.slice_ptr[slice + 1] - g0);
+    double* brow = bval + g0 * 128 + 2 * lane;            // slot j of this row: brow[j*128 + {0,1}], brow[j*128 + 64 + {0,1}]
+    for (int j = 0; j < width; ++j) {                     // rows beyond n (last slice) stay zero
+        *(double2*)(brow + (size_t)j * 128) = make_double2(0.0, 0.0);
+        *(double2*)(brow + (size_t)j * 128 + 64) = make_double2(0.0, 0.0);
     }
-    double x0 = __shfl_sync(0xffffffffu, px, 0), y0 = __shfl_sync(0xffffffffu, py, 0);
-    double x1 = __shfl_sync(0xffffffffu, px, 1), y1 = __shfl_sync(0xffffffffu, py, 1);
-    double x2 = __shfl_sync(0xffffffffu, px, 2), y2 = __shfl_sync(0xffffffffu, py, 2);
-    TriGeom g;
-    tri_geom(x0, y0, x1, y1, x2, y2, g);
-    const int reg = elem_reg[e];
-    const double lam = s_mat[2 * reg], mu = s_mat[2 * reg + 1];
-    int a = 0, b = 0;
-    pair_ab(lane < 21 ? lane : 0, a, b);
-    const int ra = __shfl_sync(0xffffffffu, row, a);
-    const int rb = __shfl_sync(0xffffffffu, row, b);
-    if (lane < 21 && ra >= 0 && rb >= 0) {
-        double K[4];
-        p2_stiff_block(g, a, b, lam, mu, K);
-        const int rbase = wt.row_base[sys], w0 = wt.sys_win0[sys];
-        {
-            const int rl = (ra - rbase) % RVE_WIN, slice = wt.win_slice0[w0 + (ra - rbase) / RVE_WIN] + (rl >> 5);
-            const size_t g0 = (size_t)sl.slice_ptr[slice] + emap[(size_t)e * 36 + a * 6 + b];
-            double* d = bval + g0 * 128 + 2 * (rl & 31);
-            atomicAdd(d + 0, K[0]); atomicAdd(d + 1, K[1]); atomicAdd(d + 64, K[2]); atomicAdd(d + 65, K[3]);
+    if (t >= n) return;
+    const int r = wt.win_row0[w] + t;
+    double wm = 0.0;
+    for (unsigned i = adjf_ptr[r]; i < adjf_ptr[r + 1]; ++i) {
+        const int e = adjf[i];
+        const int* en = elem_node + 6 * (size_t)e;
+        int a = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (node_row[en[k]] == r) a = k;
+        const double* p0 = node_xy + 2 * (size_t)en[0]; const double* p1 = node_xy + 2 * (size_t)en[1]; const double* p2 = node_xy + 2 * (size_t)en[2];
+        TriGeom g;
+        tri_geom(p0[0], p0[1], p1[0], p1[1], p2[0], p2[1], g);
+        const int reg = elem_reg[e];
+        const double lam = s_mat[2 * reg], mu = s_mat[2 * reg + 1], wq = g.area * (1.0 / 3.0);
+        if (a >= 3) wm += wq;
+        double ax[3], ay[3];                               // grad phi_a at the 3 quadrature points
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double* c = s_c[q][a];
+            ax[q] = c[0] * g.gl[0][0] + c[1] * g.gl[1][0] + c[2] * g.gl[2][0];
+            ay[q] = c[0] * g.gl[0][1] + c[1] * g.gl[1][1] + c[2] * g.gl[2][1];
         }
-        if (a != b) {   // transposed block in the row of local node b
-            const int rl = (rb - rbase) % RVE_WIN, slice = wt.win_slice0[w0 + (rb - rbase) / RVE_WIN] + (rl >> 5);
-            const size_t g0 = (size_t)sl.slice_ptr[slice] + emap[(size_t)e * 36 + b * 6 + a];
-            double* dt = bval + g0 * 128 + 2 * (rl & 31);
-            atomicAdd(dt + 0, K[0]); atomicAdd(dt + 1, K[2]); atomicAdd(dt + 64, K[1]); atomicAdd(dt + 65, K[3]);
+        const unsigned char* em = emap + (size_t)e * 36 + a * 6;
+#pragma unroll 2
+        for (int k = 0; k < 6; ++k) {
+            const int j = em[k];
+            if (j == 0xff) continue;
+            double G00 = 0, G01 = 0, G10 = 0, G11 = 0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const double* c = s_c[q][k];
+                const double bx = c[0] * g.gl[0][0] + c[1] * g.gl[1][0] + c[2] * g.gl[2][0];
+                const double by = c[0] * g.gl[0][1] + c[1] * g.gl[1][1] + c[2] * g.gl[2][1];
+                G00 += ax[q] * bx; G01 += ax[q] * by; G10 += ay[q] * bx; G11 += ay[q] * by;
+            }
+            G00 *= wq; G01 *= wq; G10 *= wq; G11 *= wq;
+            const double tr = G00 + G11;
+            double2* d0 = (double2*)(brow + (size_t)j * 128);
+            double2* d1 = (double2*)(brow + (size_t)j * 128 + 64);
+            double2 v0 = *d0, v1 = *d1;
+            v0.x += lam * G00 + mu * G00 + mu * tr; v0.y += lam * G01 + mu * G10;
+            v1.x += lam * G10 + mu * G01;           v1.y += lam * G11 + mu * G11 + mu * tr;
+            *d0 = v0; *d1 = v1;
         }
     }
-    // int phi_a dx: A/3 for the mid-edge functions (mean-value constraint of 'per' / 'MR')
-    if (lane >= 3 && lane < 6 && row >= 0) atomicAdd(wmean + row, g.area * (1.0 / 3.0));
+    wmean[r] = wm;
 }
 
 // 2x2 inverse of the diagonal blocks (block-Jacobi), stored in fp32: CTA per window, thread per row
