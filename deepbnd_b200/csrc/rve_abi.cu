@@ -121,7 +121,7 @@ struct rve_batch_s {
     DBuf<RowInfo> rowinfo;
     DBuf<double> lvA[RVE_MAXLEV], lvD[RVE_MAXLEV];
     DBuf<float> lvR[RVE_MAXLEV], lvX[RVE_MAXLEV], lvT[RVE_MAXLEV];   // V-cycle vectors (fp32)
-    DBuf<float4> lvA4[RVE_MAXLEV], lvH4[RVE_MAXLEV];
+    DBuf<stv> lvA4[RVE_MAXLEV], lvH4[RVE_MAXLEV];
     DBuf<double> p, q, x, r, b, part, sc, cpart;
     DBuf<double> eps, eps_eff, Bmat, uD, gval, d_vbox, U, acc, sigL, sigT, aout, Bout, sol, Mx, Gaff, aaff;
     DBuf<double> MWt, transl, Yd, gradT;

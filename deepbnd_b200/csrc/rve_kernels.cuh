@@ -19,6 +19,7 @@
 // Per-window partial dot products are combined in a fixed order by the last CTA of each system.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "../../include/rve_b200.h"
@@ -38,6 +39,27 @@ struct Grid {
 
 typedef float2 cvec;   // one rhs of a coarse node
 
+// Storage of the coarse 2x2 stencil blocks read by the V-cycle (preconditioner arithmetic only): fp16 by default
+// (8 bytes per block: the stencil arrays are the V-cycle's dominant traffic), fp32 with -DRVE_STENCIL_HALF=0.
+#ifndef RVE_STENCIL_HALF
+#define RVE_STENCIL_HALF 1
+#endif
+#if RVE_STENCIL_HALF
+typedef uint2 stv;
+__device__ __forceinline__ stv st_pack(float a, float b, float c, float d) {
+    const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    return make_uint2(*(const unsigned*)&lo, *(const unsigned*)&hi);
+}
+__device__ __forceinline__ float4 st_unpack(stv v) {
+    const float2 lo = __half22float2(*(const __half2*)&v.x), hi = __half22float2(*(const __half2*)&v.y);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+#else
+typedef float4 stv;
+__device__ __forceinline__ stv st_pack(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
+__device__ __forceinline__ float4 st_unpack(stv v) { return v; }
+#endif
+
 struct Levels {
     int L;          // number of coarse levels
     int K;          // rhs count
@@ -47,8 +69,8 @@ struct Levels {
     float* rc[RVE_MAXLEV];      // [n_sys][G][K][2]  the V-cycle runs in fp32 (preconditioner arithmetic only)
     float* xc[RVE_MAXLEV];
     float* tc[RVE_MAXLEV];
-    float4* A4[RVE_MAXLEV];     // [n_sys][25][G] fp32 copy of A (a00,a01,a10,a11): preconditioner arithmetic only
-    float4* H4[RVE_MAXLEV];     // [n_sys][25][G] A_ij * (omega Dinv_j): residual after the first Jacobi step
+    stv* A4[RVE_MAXLEV];        // [n_sys][25][G] reduced-precision copy of A (a00,a01,a10,a11): preconditioner arithmetic only
+    stv* H4[RVE_MAXLEV];        // [n_sys][25][G] A_ij * (omega Dinv_j): residual after the first Jacobi step
 };
 
 struct WinTab {
@@ -989,7 +1011,7 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
 // fp32 copies of a coarse level: A4 = A, H4_ij = A_ij (omega Dinv_j) (so that the residual after the
 // first damped-Jacobi step, rc - A (omega Dinv rc), is ONE stencil pass over rc).  thread per (sys,slot,node)
 __global__ void k_coarse_pack(int n_sys, Grid g, const double* __restrict__ A, const double* __restrict__ dinv,
-                              float4* __restrict__ A4, float4* __restrict__ H4) {
+                              stv* __restrict__ A4, stv* __restrict__ H4) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)n_sys * 25 * g.G) return;
     const int I = (int)(gid % g.G);
@@ -997,7 +1019,7 @@ __global__ void k_coarse_pack(int n_sys, Grid g, const double* __restrict__ A, c
     const int sys = (int)(gid / ((long long)25 * g.G));
     const double* a = A + (size_t)sys * 100 * g.G + (size_t)slot * 4 * g.G + I;
     const double a00 = a[0], a01 = a[g.G], a10 = a[2 * (size_t)g.G], a11 = a[3 * (size_t)g.G];
-    A4[gid] = make_float4((float)a00, (float)a01, (float)a10, (float)a11);
+    A4[gid] = st_pack((float)a00, (float)a01, (float)a10, (float)a11);
     int nb;
     double h00 = 0, h01 = 0, h10 = 0, h11 = 0;
     if (grid_node(g, I % g.nx + slot % 5 - 2, I / g.nx + slot / 5 - 2, nb)) {
@@ -1006,14 +1028,14 @@ __global__ void k_coarse_pack(int n_sys, Grid g, const double* __restrict__ A, c
         h00 = om * (a00 * d[0] + a01 * d[2]); h01 = om * (a00 * d[1] + a01 * d[3]);
         h10 = om * (a10 * d[0] + a11 * d[2]); h11 = om * (a10 * d[1] + a11 * d[3]);
     }
-    H4[gid] = make_float4((float)h00, (float)h01, (float)h10, (float)h11);
+    H4[gid] = st_pack((float)h00, (float)h01, (float)h10, (float)h11);
 }
 
 // Coarse V-cycle on the restricted residual (damped block-Jacobi V(1,1) on 25-point block stencils).
 // out += S x over the 25 slots of node (i,j); branch-free: entries towards nodes outside the coarse
 // space are zero by construction, so their x is read from the node itself.
 template <int K>
-__device__ __forceinline__ void stencil_apply(const Grid& g, const float4* __restrict__ S4,
+__device__ __forceinline__ void stencil_apply(const Grid& g, const stv* __restrict__ S4,
                                               const cvec* __restrict__ x, int i, int j, cvec* out) {
     const int idx = j * g.nx + i;
 #pragma unroll
@@ -1022,7 +1044,7 @@ __device__ __forceinline__ void stencil_apply(const Grid& g, const float4* __res
         for (int di = -2; di <= 2; ++di) {
             int nb;
             if (!grid_node_fast(g, i + di, j + dj, nb)) nb = idx;
-            const float4 a = S4[(size_t)((dj + 2) * 5 + (di + 2)) * g.G + idx];
+            const float4 a = st_unpack(S4[(size_t)((dj + 2) * 5 + (di + 2)) * g.G + idx]);
             const cvec* xn = x + (size_t)nb * K;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -1102,7 +1124,7 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
         }
         __syncthreads();
         // x = om Dinv rc ; t = rc - H rc
-        const float4* H4 = LV.H4[l] + (size_t)sys * 25 * g.G;
+        const stv* H4 = LV.H4[l] + (size_t)sys * 25 * g.G;
         for (int idx = tid; idx < g.G; idx += nth) {
             const double* d = Di + 4 * (size_t)idx;
             const float d0 = om * (float)d[0], d1 = om * (float)d[1], d2 = om * (float)d[2], d3 = om * (float)d[3];
@@ -1124,7 +1146,7 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
         const int l = LV.L - 1;
         const Grid g = LV.g[l];
         const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
-        const float4* A4 = LV.A4[l] + (size_t)sys * 25 * g.G;
+        const stv* A4 = LV.A4[l] + (size_t)sys * 25 * g.G;
         const cvec* rc = (const cvec*)LV.rc[l] + (size_t)sys * g.G * K;
         cvec* xc = (cvec*)LV.xc[l] + (size_t)sys * g.G * K;
         cvec* tc = (cvec*)LV.tc[l] + (size_t)sys * g.G * K;
@@ -1185,7 +1207,7 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
         }
         __syncthreads();
         const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
-        const float4* A4 = LV.A4[l] + (size_t)sys * 25 * g.G;
+        const stv* A4 = LV.A4[l] + (size_t)sys * 25 * g.G;
         const cvec* rc = (const cvec*)LV.rc[l] + (size_t)sys * g.G * K;
         cvec* tc = (cvec*)LV.tc[l] + (size_t)sys * g.G * K;
         for (int idx = tid; idx < g.G; idx += nth) {
