@@ -196,8 +196,9 @@ class DoubleBuffer:
     the other.  `store(job, result)` runs on the caller's thread in job order (file writes stay serial and ordered).
     ctypes releases the GIL during the library calls."""
 
-    def __init__(self, device=0):
-        self.h = [RVEBatch(device), RVEBatch(device)]
+    def __init__(self, device=0, handles=None):
+        # `handles`: two ready-made handle objects (the CPU tests pass stand-ins to check ordering / error propagation)
+        self.h = list(handles) if handles is not None else [RVEBatch(device), RVEBatch(device)]
 
     def run(self, jobs, prepare, solve, store=None):
         import threading
