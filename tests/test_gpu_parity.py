@@ -488,3 +488,39 @@ def test_two_handles_solve_concurrently(reduced_meshes, full_mesh):
         scale = np.abs(ref[k][0]).max()
         for sol in got[k]:
             assert np.abs(sol - ref[k][0]).max() <= 1e-8 * scale
+
+
+def test_device_symbolic_rejects_bad_meshes(coarse_reduced_meshes):
+    """the GPU symbolic phase validates the meshes itself (region tags, degenerate / non-manifold triangles, periodic
+    boundary matching, Vref box) and reports RVE_E_MESH with the offending system; a good batch still works after."""
+    from deepbnd_b200.batch import RVEBatch
+    from deepbnd_b200 import _lib as L
+    xy, tri, reg = [np.array(a) for a in coarse_reduced_meshes[0]]
+    good = (xy, tri, reg)
+    b = RVEBatch()
+
+    def expect_mesh_error(meshes, model, text, **kw):
+        with pytest.raises(L.RVEError) as ei:
+            b.set_meshes(meshes, PARAM, model=model, **kw)
+        assert ei.value.code == -4 and text in str(ei.value), str(ei.value)
+
+    bad_reg = reg.copy(); bad_reg[0] = reg.min() + 7
+    expect_mesh_error([good, (xy, tri, bad_reg)], "lin", "system 1: region tag")
+    flat = tri.copy(); flat[5] = [tri[5, 0], tri[5, 1], tri[5, 0]]                   # zero-area triangle
+    expect_mesh_error([(xy, flat, reg)], "lin", "degenerate triangle")
+    dup = np.vstack([tri, tri[:1]]); dup_reg = np.append(reg, reg[0])                 # an element twice: edges with 3-4 owners
+    expect_mesh_error([(xy, dup.astype(np.int32), dup_reg.astype(np.int32))], "lin", "non-manifold")
+    # periodic model on a mesh whose right side is shifted: no partner on the left side
+    onr = np.abs(xy[:, 0] - xy[:, 0].max()) < 1e-12
+    inner = onr & (np.abs(xy[:, 1] - xy[:, 1].min()) > 1e-9) & (np.abs(xy[:, 1] - xy[:, 1].max()) > 1e-9)
+    moved = xy.copy(); moved[np.flatnonzero(inner)[0], 1] += 1e-3
+    expect_mesh_error([(moved, tri, reg)], "per", "periodic")
+    # dnn: the mesh boundary must coincide with the Vref box
+    expect_mesh_error([good], "dnn", "Vref box", vref_box=(xy[:, 0].min() - 0.1, xy[:, 1].min(), np.ptp(xy[:, 0]), np.ptp(xy[:, 1])))
+    # Vref sample points outside the mesh
+    expect_mesh_error([good], "lin", "outside the mesh", vref_box=(xy[:, 0].min() - 1.0, xy[:, 1].min(), np.ptp(xy[:, 0]), np.ptp(xy[:, 1])))
+    b.set_meshes([good], PARAM, model="lin").assemble()
+    b.solve(EPS3[None].copy())
+    C = b.tangent()[0]
+    assert np.all(np.linalg.eigvalsh(0.5 * (C + C.T)) > 0)
+    b.close()
