@@ -939,14 +939,18 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
         acc = warp_sum(acc);
         if (lane == 0) s_fin[wv] = acc;
     }
-    // restriction: 4 threads per coarse node of the window split the node's (row, corner) list, all rhs at once;
-    // weights from the staged (s,t); one vector RED (8 / 16 bytes) per node into the fp32 level-1 residual
+    // restriction: 4 threads split the (row, corner) list of a coarse node of the window, weights from the staged
+    // (s,t), vector REDs into the fp32 level-1 residual.  K = 2: both rhs per thread, one 16-byte RED per node;
+    // otherwise one task per (node, rhs) (more parallelism for the 768-thread CTAs of K = 3), 8-byte REDs
     if (precond) {
-        for (int t = tid; t < ((ncn * 4 + 31) & ~31); t += TPB) {
-            const int jn = t >> 2, sub = t & 3;
-            double a[K][2];
+        constexpr int KT = (K == 2) ? 2 : 1;              // rhs per task
+        constexpr int TPN = K / KT;                       // tasks per node
+        for (int t = tid; t < ((ncn * TPN * 4 + 31) & ~31); t += TPB) {
+            const int task = t >> 2, sub = t & 3;
+            const int jn = task / TPN, k0 = (task % TPN) * KT;
+            double a[KT][2];
 #pragma unroll
-            for (int kk = 0; kk < K; ++kk) { a[kk][0] = 0.0; a[kk][1] = 0.0; }
+            for (int kk = 0; kk < KT; ++kk) { a[kk][0] = 0.0; a[kk][1] = 0.0; }
             if (jn < ncn) {
                 const unsigned b0 = cn_beg[cn0 + jn] - ent0, b1 = cn_beg[cn0 + jn + 1] - ent0;
                 for (unsigned e = b0 + sub; e < b1; e += 4) {
@@ -955,27 +959,23 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
                     const float2 st = s_st[rl];
                     const double wgt = (double)((c & 1) ? st.x : 1.0f - st.x) * (double)((c & 2) ? st.y : 1.0f - st.y);
 #pragma unroll
-                    for (int kk = 0; kk < K; ++kk) {
-                        const double2 v = s_r[rl * K + kk];
+                    for (int kk = 0; kk < KT; ++kk) {
+                        const double2 v = s_r[rl * K + k0 + kk];
                         a[kk][0] += wgt * v.x; a[kk][1] += wgt * v.y;
                     }
                 }
             }
 #pragma unroll
-            for (int kk = 0; kk < K; ++kk)
+            for (int kk = 0; kk < KT; ++kk)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     a[kk][c] += __shfl_xor_sync(0xffffffffu, a[kk][c], 1);
                     a[kk][c] += __shfl_xor_sync(0xffffffffu, a[kk][c], 2);
                 }
             if (jn < ncn && sub == 0) {
-                float* d = rc1 + ((size_t)sys * G + cn_node[cn0 + jn]) * K * 2;
-                if (K == 2) {
-                    atomicAdd((float4*)d, make_float4((float)a[0][0], (float)a[0][1], (float)a[K - 1][0], (float)a[K - 1][1]));
-                } else {
-#pragma unroll
-                    for (int kk = 0; kk < K; ++kk) atomicAdd((float2*)d + kk, make_float2((float)a[kk][0], (float)a[kk][1]));
-                }
+                float* d = rc1 + (((size_t)sys * G + cn_node[cn0 + jn]) * K + k0) * 2;
+                if (KT == 2) atomicAdd((float4*)d, make_float4((float)a[0][0], (float)a[0][1], (float)a[KT - 1][0], (float)a[KT - 1][1]));
+                else atomicAdd((float2*)d, make_float2((float)a[0][0], (float)a[0][1]));
             }
         }
     }
