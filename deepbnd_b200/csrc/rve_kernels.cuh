@@ -1084,8 +1084,9 @@ k_vc_down1(Levels LV, int l, const int* __restrict__ active) {
 
 // levels >= l0 (the small ones): one CTA per system.  Restricts t_{l0-1}, runs the rest of the V-cycle down to
 // the coarsest level and back up to level l0 (post-smoothed result in xc[l0]).
+// (4 CTAs per SM: the kernel is bound by the latency of its phases, 48 registers with a few spilled words beat 68)
 template <int K>
-__global__ void __launch_bounds__(320, 3)
+__global__ void __launch_bounds__(320, 4)
 k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
     const int sys = blockIdx.x;
     if (!active[sys]) return;
