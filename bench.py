@@ -37,6 +37,7 @@ PARAM_MAT = (0.3, 10.0, 0.3, 1.0)           # simulation_snapshots.py:120-123
 WORKLOADS = {
     # name: (ns per GPU, mesh size, model, loads (Voigt ids), project?)
     "C2_snapshots_1k_full_per": dict(ns=1000, size="full", model="per", loads=(2, 0), project=True),
+    "C2_snapshots_1k_full_MR": dict(ns=1000, size="full", model="MR", loads=(2, 0), project=True),
     "C3_tangents_10k_reduced_dnn": dict(ns=10000, size="reduced", model="dnn", loads=(0, 1, 2), project=False),
     "C4_tangents_10k_reduced_per": dict(ns=10000, size="reduced", model="per", loads=(0, 1, 2), project=False),
     "C4_tangents_10k_reduced_lin": dict(ns=10000, size="reduced", model="lin", loads=(0, 1, 2), project=False),
