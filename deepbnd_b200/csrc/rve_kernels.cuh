@@ -15,7 +15,8 @@
 //   window-local slots of the 4 level-1 nodes around the row), cn_node/cn_beg/cn_ent (per window: the
 //   level-1 nodes it touches and, per node, the (row, corner) pairs restricting to it).
 //   Coarse level l (structured (ncx+1)x(ncy+1) grid per system, 25-point block stencil):
-//                A[sys][slot 25][4][G], dinv[sys][G][4], vectors [sys][G][K][2].
+//                A[sys][slot 25][4][G] fp64 (set-up), A4/H4[sys][25][G] fp16 blocks (V-cycle), dinv[sys][G][4],
+//                V-cycle vectors rc/xc/tc[sys][G][K] float2.
 // Per-window partial dot products are combined in a fixed order by the last CTA of each system.
 #pragma once
 #include <cuda_runtime.h>
@@ -27,7 +28,9 @@
 #include "rve_symbolic.hpp"   // RVE_WIN, RowInfo
 
 #define RVE_MAXLEV 8
+#ifndef RVE_OMEGA
 #define RVE_OMEGA 0.8      // damped block-Jacobi smoother on the coarse levels
+#endif
 
 struct Mat8 { double v[8]; };  // [4][2] lambda*, mu per region
 
@@ -139,10 +142,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// (0) device half of the symbolic phase.  The host sends, per row, its length and the elements around
-//     it; the GPU finds the block columns (k_sym_cols) and, per window, the halo list and the
-//     window-local 16-bit SELL columns (k_sym_window: shared-memory bitmap over the rows of the system,
-//     popcount prefix = rank of a halo row; halo segments are claimed with one atomic per window).
+// (0) second half of the symbolic phase (the first half — numbering, row order, element fans — is rve_devsym.cuh).
+//     From the capacity of every row and the elements around it the GPU finds the block columns (k_sym_cols) and,
+//     per window, the halo list and the window-local 16-bit SELL columns (k_sym_window: shared-memory bitmap over
+//     the rows of the system, popcount prefix = rank of a halo row; halo segments are claimed with one atomic per
+//     window), then the level-1 nodes a window touches and its restriction lists (k_sym_coarse).
 // ---------------------------------------------------------------------------------------------
 // counters: [0] halo entries used, [1] max rows of a p-tile (own + halo), [2] error code
 __global__ void __launch_bounds__(RVE_WIN)
@@ -156,7 +160,7 @@ k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __re
         const int r = wt.win_row0[w] + t;
         const unsigned o = row_ptr[r];
         const int cap = (int)(row_ptr[r + 1] - o);   // capacity of the row (>= its true length)
-        int* cols = csr_col + o;                     // unique rows in discovery order (same order as the host path)
+        int* cols = csr_col + o;                     // unique rows in discovery order (same order as rve_symbolic.hpp)
         for (unsigned i = adjf_ptr[r]; i < adjf_ptr[r + 1]; ++i) {
             const int e = adjf[i];
             const int* en = elem_node + 6 * (size_t)e;
