@@ -113,7 +113,7 @@ struct rve_batch_s {
     DBuf<double> d_xy, sys_ext;
     DBuf<int> d_tri, d_region, d_voff, d_toff, scrA, scrB, sys_cnt, node_va, node_vb, d_node_base, d_bnd_base, d_cellrank, d_slice_base;
     DBuf<unsigned> d_blk_base, d_grp_base, d_adjf_base;
-    DBuf<unsigned char> emap, rlen;
+    DBuf<unsigned char> emap, rlen, win_active;
     DBuf<int> sys_blocks;
     std::vector<long long> true_blocks;   // per system, found by the device pattern build
     std::vector<long long> adjf_base;
@@ -183,7 +183,7 @@ static cudaError_t upload(DBuf<T>& d, const std::vector<T>& v, cudaStream_t s) {
 static WinTab win_tab(rve_batch_s* h) {
     WinTab wt;
     wt.win_sys = h->win_sys.p; wt.win_row0 = h->win_row0.p; wt.win_n = h->win_n.p; wt.win_slice0 = h->win_slice0.p;
-    wt.win_halo0 = h->win_halo0.p; wt.win_nhalo = h->win_nhalo.p; wt.win_cn0 = h->win_cn0.p; wt.win_ncn = h->win_ncn.p; wt.sys_win0 = h->sys_win0.p; wt.row_base = h->d_row_base.p;
+    wt.win_halo0 = h->win_halo0.p; wt.win_nhalo = h->win_nhalo.p; wt.win_cn0 = h->win_cn0.p; wt.win_ncn = h->win_ncn.p; wt.win_active = h->win_active.p; wt.sys_win0 = h->sys_win0.p; wt.row_base = h->d_row_base.p;
     return wt;
 }
 
@@ -564,7 +564,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     CU(h->win_halo0.alloc(n_win)); CU(h->win_nhalo.alloc(n_win)); CU(h->sym_cnt.alloc(8));
     CU(cudaMemsetAsync(h->sym_cnt.p, 0, 8 * sizeof(int), st));
     const long long cn_cap = h->R + (long long)n_win + 4096;      // level-1 nodes touched per window are far fewer than its rows
-    CU(h->win_cn0.alloc(n_win)); CU(h->win_ncn.alloc(n_win)); CU(h->cn_node.alloc((size_t)cn_cap)); CU(h->cn_beg.alloc((size_t)cn_cap));
+    CU(h->win_cn0.alloc(n_win)); CU(h->win_ncn.alloc(n_win)); CU(h->win_active.alloc(n_win)); CU(h->cn_node.alloc((size_t)cn_cap)); CU(h->cn_beg.alloc((size_t)cn_cap));
     CU(h->cn_ent.alloc(4 * (size_t)h->R)); CU(h->rowinfo.alloc((size_t)h->R));
     {
         WinTab wt = win_tab(h);
@@ -811,6 +811,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     CU(cudaMemsetAsync(h->d_iters.p, 0, n_sys * sizeof(int), st));
     std::vector<int> ones(n_sys, 1);
     CU(cudaMemcpyAsync(h->active.p, ones.data(), n_sys * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->win_active.p, 1, (size_t)h->n_win, st));
     CU(cudaMemcpyAsync(h->n_active.p, &n_sys, sizeof(int), cudaMemcpyHostToDevice, st));
     PcgArgs pa;
     pa.wt = win_tab(h); pa.sl = sell_tab(h); pa.LV = h->LV; pa.LV.K = K;
@@ -1059,6 +1060,7 @@ int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_l
     CU(cudaMemcpyAsync(p.p, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     std::vector<int> ones(n_sys, 1);
     CU(cudaMemcpyAsync(active.p, ones.data(), n_sys * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->win_active.p, 1, (size_t)h->n_win, st));   // every window on (a finished solve leaves them off)
     CU(cudaMemsetAsync(cnt.p, 0, n_sys * sizeof(int), st));
     CU(cudaMemsetAsync(sc.p, 0, sc.n * sizeof(double), st));
     PcgArgs pa;

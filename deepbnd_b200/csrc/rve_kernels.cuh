@@ -85,6 +85,7 @@ struct WinTab {
     const int* win_nhalo;    // [n_win] halo rows of the window
     const int* win_cn0;      // [n_win] offset of the window's coarse-node list (claimed on the device; ncn + 1 slots)
     const int* win_ncn;      // [n_win] level-1 nodes the window touches
+    unsigned char* win_active;   // [n_win] copy of active[win_sys[w]]: the PCG kernels test it without the hop over win_sys
     const int* sys_win0;     // [n_sys+1]
     const int* row_base;     // [n_sys+1] first global row of a system
 };
@@ -749,7 +750,7 @@ k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __re
     __shared__ unsigned s_g0[RVE_WIN / 32 + 1];
     const int win = blockIdx.x;
     const int sys = wt.win_sys[win];
-    if (!active[sys]) return;
+    if (!wt.win_active[win]) return;
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
     const int h0 = wt.win_halo0[win], nh = wt.win_nhalo[win];
@@ -882,7 +883,7 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
     constexpr int EPT = RVE_EPT_UPD(K), TPB = RVE_UPD_THREADS(K);   // TPB % K == 0: a thread keeps its rhs index
     const int win = blockIdx.x;
     const int sys = wt.win_sys[win];
-    if (!active[sys]) return;
+    if (!wt.win_active[win]) return;
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
     const int k = tid % K;
@@ -1007,7 +1008,11 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
                 iters[sys] = init ? 0 : iter + 1;
                 atomicSub(n_active, 1);
             }
+            s_out[0][0] = done ? 1.0 : 0.0;
         }
+        __syncthreads();
+        if (s_out[0][0] != 0.0)                        // converged: switch the windows of the system off
+            for (int wq = c0 + tid; wq < c1; wq += TPB) wt.win_active[wq] = 0;
     }
 }
 
@@ -1412,7 +1417,7 @@ k_direction(WinTab wt, double2* __restrict__ p, const double2* __restrict__ r, c
     constexpr int EPT = RVE_EPT_DIR(K), TPB = RVE_DIR_THREADS(K);
     const int win = blockIdx.x;
     const int sys = wt.win_sys[win];
-    if (!active[sys]) return;
+    if (!wt.win_active[win]) return;
     const int tid = threadIdx.x;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
     const int k = tid % K;
