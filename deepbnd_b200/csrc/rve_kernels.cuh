@@ -740,7 +740,11 @@ __device__ __forceinline__ bool last_block_sum(double* part, int* cnt, int sys, 
 // column load, two coalesced LDG.128 of the 2x2 block and K LDS.128 gathers from the tile; the loads of
 // the next slot pair (also across a slice boundary) are in flight while the current pair is multiplied.
 // No cross-lane reduction; q leaves through shared memory so the global store is coalesced.
-#define RVE_SPMV_WARPS 2
+// warps per CTA (window): measured 2 -> 4: SpMV -4 % (K = 2) / -7 % (K = 3), the p-tile is shared by more warps and the
+// shared-memory-limited occupancy doubles; 8 (one slice per warp: 2 long + 6 short slices) is 15-30 % slower
+#ifndef RVE_SPMV_WARPS
+#define RVE_SPMV_WARPS 4
+#endif
 #define RVE_SPMV_THREADS (32 * RVE_SPMV_WARPS)
 template <int K>
 __global__ void __launch_bounds__(RVE_SPMV_THREADS)
