@@ -81,3 +81,31 @@ def test_full_size_properties(full_meshes_default, model):
                 lam, *_ = np.linalg.lstsq(Call.T, R[k], rcond=None)
                 assert np.abs(R[k] - Call.T @ lam).max() < 1e-8 * np.abs(F).max()
     b.close()
+
+
+@pytest.mark.gpu
+def test_piola_rotation_matches_a_rotated_rve(reduced_meshes):
+    """physical check of bc_prediction.PiolaTransform_rotation_matricial and of the Vref node order: the boundary
+    fluctuation of the RVE rotated by B under the load B eps B^T is B u(B^T x), i.e. P times the original Vref vector
+    (the identity NN_elast.py:48-55 uses to get the eps22 prediction from the eps11 network)."""
+    from deepbnd_b200.batch import RVEBatch
+    from deepbnd_b200.bc_prediction import PiolaTransform_rotation_matricial
+    xy, tri, reg = [np.asarray(a) for a in reduced_meshes[0]]
+    x0, y0 = xy.min(0)
+    L = np.ptp(xy[:, 0])
+    assert abs(x0 + 0.5 * L) < 1e-12 and abs(y0 + 0.5 * L) < 1e-12 and abs(np.ptp(xy[:, 1]) - L) < 1e-12
+    theta = 3 * np.pi / 2
+    s, c = np.sin(theta), np.cos(theta)
+    B = np.array([[c, -s], [s, c]])
+    eps22 = np.array([[[0.0, 1.0, 0.0]]])                               # Voigt (e11, e22, g12)
+    eps11 = np.array([[[1.0, 0.0, 0.0]]])                               # B e2 = e1: B eps22 B^T = eps11
+    b = RVEBatch()
+    b.set_meshes([(xy, tri, reg)], PARAM, model="per", vref_nb=21).assemble()
+    b.solve(eps22.copy())
+    S = b.snapshot()["sol"][0, 0]
+    b.set_meshes([(np.ascontiguousarray(xy @ B.T), tri, reg)], PARAM, model="per", vref_nb=21).assemble()
+    b.solve(eps11.copy())
+    Sr = b.snapshot()["sol"][0, 0]
+    b.close()
+    P = PiolaTransform_rotation_matricial(theta, box=(x0, y0, L, L), nb=21)
+    assert np.abs(Sr - P @ S).max() <= 1e-8 * np.abs(S).max()
