@@ -50,9 +50,19 @@ def test_jobs_alternate_handles_and_store_is_ordered():
 
 def test_workers_overlap():
     db = DoubleBuffer(handles=[_Handle("a"), _Handle("b")])
-    t0 = time.perf_counter()
-    db.run(range(6), lambda j, h: None, lambda j, h, p: time.sleep(0.1))
-    assert time.perf_counter() - t0 < 0.5          # 6 x 0.1 s of work on two workers: ~0.3 s, serial would be 0.6 s
+    lock = threading.Lock()
+    state = {"active": 0, "peak": 0}
+
+    def solve(job, handle, prepared):
+        with lock:
+            state["active"] += 1
+            state["peak"] = max(state["peak"], state["active"])
+        time.sleep(0.05)
+        with lock:
+            state["active"] -= 1
+
+    db.run(range(6), lambda j, h: None, solve)
+    assert state["peak"] == 2                      # the two handles are driven at the same time, never more than two jobs
 
 
 def test_worker_exception_reaches_the_caller():
