@@ -61,13 +61,16 @@ const char* rve_last_error(rve_handle_t h);
  *   vref_nb                Nb of degeneratedBoundaryRectangleMesh (21 in the reference), 0 = no Vref
  *   vref_box[4]            x0,y0,Lx,Ly of Vref (NULL: the mesh bounding box)
  * Vref DOF order is the library's own: node k = 0..4(Nb-1)-1 counter-clockwise from (x0,y0),
- * centre node last, DOF = 2*node + comp. */
+ * centre node last, DOF = 2*node + comp.
+ * The raw arrays are copied to the GPU and the whole symbolic phase (P2 numbering, boundary detection, constraint
+ * maps, row order, sparsity pattern, Vref point location) runs there; invalid meshes come back as RVE_E_MESH with
+ * "system <s>: <reason>" in rve_last_error.  All systems of a batch must share the box size. */
 int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const int64_t* tri_off,
                   const double* xy, const int32_t* tri, const int32_t* region, const double* mat,
                   int32_t model, int32_t vref_nb, const double* vref_box);
 
 /* replaces: A = mp.block_assemble(a); bcs.apply(A) (micro_model.py:60-62, micro_model_dnn.py:65-67).
- * Numeric P2 element-stiffness assembly of every system into node-block CSR + preconditioner set-up. */
+ * Numeric P2 stiffness assembly of every system into the SELL-32 node-block matrix + preconditioner set-up. */
 int rve_assemble(rve_handle_t h);
 
 /* parity-test accessors (not on the hot path) */
@@ -146,9 +149,9 @@ int rve_timings(rve_handle_t h, double* t, double* c);
 int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_launch,
                    double* alg_bytes_per_launch);
 
-/* Host-only test hook (no CUDA call): symbolic phase of ONE system — P2 numbering, constraint map,
- * rows ordered by coarse cell, node-block pattern, Vref sample location.  Lets the CPU test-suite
- * check the host logic against the oracle without a GPU.  Arrays are caller-allocated with the
+/* Host-only test hook (no CUDA call, not used by the product): CPU restatement of the symbolic phase of ONE system —
+ * P2 numbering, constraint map, rows ordered by coarse cell, node-block pattern, Vref sample location.  The CPU
+ * test-suite checks it against the oracle's pattern, the GPU tests check the device numbering against it.  Arrays are caller-allocated with the
  * given capacities (node_row: nv + 3*nt entries is always enough). */
 int rve_host_symbolic(const double* xy, int32_t nv, const int32_t* tri, const int32_t* region, int32_t nt,
                       int32_t model, int32_t vref_nb, int32_t cap_rows, int32_t cap_blocks, int32_t* n_nodes,
