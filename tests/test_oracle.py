@@ -153,3 +153,38 @@ def test_homogenisation_gen_consistency(coarse_reduced_meshes):
     assert np.abs(H["eps"] - np.eye(3)).max() < 1e-10
     C = OracleRVE(*mesh, param=PARAM, model="lin").compute_tangent()
     assert np.abs(H["tangent"] - C[[0, 1, 2]][:, :]).max() < 1e-9 * np.abs(C).max()
+
+
+def test_p2_element_stiffness_against_closed_form_integrals():
+    """pins the oracle's element matrices without any quadrature: grad phi_a is linear in the barycentric coordinates,
+    so int d_c phi_a d_d phi_b follows from int 1 = A, int lam_i = A/3, int lam_i lam_j = A (1 + delta_ij) / 12, and
+    K[(a,c),(b,d)] = lam G_cd + mu G_dc + mu tr(G) delta_cd (sigma(u):eps(v) with sigma = lam tr(eps) I + 2 mu eps,
+    micro_model.py:49).  Random, badly shaped triangles in both orientations."""
+    import oracle.rve_oracle as O
+    rs = np.random.RandomState(11)
+    nt = 40
+    xy = rs.randn(3 * nt, 2) * np.array([1.0, 0.2]) + rs.randn(3 * nt, 2) * 0.05
+    tri = np.arange(3 * nt).reshape(nt, 3)
+    reg = rs.randint(0, 2, nt)
+    mesh = O.P2Mesh(xy, tri, reg)
+    mat = O.lame_table(0.3, 10.0, 0.25, 1.0)
+    Ke = O.assemble(mesh, mat)[1]['Ke']
+    # grad phi_a = sum_i (alpha[a,i] + sum_m beta[a,i,m] lam_m) g_i
+    alpha = np.zeros((6, 3)); beta = np.zeros((6, 3, 3))
+    for a in range(3):
+        alpha[a, a] = -1.0; beta[a, a, a] = 4.0
+    for a, (i, j) in zip((3, 4, 5), ((0, 1), (1, 2), (2, 0))):
+        beta[a, i, j] = 4.0; beta[a, j, i] = 4.0
+    M2 = (1.0 + np.eye(3)) / 12.0
+    I = (np.einsum('ai,bj->aibj', alpha, alpha)
+         + (np.einsum('ai,bj->aibj', alpha, beta.sum(2)) + np.einsum('ai,bj->aibj', beta.sum(2), alpha)) / 3.0
+         + np.einsum('aim,bjn,mn->aibj', beta, beta, M2))                  # per unit area
+    for t in range(nt):
+        g, A = mesh.gradlam[t], mesh.area[t]
+        assert A > 0
+        G = A * np.einsum('ic,jd,aibj->abcd', g, g, I)                      # int d_c phi_a d_d phi_b
+        lam, mu = mat[mesh.region[t]]
+        K = lam * G + mu * G.transpose(0, 1, 3, 2) + mu * np.einsum('abkk,cd->abcd', G, np.eye(2))
+        K = K.transpose(0, 2, 1, 3).reshape(12, 12)                         # dof = 2 a + c
+        assert np.abs(K - Ke[t]).max() <= 1e-12 * np.abs(Ke[t]).max()
+        assert np.abs(Ke[t] @ np.tile([1.0, 0.0], 6)).max() <= 1e-12 * np.abs(Ke[t]).max()     # rigid translation
