@@ -50,15 +50,29 @@ def _mesh_job(args):
     return load_mesh(meshname), row
 
 
-def get_meshes(paramRVEdata, meshnames, size, createMesh, nproc=None):
-    """Mesh every row (multi-process, results cached as .npz next to the reference's mesh name)."""
+def make_mesh_pool(nproc=None):
+    """Process pool for the meshing jobs, to be created BEFORE the GPU handles and their host worker threads exist
+    (the workers are forked from a single-threaded, CUDA-free parent and re-used for every batch).  None = serial."""
+    nproc = nproc or (os.cpu_count() or 1)
+    return mp.get_context("fork").Pool(nproc) if nproc > 1 else None
+
+
+def get_meshes(paramRVEdata, meshnames, size, createMesh, nproc=None, template=None, pool=None):
+    """Mesh every row (multi-process, results cached as .npz next to the reference's mesh name).  With a
+    `template` (deepbnd_b200.mesh.rve_morph.MorphTemplate) the meshes are morphed from it instead: fixed topology,
+    ~0.1 ms each, nothing cached.  `pool`: a pool from make_mesh_pool (otherwise a temporary one is forked here)."""
+    if template is not None:
+        from .mesh.rve_morph import buildRVEmesh_morphed
+        return [buildRVEmesh_morphed(paramRVEdata[i], template) for i in range(len(meshnames))]
     jobs = [(paramRVEdata[i], meshnames[i], size, createMesh) for i in range(len(meshnames))]
     nproc = nproc or min(len(jobs), os.cpu_count() or 1)
-    if nproc <= 1 or len(jobs) < 4:
+    if pool is not None and len(jobs) >= 4:
+        res = pool.map(_mesh_job, jobs, chunksize=max(1, len(jobs) // (4 * nproc)))
+    elif nproc <= 1 or len(jobs) < 4:
         res = [_mesh_job(j) for j in jobs]
     else:
-        with mp.get_context("fork").Pool(nproc) as pool:
-            res = pool.map(_mesh_job, jobs, chunksize=max(1, len(jobs) // (4 * nproc)))
+        with mp.get_context("fork").Pool(nproc) as tmp:
+            res = tmp.map(_mesh_job, jobs, chunksize=max(1, len(jobs) // (4 * nproc)))
     for i, (_, row) in enumerate(res):
         paramRVEdata[i] = row                                               # keep the reference's in-place permutation
     return [m for m, _ in res]
@@ -95,7 +109,7 @@ def _store_snapshots(rows, out, datasets):
 
 
 def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs, comm_self=None,
-                   device=None, batch_size=256, rtol=1e-10, nproc=None):
+                   device=None, batch_size=256, rtol=1e-10, nproc=None, mesher="delaunay"):
     bndMeshname, paramRVEname, snapshotsname, meshname = filesnames
     box, nb = vref_box_from_mesh(bndMeshname)
     nh = 2 * (4 * (nb - 1) + 1)                                             # Vref.dim()
@@ -112,10 +126,17 @@ def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs
     ids = snapshots[0]
     paramRVEdata = myhd.loadhd5(paramRVEname, 'param')[ids_run]
 
+    template = None
+    if mesher == "morph":                     # one template mesh per rank, every snapshot morphed from it (rve_morph.py)
+        from .mesh.rve_morph import MorphTemplate
+        template = MorphTemplate(paramRVEdata[0], size='full')
+    elif mesher != "delaunay":
+        raise ValueError("mesher must be 'delaunay' or 'morph'")
+
     def prepare(rows, batch):
         # the reference reuses ONE temporary mesh name per rank; a batch needs one cache entry per snapshot
         names = [meshname.replace(".xdmf", "_%d.xdmf" % int(ids_run[i])) for i in rows]
-        meshes = get_meshes(paramRVEdata[rows], names, 'full', createMesh, nproc)
+        meshes = get_meshes(paramRVEdata[rows], names, 'full', createMesh, nproc, template, pool)
         batch.set_meshes(meshes, tuple(paramMaterial), model=opModel, vref_nb=nb, vref_box=box)
 
     def solve(rows, batch, _):
@@ -127,9 +148,14 @@ def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs
         _store_snapshots(rows, out, snapshots)
         fsnaps.flush()
 
+    pool = make_mesh_pool(nproc) if template is None else None             # forked before the GPU threads exist
     db = DoubleBuffer(run if device is None else device)
-    db.run([np.arange(b0, min(nrun, b0 + batch_size)) for b0 in range(0, nrun, batch_size)], prepare, solve, store)
-    db.close()
+    try:
+        db.run([np.arange(b0, min(nrun, b0 + batch_size)) for b0 in range(0, nrun, batch_size)], prepare, solve, store)
+    finally:
+        db.close()
+        if pool is not None:
+            pool.close(); pool.join()
     fsnaps.close()
 
 

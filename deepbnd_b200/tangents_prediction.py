@@ -14,11 +14,11 @@ import numpy as np
 from . import wrapper_h5py as myhd
 from .batch import DoubleBuffer
 from .elasticity import macro_strain_voigt
-from .simulation_snapshots import get_meshes, vref_box_from_mesh
+from .simulation_snapshots import get_meshes, make_mesh_pool, vref_box_from_mesh
 
 
 def predictTangents(num, num_runs, modelBnd, namefiles, createMesh, meshSize, device=None, batch_size=2048,
-                    rtol=1e-10, nproc=None):
+                    rtol=1e-10, nproc=None, mesher="delaunay"):
     nameMeshRefBnd, paramRVEname, tangentName, BCname, meshMicroName = namefiles
     run = num
     start = timer()
@@ -46,9 +46,16 @@ def predictTangents(num, num_runs, modelBnd, namefiles, createMesh, meshSize, de
     eps3 = np.stack([macro_strain_voigt(i) for i in range(3)])
     box, nb = vref
 
+    template = None
+    if mesher == "morph":
+        from .mesh.rve_morph import MorphTemplate
+        template = MorphTemplate(paramRVEdata[0], size=meshSize)
+    elif mesher != "delaunay":
+        raise ValueError("mesher must be 'delaunay' or 'morph'")
+
     def prepare(rows, batch):
         names = [meshMicroName.format(int(ids[i]) if np.any(ids) else int(i), meshSize) for i in rows]
-        meshes = get_meshes(paramRVEdata[rows], names, meshSize, createMesh, nproc)
+        meshes = get_meshes(paramRVEdata[rows], names, meshSize, createMesh, nproc, template, pool)
         batch.set_meshes(meshes, tuple(param), model=modelBnd, vref_nb=nb, vref_box=box)
 
     def solve(rows, batch, _):
@@ -64,9 +71,14 @@ def predictTangents(num, num_runs, modelBnd, namefiles, createMesh, meshSize, de
         f.flush()
         sys.stdout.flush()
 
+    pool = make_mesh_pool(nproc) if template is None else None             # forked before the GPU threads exist
     db = DoubleBuffer(run if device is None else device)
-    db.run([np.arange(b0, min(ns, b0 + batch_size)) for b0 in range(0, ns, batch_size)], prepare, solve, store)
-    db.close()
+    try:
+        db.run([np.arange(b0, min(ns, b0 + batch_size)) for b0 in range(0, ns, batch_size)], prepare, solve, store)
+    finally:
+        db.close()
+        if pool is not None:
+            pool.close(); pool.join()
     f.close()
     print("tangents of", ns, "RVEs concluded in", timer() - start)
 

@@ -110,3 +110,27 @@ def test_micro_model_gen_matches_oracle(full_mesh, model):
     for k in ("sigma", "sigmaL", "eps", "epsL", "tangent", "tangentL"):
         assert np.abs(Hg[k] - Ho[k]).max() < 1e-8 * np.abs(Ho[k]).max(), (model, k)
     assert mm.getHomogenisation() is Hg
+
+
+def test_predictTangents_with_morphed_meshes(tmp_path):
+    """mesher='morph' (one template per rank, fixed topology): tangents equal the oracle's on the same morphed
+    meshes to 1e-8, and differ from the re-meshed run only at the level of the discretisation error."""
+    import deepbnd_b200.wrapper_h5py as myhd
+    from deepbnd_b200.tangents_prediction import predictTangents
+    from deepbnd_b200.mesh.rve_morph import MorphTemplate, buildRVEmesh_morphed
+    from oracle.rve_oracle import OracleRVE
+    ns = 5
+    par = synthetic_param(ns, seed=7)
+    pfile, bfile = str(tmp_path / "paramRVEdataset.hd5"), str(tmp_path / "bcs.hd5")
+    myhd.savehd5(pfile, par, 'param', 'w')
+    mname = str(tmp_path / "meshes" / "mesh_micro_{0}_{1}.xdmf")
+    out = {}
+    for mesher in ("morph", "delaunay"):
+        tfile = str(tmp_path / ("tangents_%s.hd5" % mesher))
+        predictTangents(0, 1, 'per', ["", pfile, tfile, bfile, mname], True, 'reduced', device=0, mesher=mesher)
+        out[mesher] = myhd.loadhd5(tfile, 'tangent')
+    tpl = MorphTemplate(par[0], size='reduced')
+    for s in (0, 3):
+        Co = OracleRVE(*buildRVEmesh_morphed(par[s].copy(), tpl), param=tuple(PARAM), model='per').compute_tangent()
+        assert np.abs(out["morph"][s] - Co).max() < 1e-8 * np.abs(Co).max()
+    assert np.abs(out["morph"] - out["delaunay"]).max() < 5e-3 * np.abs(out["delaunay"]).max()
