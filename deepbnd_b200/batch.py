@@ -177,7 +177,7 @@ class RVEBatch:
     def timings(self):
         t, c = np.zeros(8), np.zeros(8)
         self._check(self.lib.rve_timings(self.h, L.dptr(t), L.dptr(c)))
-        keys = ["symbolic_host", "upload", "assemble", "precond_setup", "rhs", "pcg", "spmv", "epilogue"]
+        keys = ["set_batch_numbering", "set_batch_pattern", "assemble", "precond_setup", "rhs", "pcg", "spmv", "epilogue"]
         return dict(zip(keys, t.tolist())), dict(spmv_launches=c[0], spmv_alg_bytes=c[1], pcg_iters_launched=c[2],
                                                  sum_iters=c[3], kernel_launches=c[4], post_ms=c[5], h2d_bytes=c[6],
                                                  d2h_bytes=c[7])
