@@ -188,3 +188,28 @@ def test_p2_element_stiffness_against_closed_form_integrals():
         K = K.transpose(0, 2, 1, 3).reshape(12, 12)                         # dof = 2 a + c
         assert np.abs(K - Ke[t]).max() <= 1e-12 * np.abs(Ke[t]).max()
         assert np.abs(Ke[t] @ np.tile([1.0, 0.0], 6)).max() <= 1e-12 * np.abs(Ke[t]).max()     # rigid translation
+
+
+def test_periodic_model_equals_the_lagrange_multiplier_formulation(coarse_reduced_meshes):
+    """the reference imposes periodicity and the zero mean with Lagrange multipliers (multiphenics block system behind
+    listMultiscaleModels['per'], micro_model.py:56-62); the oracle eliminates the slave DOFs.  Same solution."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import oracle.rve_oracle as O
+    o = O.OracleRVE(*coarse_reduced_meshes[0], param=PARAM, model='per')
+    m = o.mesh
+    master = O.periodic_map(m)
+    slaves = np.flatnonzero(master != np.arange(m.nn))
+    assert slaves.size > 0
+    rows, cols, vals = [], [], []
+    for r, s in enumerate(slaves):
+        for c in range(2):
+            rows += [2 * r + c, 2 * r + c]; cols += [2 * s + c, 2 * master[s] + c]; vals += [1.0, -1.0]
+    Cp = sp.coo_matrix((vals, (rows, cols)), shape=(2 * slaves.size, 2 * m.nn)).tocsr()
+    C = sp.vstack([Cp, sp.csr_matrix(O.mean_constraint(m))]).tocsr()
+    lu = spla.splu(sp.bmat([[o.K, C.T], [C, None]]).tocsc())
+    for i in range(3):
+        u = o.solve_load(i)
+        F = O.load_vector(m, o.ed, O.strain2voigt(O.macro_strain(i)))
+        x = lu.solve(np.concatenate([F, np.zeros(C.shape[0])]))
+        assert np.abs(x[:2 * m.nn] - u).max() < 1e-9 * np.abs(u).max()
