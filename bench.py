@@ -31,7 +31,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 _OUT = sys.stdout
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 PARAM_MAT = (0.3, 10.0, 0.3, 1.0)           # simulation_snapshots.py:120-123
 WORKLOADS = {
@@ -172,6 +171,8 @@ def main():
     ap.add_argument("--precond", default="twolevel", choices=["twolevel", "jacobi"])
     ap.add_argument("--unique", type=int, default=256, help="distinct synthetic RVEs meshed per rank (cycled to --ns); 0 = all")
     ap.add_argument("--chunks", type=int, default=4, help="chunks per step in the pipelined e2e loop")
+    ap.add_argument("--operator", default="matfree", choices=["matfree", "assembled"],
+                    help="q = A p inside the PCG: element-wise (default) or the assembled SELL-32 SpMV")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="RVEs in the CPU baseline sample (default: one per core)")
     args = ap.parse_args()
@@ -189,7 +190,7 @@ def main():
         os.environ.setdefault("RVE_HOST_THREADS", str(max(1, ncpu // world)))
         if ncpu // world < 8:
             os.environ.setdefault("RVE_BLOCKING_SYNC", "1")   # few cores per rank: the kernel-feeding thread sleeps while it waits
-    from conftest import synthetic_param, smooth_uD
+    from deepbnd_b200.synthetic import synthetic_param, smooth_uD
 
     if args.impl == "reference":
         # CPU reference arm: rank 0 alone, bounded sample per step (one RVE per host core)
@@ -276,7 +277,7 @@ def main():
     # two handles: while one batch is being solved, a second host thread uploads the next one and runs its symbolic phase
     # one on the other handle from a second host thread (ctypes releases the GIL)
     from concurrent.futures import ThreadPoolExecutor
-    hb = [RVEBatch(local_rank), RVEBatch(local_rank)]
+    hb = [RVEBatch(local_rank).set_operator(args.operator), RVEBatch(local_rank).set_operator(args.operator)]
     b = hb[0]
     pool = ThreadPoolExecutor(max_workers=2)
     maxit = 4000

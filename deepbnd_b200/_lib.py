@@ -12,12 +12,14 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 
 MODEL = {"lin": 0, "dnn": 1, "per": 2, "MR": 3}
 PRECOND = {"jacobi": 0, "twolevel": 1}
+OPT_SYM_B, OPT_OPERATOR = 1, 2
+OPERATOR = {"assembled": 0, "matfree": 1}
 
 # every symbol include/rve_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["rve_create", "rve_destroy", "rve_last_error", "rve_set_batch", "rve_assemble", "rve_get_sizes",
            "rve_get_csr", "rve_get_rowmap", "rve_get_nodemap", "rve_get_rhs", "rve_get_solution",
            "rve_get_coarse_dim", "rve_get_coarse_dense", "rve_solve", "rve_epilogue_tangent",
-           "rve_epilogue_snapshot", "rve_epilogue_homogenisation", "rve_set_option", "rve_project", "rve_timings", "rve_bench_spmv", "rve_host_symbolic"]
+           "rve_epilogue_snapshot", "rve_epilogue_homogenisation", "rve_set_option", "rve_project", "rve_timings", "rve_bench_spmv", "rve_apply_operator", "rve_host_symbolic"]
 
 _lib = None
 
@@ -62,6 +64,7 @@ def load():
     lib.rve_project.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_double_p, c_double_p, c_double_p,
                                 c_double_p]
     lib.rve_timings.argtypes = [ctypes.c_void_p, c_double_p, c_double_p]
+    lib.rve_apply_operator.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p]
     lib.rve_bench_spmv.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_double_p, c_double_p]
     lib.rve_host_symbolic.argtypes = [c_double_p, ctypes.c_int32, c_int32_p, c_int32_p, ctypes.c_int32, ctypes.c_int32,
                                       ctypes.c_int32, ctypes.c_int32, ctypes.c_int32] + [c_int32_p] * 10 + [c_double_p]

@@ -97,6 +97,18 @@ class RVEBatch:
         self._check(self.lib.rve_set_option(self.h, int(option), int(value)))
         return self
 
+    def set_operator(self, name):
+        """'matfree' (default: element-wise application, the matrix is never stored) or 'assembled' (SELL-32 SpMV);
+        call before assemble()."""
+        return self.set_option(L.OPT_OPERATOR, L.OPERATOR[name])
+
+    def apply_operator(self, p):
+        """test accessor: q = A p for the whole batch; p (total rows, n_rhs, 2)."""
+        p = L.f64(p)
+        q = np.zeros_like(p)
+        self._check(self.lib.rve_apply_operator(self.h, p.shape[1], L.dptr(p), L.dptr(q)))
+        return q
+
     def homogenisation(self):
         """sigmaL, sigmaT (n,k,3), gradL, gradT (n,k,2,2), eps_eff (n,k,3) of the last solve
         (micro_model_gen.py:139-147)."""

@@ -13,6 +13,7 @@
 #include "rve_kernels.cuh"
 #include "rve_symbolic.hpp"
 #include "rve_devsym.cuh"
+#include "rve_matfree.cuh"
 
 namespace {
 
@@ -126,6 +127,15 @@ struct rve_batch_s {
     DBuf<double> eps, eps_eff, Bmat, uD, gval, d_vbox, U, acc, sigL, sigT, aout, Bout, sol, Mx, Gaff, aaff;
     DBuf<double> MWt, transl, Yd, gradT;
     int opt_sym_B = 0;
+    // matrix-free operator (rve_matfree.cuh): window-element tables; the SELL values (bval) are built on demand only
+    int opt_operator = RVE_OPERATOR_MATFREE;
+    bool have_bval = false;
+    int max_slots = 0;
+    long long n_we = 0;
+    DBuf<int> win_we0, win_nwe, we_elem;
+    DBuf<unsigned char> win_sw, row_nadj;
+    DBuf<uint16_t> we_col, we_dst;
+    DBuf<double> we_geo;
     int* h_nactive = nullptr;  // pinned
     PinnedArena arena;
     std::vector<cudaEvent_t> evpool;  // per-iteration SpMV timing
@@ -197,6 +207,7 @@ static Sell sell_tab(rve_batch_s* h) {
 static size_t smem_spmv(rve_batch_s* h, int K) { return (size_t)h->max_tile * K * sizeof(double2); }
 static size_t smem_update(int K) { return (size_t)RVE_WIN * K * sizeof(double2) + RVE_WIN * sizeof(float2) + 4 * RVE_WIN * sizeof(uint16_t); }
 static size_t smem_direction(rve_batch_s* h, int K) { return (size_t)h->max_cn * K * sizeof(double2); }
+static size_t smem_apply(rve_batch_s* h, int K) { return ((size_t)h->max_tile + h->max_slots) * K * sizeof(double2); }
 
 // Opt-in dynamic shared memory of the kernels that size their tiles at run time.  The attribute belongs to the
 // FUNCTION (shared by every handle and host thread of the process), so it is raised once, to the device limit
@@ -218,7 +229,8 @@ static cudaError_t raise_smem_limits(int device) {
     RAISE_(k_spmv<1>); RAISE_(k_spmv<2>); RAISE_(k_spmv<3>);
     RAISE_(k_update<1>); RAISE_(k_update<2>); RAISE_(k_update<3>);
     RAISE_(k_direction<1>); RAISE_(k_direction<2>); RAISE_(k_direction<3>);
-    RAISE_(k_sym_window); RAISE_(k_sym_coarse);
+    RAISE_(k_sym_window); RAISE_(k_sym_coarse); RAISE_(k_sym_elems);
+    RAISE_(k_apply<1>); RAISE_(k_apply<2>); RAISE_(k_apply<3>);
 #undef RAISE_
     return cudaSuccess;
 }
@@ -227,12 +239,25 @@ struct PcgArgs {
     WinTab wt; Sell sl; Levels LV;
     int n_win, n_sys, K, precond;
     double rtol2;
-    size_t sm_spmv, sm_upd, sm_dir;
+    size_t sm_spmv, sm_upd, sm_dir, sm_apply;
+    int op;
 };
+
+static MfTab mf_tab(rve_batch_s* h) {
+    MfTab mf;
+    mf.win_we0 = h->win_we0.p; mf.win_nwe = h->win_nwe.p; mf.win_sw = h->win_sw.p; mf.row_nadj = h->row_nadj.p;
+    mf.we_col = h->we_col.p; mf.we_dst = h->we_dst.p; mf.we_geo = h->we_geo.p;
+    return mf;
+}
 
 template <int K>
 static void launch_spmv(rve_batch_s* h, const PcgArgs& a, const double* p, double* q, int* active, double* part, int* cnt,
                         double* sc, cudaStream_t st) {
+    if (a.op == RVE_OPERATOR_MATFREE) {
+        k_apply<K><<<a.n_win, RVE_APPLY_THREADS(K), a.sm_apply, st>>>(a.wt, a.sl, mf_tab(h), (const double2*)p, (double2*)q, h->max_tile,
+                                                                      part, cnt, sc);
+        return;
+    }
     k_spmv<K><<<a.n_win, RVE_SPMV_THREADS, a.sm_spmv, st>>>(a.wt, a.sl, (const double2*)h->bval.p, (const double2*)p, (double2*)q,
                                                   active, part, cnt, sc);
 }
@@ -527,7 +552,8 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     if (std::getenv("RVE_DEBUG_TIMING"))
         fprintf(stderr, "[rve_set_batch] n_sys %d: copy + edges %.1f ms, rows + finish (enqueue) %.1f ms\n", n_sys,
                 std::chrono::duration<double, std::milli>(tp1 - t0).count(), std::chrono::duration<double, std::milli>(t1 - tp1).count());
-    CU(h->bval.alloc(128 * (size_t)h->NG)); CU(h->dinv.alloc((size_t)h->R)); CU(h->wmean.alloc(h->R));
+    h->have_bval = false;                       // SELL values: rve_assemble (assembled operator) or on demand
+    CU(h->dinv.alloc((size_t)h->R)); CU(h->wmean.alloc(h->R));
     CU(h->active.alloc(n_sys)); CU(h->cnt.alloc(n_sys)); CU(h->d_iters.alloc(n_sys)); CU(h->n_active.alloc(1));
     CU(h->err_flag.alloc(1));
     CU(h->part.alloc((size_t)h->n_win * 8));  CU(h->sc.alloc((size_t)n_sys * 4 * SC_N));
@@ -581,6 +607,31 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         h->launches += 3;
     }
     int scnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // window-element tables of the matrix-free operator (after the halo lists: columns are tile-local)
+    CU(h->win_we0.alloc(n_win)); CU(h->win_nwe.alloc(n_win)); CU(h->win_sw.alloc(8 * (size_t)n_win)); CU(h->row_nadj.alloc((size_t)h->R));
+    {
+        int max_ne = 0;
+        for (int s = 0; s < n_sys; ++s) max_ne = std::max(max_ne, I[s].nt);
+        const size_t sme = 2 * (size_t)((max_ne + 31) / 32) * sizeof(unsigned);
+        if (sme > 150 * 1024) FAIL(RVE_E_MESH, "system too large for the element bitmap in shared memory");
+        long long we_cap = 2 * h->E + 32LL * n_win + 1024;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (6 * we_cap > 2000000000LL) FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
+            CU(h->we_elem.alloc((size_t)we_cap)); CU(h->we_col.alloc(6 * (size_t)we_cap)); CU(h->we_dst.alloc(6 * (size_t)we_cap));
+            CU(cudaMemsetAsync(h->sym_cnt.p + 6, 0, 2 * sizeof(int), st));
+            k_sym_elems<<<n_win, RVE_WIN, sme, st>>>(win_tab(h), sell_tab(h), h->d_toff.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p,
+                                                      h->node_row.p, h->win_we0.p, h->win_nwe.p, h->win_sw.p, h->row_nadj.p,
+                                                      h->we_elem.p, h->we_col.p, h->we_dst.p, we_cap, h->sym_cnt.p);
+            h->launches += 1;
+            CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(stream_wait(h));
+            if (scnt[2] != 5 || scnt[6] <= we_cap) break;       // capacity was enough (or another error)
+            we_cap = scnt[6];                                   // the counter kept running: exact need
+            CU(cudaMemsetAsync(h->sym_cnt.p + 2, 0, sizeof(int), st));
+        }
+        h->n_we = scnt[6]; h->max_slots = scnt[7];
+        CU(h->we_geo.alloc(6 * (size_t)std::max<long long>(h->n_we, 1)));
+    }
     CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     std::vector<int> sb(n_sys);
     CU(cudaMemcpyAsync(sb.data(), h->sys_blocks.p, n_sys * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -590,8 +641,9 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     h->true_blocks.assign(sb.begin(), sb.end());
     if (scnt[2] == 3) FAIL(RVE_E_MESH, "device pattern build: halo list overflow");
     if (scnt[2] == 4) FAIL(RVE_E_MESH, "device pattern build: coarse-node list overflow");
+    if (scnt[2] == 5) FAIL(RVE_E_MESH, "device pattern build: a window touches more than 1024 elements");
     h->max_tile = scnt[1]; h->max_cn = scnt[5];
-    if ((size_t)h->max_tile * 3 * sizeof(double2) > 200 * 1024) FAIL(RVE_E_MESH, "window halo too large for shared memory");
+    if (((size_t)h->max_tile + h->max_slots) * 3 * sizeof(double2) > 200 * 1024) FAIL(RVE_E_MESH, "window halo too large for shared memory");
     auto t2 = std::chrono::steady_clock::now();
     h->t_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
     h->have_batch = true;
@@ -604,9 +656,20 @@ int rve_assemble(rve_handle_t h) {
     cudaStream_t st = h->stream;
     CU(cudaEventRecord(h->ev[0], st));
     CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), st));
-    k_assemble<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), sell_tab(h), h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->elem_reg.p,
-                                              h->node_xy.p, h->node_row.p, h->emap.p, h->bval.p, h->wmean.p, h->mat);
-    k_dinv<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), sell_tab(h), h->bval.p, h->dinv.p);
+    if (h->opt_operator == RVE_OPERATOR_MATFREE) {
+        // matrix-free operator: geometry x material of the window elements, block-Jacobi diagonal from the element fans
+        k_we_geo<<<h->n_win, RVE_WIN, 0, st>>>(h->n_win, h->win_we0.p, h->win_nwe.p, h->we_elem.p, h->elem_node.p, h->elem_reg.p,
+                                                h->node_xy.p, h->we_geo.p, h->mat);
+        k_diag<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->elem_reg.p, h->node_xy.p,
+                                              h->node_row.p, h->dinv.p, h->wmean.p, h->mat);
+        h->have_bval = false;
+    } else {
+        CU(h->bval.alloc(128 * (size_t)h->NG));
+        k_assemble<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), sell_tab(h), h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->elem_reg.p,
+                                                  h->node_xy.p, h->node_row.p, h->emap.p, h->bval.p, h->wmean.p, h->mat);
+        k_dinv<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), sell_tab(h), h->bval.p, h->dinv.p);
+        h->have_bval = true;
+    }
     CU(cudaEventRecord(h->ev[1], st));
     // two-level preconditioner: Galerkin hierarchy
     Levels& LV = h->LV;
@@ -636,6 +699,20 @@ int rve_assemble(rve_handle_t h) {
     return 0;
 }
 
+// SELL values of the assembled operator, built on demand when the batch was set up for the matrix-free one
+static int ensure_bval(rve_handle_t h) {
+    if (h->have_bval) return 0;
+    cudaStream_t st = h->stream;
+    CU(h->bval.alloc(128 * (size_t)h->NG));
+    k_assemble<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), sell_tab(h), h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->elem_reg.p,
+                                              h->node_xy.p, h->node_row.p, h->emap.p, h->bval.p, h->wmean.p, h->mat);
+    h->launches += 1;
+    CU(stream_wait(h));
+    CU(cudaGetLastError());
+    h->have_bval = true;
+    return 0;
+}
+
 int rve_get_sizes(rve_handle_t h, int32_t sys, int64_t* n_nodes, int64_t* n_rows, int64_t* n_blocks, int64_t* n_elems) {
     H_CHECK(h);
     if (!h->have_batch || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_ARG, "bad system index");
@@ -649,6 +726,7 @@ int rve_get_sizes(rve_handle_t h, int32_t sys, int64_t* n_nodes, int64_t* n_rows
 int rve_get_csr(rve_handle_t h, int32_t sys, int32_t* rowptr, int32_t* col, double* val) {
     H_CHECK(h);
     if (!h->assembled || sys < 0 || sys >= h->n_sys) FAIL(RVE_E_STATE, "not assembled / bad system index");
+    if (int rc = ensure_bval(h)) return rc;
     const SysInfo& Y = h->info[sys];
     const size_t ng = (size_t)Y.ngrp;
     const int rb0 = h->row_base[sys], sl0 = h->slice_base[sys];
@@ -770,6 +848,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     const int NL = n_rhs;
     const int K = (h->model == RVE_MODEL_MR) ? 3 : n_rhs;
     const int n_sys = h->n_sys;
+    if (h->opt_operator == RVE_OPERATOR_ASSEMBLED) { if (int rc = ensure_bval(h)) return rc; }
     h->K = K; h->NL = NL; h->solved = false;
     cudaStream_t st = h->stream;
     const size_t RK = (size_t)h->R * K * 2;
@@ -817,6 +896,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     pa.wt = win_tab(h); pa.sl = sell_tab(h); pa.LV = h->LV; pa.LV.K = K;
     pa.n_win = h->n_win; pa.n_sys = n_sys; pa.K = K; pa.precond = precond; pa.rtol2 = rtol * rtol;
     pa.sm_spmv = smem_spmv(h, K); pa.sm_upd = smem_update(K); pa.sm_dir = smem_direction(h, K);
+    pa.sm_apply = smem_apply(h, K); pa.op = h->opt_operator;
     const Levels& LV = pa.LV;
     CU(cudaMemsetAsync(LV.rc[0], 0, h->lvR[0].n * sizeof(float), st));
 #define UPD0_(KK) launch_update<KK>(h, pa, 1, -1, st)
@@ -979,6 +1059,12 @@ int rve_epilogue_snapshot(rve_handle_t h, double* sol, double* sigma, double* a,
 int rve_set_option(rve_handle_t h, int32_t option, int32_t value) {
     H_CHECK(h);
     if (option == RVE_OPT_SYM_B) { h->opt_sym_B = value ? 1 : 0; return 0; }
+    if (option == RVE_OPT_OPERATOR) {
+        if (value != RVE_OPERATOR_ASSEMBLED && value != RVE_OPERATOR_MATFREE) FAIL(RVE_E_ARG, "unknown operator");
+        if (value == RVE_OPERATOR_MATFREE && h->assembled && h->opt_operator != RVE_OPERATOR_MATFREE) h->assembled = false;   // needs k_we_geo
+        h->opt_operator = value;
+        return 0;
+    }
     FAIL(RVE_E_ARG, "unknown option");
 }
 
@@ -1049,6 +1135,7 @@ int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_l
     H_CHECK(h);
     if (!h->assembled) FAIL(RVE_E_STATE, "rve_bench_spmv before rve_assemble");
     if (n_rhs < 1 || n_rhs > 3 || reps < 1) FAIL(RVE_E_ARG, "bad arguments");
+    if (h->opt_operator == RVE_OPERATOR_ASSEMBLED) { if (int rc = ensure_bval(h)) return rc; }
     cudaStream_t st = h->stream;
     const int K = n_rhs, n_sys = h->n_sys;
     DBuf<double> p, q, part, sc;
@@ -1066,6 +1153,7 @@ int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_l
     PcgArgs pa;
     pa.wt = win_tab(h); pa.sl = sell_tab(h); pa.LV = h->LV; pa.n_win = h->n_win; pa.n_sys = n_sys; pa.K = K;
     pa.precond = 0; pa.rtol2 = 0; pa.sm_spmv = smem_spmv(h, K); pa.sm_upd = smem_update(K); pa.sm_dir = smem_direction(h, K);
+    pa.sm_apply = smem_apply(h, K); pa.op = h->opt_operator;
 #define SPMV_(KK) launch_spmv<KK>(h, pa, p.p, q.p, active.p, part.p, cnt.p, sc.p, st)
     for (int wu = 0; wu < 3; ++wu) K_DISPATCH(K, SPMV_);
     CU(cudaEventRecord(h->ev[0], st));
@@ -1083,6 +1171,39 @@ int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_l
         const double n = 2.0 * (double)h->R, nnz = 4.0 * blocks;
         *alg_bytes_per_launch = 12.0 * nnz + 4.0 * (n + n_sys) + 16.0 * n * K;
     }
+    return 0;
+}
+
+// parity-test accessor: q = A p with the operator RVE_OPT_OPERATOR selects, whole batch
+int rve_apply_operator(rve_handle_t h, int32_t n_rhs, const double* p_host, double* q_host) {
+    H_CHECK(h);
+    if (!h->assembled) FAIL(RVE_E_STATE, "rve_apply_operator before rve_assemble");
+    if (n_rhs < 1 || n_rhs > 3 || !p_host || !q_host) FAIL(RVE_E_ARG, "bad arguments");
+    if (h->opt_operator == RVE_OPERATOR_ASSEMBLED) { if (int rc = ensure_bval(h)) return rc; }
+    cudaStream_t st = h->stream;
+    const int K = n_rhs, n_sys = h->n_sys;
+    const size_t RK = (size_t)h->R * K * 2;
+    DBuf<double> p, q, part, sc;
+    DBuf<int> active, cnt;
+    CU(p.alloc(RK)); CU(q.alloc(RK)); CU(part.alloc((size_t)h->n_win * 8));
+    CU(sc.alloc((size_t)n_sys * 4 * SC_N)); CU(active.alloc(n_sys)); CU(cnt.alloc(n_sys));
+    CU(cudaMemcpyAsync(p.p, p_host, RK * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<int> ones(n_sys, 1);
+    CU(cudaMemcpyAsync(active.p, ones.data(), n_sys * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->win_active.p, 1, (size_t)h->n_win, st));
+    CU(cudaMemsetAsync(cnt.p, 0, n_sys * sizeof(int), st));
+    CU(cudaMemsetAsync(sc.p, 0, sc.n * sizeof(double), st));
+    CU(cudaMemsetAsync(q.p, 0, RK * sizeof(double), st));
+    PcgArgs pa;
+    pa.wt = win_tab(h); pa.sl = sell_tab(h); pa.LV = h->LV; pa.n_win = h->n_win; pa.n_sys = n_sys; pa.K = K;
+    pa.precond = 0; pa.rtol2 = 0; pa.sm_spmv = smem_spmv(h, K); pa.sm_upd = smem_update(K); pa.sm_dir = smem_direction(h, K);
+    pa.sm_apply = smem_apply(h, K); pa.op = h->opt_operator;
+#define SPMV_(KK) launch_spmv<KK>(h, pa, p.p, q.p, active.p, part.p, cnt.p, sc.p, st)
+    K_DISPATCH(K, SPMV_);
+#undef SPMV_
+    CU(cudaMemcpyAsync(q_host, q.p, RK * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(stream_wait(h));
+    CU(cudaGetLastError());
     return 0;
 }
 

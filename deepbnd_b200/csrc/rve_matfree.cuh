@@ -1,0 +1,312 @@
+// rve_matfree.cuh — matrix-free application of the P2 elasticity operator (sm_100a).
+//
+// The PCG's q = A p does not need the assembled matrix: the stored SELL-32 operator is 34 B per 2x2 block (about
+// 15 MB per `full` RVE, read once per iteration), while the same operator is defined by 72 B per element (about
+// 1.7 MB per RVE, counting the elements on window borders twice): 6 tile-local columns, 6 destination slots, and
+// 6 doubles of geometry x material.  The fp64 pipe of the B200 has the headroom (about 150 fp64 operations per
+// element and right-hand side), so the application becomes a gather -> element product -> gather pass over
+// shared memory with coalesced streams only:
+//
+//   window w (RVE_WIN rows, one CTA): the elements touching its own rows ("window elements", found by
+//   k_sym_elems with a shared-memory bitmap over the elements of the system; elements on a border belong to
+//   several windows and are applied by each of them, no inter-CTA exchange, no atomics, deterministic)
+//     phase 0  p-tile: own rows (coalesced) + halo rows (list-driven gather) -> shared memory   [same as k_spmv]
+//     phase 1  thread per (window element, rhs): u_e from the tile, f_e = K_e u_e by p2_apply (K_e never formed),
+//              the nodal forces of the element's OWN-row nodes go to their slots in shared memory
+//              (slot = position j of the element in that row's fan, sliced ELL [slice][j][32 rows])
+//     phase 2  thread per (row, rhs): q = sum of the row's slots (conflict-free), p.q partial, coalesced store
+//
+// Replaces mp.block_assemble(a) + PETSc's matrix-vector product inside the solve (micro_model.py:60-66): the
+// assembled matrix is only built on demand (rve_get_csr, rve_bench_spmv, RVE_OPT_OPERATOR = assembled).
+#pragma once
+#include "rve_kernels.cuh"
+
+struct MfTab {
+    const int* win_we0;           // [n_win] first window element (multiple of 32); arrays below are indexed 6*we0 + a*nep + e
+    const int* win_nwe;           // [n_win] window elements (nep = nwe rounded up to 32)
+    const unsigned char* win_sw;  // [n_win][8] slots per row of every 32-row slice (max fan size in the slice)
+    const unsigned char* row_nadj;// [R] elements around the row
+    const uint16_t* we_col;       // tile-local column of the element's 6 nodes (0xffff: no row = homogeneous Dirichlet)
+    const uint16_t* we_dst;       // slot of the nodal force (0xffff: not an own row of this window)
+    const double* we_geo;         // g0x g0y g1x g1y w*lam w*mu
+};
+
+#define RVE_MF_MAXWE 1024         // window elements per window (a 256-row window touches about 200)
+
+// counters: [2] error code (5: window-element overflow), [6] window elements used, [7] max slots of a window
+__global__ void __launch_bounds__(RVE_WIN)
+k_sym_elems(WinTab wt, Sell sl, const int* __restrict__ elem_base, const unsigned* __restrict__ adjf_ptr,
+            const int* __restrict__ adjf, const int* __restrict__ elem_node, const int* __restrict__ node_row,
+            int* __restrict__ win_we0, int* __restrict__ win_nwe, unsigned char* __restrict__ win_sw,
+            unsigned char* __restrict__ row_nadj, int* __restrict__ we_elem, uint16_t* __restrict__ we_col,
+            uint16_t* __restrict__ we_dst, long long we_cap, int* counters) {
+    extern __shared__ unsigned s_bm[];           // [words] bitmap over the elements of the system, then popcount prefix
+    __shared__ int s_scan[RVE_WIN];
+    __shared__ int s_el[RVE_MF_MAXWE];
+    __shared__ int s_sb[RVE_WIN / 32 + 1];
+    __shared__ int s_w0;
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const int sys = wt.win_sys[w];
+    const int e0 = elem_base[sys], ne = elem_base[sys + 1] - e0;
+    const int words = (ne + 31) >> 5;
+    unsigned* s_pre = s_bm + words;
+    const int r0 = wt.win_row0[w], n = wt.win_n[w];
+    for (int i = tid; i < words; i += RVE_WIN) s_bm[i] = 0u;
+    __syncthreads();
+    unsigned a0 = 0; int cnt = 0;
+    if (tid < n) {
+        a0 = adjf_ptr[r0 + tid]; cnt = (int)(adjf_ptr[r0 + tid + 1] - a0);
+        for (int j = 0; j < cnt; ++j) { const int e = adjf[a0 + j] - e0; atomicOr(&s_bm[e >> 5], 1u << (e & 31)); }
+        row_nadj[r0 + tid] = (unsigned char)cnt;
+    }
+    // slots per row of the slice = largest fan in it
+    int mx = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) s_sb[(tid >> 5) + 1] = mx;
+    __syncthreads();
+    const int wpt = (words + RVE_WIN - 1) / RVE_WIN;
+    const int wa = min(words, tid * wpt), wb = min(words, wa + wpt);
+    int sum = 0;
+    for (int i = wa; i < wb; ++i) sum += __popc(s_bm[i]);
+    s_scan[tid] = sum;
+    __syncthreads();
+    for (int d = 1; d < RVE_WIN; d <<= 1) {
+        const int v = tid >= d ? s_scan[tid - d] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    int run = s_scan[tid] - sum;
+    for (int i = wa; i < wb; ++i) { s_pre[i] = (unsigned)run; run += __popc(s_bm[i]); }
+    const int nwe = s_scan[RVE_WIN - 1];
+    const int nep = (nwe + 31) & ~31;
+    if (tid == 0) {
+        int tot = 0;
+        for (int s = 0; s < RVE_WIN / 32; ++s) {
+            const int wd = s_sb[s + 1];
+            win_sw[(size_t)w * 8 + s] = (unsigned char)wd;
+            s_sb[s] = tot; tot += wd * 32;             // first slot of the slice
+        }
+        s_sb[RVE_WIN / 32] = tot;
+        atomicMax(counters + 7, tot);
+        int we0 = atomicAdd(counters + 6, nep);
+        if ((long long)we0 + nep > we_cap || nwe > RVE_MF_MAXWE) { atomicExch(counters + 2, 5); we0 = -1; }
+        s_w0 = we0;
+        win_we0[w] = we0 < 0 ? 0 : we0;
+        win_nwe[w] = we0 < 0 ? 0 : nwe;
+    }
+    __syncthreads();
+    const int we0 = s_w0;
+    if (we0 < 0) return;
+    for (int i = tid; i < words; i += RVE_WIN) {       // window-local element list (ascending element id)
+        unsigned bits = s_bm[i];
+        int pos = (int)s_pre[i];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            s_el[pos++] = i * 32 + b;
+            bits &= bits - 1;
+        }
+    }
+    uint16_t* col = we_col + 6 * (size_t)we0;
+    uint16_t* dst = we_dst + 6 * (size_t)we0;
+    for (int i = tid; i < 6 * nep; i += RVE_WIN) dst[i] = (uint16_t)0xffffu;
+    __syncthreads();
+    // columns of the 6 nodes of every window element: own rows first, then the position in the (sorted) halo list
+    const int h0 = wt.win_halo0[w], nh = wt.win_nhalo[w];
+    for (int el = tid; el < nep; el += RVE_WIN) {
+        if (el >= nwe) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) col[a * nep + el] = (uint16_t)0xffffu;
+            we_elem[we0 + el] = -1;
+            continue;
+        }
+        const int e = e0 + s_el[el];
+        we_elem[we0 + el] = e;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const int c = node_row[elem_node[6 * (size_t)e + a]];
+            int lc = 0xffff;
+            if (c >= r0 && c < r0 + n) lc = c - r0;
+            else if (c >= 0) {
+                int lo = 0, hi = nh;                   // first halo entry >= c
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (sl.halo[h0 + mid] < c) lo = mid + 1; else hi = mid; }
+                lc = n + lo;
+            }
+            col[a * nep + el] = (uint16_t)lc;
+        }
+    }
+    // destination slots: row t, j-th element of its fan
+    if (tid < n) {
+        const int r = r0 + tid;
+        const int sbase = s_sb[tid >> 5] + (tid & 31);
+        for (int j = 0; j < cnt; ++j) {
+            const int e = adjf[a0 + j];
+            const int* en = elem_node + 6 * (size_t)e;
+            int a = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) if (node_row[en[k]] == r) a = k;
+            const int el = (int)s_pre[(e - e0) >> 5] + __popc(s_bm[(e - e0) >> 5] & ((1u << ((e - e0) & 31)) - 1u));
+            dst[a * nep + el] = (uint16_t)(sbase + j * 32);
+        }
+    }
+}
+
+// geometry x material of the window elements (numeric half: redone when coordinates or materials change)
+__global__ void __launch_bounds__(RVE_WIN)
+k_we_geo(int n_win, const int* __restrict__ win_we0, const int* __restrict__ win_nwe, const int* __restrict__ we_elem,
+         const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
+         const double* __restrict__ node_xy, double* __restrict__ we_geo, Mat8 mat) {
+    const int w = blockIdx.x;
+    const int we0 = win_we0[w], nwe = win_nwe[w], nep = (nwe + 31) & ~31;
+    double* geo = we_geo + 6 * (size_t)we0;
+    for (int el = threadIdx.x; el < nep; el += RVE_WIN) {
+        double gv[6] = {0, 0, 0, 0, 0, 0};
+        if (el < nwe) {
+            const int e = we_elem[we0 + el];
+            const int* en = elem_node + 6 * (size_t)e;
+            const double* p0 = node_xy + 2 * (size_t)en[0]; const double* p1 = node_xy + 2 * (size_t)en[1]; const double* p2 = node_xy + 2 * (size_t)en[2];
+            TriGeom g;
+            tri_geom(p0[0], p0[1], p1[0], p1[1], p2[0], p2[1], g);
+            const int reg = elem_reg[e];
+            p2_apply_geo(g, mat.v[2 * reg], mat.v[2 * reg + 1], gv);
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) geo[j * nep + el] = gv[j];
+    }
+}
+
+// block-Jacobi diagonal and the mean-value weights without the assembled matrix: thread per block row walks the
+// elements around it (the diagonal block of K_e for its own local node); CTA per window
+__global__ void __launch_bounds__(RVE_WIN)
+k_diag(WinTab wt, const unsigned* __restrict__ adjf_ptr, const int* __restrict__ adjf, const int* __restrict__ elem_node,
+       const unsigned char* __restrict__ elem_reg, const double* __restrict__ node_xy, const int* __restrict__ node_row,
+       float4* __restrict__ dinv32, double* __restrict__ wmean, Mat8 mat) {
+    const int w = blockIdx.x, t = threadIdx.x;
+    if (t >= wt.win_n[w]) return;
+    const int r = wt.win_row0[w] + t;
+    double d00 = 0, d01 = 0, d10 = 0, d11 = 0, wm = 0;
+    for (unsigned i = adjf_ptr[r]; i < adjf_ptr[r + 1]; ++i) {
+        const int e = adjf[i];
+        const int* en = elem_node + 6 * (size_t)e;
+        int a = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (node_row[en[k]] == r) a = k;
+        const double* p0 = node_xy + 2 * (size_t)en[0]; const double* p1 = node_xy + 2 * (size_t)en[1]; const double* p2 = node_xy + 2 * (size_t)en[2];
+        TriGeom g;
+        tri_geom(p0[0], p0[1], p1[0], p1[1], p2[0], p2[1], g);
+        const int reg = elem_reg[e];
+        double Kb[4];
+        p2_stiff_block(g, a, a, mat.v[2 * reg], mat.v[2 * reg + 1], Kb);
+        d00 += Kb[0]; d01 += Kb[1]; d10 += Kb[2]; d11 += Kb[3];
+        if (a >= 3) wm += g.area * (1.0 / 3.0);
+    }
+    const double det = d00 * d11 - d01 * d10;
+    const double inv = det != 0.0 ? 1.0 / det : 0.0;
+    dinv32[r] = make_float4((float)(d11 * inv), (float)(-d01 * inv), (float)(-d10 * inv), (float)(d00 * inv));
+    wmean[r] = wm;
+}
+
+#define RVE_APPLY_THREADS(K) ((K) == 3 ? 384 : 256)
+#ifndef RVE_APPLY_MINB
+#define RVE_APPLY_MINB(K) ((K) == 3 ? 2 : 3)
+#endif
+
+// q = A p, p.q per system (alpha by the last CTA of the system): see the header of this file
+template <int K>
+__global__ void __launch_bounds__(RVE_APPLY_THREADS(K), RVE_APPLY_MINB(K))
+k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __restrict__ q, int tile_cap,
+        double* part, int* cnt, double* sc) {
+    extern __shared__ double2 s_tile[];           // [tile_cap * K] p-tile, then [max_slots * K] nodal-force slots
+    constexpr int TPB = RVE_APPLY_THREADS(K);
+    const int win = blockIdx.x;
+    if (!wt.win_active[win]) return;
+    const int sys = wt.win_sys[win];
+    const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int row0 = wt.win_row0[win], n = wt.win_n[win];
+    const int h0 = wt.win_halo0[win], nh = wt.win_nhalo[win];
+    double2* s_f = s_tile + (size_t)tile_cap * K;
+    __shared__ int s_sb[RVE_WIN / 32];
+    if (tid == 0) {
+        const uint2 v = *(const uint2*)(mf.win_sw + (size_t)win * 8);
+        int tot = 0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) { s_sb[s] = tot; tot += 32 * (int)(((s < 4 ? v.x : v.y) >> (8 * (s & 3))) & 0xffu); }
+    }
+    {
+        const double2* src = p + (size_t)row0 * K;
+        for (int e = tid; e < n * K; e += TPB) s_tile[e] = src[e];
+        double2* dstt = s_tile + n * K;
+        for (int e = tid; e < nh * K; e += TPB) {
+            const int hr = sl.halo[h0 + e / K];
+            dstt[e] = p[(size_t)hr * K + (e % K)];
+        }
+    }
+    __syncthreads();
+    // phase 1: element products
+    {
+        const int we0 = mf.win_we0[win], nwe = mf.win_nwe[win], nep = (nwe + 31) & ~31;
+        const uint16_t* col = mf.we_col + 6 * (size_t)we0;
+        const uint16_t* dst = mf.we_dst + 6 * (size_t)we0;
+        const double* geo = mf.we_geo + 6 * (size_t)we0;
+        for (int item = tid; item < nwe * K; item += TPB) {
+            const int e = item / K, k = item - e * K;
+            double gv[6], u[12], f[12];
+            int c[6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) c[a] = col[a * nep + e];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) gv[j] = geo[j * nep + e];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const double2 v = (c[a] != 0xffff) ? s_tile[c[a] * K + k] : make_double2(0.0, 0.0);
+                u[2 * a] = v.x; u[2 * a + 1] = v.y;
+            }
+            p2_apply(gv, u, f);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const int d = dst[a * nep + e];
+                if (d != 0xffff) s_f[d * K + k] = make_double2(f[2 * a], f[2 * a + 1]);
+            }
+        }
+    }
+    __syncthreads();
+    // phase 2: rows gather their slots
+    double dot = 0.0;
+    {
+        double2* qd = q + (size_t)row0 * K;
+        for (int item = tid; item < n * K; item += TPB) {
+            const int r = item / K, k = item - r * K;
+            const int na = mf.row_nadj[row0 + r];
+            const double2* src = s_f + (size_t)(s_sb[r >> 5] + (r & 31)) * K + k;
+            double2 acc = make_double2(0.0, 0.0);
+            for (int j = 0; j < na; ++j) { const double2 v = src[(size_t)j * 32 * K]; acc.x += v.x; acc.y += v.y; }
+            qd[item] = acc;
+            const double2 pv = s_tile[item];
+            dot += acc.x * pv.x + acc.y * pv.y;
+        }
+    }
+    // p.q of the window per rhs (thread's rhs index is fixed: TPB % K == 0), then the system-wide sum
+    __shared__ double s_a[TPB];
+    __shared__ double s_dot[4];
+    __shared__ double s_out[4][1];
+    s_a[tid] = dot;
+    __syncthreads();
+    if (wv < K) {
+        double acc = 0.0;
+        for (int m = lane; m < TPB / K; m += 32) acc += s_a[wv + K * m];
+        acc = warp_sum(acc);
+        if (lane == 0) s_dot[wv] = acc;
+    }
+    __syncthreads();
+    const double my = (tid < K) ? s_dot[tid] : 0.0;
+    const int w0 = wt.sys_win0[sys], w1 = wt.sys_win0[sys + 1];
+    if (last_block_sum<1>(part, cnt, sys, win, w0, w1, my, s_out)) {
+        if (tid < K) {
+            double* s_ = sc + ((size_t)sys * 4 + tid) * SC_N;
+            const double pq = s_out[tid][0];
+            s_[SC_PQ] = pq;
+            s_[SC_ALPHA] = (pq > 0.0) ? s_[SC_RZ] / pq : 0.0;
+        }
+    }
+}

@@ -113,3 +113,47 @@ RVE_HD void pair_ab(int p, int& a, int& b) {
         base += len;
     }
 }
+
+// Matrix-free element operator: f = K_e u for one P2 element and one right-hand side, K_e never formed.
+// geo = {g0x, g0y, g1x, g1y, w*lam, w*mu} with g_i = grad lambda_i (g2 = -g0 - g1) and w = area/3.  With the
+// gradient table of the edge-midpoint rule, grad u(q) = (v0-v2) (x) g0 + (v1-v2) (x) g1, v_i = sum_a c[q][a][i] u_a,
+// and the nodal forces are the transposed combination of t_i = sigma(q) g_i (same form as p2_stiff_block:
+// sigma = lam* tr(grad u) I + mu (grad u + grad u^T), micro_model_dnn.py:53).  u, f: [6][2] in the local order
+// v0 v1 v2 m01 m12 m20.
+RVE_HD void p2_apply(const double geo[6], const double u[12], double f[12]) {
+    const double g0x = geo[0], g0y = geo[1], g1x = geo[2], g1y = geo[3], wl = geo[4], wm = geo[5];
+    double d0[3][2], d1[3][2];     // (v0 - v2), (v1 - v2) at the three quadrature points
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const double u0 = u[c], u1 = u[2 + c], u2 = u[4 + c], u3 = u[6 + c], u4 = u[8 + c], u5 = u[10 + c];
+        const double m = 2.0 * (u3 - u4 - u5) + u2;
+        d0[0][c] = u0 + m;                          d1[0][c] = u1 + m;
+        d0[1][c] = 2.0 * (u3 + u5 - u4) - u0 - u2;  d1[1][c] = u1 - u2;
+        d0[2][c] = u0 - u2;                         d1[2][c] = 2.0 * (u3 + u4 - u5) - u1 - u2;
+    }
+    double t0[3][2], t1[3][2];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const double H00 = d0[q][0] * g0x + d1[q][0] * g1x, H01 = d0[q][0] * g0y + d1[q][0] * g1y;
+        const double H10 = d0[q][1] * g0x + d1[q][1] * g1x, H11 = d0[q][1] * g0y + d1[q][1] * g1y;
+        const double tr = wl * (H00 + H11);
+        const double s00 = tr + 2.0 * wm * H00, s11 = tr + 2.0 * wm * H11, s01 = wm * (H01 + H10);
+        t0[q][0] = s00 * g0x + s01 * g0y; t0[q][1] = s01 * g0x + s11 * g0y;
+        t1[q][0] = s00 * g1x + s01 * g1y; t1[q][1] = s01 * g1x + s11 * g1y;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const double s = t0[0][c] + t1[0][c];       // -t2 at q0
+        f[c] = t0[0][c] - t0[1][c] + t0[2][c];
+        f[2 + c] = t1[0][c] + t1[1][c] - t1[2][c];
+        f[4 + c] = s - (t0[1][c] + t1[1][c]) - (t0[2][c] + t1[2][c]);
+        f[6 + c] = 2.0 * (s + t0[1][c] + t1[2][c]);
+        f[8 + c] = 2.0 * (t1[2][c] - s - t0[1][c]);
+        f[10 + c] = 2.0 * (t0[1][c] - s - t1[2][c]);
+    }
+}
+
+RVE_HD void p2_apply_geo(const TriGeom& g, double lam, double mu, double geo[6]) {
+    const double w = g.area * (1.0 / 3.0);
+    geo[0] = g.gl[0][0]; geo[1] = g.gl[0][1]; geo[2] = g.gl[1][0]; geo[3] = g.gl[1][1]; geo[4] = w * lam; geo[5] = w * mu;
+}

@@ -17,7 +17,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def fit_linear_net(nameXY, label, nrb, prefix):
@@ -47,7 +46,7 @@ def main():
     ns = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     nt = int(sys.argv[3]) if len(sys.argv) > 3 else 256
     os.makedirs(os.path.join(out, "meshes"), exist_ok=True)
-    from conftest import synthetic_param
+    from deepbnd_b200.synthetic import synthetic_param
     import deepbnd_b200.wrapper_h5py as myhd
     from deepbnd_b200.simulation_snapshots import buildSnapshots
     from deepbnd_b200.tangents_prediction import predictTangents

@@ -126,6 +126,13 @@ int rve_epilogue_homogenisation(rve_handle_t h, double* sigmaL, double* sigmaT, 
 /* solver options.  RVE_OPT_SYM_B: symmetrise the dnn correction B = 0.5 (B + B^T) like
  * micro_model_gen.py:122 (default 0: full B, micro_model_dnn.py:88). */
 #define RVE_OPT_SYM_B 1
+/* RVE_OPT_OPERATOR: how q = A p is applied inside the PCG.  RVE_OPERATOR_MATFREE (default): element by element
+ * from 72 bytes per element, the stiffness matrix is never stored (rve_matfree.cuh);  RVE_OPERATOR_ASSEMBLED: the
+ * SELL-32 node-block matrix written by the assembly kernel (34 bytes per 2x2 block) and the SpMV kernel.  Both give
+ * the same operator to rounding; rve_get_csr always returns the assembled matrix.  Set it before rve_assemble. */
+#define RVE_OPT_OPERATOR 2
+#define RVE_OPERATOR_ASSEMBLED 0
+#define RVE_OPERATOR_MATFREE 1
 int rve_set_option(rve_handle_t h, int32_t option, int32_t value);
 
 /* replaces getAlphas_fast (creation_model/RB/RB_utils.py:211-213): Y = U M W[:nmax]^T on the
@@ -143,11 +150,15 @@ int rve_project(rve_handle_t h, int32_t nmax, int32_t nh, const double* W, const
  *   rve_create; t has 8 entries, c has 8 entries */
 int rve_timings(rve_handle_t h, double* t, double* c);
 
-/* SpMV micro-benchmark on the assembled batch: runs `reps` launches of the production SpMV kernel
- * (n_rhs right-hand sides) on a dedicated stream and returns the average launch time in ms and the
+/* Operator micro-benchmark on the assembled batch: runs `reps` launches of the kernel RVE_OPT_OPERATOR selects
+ * (k_apply or k_spmv; n_rhs right-hand sides) on a dedicated stream and returns the average launch time in ms and the
  * algorithmic bytes per launch. */
 int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_launch,
                    double* alg_bytes_per_launch);
+
+/* parity-test accessor (not on the hot path): q = A p for the whole batch with the operator RVE_OPT_OPERATOR
+ * selects; p, q: [total rows][n_rhs][2], rows of system s start at the sum of n_rows of the systems before it. */
+int rve_apply_operator(rve_handle_t h, int32_t n_rhs, const double* p, double* q);
 
 /* Host-only test hook (no CUDA call, not used by the product): CPU restatement of the symbolic phase of ONE system —
  * P2 numbering, constraint map, rows ordered by coarse cell, node-block pattern, Vref sample location.  The CPU
