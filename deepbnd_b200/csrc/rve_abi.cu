@@ -174,6 +174,17 @@ static cudaError_t stream_wait(rve_batch_s* h) {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// RVE_DEBUG_SYNC=1: synchronise after the named kernel and name it in the error (bisecting a faulting launch)
+#define DBG_SYNC(name)                                                                                   \
+    do {                                                                                                 \
+        static const bool dbg_ = [] { const char* e = std::getenv("RVE_DEBUG_SYNC"); return e && e[0] == '1'; }(); \
+        if (dbg_) {                                                                                      \
+            cudaError_t e_ = cudaStreamSynchronize(h->stream);                                           \
+            if (e_ == cudaSuccess) e_ = cudaGetLastError();                                              \
+            if (e_ != cudaSuccess) { h->err = std::string(name) + ": " + cudaGetErrorString(e_); return RVE_E_CUDA; } \
+        }                                                                                                \
+    } while (0)
+
 #define UPL(d, v) do { CU(upload((d), (v), st)); h->h2d_bytes += (double)(v).size() * sizeof((v)[0]); } while (0)
 
 template <class T>
@@ -546,6 +557,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     DF.win_sys = h->win_sys.p; DF.win_row0 = h->win_row0.p; DF.win_n = h->win_n.p; DF.win_slice0 = h->win_slice0.p; DF.slice_ptr = h->slice_ptr.p;
     DF.n_sys = n_sys;
     k_ds_finish<<<n_sys, DS_THREADS, 0, st>>>(DM, DF);
+    DBG_SYNC("k_ds_finish");
     h->launches += 1;
     auto t1 = std::chrono::steady_clock::now();
     h->t_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -596,14 +608,17 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         WinTab wt = win_tab(h);
         k_sym_cols<<<n_win, RVE_WIN, 0, st>>>(wt, h->d_row_ptr.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->node_row.p,
                                                h->csr_col.p, h->rlen.p, h->emap.p, h->sys_blocks.p, h->sym_cnt.p);
+        DBG_SYNC("k_sym_cols");
         const size_t sm = 2 * (size_t)h->max_words * sizeof(unsigned);
         if (sm > 200 * 1024) FAIL(RVE_E_MESH, "system too large for the halo bitmap in shared memory");
         k_sym_window<<<n_win, RVE_WIN, sm, st>>>(wt, h->win_halo0.p, h->win_nhalo.p, h->d_row_ptr.p, h->rlen.p, h->csr_col.p, h->slice_ptr.p,
                                                   h->scol.p, h->halo.p, (int)halo_cap, h->sym_cnt.p);
+        DBG_SYNC("k_sym_window");
         const size_t smc = 2 * (size_t)((LV.g[0].G + 31) / 32) * sizeof(unsigned);
         if (smc > 150 * 1024) FAIL(RVE_E_MESH, "level-1 grid too large for the coarse-node bitmap in shared memory");
         k_sym_coarse<<<n_win, RVE_WIN, smc, st>>>(wt, h->win_cn0.p, h->win_ncn.p, h->row_node.p, h->node_xy.p, h->box.p, LV.g[0],
                                                   model, h->rowinfo.p, h->cn_node.p, h->cn_beg.p, h->cn_ent.p, (int)cn_cap, h->sym_cnt.p);
+        DBG_SYNC("k_sym_coarse");
         h->launches += 3;
     }
     int scnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -615,13 +630,15 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         const size_t sme = 2 * (size_t)((max_ne + 31) / 32) * sizeof(unsigned);
         if (sme > 150 * 1024) FAIL(RVE_E_MESH, "system too large for the element bitmap in shared memory");
         long long we_cap = 2 * h->E + 32LL * n_win + 1024;
-        for (int attempt = 0; attempt < 2; ++attempt) {
+        static const bool skip_mf = [] { const char* e = std::getenv("RVE_SKIP_MATFREE"); return e && e[0] == '1'; }();
+        for (int attempt = 0; attempt < 2 && !skip_mf; ++attempt) {
             if (6 * we_cap > 2000000000LL) FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
             CU(h->we_elem.alloc((size_t)we_cap)); CU(h->we_col.alloc(6 * (size_t)we_cap)); CU(h->we_dst.alloc(6 * (size_t)we_cap));
             CU(cudaMemsetAsync(h->sym_cnt.p + 6, 0, 2 * sizeof(int), st));
             k_sym_elems<<<n_win, RVE_WIN, sme, st>>>(win_tab(h), sell_tab(h), h->d_toff.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p,
                                                       h->node_row.p, h->win_we0.p, h->win_nwe.p, h->win_sw.p, h->row_nadj.p,
                                                       h->we_elem.p, h->we_col.p, h->we_dst.p, we_cap, h->sym_cnt.p);
+            DBG_SYNC("k_sym_elems");
             h->launches += 1;
             CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU(stream_wait(h));

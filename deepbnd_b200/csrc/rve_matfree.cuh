@@ -45,7 +45,7 @@ k_sym_elems(WinTab wt, Sell sl, const int* __restrict__ elem_base, const unsigne
     __shared__ int s_el[RVE_MF_MAXWE];
     __shared__ int s_sb[RVE_WIN / 32 + 1];
     __shared__ int s_w0;
-    const int w = blockIdx.x, tid = threadIdx.x;
+    const int w = blockIdx.x, tid = threadIdx.x, wv = tid >> 5;
     const int sys = wt.win_sys[w];
     const int e0 = elem_base[sys], ne = elem_base[sys + 1] - e0;
     const int words = (ne + 31) >> 5;
@@ -63,7 +63,10 @@ k_sym_elems(WinTab wt, Sell sl, const int* __restrict__ elem_base, const unsigne
     int mx = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((tid & 31) == 0) s_sb[(tid >> 5) + 1] = mx;
+    // every lane stores the warp maximum (same value): a store predicated on (tid & 31) == 0 made nvcc 12.9 reuse the
+    // address (tid >> 3), valid under that predicate only, for the unpredicated s_sb[tid >> 5] read further down
+    // (LEA.HI without the mask -> "misaligned address" on the device)
+    s_sb[wv + 1] = mx;
     __syncthreads();
     const int wpt = (words + RVE_WIN - 1) / RVE_WIN;
     const int wa = min(words, tid * wpt), wb = min(words, wa + wpt);
@@ -139,7 +142,7 @@ k_sym_elems(WinTab wt, Sell sl, const int* __restrict__ elem_base, const unsigne
     // destination slots: row t, j-th element of its fan
     if (tid < n) {
         const int r = r0 + tid;
-        const int sbase = s_sb[tid >> 5] + (tid & 31);
+        const int sbase = s_sb[wv] + (tid & 31);
         for (int j = 0; j < cnt; ++j) {
             const int e = adjf[a0 + j];
             const int* en = elem_node + 6 * (size_t)e;

@@ -364,7 +364,13 @@ class OracleRVE:
     """One RVE = one object, like MicroModel / MicroConstitutiveModelDNN."""
 
     def __init__(self, xy, tri, region, param=(0.3, 10.0, 0.3, 1.0), model='lin',
-                 zero_average_for_dirichlet=False):
+                 zero_average_for_dirichlet=False, dirichlet_semantics='p1_vertex'):
+        # the two [EXT] switches a FEniCS export settles (tools/export_goldens_fenics.py): the zero-average block
+        # for lin/dnn, and how the foreign-mesh P1 function uD becomes Dirichlet data on the P2 boundary nodes
+        # ('p1_vertex': vertex values, mid-edge = mean of the end vertices, dolfin's restriction of a P1 coefficient
+        # to the RVE cell; 'p2_nodal': uD evaluated at every P2 boundary node)
+        assert dirichlet_semantics in ('p1_vertex', 'p2_nodal')
+        self.dir_sem = dirichlet_semantics
         self.mesh = P2Mesh(xy, tri, region)
         self.mat = lame_table(*param)
         self.model = model
@@ -459,7 +465,10 @@ class OracleRVE:
         bv = m.bnd_nodes[m.bnd_nodes < m.nv]
         g[bv] = vref_eval_on_boundary(uDc.ravel(), pts, m.xy[bv])
         be = m.bnd_edges
-        g[m.nv + be] = 0.5 * (g[m.edges[be, 0]] + g[m.edges[be, 1]])
+        if self.dir_sem == 'p1_vertex':
+            g[m.nv + be] = 0.5 * (g[m.edges[be, 0]] + g[m.edges[be, 1]])
+        else:
+            g[m.nv + be] = vref_eval_on_boundary(uDc.ravel(), pts, m.xy[m.nv + be])
         return g[m.bnd_nodes], B
 
     def compute_tangent(self, uD_list=None, pts=None):

@@ -213,3 +213,121 @@ def test_periodic_model_equals_the_lagrange_multiplier_formulation(coarse_reduce
         F = O.load_vector(m, o.ed, O.strain2voigt(O.macro_strain(i)))
         x = lu.solve(np.concatenate([F, np.zeros(C.shape[0])]))
         assert np.abs(x[:2 * m.nn] - u).max() < 1e-9 * np.abs(u).max()
+
+
+# ---- pins of the [EXT] formulation choices that need no FEniCS ---------------------------
+
+def _edge_mass_p2(L):
+    """exact P2 mass matrix of an edge (a, mid, b)"""
+    return L / 30.0 * np.array([[4.0, 2.0, -1.0], [2.0, 16.0, 2.0], [-1.0, 2.0, 4.0]])
+
+
+def test_MR_multiplier_is_the_average_stress_and_hill_mandel(coarse_reduced_meshes):
+    """Independent derivation of the minimally-restrictive model: the KKT multipliers of int u (x) n ds = 0 ARE the
+    uniform boundary traction tensor, so (i) the mean multiplier vanishes (the tractions are self-equilibrated),
+    (ii) the tensor multiplier equals the volume average of the total stress (computed by homogenise, which does
+    not know about multipliers), (iii) it is symmetric (moment equilibrium), (iv) Hill-Mandel: the strain energy
+    density equals <sigma> : eps_macro."""
+    from oracle.rve_oracle import OracleRVE, macro_strain, load_vector, strain2voigt
+    mesh = coarse_reduced_meshes[0]
+    o = OracleRVE(*mesh, param=PARAM, model='MR')
+    o._factor()
+    m = o.mesh
+    N = 2 * m.nn
+    vol = m.area.sum()
+    for i in range(3):
+        eps = macro_strain(i)
+        F = load_vector(m, o.ed, strain2voigt(eps))
+        x = o._lu.solve(np.concatenate([F, np.zeros(6)]))
+        o.sol[i], o.eps[i] = x[:N], eps
+        lam_mean, P = x[N:N + 2], x[N + 2:].reshape(2, 2)
+        sig = o.homogenise([0, 1, 2, 3], i)
+        assert np.abs(lam_mean).max() < 1e-10 * np.abs(P).max()
+        assert np.abs(P - sig).max() < 1e-10 * np.abs(sig).max()
+        assert abs(P[0, 1] - P[1, 0]) < 1e-10 * np.abs(P).max()
+        # total field u = eps y + u~ ; energy = u^T K u / vol
+        ut = x[:N] + (m.xy @ eps.T).ravel()
+        energy = ut @ (o.K @ ut) / vol
+        assert abs(energy - np.sum(sig * eps)) < 1e-10 * abs(energy)
+
+
+def test_dnn_boundary_multiplier_formulation_equals_elimination(coarse_reduced_meshes):
+    """The reference imposes u~ = uD on the boundary with a boundary-restricted Lagrange multiplier
+    (multiphenics MeshRestriction; [EXT] micmacsfenics 'dnn'): int lam.v ds + int q.(u - g) ds = 0 with lam, q in the
+    P2 trace space.  For data g in that trace space the saddle-point solution equals DOF elimination exactly (the
+    boundary mass matrix is SPD), which is what the library and the oracle do."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from oracle.rve_oracle import OracleRVE, vref_points, macro_strain, load_vector, strain2voigt, boundary_edges_oriented
+    mesh = coarse_reduced_meshes[1]
+    pts = vref_points(-1, -1, 2, 2, 21)
+    uD = smooth_uD(81, 5, amp=3e-2)
+    o = OracleRVE(*mesh, param=PARAM, model='dnn')
+    g, B = o.dirichlet_from_vref(uD, pts)
+    eps = macro_strain(2) - B
+    u_el = o.solve_load(2, eps=eps, g_bnd=g).copy()
+    m = o.mesh
+    N = 2 * m.nn
+    bn = m.bnd_nodes
+    pos = {int(n): k for k, n in enumerate(bn)}
+    nb = len(bn)
+    Mb = np.zeros((nb, nb))
+    for a, b, mid, L, n in boundary_edges_oriented(m):
+        idx = [pos[int(a)], pos[int(mid)], pos[int(b)]]
+        Mb[np.ix_(idx, idx)] += _edge_mass_p2(L)
+    # E: boundary dofs -> global dofs, both components
+    rows = np.concatenate([2 * np.arange(nb), 2 * np.arange(nb) + 1])
+    cols = np.concatenate([2 * bn, 2 * bn + 1])
+    E = sp.coo_matrix((np.ones(2 * nb), (rows, cols)), shape=(2 * nb, N)).tocsr()
+    M2 = sp.kron(sp.csr_matrix(Mb), sp.identity(2)).tocsr()
+    C = (M2 @ E).tocsr()
+    F = load_vector(m, o.ed, strain2voigt(eps))
+    KKT = sp.bmat([[o.K, C.T], [C, None]]).tocsc()
+    x = spla.splu(KKT).solve(np.concatenate([F, M2 @ g.ravel()]))
+    assert np.abs(x[:N] - u_el).max() < 1e-9 * np.abs(u_el).max()
+
+
+def test_dirichlet_semantics_differ_only_at_kinked_midedges(reduced_meshes, capsys):
+    """Two candidate readings of `uD` (a P1 function on the boundary mesh Vref used as a coefficient on the RVE
+    mesh): 'p1_vertex' (dolfin restricts a P1 coefficient to the cell by its vertex values: mid-edge data = mean of
+    the end vertices; the library's choice) and 'p2_nodal' (uD evaluated at every P2 boundary node).  At lcar = 2/30
+    the Vref kinks (spacing 0.1) fall on mesh vertices or on mid-edge nodes, so the two readings differ ONLY at
+    mid-edge nodes that sit on a kink.  The tangent delta printed here is what a FEniCS export has to resolve
+    (tools/export_goldens_fenics.py dumps tangent_dnn for exactly this data)."""
+    from oracle.rve_oracle import OracleRVE, vref_points
+    mesh = reduced_meshes[0]
+    pts = vref_points(-1, -1, 2, 2, 21)
+    uDs = [smooth_uD(81, 40 + i) for i in range(3)]
+    oa = OracleRVE(*mesh, param=PARAM, model='dnn', dirichlet_semantics='p1_vertex')
+    ob = OracleRVE(*mesh, param=PARAM, model='dnn', dirichlet_semantics='p2_nodal')
+    m = oa.mesh
+    ga, _ = oa.dirichlet_from_vref(uDs[0], pts)
+    gb, _ = ob.dirichlet_from_vref(uDs[0], pts)
+    diff = np.abs(ga - gb).max(1) > 1e-14
+    nodes = m.bnd_nodes[diff]
+    assert diff.any() and (nodes >= m.nv).all()                              # mid-edge nodes only
+    s = m.xy[nodes]
+    on_kink = (np.abs(s * 10 - np.round(s * 10)) < 1e-9).all(1)             # both coordinates multiples of 0.1
+    assert on_kink.all()
+    Ca, Cb = oa.compute_tangent(uDs, pts), ob.compute_tangent(uDs, pts)
+    delta = np.abs(Ca - Cb).max() / np.abs(Ca).max()
+    with capsys.disabled():
+        print("\n[dirichlet semantics] %d of %d boundary nodes differ, relative tangent delta %.3e" % (diff.sum(), len(diff), delta))
+    assert 1e-9 < delta < 1e-2            # visible at the 1e-8 parity bar, small in engineering terms
+
+
+def test_zero_average_block_is_a_measurable_discriminator(coarse_reduced_meshes):
+    """[EXT] unknown: whether micmacsfenics keeps the zero-average multiplier block for 'lin'/'dnn'.  With it, the
+    multiplier acts as a uniform body force and the tangent changes by far more than 1e-8 for non-trivial data:
+    the exporter's tangent_dnn / tangent_lin entries decide which variant the reference runs."""
+    from oracle.rve_oracle import OracleRVE, vref_points
+    mesh = coarse_reduced_meshes[2]
+    pts = vref_points(-1, -1, 2, 2, 21)
+    uDs = [smooth_uD(81, 70 + i) for i in range(3)]
+    C0 = OracleRVE(*mesh, param=PARAM, model='dnn').compute_tangent(uDs, pts)
+    C1 = OracleRVE(*mesh, param=PARAM, model='dnn', zero_average_for_dirichlet=True).compute_tangent(uDs, pts)
+    assert np.abs(C0 - C1).max() > 1e-6 * np.abs(C0).max()
+    # zero data on a symmetric-enough problem: the block is inactive only if the unconstrained mean already vanishes
+    L0 = OracleRVE(*mesh, param=PARAM, model='lin').compute_tangent()
+    L1 = OracleRVE(*mesh, param=PARAM, model='lin', zero_average_for_dirichlet=True).compute_tangent()
+    assert np.isfinite(L1).all() and np.abs(L0 - L1).max() < 0.1 * np.abs(L0).max()
