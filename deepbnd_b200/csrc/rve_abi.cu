@@ -134,8 +134,8 @@ struct rve_batch_s {
     long long n_we = 0;
     DBuf<int> win_we0, win_nwe, we_elem;
     DBuf<unsigned char> win_sw, row_nadj;
-    DBuf<uint16_t> we_col, we_dst;
-    DBuf<double> we_geo;
+    DBuf<uint32_t> we_idx;
+    DBuf<double2> we_geo;
     int* h_nactive = nullptr;  // pinned
     PinnedArena arena;
     std::vector<cudaEvent_t> evpool;  // per-iteration SpMV timing
@@ -257,7 +257,7 @@ struct PcgArgs {
 static MfTab mf_tab(rve_batch_s* h) {
     MfTab mf;
     mf.win_we0 = h->win_we0.p; mf.win_nwe = h->win_nwe.p; mf.win_sw = h->win_sw.p; mf.row_nadj = h->row_nadj.p;
-    mf.we_col = h->we_col.p; mf.we_dst = h->we_dst.p; mf.we_geo = h->we_geo.p;
+    mf.we_idx = h->we_idx.p; mf.we_geo = h->we_geo.p;
     return mf;
 }
 
@@ -265,8 +265,8 @@ template <int K>
 static void launch_spmv(rve_batch_s* h, const PcgArgs& a, const double* p, double* q, int* active, double* part, int* cnt,
                         double* sc, cudaStream_t st) {
     if (a.op == RVE_OPERATOR_MATFREE) {
-        k_apply<K><<<a.n_win, RVE_APPLY_THREADS(K), a.sm_apply, st>>>(a.wt, a.sl, mf_tab(h), (const double2*)p, (double2*)q, h->max_tile,
-                                                                      part, cnt, sc);
+        k_apply<K><<<a.n_win, RVE_APPLY_THREADS, a.sm_apply, st>>>(a.wt, a.sl, mf_tab(h), (const double2*)p, (double2*)q, h->max_tile,
+                                                                   h->max_slots, part, cnt, sc);
         return;
     }
     k_spmv<K><<<a.n_win, RVE_SPMV_THREADS, a.sm_spmv, st>>>(a.wt, a.sl, (const double2*)h->bval.p, (const double2*)p, (double2*)q,
@@ -633,11 +633,11 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         static const bool skip_mf = [] { const char* e = std::getenv("RVE_SKIP_MATFREE"); return e && e[0] == '1'; }();
         for (int attempt = 0; attempt < 2 && !skip_mf; ++attempt) {
             if (6 * we_cap > 2000000000LL) FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
-            CU(h->we_elem.alloc((size_t)we_cap)); CU(h->we_col.alloc(6 * (size_t)we_cap)); CU(h->we_dst.alloc(6 * (size_t)we_cap));
+            CU(h->we_elem.alloc((size_t)we_cap)); CU(h->we_idx.alloc(6 * (size_t)we_cap));
             CU(cudaMemsetAsync(h->sym_cnt.p + 6, 0, 2 * sizeof(int), st));
             k_sym_elems<<<n_win, RVE_WIN, sme, st>>>(win_tab(h), sell_tab(h), h->d_toff.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p,
                                                       h->node_row.p, h->win_we0.p, h->win_nwe.p, h->win_sw.p, h->row_nadj.p,
-                                                      h->we_elem.p, h->we_col.p, h->we_dst.p, we_cap, h->sym_cnt.p);
+                                                      h->we_elem.p, h->we_idx.p, we_cap, h->sym_cnt.p);
             DBG_SYNC("k_sym_elems");
             h->launches += 1;
             CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -647,7 +647,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
             CU(cudaMemsetAsync(h->sym_cnt.p + 2, 0, sizeof(int), st));
         }
         h->n_we = scnt[6]; h->max_slots = scnt[7];
-        CU(h->we_geo.alloc(6 * (size_t)std::max<long long>(h->n_we, 1)));
+        CU(h->we_geo.alloc(3 * (size_t)std::max<long long>(h->n_we, 1)));
     }
     CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     std::vector<int> sb(n_sys);
@@ -986,6 +986,16 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
             cudaEventElapsedTime(&ms, h->evdbg[3 * i], h->evdbg[3 * i + 1]); tv += ms;
             cudaEventElapsedTime(&ms, h->evdbg[3 * i + 1], h->evpool[2 * i]); td += ms;
             cudaEventElapsedTime(&ms, h->evpool[2 * i + 1], h->evdbg[3 * i + 2]); tu += ms;
+        }
+        if (const char* e = std::getenv("RVE_KTIME_SERIES")) {      // time of every launched iteration (us): tail cost of the converged systems
+            if (e[0] == '1') {
+                fprintf(stderr, "[rve_solve] iteration series (us):");
+                for (int i = 0; i < launched; ++i) {
+                    cudaEventElapsedTime(&ms, h->evdbg[3 * i], h->evdbg[3 * i + 2]);
+                    fprintf(stderr, " %.0f", 1e3 * ms);
+                }
+                fprintf(stderr, "\n");
+            }
         }
         fprintf(stderr, "[rve_solve] n_sys %d K %d its %d: per iteration (us) vcycle %.1f direction %.1f spmv %.1f update %.1f\n", n_sys, K,
                 launched, 1e3 * tv / launched, 1e3 * td / launched, 1e3 * spmv_ms / launched, 1e3 * tu / launched);

@@ -26,9 +26,9 @@ struct MfTab {
     const int* win_nwe;           // [n_win] window elements (nep = nwe rounded up to 32)
     const unsigned char* win_sw;  // [n_win][8] slots per row of every 32-row slice (max fan size in the slice)
     const unsigned char* row_nadj;// [R] elements around the row
-    const uint16_t* we_col;       // tile-local column of the element's 6 nodes (0xffff: no row = homogeneous Dirichlet)
-    const uint16_t* we_dst;       // slot of the nodal force (0xffff: not an own row of this window)
-    const double* we_geo;         // g0x g0y g1x g1y w*lam w*mu
+    const uint32_t* we_idx;       // [6][nep] per window: words 0-2 = tile-local columns of the element's 6 nodes (two uint16 per word,
+                                  // 0xffff: no row = homogeneous Dirichlet), words 3-5 = slots of the nodal forces (0xffff: not an own row)
+    const double2* we_geo;        // [3][nep] per window: (g0x,g0y) (g1x,g1y) (w*lam,w*mu)
 };
 
 #define RVE_MF_MAXWE 1024         // window elements per window (a 256-row window touches about 200)
@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(RVE_WIN)
 k_sym_elems(WinTab wt, Sell sl, const int* __restrict__ elem_base, const unsigned* __restrict__ adjf_ptr,
             const int* __restrict__ adjf, const int* __restrict__ elem_node, const int* __restrict__ node_row,
             int* __restrict__ win_we0, int* __restrict__ win_nwe, unsigned char* __restrict__ win_sw,
-            unsigned char* __restrict__ row_nadj, int* __restrict__ we_elem, uint16_t* __restrict__ we_col,
-            uint16_t* __restrict__ we_dst, long long we_cap, int* counters) {
+            unsigned char* __restrict__ row_nadj, int* __restrict__ we_elem, uint32_t* __restrict__ we_idx,
+            long long we_cap, int* counters) {
     extern __shared__ unsigned s_bm[];           // [words] bitmap over the elements of the system, then popcount prefix
     __shared__ int s_scan[RVE_WIN];
     __shared__ int s_el[RVE_MF_MAXWE];
@@ -111,16 +111,18 @@ k_sym_elems(WinTab wt, Sell sl, const int* __restrict__ elem_base, const unsigne
             bits &= bits - 1;
         }
     }
-    uint16_t* col = we_col + 6 * (size_t)we0;
-    uint16_t* dst = we_dst + 6 * (size_t)we0;
-    for (int i = tid; i < 6 * nep; i += RVE_WIN) dst[i] = (uint16_t)0xffffu;
+    // packed record, viewed as uint16: column of node a = half (a & 1) of word a >> 1, slot of node a = the same in word 3 + (a >> 1)
+    uint16_t* rec = (uint16_t*)(we_idx + 6 * (size_t)we0);
+#define WE_COL(a, el) rec[2 * (((a) >> 1) * nep + (el)) + ((a) & 1)]
+#define WE_DST(a, el) rec[2 * ((3 + ((a) >> 1)) * nep + (el)) + ((a) & 1)]
+    for (int i = tid; i < 6 * nep; i += RVE_WIN) rec[6 * nep + i] = (uint16_t)0xffffu;
     __syncthreads();
     // columns of the 6 nodes of every window element: own rows first, then the position in the (sorted) halo list
     const int h0 = wt.win_halo0[w], nh = wt.win_nhalo[w];
     for (int el = tid; el < nep; el += RVE_WIN) {
         if (el >= nwe) {
 #pragma unroll
-            for (int a = 0; a < 6; ++a) col[a * nep + el] = (uint16_t)0xffffu;
+            for (int a = 0; a < 6; ++a) WE_COL(a, el) = (uint16_t)0xffffu;
             we_elem[we0 + el] = -1;
             continue;
         }
@@ -136,7 +138,7 @@ k_sym_elems(WinTab wt, Sell sl, const int* __restrict__ elem_base, const unsigne
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (sl.halo[h0 + mid] < c) lo = mid + 1; else hi = mid; }
                 lc = n + lo;
             }
-            col[a * nep + el] = (uint16_t)lc;
+            WE_COL(a, el) = (uint16_t)lc;
         }
     }
     // destination slots: row t, j-th element of its fan
@@ -150,7 +152,7 @@ k_sym_elems(WinTab wt, Sell sl, const int* __restrict__ elem_base, const unsigne
 #pragma unroll
             for (int k = 0; k < 6; ++k) if (node_row[en[k]] == r) a = k;
             const int el = (int)s_pre[(e - e0) >> 5] + __popc(s_bm[(e - e0) >> 5] & ((1u << ((e - e0) & 31)) - 1u));
-            dst[a * nep + el] = (uint16_t)(sbase + j * 32);
+            WE_DST(a, el) = (uint16_t)(sbase + j * 32);
         }
     }
 }
@@ -159,10 +161,10 @@ k_sym_elems(WinTab wt, Sell sl, const int* __restrict__ elem_base, const unsigne
 __global__ void __launch_bounds__(RVE_WIN)
 k_we_geo(int n_win, const int* __restrict__ win_we0, const int* __restrict__ win_nwe, const int* __restrict__ we_elem,
          const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
-         const double* __restrict__ node_xy, double* __restrict__ we_geo, Mat8 mat) {
+         const double* __restrict__ node_xy, double2* __restrict__ we_geo, Mat8 mat) {
     const int w = blockIdx.x;
     const int we0 = win_we0[w], nwe = win_nwe[w], nep = (nwe + 31) & ~31;
-    double* geo = we_geo + 6 * (size_t)we0;
+    double2* geo = we_geo + 3 * (size_t)we0;
     for (int el = threadIdx.x; el < nep; el += RVE_WIN) {
         double gv[6] = {0, 0, 0, 0, 0, 0};
         if (el < nwe) {
@@ -175,7 +177,7 @@ k_we_geo(int n_win, const int* __restrict__ win_we0, const int* __restrict__ win
             p2_apply_geo(g, mat.v[2 * reg], mat.v[2 * reg + 1], gv);
         }
 #pragma unroll
-        for (int j = 0; j < 6; ++j) geo[j * nep + el] = gv[j];
+        for (int j = 0; j < 3; ++j) geo[j * nep + el] = make_double2(gv[2 * j], gv[2 * j + 1]);
     }
 }
 
@@ -210,99 +212,139 @@ k_diag(WinTab wt, const unsigned* __restrict__ adjf_ptr, const int* __restrict__
     wmean[r] = wm;
 }
 
-#define RVE_APPLY_THREADS(K) ((K) == 3 ? 384 : 256)
+#define RVE_APPLY_THREADS 256
 #ifndef RVE_APPLY_MINB
-#define RVE_APPLY_MINB(K) ((K) == 3 ? 2 : 3)
+#define RVE_APPLY_MINB(K) ((K) == 3 ? 3 : 4)
 #endif
 
-// q = A p, p.q per system (alpha by the last CTA of the system): see the header of this file
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// q = A p, p.q per system (alpha by the last CTA of the system): see the header of this file.
+// Latency plan: the p-tile travels global -> shared with cp.async (LDGSTS, no registers, no wait), the halo row ids
+// and the element record of the thread's first element are requested before anything is waited for, so the three
+// dependent latencies (halo ids -> halo rows, tile -> element product) overlap.
 template <int K>
-__global__ void __launch_bounds__(RVE_APPLY_THREADS(K), RVE_APPLY_MINB(K))
-k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __restrict__ q, int tile_cap,
+__global__ void __launch_bounds__(RVE_APPLY_THREADS, RVE_APPLY_MINB(K))
+k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __restrict__ q, int tile_cap, int slot_cap,
         double* part, int* cnt, double* sc) {
-    extern __shared__ double2 s_tile[];           // [tile_cap * K] p-tile, then [max_slots * K] nodal-force slots
-    constexpr int TPB = RVE_APPLY_THREADS(K);
+    extern __shared__ double2 s_tile[];           // [tile_cap * K] p-tile (row-major, rhs interleaved), then K planes [slot_cap] of nodal forces
+    constexpr int TPB = RVE_APPLY_THREADS;
     const int win = blockIdx.x;
     if (!wt.win_active[win]) return;
     const int sys = wt.win_sys[win];
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
     const int h0 = wt.win_halo0[win], nh = wt.win_nhalo[win];
+    const int we0 = mf.win_we0[win], nwe = mf.win_nwe[win], nep = (nwe + 31) & ~31;
     double2* s_f = s_tile + (size_t)tile_cap * K;
     __shared__ int s_sb[RVE_WIN / 32];
+    // halo row ids first (the gather below depends on them)
+    int hr[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) { const int e = tid + it * TPB; hr[it] = (e < nh) ? sl.halo[h0 + e] : -1; }
     if (tid == 0) {
         const uint2 v = *(const uint2*)(mf.win_sw + (size_t)win * 8);
         int tot = 0;
 #pragma unroll
         for (int s = 0; s < 8; ++s) { s_sb[s] = tot; tot += 32 * (int)(((s < 4 ? v.x : v.y) >> (8 * (s & 3))) & 0xffu); }
     }
-    {
+    {   // own rows: one contiguous copy
         const double2* src = p + (size_t)row0 * K;
-        for (int e = tid; e < n * K; e += TPB) s_tile[e] = src[e];
+        for (int e = tid; e < n * K; e += TPB) cp_async16(s_tile + e, src + e);
+    }
+    // element record of the first element of this thread, rows' fan sizes
+    const uint32_t* idx = mf.we_idx + 6 * (size_t)we0;
+    const double2* geo = mf.we_geo + 3 * (size_t)we0;
+    uint32_t ix[6];
+    double2 gv[3];
+    if (tid < nwe) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) ix[j] = idx[j * nep + tid];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gv[j] = geo[j * nep + tid];
+    }
+    const int na = (tid < n) ? mf.row_nadj[row0 + tid] : 0;
+    {   // halo rows
         double2* dstt = s_tile + n * K;
-        for (int e = tid; e < nh * K; e += TPB) {
-            const int hr = sl.halo[h0 + e / K];
-            dstt[e] = p[(size_t)hr * K + (e % K)];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int e = tid + it * TPB;
+            if (e < nh) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) cp_async16(dstt + e * K + k, p + (size_t)hr[it] * K + k);
+            }
+        }
+        for (int e = tid + 2 * TPB; e < nh; e += TPB) {           // (a window has fewer than 512 halo rows in practice)
+            const int h = sl.halo[h0 + e];
+#pragma unroll
+            for (int k = 0; k < K; ++k) cp_async16(dstt + e * K + k, p + (size_t)h * K + k);
         }
     }
+    cp_async_wait_all();
     __syncthreads();
-    // phase 1: element products
-    {
-        const int we0 = mf.win_we0[win], nwe = mf.win_nwe[win], nep = (nwe + 31) & ~31;
-        const uint16_t* col = mf.we_col + 6 * (size_t)we0;
-        const uint16_t* dst = mf.we_dst + 6 * (size_t)we0;
-        const double* geo = mf.we_geo + 6 * (size_t)we0;
-        for (int item = tid; item < nwe * K; item += TPB) {
-            const int e = item / K, k = item - e * K;
-            double gv[6], u[12], f[12];
-            int c[6];
+    // phase 1: element products, thread per window element, right-hand sides in turn
+    for (int e = tid; e < nwe; e += TPB) {
+        if (e != tid) {
 #pragma unroll
-            for (int a = 0; a < 6; ++a) c[a] = col[a * nep + e];
+            for (int j = 0; j < 6; ++j) ix[j] = idx[j * nep + e];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) gv[j] = geo[j * nep + e];
+            for (int j = 0; j < 3; ++j) gv[j] = geo[j * nep + e];
+        }
+        const double g6[6] = {gv[0].x, gv[0].y, gv[1].x, gv[1].y, gv[2].x, gv[2].y};
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            double u[12], f[12];
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
-                const double2 v = (c[a] != 0xffff) ? s_tile[c[a] * K + k] : make_double2(0.0, 0.0);
+                const unsigned c = (ix[a >> 1] >> (16 * (a & 1))) & 0xffffu;
+                const double2 v = (c != 0xffffu) ? s_tile[c * K + k] : make_double2(0.0, 0.0);
                 u[2 * a] = v.x; u[2 * a + 1] = v.y;
             }
-            p2_apply(gv, u, f);
+            p2_apply(g6, u, f);
+            double2* fk = s_f + (size_t)k * slot_cap;
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
-                const int d = dst[a * nep + e];
-                if (d != 0xffff) s_f[d * K + k] = make_double2(f[2 * a], f[2 * a + 1]);
+                const unsigned d = (ix[3 + (a >> 1)] >> (16 * (a & 1))) & 0xffffu;
+                if (d != 0xffffu) fk[d] = make_double2(f[2 * a], f[2 * a + 1]);
             }
         }
     }
     __syncthreads();
-    // phase 2: rows gather their slots
-    double dot = 0.0;
-    {
-        double2* qd = q + (size_t)row0 * K;
-        for (int item = tid; item < n * K; item += TPB) {
-            const int r = item / K, k = item - r * K;
-            const int na = mf.row_nadj[row0 + r];
-            const double2* src = s_f + (size_t)(s_sb[r >> 5] + (r & 31)) * K + k;
-            double2 acc = make_double2(0.0, 0.0);
-            for (int j = 0; j < na; ++j) { const double2 v = src[(size_t)j * 32 * K]; acc.x += v.x; acc.y += v.y; }
-            qd[item] = acc;
-            const double2 pv = s_tile[item];
-            dot += acc.x * pv.x + acc.y * pv.y;
+    // phase 2: thread per row gathers its slots (conflict-free: consecutive rows, consecutive slots), p.q partials
+    double dot[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) dot[k] = 0.0;
+    if (tid < n) {
+        const int sb = s_sb[wv] + lane;
+        double2 acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+        for (int j = 0; j < na; ++j)
+#pragma unroll
+            for (int k = 0; k < K; ++k) { const double2 v = s_f[(size_t)k * slot_cap + sb + j * 32]; acc[k].x += v.x; acc[k].y += v.y; }
+        double2* qd = q + ((size_t)row0 + tid) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            qd[k] = acc[k];
+            const double2 pv = s_tile[tid * K + k];
+            dot[k] = acc[k].x * pv.x + acc[k].y * pv.y;
         }
     }
-    // p.q of the window per rhs (thread's rhs index is fixed: TPB % K == 0), then the system-wide sum
-    __shared__ double s_a[TPB];
-    __shared__ double s_dot[4];
+    __shared__ double s_dot[RVE_APPLY_THREADS / 32][4];
     __shared__ double s_out[4][1];
-    s_a[tid] = dot;
-    __syncthreads();
-    if (wv < K) {
-        double acc = 0.0;
-        for (int m = lane; m < TPB / K; m += 32) acc += s_a[wv + K * m];
-        acc = warp_sum(acc);
-        if (lane == 0) s_dot[wv] = acc;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double v = warp_sum(dot[k]);
+        if (lane == 0) s_dot[wv][k] = v;
     }
     __syncthreads();
-    const double my = (tid < K) ? s_dot[tid] : 0.0;
+    double my = 0.0;
+    if (tid < K)
+        for (int i = 0; i < TPB / 32; ++i) my += s_dot[i][tid];
     const int w0 = wt.sys_win0[sys], w1 = wt.sys_win0[sys + 1];
     if (last_block_sum<1>(part, cnt, sys, win, w0, w1, my, s_out)) {
         if (tid < K) {

@@ -76,7 +76,7 @@ def test_matfree_full_mesh_snapshot_matches_oracle(full_mesh):
     from deepbnd_b200.elasticity import macro_strain_voigt
     from oracle.rve_oracle import OracleRVE, vref_points
     eps = np.stack([macro_strain_voigt(i) for i in (2, 0)])[None]
-    b = RVEBatch().set_meshes([full_mesh], PARAM, model="per").assemble()     # default operator
+    b = RVEBatch().set_meshes([full_mesh], PARAM, model="per", vref_box=(-1.0, -1.0, 2.0, 2.0)).assemble()     # default operator
     b.solve(eps, rtol=1e-10)
     out = b.snapshot()
     o = OracleRVE(*full_mesh, param=PARAM, model="per")
