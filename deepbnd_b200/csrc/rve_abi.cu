@@ -14,6 +14,7 @@
 #include "rve_symbolic.hpp"
 #include "rve_devsym.cuh"
 #include "rve_matfree.cuh"
+#include "rve_stream.cuh"
 
 namespace {
 
@@ -120,6 +121,7 @@ struct rve_batch_s {
     std::vector<long long> adjf_base;
     int max_words = 0;
     DBuf<RowInfo> rowinfo;
+    DBuf<WinDesc> win_desc;
     DBuf<double> lvA[RVE_MAXLEV], lvD[RVE_MAXLEV];
     DBuf<float> lvR[RVE_MAXLEV], lvX[RVE_MAXLEV], lvT[RVE_MAXLEV];   // V-cycle vectors (fp32)
     DBuf<stv> lvA4[RVE_MAXLEV], lvH4[RVE_MAXLEV];
@@ -127,6 +129,8 @@ struct rve_batch_s {
     DBuf<double> eps, eps_eff, Bmat, uD, gval, d_vbox, U, acc, sigL, sigT, aout, Bout, sol, Mx, Gaff, aaff;
     DBuf<double> MWt, transl, Yd, gradT;
     int opt_sym_B = 0;
+    int n_sm = 148;
+    int updp_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};   // resident CTAs per SM of k_update_p<K> (by precond), 0 = not asked yet
     // matrix-free operator (rve_matfree.cuh): window-element tables; the SELL values (bval) are built on demand only
     int opt_operator = RVE_OPERATOR_MATFREE;
     bool have_bval = false;
@@ -242,6 +246,7 @@ static cudaError_t raise_smem_limits(int device) {
     RAISE_(k_direction<1>); RAISE_(k_direction<2>); RAISE_(k_direction<3>);
     RAISE_(k_sym_window); RAISE_(k_sym_coarse); RAISE_(k_sym_elems);
     RAISE_(k_apply<1>); RAISE_(k_apply<2>); RAISE_(k_apply<3>);
+    RAISE_(k_update_p<1>); RAISE_(k_update_p<2>); RAISE_(k_update_p<3>);
 #undef RAISE_
     return cudaSuccess;
 }
@@ -262,23 +267,43 @@ static MfTab mf_tab(rve_batch_s* h) {
 }
 
 template <int K>
-static void launch_spmv(rve_batch_s* h, const PcgArgs& a, const double* p, double* q, int* active, double* part, int* cnt,
-                        double* sc, cudaStream_t st) {
-    if (a.op == RVE_OPERATOR_MATFREE) {
+static void launch_spmv(rve_batch_s* h, const PcgArgs& a, const double* p, double* q, int* active, double* part, double* sc, cudaStream_t st) {
+    if (a.op == RVE_OPERATOR_MATFREE)
         k_apply<K><<<a.n_win, RVE_APPLY_THREADS, a.sm_apply, st>>>(a.wt, a.sl, mf_tab(h), (const double2*)p, (double2*)q, h->max_tile,
-                                                                   h->max_slots, part, cnt, sc);
-        return;
-    }
-    k_spmv<K><<<a.n_win, RVE_SPMV_THREADS, a.sm_spmv, st>>>(a.wt, a.sl, (const double2*)h->bval.p, (const double2*)p, (double2*)q,
-                                                  active, part, cnt, sc);
+                                                                   h->max_slots, part);
+    else
+        k_spmv<K><<<a.n_win, RVE_SPMV_THREADS, a.sm_spmv, st>>>(a.wt, a.sl, (const double2*)h->bval.p, (const double2*)p, (double2*)q, part);
+    k_fin_alpha<<<cdiv(a.n_sys, 8), 256, 0, st>>>(a.n_sys, K, a.wt.sys_win0, part, active, sc);
+}
+
+// persistent bulk-copy-pipelined vector kernels (rve_stream.cuh); RVE_PIPELINE=0 selects the one-window-per-CTA kernels
+static bool use_pipeline() {
+    static const bool on = [] { const char* e = std::getenv("RVE_PIPELINE"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 template <int K>
 static void launch_update(rve_batch_s* h, const PcgArgs& a, int init, int iter, cudaStream_t st) {
-    k_update<K><<<a.n_win, RVE_UPD_THREADS(K), a.sm_upd, st>>>(a.wt, (const double2*)h->p.p, (const double2*)h->q.p, (double2*)h->x.p,
-                                                   (double2*)h->r.p, h->dinv.p, h->rowinfo.p, h->cn_node.p, h->cn_beg.p,
-                                                   h->cn_ent.p, a.LV.rc[0], a.LV.g[0].G, h->active.p, h->part.p, h->cnt.p,
-                                                   h->sc.p, init, iter, a.rtol2, a.precond, h->d_iters.p, h->n_active.p);
+    if (use_pipeline()) {
+        const int cn_pad = ((h->max_cn + 3) & ~3) + 4;
+        const size_t sm = RVE_PIPE_STAGES * updp_stage_bytes(K, cn_pad, a.precond != 0);
+        int& per_sm = h->updp_blocks[K][a.precond ? 1 : 0];
+        if (per_sm == 0) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_update_p<K>, RVE_UPDP_THREADS(K), sm);
+            if (per_sm < 1) per_sm = 1;
+        }
+        const int grid = std::min(a.n_win, per_sm * h->n_sm);
+        k_update_p<K><<<grid, RVE_UPDP_THREADS(K), sm, st>>>(a.wt, h->win_desc.p, a.n_win, (const double2*)h->p.p, (const double2*)h->q.p,
+                                                              (double2*)h->x.p, (double2*)h->r.p, h->dinv.p, h->rowinfo.p, h->cn_node.p,
+                                                              h->cn_beg.p, h->cn_ent.p, a.LV.rc[0], a.LV.g[0].G, h->part.p, h->sc.p, init,
+                                                              a.precond, cn_pad);
+    } else {
+        k_update<K><<<a.n_win, RVE_UPD_THREADS(K), a.sm_upd, st>>>(a.wt, (const double2*)h->p.p, (const double2*)h->q.p, (double2*)h->x.p,
+                                                                   (double2*)h->r.p, h->dinv.p, h->rowinfo.p, h->cn_node.p, h->cn_beg.p,
+                                                                   h->cn_ent.p, a.LV.rc[0], a.LV.g[0].G, h->part.p, h->sc.p, init, a.precond);
+    }
+    k_fin_update<<<cdiv(a.n_sys, 8), 256, 0, st>>>(a.n_sys, K, a.wt.sys_win0, h->part.p, h->active.p, a.wt.win_active, h->sc.p, init, iter,
+                                                   a.rtol2, a.precond, h->d_iters.p, h->n_active.p);
 }
 
 // coarse V-cycle: the large levels (always level 1) as grid-wide kernels (thread per coarse node), the small
@@ -305,8 +330,10 @@ static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStrea
         }
         nk += 1 + W + (W - 1);
     }
-    k_vc_up1<K><<<grid(0), 256, 0, st>>>(LV, h->active.p, h->sc.p, h->cpart.p, h->cnt.p, first);
-    h->launches += nk;
+    k_vc_up1<K><<<grid(0), 256, 0, st>>>(LV, h->active.p, h->cpart.p);
+    const int nb = (LV.g[0].G + 255) / 256;
+    k_fin_beta<<<cdiv(a.n_sys, 8), 256, 0, st>>>(a.n_sys, K, nb, h->cpart.p, h->active.p, h->sc.p, first);
+    h->launches += nk + 1;
 }
 
 template <int K>
@@ -348,6 +375,8 @@ int rve_create(int device, rve_handle_t* out) {
     if ((e = raise_smem_limits(device)) != cudaSuccess) { g_create_err = std::string("shared-memory opt-in: ") + cudaGetErrorString(e); return RVE_E_CUDA; }
     rve_batch_s* h = new rve_batch_s();
     h->device = device;
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (h->n_sm < 1) h->n_sm = 148;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_err = cudaGetErrorString(e); delete h; return RVE_E_CUDA;
     }
@@ -601,9 +630,9 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     CU(h->sys_blocks.alloc(n_sys)); CU(cudaMemsetAsync(h->sys_blocks.p, 0, n_sys * sizeof(int), st)); CU(h->halo.alloc((size_t)halo_cap)); CU(h->scol.alloc((size_t)h->NG * 32));
     CU(h->win_halo0.alloc(n_win)); CU(h->win_nhalo.alloc(n_win)); CU(h->sym_cnt.alloc(8));
     CU(cudaMemsetAsync(h->sym_cnt.p, 0, 8 * sizeof(int), st));
-    const long long cn_cap = h->R + (long long)n_win + 4096;      // level-1 nodes touched per window are far fewer than its rows
+    const long long cn_cap = h->R + 5LL * n_win + 4096;      // level-1 nodes touched per window are far fewer than its rows
     CU(h->win_cn0.alloc(n_win)); CU(h->win_ncn.alloc(n_win)); CU(h->win_active.alloc(n_win)); CU(h->cn_node.alloc((size_t)cn_cap)); CU(h->cn_beg.alloc((size_t)cn_cap));
-    CU(h->cn_ent.alloc(4 * (size_t)h->R)); CU(h->rowinfo.alloc((size_t)h->R));
+    CU(h->cn_ent.alloc(4 * (size_t)h->R + 8 * (size_t)n_win + 64)); CU(h->rowinfo.alloc((size_t)h->R)); CU(h->win_desc.alloc((size_t)n_win));
     {
         WinTab wt = win_tab(h);
         k_sym_cols<<<n_win, RVE_WIN, 0, st>>>(wt, h->d_row_ptr.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->node_row.p,
@@ -617,7 +646,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
         const size_t smc = 2 * (size_t)((LV.g[0].G + 31) / 32) * sizeof(unsigned);
         if (smc > 150 * 1024) FAIL(RVE_E_MESH, "level-1 grid too large for the coarse-node bitmap in shared memory");
         k_sym_coarse<<<n_win, RVE_WIN, smc, st>>>(wt, h->win_cn0.p, h->win_ncn.p, h->row_node.p, h->node_xy.p, h->box.p, LV.g[0],
-                                                  model, h->rowinfo.p, h->cn_node.p, h->cn_beg.p, h->cn_ent.p, (int)cn_cap, h->sym_cnt.p);
+                                                  model, h->rowinfo.p, h->cn_node.p, h->cn_beg.p, h->cn_ent.p, (int)cn_cap, h->sym_cnt.p, h->win_desc.p);
         DBG_SYNC("k_sym_coarse");
         h->launches += 3;
     }
@@ -946,7 +975,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
             K_DISPATCH(K, DIR_);
 #undef DIR_
             cudaEventRecord(pool_event(2 * (size_t)it), st);
-#define SPMV_(KK) launch_spmv<KK>(h, pa, h->p.p, h->q.p, h->active.p, h->part.p, h->cnt.p, h->sc.p, st)
+#define SPMV_(KK) launch_spmv<KK>(h, pa, h->p.p, h->q.p, h->active.p, h->part.p, h->sc.p, st)
             K_DISPATCH(K, SPMV_);
 #undef SPMV_
             cudaEventRecord(pool_event(2 * (size_t)it + 1), st);
@@ -955,7 +984,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
 #undef UPD_
             if (ktime) cudaEventRecord(dbg_event(3 * (size_t)it + 2), st);
             ++launched;
-            h->launches += 3;
+            h->launches += 5;
         }
         CU(cudaMemcpyAsync(h->h_nactive, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(stream_wait(h));
@@ -1181,7 +1210,7 @@ int rve_bench_spmv(rve_handle_t h, int32_t n_rhs, int32_t reps, double* ms_per_l
     pa.wt = win_tab(h); pa.sl = sell_tab(h); pa.LV = h->LV; pa.n_win = h->n_win; pa.n_sys = n_sys; pa.K = K;
     pa.precond = 0; pa.rtol2 = 0; pa.sm_spmv = smem_spmv(h, K); pa.sm_upd = smem_update(K); pa.sm_dir = smem_direction(h, K);
     pa.sm_apply = smem_apply(h, K); pa.op = h->opt_operator;
-#define SPMV_(KK) launch_spmv<KK>(h, pa, p.p, q.p, active.p, part.p, cnt.p, sc.p, st)
+#define SPMV_(KK) launch_spmv<KK>(h, pa, p.p, q.p, active.p, part.p, sc.p, st)
     for (int wu = 0; wu < 3; ++wu) K_DISPATCH(K, SPMV_);
     CU(cudaEventRecord(h->ev[0], st));
     for (int i = 0; i < reps; ++i) K_DISPATCH(K, SPMV_);
@@ -1225,7 +1254,7 @@ int rve_apply_operator(rve_handle_t h, int32_t n_rhs, const double* p_host, doub
     pa.wt = win_tab(h); pa.sl = sell_tab(h); pa.LV = h->LV; pa.n_win = h->n_win; pa.n_sys = n_sys; pa.K = K;
     pa.precond = 0; pa.rtol2 = 0; pa.sm_spmv = smem_spmv(h, K); pa.sm_upd = smem_update(K); pa.sm_dir = smem_direction(h, K);
     pa.sm_apply = smem_apply(h, K); pa.op = h->opt_operator;
-#define SPMV_(KK) launch_spmv<KK>(h, pa, p.p, q.p, active.p, part.p, cnt.p, sc.p, st)
+#define SPMV_(KK) launch_spmv<KK>(h, pa, p.p, q.p, active.p, part.p, sc.p, st)
     K_DISPATCH(K, SPMV_);
 #undef SPMV_
     CU(cudaMemcpyAsync(q_host, q.p, RK * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -17,7 +17,7 @@
 //   Coarse level l (structured (ncx+1)x(ncy+1) grid per system, 25-point block stencil):
 //                A[sys][slot 25][4][G] fp64 (set-up), A4/H4[sys][25][G] fp16 blocks (V-cycle), dinv[sys][G][4],
 //                V-cycle vectors rc/xc/tc[sys][G][K] float2.
-// Per-window partial dot products are combined in a fixed order by the last CTA of each system.
+// Per-window partial dot products are combined in a fixed order by the k_fin_* kernels (warp per system).
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -95,6 +95,10 @@ struct Sell {
     const uint16_t* scol;
     const int* halo;
 };
+
+// everything the streaming PCG kernels need to know about a window, in one 32-byte record (written by k_sym_coarse):
+// the producer thread of the persistent kernels turns it into bulk copies without a second dependent load
+struct WinDesc { int row0, n, cn0, ncn; unsigned ent0, nent; int sys, pad; };
 
 // per (system, rhs) scalars
 #define SC_RZ 0
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(RVE_WIN)
 k_sym_coarse(WinTab wt, int* __restrict__ win_cn0, int* __restrict__ win_ncn, const int* __restrict__ row_node,
              const double* __restrict__ node_xy, const double* __restrict__ box, Grid g1, int model,
              RowInfo* __restrict__ rowinfo, int* __restrict__ cn_node, unsigned* __restrict__ cn_beg,
-             uint16_t* __restrict__ cn_ent, int cn_cap, int* counters) {
+             uint16_t* __restrict__ cn_ent, int cn_cap, int* counters, WinDesc* __restrict__ desc) {
     extern __shared__ unsigned s_bm[];           // [words] bitmap of touched level-1 nodes, then [words] popcount prefix
     __shared__ int s_scan[RVE_WIN];
     __shared__ int s_base[2];
@@ -342,13 +346,17 @@ k_sym_coarse(WinTab wt, int* __restrict__ win_cn0, int* __restrict__ win_ncn, co
     if (tid == 0) {                               // exclusive offsets (ncn is ~50-250)
         for (int j = 0; j < ncn; ++j) s_cnt[j + 1] += s_cnt[j];
         const int nent = s_cnt[ncn];
-        int c0 = atomicAdd(counters + 3, ncn + 1);
-        int e0 = atomicAdd(counters + 4, nent);
+        // segments start on 16-byte boundaries (4 ints / 8 uint16): the persistent PCG kernels fetch them with bulk copies
+        int c0 = atomicAdd(counters + 3, (ncn + 1 + 3) & ~3);
+        int e0 = atomicAdd(counters + 4, (nent + 7) & ~7);
         atomicMax(counters + 5, ncn);
-        if (c0 + ncn + 1 > cn_cap) { atomicExch(counters + 2, 4); c0 = -1; }
+        if (c0 + ((ncn + 1 + 3) & ~3) > cn_cap) { atomicExch(counters + 2, 4); c0 = -1; }
         s_base[0] = c0; s_base[1] = e0;
         win_cn0[w] = c0 < 0 ? 0 : c0;
         win_ncn[w] = c0 < 0 ? 0 : ncn;
+        WinDesc d;
+        d.row0 = r0; d.n = n; d.cn0 = c0 < 0 ? 0 : c0; d.ncn = c0 < 0 ? 0 : ncn; d.ent0 = (unsigned)e0; d.nent = (unsigned)nent; d.sys = sys; d.pad = 0;
+        desc[w] = d;
     }
     __syncthreads();
     const int c0 = s_base[0], e0 = s_base[1];
@@ -695,43 +703,6 @@ __global__ void k_coarse_dinv(int n_sys, Grid g, const double* __restrict__ A, d
 // (3) PCG kernels (one CTA of RVE_WIN threads per window)
 // ---------------------------------------------------------------------------------------------
 
-// Deterministic combination of per-window partials by the last CTA of a system.
-// part layout: [window][4][NQ]; thread tid < 4*NQ contributes my (value index tid = rq*NQ + q);
-// result written to s_out[rq][q] (shared).
-template <int NQ>
-__device__ __forceinline__ bool last_block_sum(double* part, int* cnt, int sys, int win, int c0, int c1,
-                                               double my, double (*s_out)[NQ]) {
-    __shared__ int s_last;
-    __shared__ double s_red[RVE_WIN * 3];
-    const int tid = threadIdx.x;
-    // only the publishing threads fence (a fence by every thread would make the whole CTA wait for
-    // its x/r/q stores to land)
-    if (tid < 4 * NQ) { part[(size_t)win * 4 * NQ + tid] = my; __threadfence(); }
-    __syncthreads();
-    if (tid == 0) {
-        int old = atomicAdd(cnt + sys, 1);
-        s_last = (old == (c1 - c0 - 1));
-        if (s_last) cnt[sys] = 0;
-    }
-    __syncthreads();
-    if (!s_last) return false;
-    __threadfence();
-    const int nv = 4 * NQ;
-    const int grp = tid / nv, v = tid % nv, ngrp = (int)blockDim.x / nv;
-    double acc = 0.0;
-    if (grp < ngrp)
-        for (int c = c0 + grp; c < c1; c += ngrp) acc += __ldcg(part + (size_t)c * nv + v);
-    s_red[tid] = (grp < ngrp) ? acc : 0.0;
-    __syncthreads();
-    if (tid < nv) {
-        double t = 0.0;
-        for (int gq = 0; gq < ngrp; ++gq) t += s_red[gq * nv + tid];
-        s_out[tid / NQ][tid % NQ] = t;
-    }
-    __syncthreads();
-    return true;
-}
-
 // q = A p, pq = p.q.  CTA of RVE_SPMV_WARPS (=2) warps per window.  The CTA first stages the p entries
 // its window needs (own rows: one coalesced copy; halo rows: list-driven gather) in shared memory.
 // Then every lane owns one row of a SELL-32 slice and each warp walks the slices w, w+2, w+4, w+6 of the
@@ -749,11 +720,10 @@ __device__ __forceinline__ bool last_block_sum(double* part, int* cnt, int sys, 
 template <int K>
 __global__ void __launch_bounds__(RVE_SPMV_THREADS)
 k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __restrict__ p,
-       double2* __restrict__ q, const int* __restrict__ active, double* part, int* cnt, double* sc) {
+       double2* __restrict__ q, double* __restrict__ part) {
     extern __shared__ double2 s_tile[];           // [(n + nhalo) * K] p-tile
     __shared__ unsigned s_g0[RVE_WIN / 32 + 1];
     const int win = blockIdx.x;
-    const int sys = wt.win_sys[win];
     if (!wt.win_active[win]) return;
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
@@ -835,24 +805,16 @@ k_spmv(WinTab wt, Sell sl, const double2* __restrict__ bval, const double2* __re
         s = ns; j = nj; c0 = nc0; c1 = nc1; a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
     }
     __shared__ double s_dot[RVE_SPMV_WARPS][4];
-    __shared__ double s_out[4][1];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const double v = warp_sum(dot[k]);
         if (lane == 0) s_dot[wv][k] = v;
     }
     __syncthreads();
-    double my = 0.0;
-    if (tid < K)
+    if (tid < K) {                                   // per-window partial of p.q; k_fin_alpha adds them per system
+        double my = 0.0;
         for (int i = 0; i < RVE_SPMV_WARPS; ++i) my += s_dot[i][tid];
-    const int w0 = wt.sys_win0[sys], w1 = wt.sys_win0[sys + 1];
-    if (last_block_sum<1>(part, cnt, sys, win, w0, w1, my, s_out)) {
-        if (tid < K) {
-            double* s_ = sc + ((size_t)sys * 4 + tid) * SC_N;
-            const double pq = s_out[tid][0];
-            s_[SC_PQ] = pq;
-            s_[SC_ALPHA] = (pq > 0.0) ? s_[SC_RZ] / pq : 0.0;
-        }
+        part[(size_t)win * 4 + tid] = my;
     }
 }
 
@@ -881,8 +843,7 @@ __global__ void __launch_bounds__(RVE_UPD_THREADS(K), RVE_UPD_MINB(K))
 k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q, double2* __restrict__ x,
          double2* __restrict__ r, const float4* __restrict__ dinv32, const RowInfo* __restrict__ rowinfo,
          const int* __restrict__ cn_node, const unsigned* __restrict__ cn_beg, const uint16_t* __restrict__ cn_ent,
-         float* __restrict__ rc1, int G, int* active, double* part, int* cnt, double* sc, int init, int iter,
-         double rtol2, int precond, int* iters, int* n_active) {
+         float* __restrict__ rc1, int G, double* __restrict__ part, const double* __restrict__ sc, int init, int precond) {
     extern __shared__ double2 s_r[];              // [n*K] new residual, then float2 s_st[n], uint16 s_ent[4n]
     constexpr int EPT = RVE_EPT_UPD(K), TPB = RVE_UPD_THREADS(K);   // TPB % K == 0: a thread keeps its rhs index
     const int win = blockIdx.x;
@@ -935,7 +896,6 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
     }
     __shared__ double s_a[TPB], s_b[TPB];
     __shared__ double s_fin[8];
-    __shared__ double s_out[4][2];
     s_a[tid] = rr; s_b[tid] = rdr;
     if (tid < 8) s_fin[tid] = 0.0;
     __syncthreads();
@@ -989,35 +949,7 @@ k_update(WinTab wt, const double2* __restrict__ p, const double2* __restrict__ q
         }
     }
     __syncthreads();
-    const double my = (tid < 8) ? s_fin[tid] : 0.0;   // value index tid = rq*2 + which
-    const int c0 = wt.sys_win0[sys], c1 = wt.sys_win0[sys + 1];
-    if (last_block_sum<2>(part, cnt, sys, win, c0, c1, my, s_out)) {
-        if (tid == 0) {
-            bool done = true;
-            for (int kk = 0; kk < K; ++kk) {
-                double* s = sc + ((size_t)sys * 4 + kk) * SC_N;
-                const double vrr = s_out[kk][0], vrdr = s_out[kk][1];
-                if (init) s[SC_BB] = vrr;
-                s[SC_RR] = vrr; s[SC_RDR] = vrdr;
-                if (!(vrr <= rtol2 * s[SC_BB] || vrr <= 1e-28 * s[SC_BREF])) done = false;
-                if (precond == 0) {  // block Jacobi: z = Dinv r, finish the scalar recurrences here
-                    const double rzold = s[SC_RZ];
-                    s[SC_RZOLD] = rzold;
-                    s[SC_RZ] = vrdr;
-                    s[SC_BETA] = (!init && rzold > 0.0) ? vrdr / rzold : 0.0;
-                }
-            }
-            if (done) {
-                active[sys] = 0;
-                iters[sys] = init ? 0 : iter + 1;
-                atomicSub(n_active, 1);
-            }
-            s_out[0][0] = done ? 1.0 : 0.0;
-        }
-        __syncthreads();
-        if (s_out[0][0] != 0.0)                        // converged: switch the windows of the system off
-            for (int wq = c0 + tid; wq < c1; wq += TPB) wt.win_active[wq] = 0;
-    }
+    if (tid < 8) part[(size_t)win * 8 + tid] = s_fin[tid];    // [rhs][rr, r.Dinv r]; k_fin_update adds them per system
 }
 
 
@@ -1355,7 +1287,7 @@ k_vc_upl(Levels LV, int l, const int* __restrict__ active) {
 // r.z = rc . z1, beta; clears rc for the next restriction.  grid (ceil(G/256), n_sys)
 template <int K>
 __global__ void __launch_bounds__(256)
-k_vc_up1(Levels LV, const int* __restrict__ active, double* sc, double* part, int* cnt, int first) {
+k_vc_up1(Levels LV, const int* __restrict__ active, double* __restrict__ part) {
     const int sys = blockIdx.y;
     if (!active[sys]) return;
     const Grid g = LV.g[0];
@@ -1387,21 +1319,93 @@ k_vc_up1(Levels LV, const int* __restrict__ active, double* sc, double* part, in
         }
     }
     __shared__ double s_dot[8][4];
-    __shared__ double s_out[4][1];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const double v = warp_sum(dot[k]);
         if (lane == 0) s_dot[wv][k] = v;
     }
     __syncthreads();
-    double my = 0.0;
-    if (threadIdx.x < K)
+    if (threadIdx.x < K) {                           // per-CTA partial of rc.z1; k_fin_beta adds them per system
+        double my = 0.0;
         for (int i = 0; i < 8; ++i) my += s_dot[i][threadIdx.x];
-    const int nb = gridDim.x;
-    if (last_block_sum<1>(part, cnt, sys, sys * nb + blockIdx.x, sys * nb, sys * nb + nb, my, s_out)) {
-        if (threadIdx.x < K) {
-            double* s = sc + ((size_t)sys * 4 + threadIdx.x) * SC_N;
-            const double rz = s[SC_RDR] + s_out[threadIdx.x][0];
+        part[((size_t)sys * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = my;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-system scalar recurrences of the PCG, one warp per system.  The kernels above leave per-window (per-CTA)
+// partial sums; these add them in a fixed order (lane-strided, then a butterfly), so the scalars are reproducible
+// run to run, and the streaming kernels carry no fence / atomic / "last CTA" tail.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sys_sum(const double* __restrict__ v, int first, int last, int stride, int off) {
+    double acc = 0.0;
+    for (int c = first + (int)(threadIdx.x & 31); c < last; c += 32) acc += v[(size_t)c * stride + off];
+    return warp_sum(acc);
+}
+
+// alpha = r.z / p.q after the operator application
+__global__ void __launch_bounds__(256)
+k_fin_alpha(int n_sys, int K, const int* __restrict__ sys_win0, const double* __restrict__ part, const int* __restrict__ active,
+            double* __restrict__ sc) {
+    const int sys = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (sys >= n_sys || !active[sys]) return;
+    const int w0 = sys_win0[sys], w1 = sys_win0[sys + 1];
+    for (int k = 0; k < K; ++k) {
+        const double pq = sys_sum(part, w0, w1, 4, k);
+        if ((threadIdx.x & 31) == 0) {
+            double* s_ = sc + ((size_t)sys * 4 + k) * SC_N;
+            s_[SC_PQ] = pq;
+            s_[SC_ALPHA] = (pq > 0.0) ? s_[SC_RZ] / pq : 0.0;
+        }
+    }
+}
+
+// r.r, r.Dinv r after the update; convergence test; a converged system switches itself and its windows off
+__global__ void __launch_bounds__(256)
+k_fin_update(int n_sys, int K, const int* __restrict__ sys_win0, const double* __restrict__ part, int* __restrict__ active,
+             unsigned char* __restrict__ win_active, double* __restrict__ sc, int init, int iter, double rtol2, int precond,
+             int* __restrict__ iters, int* n_active) {
+    const int sys = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (sys >= n_sys || !active[sys]) return;
+    const int lane = threadIdx.x & 31;
+    const int w0 = sys_win0[sys], w1 = sys_win0[sys + 1];
+    bool done = true;
+    for (int k = 0; k < K; ++k) {
+        const double vrr = sys_sum(part, w0, w1, 8, 2 * k), vrdr = sys_sum(part, w0, w1, 8, 2 * k + 1);
+        double* s = sc + ((size_t)sys * 4 + k) * SC_N;
+        const double bb = init ? vrr : s[SC_BB];
+        if (!(vrr <= rtol2 * bb || vrr <= 1e-28 * s[SC_BREF])) done = false;
+        if (lane == 0) {
+            if (init) s[SC_BB] = vrr;
+            s[SC_RR] = vrr; s[SC_RDR] = vrdr;
+            if (precond == 0) {  // block Jacobi: z = Dinv r, finish the scalar recurrences here
+                const double rzold = s[SC_RZ];
+                s[SC_RZOLD] = rzold;
+                s[SC_RZ] = vrdr;
+                s[SC_BETA] = (!init && rzold > 0.0) ? vrdr / rzold : 0.0;
+            }
+        }
+    }
+    if (!done) return;
+    if (lane == 0) {
+        active[sys] = 0;
+        iters[sys] = init ? 0 : iter + 1;
+        atomicSub(n_active, 1);
+    }
+    for (int wq = w0 + lane; wq < w1; wq += 32) win_active[wq] = 0;
+}
+
+// r.z = r.Dinv r + rc.z1 after the V-cycle; beta
+__global__ void __launch_bounds__(256)
+k_fin_beta(int n_sys, int K, int nb, const double* __restrict__ cpart, const int* __restrict__ active, double* __restrict__ sc,
+           int first) {
+    const int sys = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (sys >= n_sys || !active[sys]) return;
+    for (int k = 0; k < K; ++k) {
+        const double cz = sys_sum(cpart, sys * nb, sys * nb + nb, 4, k);
+        if ((threadIdx.x & 31) == 0) {
+            double* s = sc + ((size_t)sys * 4 + k) * SC_N;
+            const double rz = s[SC_RDR] + cz;
             const double rzold = s[SC_RZ];
             s[SC_RZOLD] = rzold;
             s[SC_RZ] = rz;

@@ -223,19 +223,18 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-// q = A p, p.q per system (alpha by the last CTA of the system): see the header of this file.
+// q = A p and the per-window partial of p.q: see the header of this file.
 // Latency plan: the p-tile travels global -> shared with cp.async (LDGSTS, no registers, no wait), the halo row ids
 // and the element record of the thread's first element are requested before anything is waited for, so the three
 // dependent latencies (halo ids -> halo rows, tile -> element product) overlap.
 template <int K>
 __global__ void __launch_bounds__(RVE_APPLY_THREADS, RVE_APPLY_MINB(K))
 k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __restrict__ q, int tile_cap, int slot_cap,
-        double* part, int* cnt, double* sc) {
+        double* __restrict__ part) {
     extern __shared__ double2 s_tile[];           // [tile_cap * K] p-tile (row-major, rhs interleaved), then K planes [slot_cap] of nodal forces
     constexpr int TPB = RVE_APPLY_THREADS;
     const int win = blockIdx.x;
     if (!wt.win_active[win]) return;
-    const int sys = wt.win_sys[win];
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
     const int h0 = wt.win_halo0[win], nh = wt.win_nhalo[win];
@@ -335,23 +334,15 @@ k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __
         }
     }
     __shared__ double s_dot[RVE_APPLY_THREADS / 32][4];
-    __shared__ double s_out[4][1];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const double v = warp_sum(dot[k]);
         if (lane == 0) s_dot[wv][k] = v;
     }
     __syncthreads();
-    double my = 0.0;
-    if (tid < K)
+    if (tid < K) {                                   // per-window partial of p.q; k_fin_alpha adds them per system
+        double my = 0.0;
         for (int i = 0; i < TPB / 32; ++i) my += s_dot[i][tid];
-    const int w0 = wt.sys_win0[sys], w1 = wt.sys_win0[sys + 1];
-    if (last_block_sum<1>(part, cnt, sys, win, w0, w1, my, s_out)) {
-        if (tid < K) {
-            double* s_ = sc + ((size_t)sys * 4 + tid) * SC_N;
-            const double pq = s_out[tid][0];
-            s_[SC_PQ] = pq;
-            s_[SC_ALPHA] = (pq > 0.0) ? s_[SC_RZ] / pq : 0.0;
-        }
+        part[(size_t)win * 4 + tid] = my;
     }
 }

@@ -1,0 +1,252 @@
+// rve_stream.cuh — persistent, bulk-copy-pipelined versions of the PCG vector kernels (sm_100a).
+//
+// k_update / k_direction stream 6 resp. 3 vector passes per window and then do a short, latency-bound shared-memory
+// phase (restriction to the level-1 grid, block sums, the last-CTA bookkeeping).  With one window per CTA nothing is
+// in flight for that CTA during the second phase, and the measured bandwidth stops at 60-66 % of the copy peak.
+// Here a CTA is persistent (grid = resident CTAs), walks the windows w = blockIdx.x, += gridDim.x and keeps the NEXT
+// window's operands in flight while it works on the current one:
+//
+//   producer = lane 0 of warp 0: one 32-byte WinDesc load, then cp.async.bulk (UBLKCP, the 1-D TMA path) of the
+//   contiguous per-window pieces r, p, q, x, dinv, rowinfo, restriction lists into a 2-stage shared-memory ring,
+//   completion counted in bytes by an mbarrier per stage;
+//   consumers = all threads: mbarrier wait, elementwise update out of shared memory, coalesced stores of x and r,
+//   the new residual stays in the stage for the restriction.
+//
+// No register staging, no per-thread address arithmetic for the loads, and the copy engine keeps HBM busy during the
+// reduction phases.
+#pragma once
+#include "rve_kernels.cuh"
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned), completion on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// order generic-proxy accesses of shared memory before the async proxy overwrites it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// first active window at or after w in the sequence w, w+stride, ... (whole warp; returns n_win when there is none)
+__device__ __forceinline__ int next_active_window(const unsigned char* __restrict__ act, int w, int n_win, int stride) {
+    const int lane = threadIdx.x & 31;
+    while (w < n_win) {
+        const long long cand = (long long)w + (long long)lane * stride;
+        const bool a = cand < n_win && __ldcg(act + cand) != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, a);
+        if (m) return w + (__ffs(m) - 1) * stride;
+        if ((long long)w + 32LL * stride >= n_win) break;
+        w += 32 * stride;
+    }
+    return n_win;
+}
+
+#define RVE_PIPE_STAGES 2
+#define RVE_UPDP_THREADS(K) ((K) == 3 ? 384 : 256)
+
+// shared-memory footprint of one stage (bytes); cn_pad = level-1 nodes per window rounded up to 4, + 4
+__host__ __device__ inline size_t updp_stage_bytes(int K, int cn_pad, bool precond) {
+    size_t b = 4 * (size_t)RVE_WIN * K * 16 + (size_t)RVE_WIN * 16;                     // r p q x, dinv
+    if (precond) b += (size_t)RVE_WIN * 16 + (4 * (size_t)RVE_WIN + 8) * 2 + 2 * (size_t)cn_pad * 4;   // rowinfo, ent, beg, node
+    return (b + 127) & ~(size_t)127;
+}
+
+// x += alpha p ; r -= alpha q ; per-window partials of r.r and r.Dinv r ; rc += Z^T r.
+// Same arithmetic as k_update (rve_kernels.cuh), persistent + bulk-copy pipelined.
+template <int K>
+__global__ void __launch_bounds__(RVE_UPDP_THREADS(K), 1)
+k_update_p(WinTab wt, const WinDesc* __restrict__ desc, int n_win, const double2* __restrict__ p, const double2* __restrict__ q,
+           double2* __restrict__ x, double2* __restrict__ r, const float4* __restrict__ dinv32, const RowInfo* __restrict__ rowinfo,
+           const int* __restrict__ cn_node, const unsigned* __restrict__ cn_beg, const uint16_t* __restrict__ cn_ent,
+           float* __restrict__ rc1, int G, double* __restrict__ part, const double* __restrict__ sc, int init, int precond, int cn_pad) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    constexpr int TPB = RVE_UPDP_THREADS(K);
+    __shared__ __align__(8) uint64_t s_full[RVE_PIPE_STAGES];
+    __shared__ WinDesc s_desc[RVE_PIPE_STAGES];
+    __shared__ int s_win[RVE_PIPE_STAGES];
+    __shared__ double s_a[TPB], s_b[TPB];
+    __shared__ double s_fin[8];
+    const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int k = tid % K;
+    const size_t stage_bytes = updp_stage_bytes(K, cn_pad, precond != 0);
+    const int stride = (int)gridDim.x;
+
+    // stage layout
+    auto st_r = [&](int s) { return (double2*)(s_raw + (size_t)s * stage_bytes); };
+    auto st_p = [&](int s) { return st_r(s) + (size_t)RVE_WIN * K; };
+    auto st_q = [&](int s) { return st_r(s) + 2 * (size_t)RVE_WIN * K; };
+    auto st_x = [&](int s) { return st_r(s) + 3 * (size_t)RVE_WIN * K; };
+    auto st_d = [&](int s) { return (float4*)(st_r(s) + 4 * (size_t)RVE_WIN * K); };
+    auto st_ri = [&](int s) { return (RowInfo*)(st_d(s) + RVE_WIN); };
+    auto st_ent = [&](int s) { return (uint16_t*)(st_ri(s) + RVE_WIN); };
+    auto st_beg = [&](int s) { return (unsigned*)(st_ent(s) + 4 * RVE_WIN + 8); };
+    auto st_node = [&](int s) { return (int*)(st_beg(s) + cn_pad); };
+
+    if (tid == 0) {
+        for (int s = 0; s < RVE_PIPE_STAGES; ++s) mbar_init(&s_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // producer (lane 0 of warp 0): descriptor of window w -> bulk copies into stage s
+    auto issue = [&](int s, int w, const WinDesc& d) {
+        s_win[s] = w;
+        s_desc[s] = d;
+        if (w >= n_win) return;
+        fence_proxy_async();
+        const unsigned vb = (unsigned)d.n * K * 16, rb = (unsigned)d.n * 16;
+        unsigned tot = vb + rb + (init ? 0u : 3u * vb);
+        unsigned eb = 0, bb = 0, nb = 0;
+        if (precond) {
+            eb = ((d.nent + 7u) & ~7u) * 2u; bb = (((unsigned)d.ncn + 1u + 3u) & ~3u) * 4u; nb = (((unsigned)d.ncn + 3u) & ~3u) * 4u;
+            tot += rb + eb + bb + nb;
+        }
+        mbar_expect_tx(&s_full[s], tot);
+        const size_t base = (size_t)d.row0 * K;
+        bulk_g2s(st_r(s), r + base, vb, &s_full[s]);
+        if (!init) {
+            bulk_g2s(st_p(s), p + base, vb, &s_full[s]);
+            bulk_g2s(st_q(s), q + base, vb, &s_full[s]);
+            bulk_g2s(st_x(s), x + base, vb, &s_full[s]);
+        }
+        bulk_g2s(st_d(s), dinv32 + d.row0, rb, &s_full[s]);
+        if (precond) {
+            bulk_g2s(st_ri(s), rowinfo + d.row0, rb, &s_full[s]);
+            if (eb) bulk_g2s(st_ent(s), cn_ent + d.ent0, eb, &s_full[s]);
+            bulk_g2s(st_beg(s), cn_beg + d.cn0, bb, &s_full[s]);
+            if (nb) bulk_g2s(st_node(s), cn_node + d.cn0, nb, &s_full[s]);
+        }
+    };
+
+    // prologue: first two windows of this CTA
+    int w_cur = n_win, w_nxt = n_win;
+    WinDesc d_nxt;
+    d_nxt.n = -1;
+    if (wv == 0) {
+        w_cur = next_active_window(wt.win_active, (int)blockIdx.x, n_win, stride);
+        WinDesc d0;
+        d0.n = -1;
+        if (w_cur < n_win) d0 = desc[w_cur];
+        if (lane == 0) issue(0, w_cur, d0);
+        w_nxt = (w_cur < n_win && (long long)w_cur + stride < n_win) ? next_active_window(wt.win_active, w_cur + stride, n_win, stride) : n_win;
+        if (w_nxt < n_win) d_nxt = desc[w_nxt];
+    }
+    __syncthreads();
+    unsigned phase_bits = 0;
+    for (int stage = 0;; stage ^= 1) {
+        const int win = s_win[stage];
+        if (win >= n_win) break;
+        // next window's operands first
+        if (wv == 0 && lane == 0) issue(stage ^ 1, w_nxt, d_nxt);
+        const WinDesc d = s_desc[stage];
+        const int sys = d.sys, row0 = d.row0, n = d.n, ncn = d.ncn;
+        const double alpha = sc[((size_t)sys * 4 + k) * SC_N + SC_ALPHA];
+        mbar_wait(&s_full[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= 1u << stage;
+        double2* sr = st_r(stage);
+        double rr = 0.0, rdr = 0.0;
+        {
+            const double2* sp = st_p(stage); const double2* sq = st_q(stage); const double2* sx = st_x(stage);
+            const float4* sd = st_d(stage);
+            const size_t base = (size_t)row0 * K;
+            for (int e = tid; e < n * K; e += TPB) {
+                double2 rw = sr[e];
+                if (!init) {
+                    double2 xw = sx[e];
+                    const double2 pv = sp[e], qv = sq[e];
+                    xw.x += alpha * pv.x; xw.y += alpha * pv.y;
+                    rw.x -= alpha * qv.x; rw.y -= alpha * qv.y;
+                    x[base + e] = xw; r[base + e] = rw;
+                    sr[e] = rw;
+                }
+                const float4 dv = sd[e / K];
+                rr += rw.x * rw.x + rw.y * rw.y;
+                rdr += rw.x * ((double)dv.x * rw.x + (double)dv.y * rw.y) + rw.y * ((double)dv.z * rw.x + (double)dv.w * rw.y);
+            }
+        }
+        s_a[tid] = rr; s_b[tid] = rdr;
+        if (tid < 8) s_fin[tid] = 0.0;
+        __syncthreads();
+        // look for the window after next while the reductions run (consumed at the end of this iteration)
+        int w_after = n_win;
+        WinDesc d_after;
+        d_after.n = -1;
+        if (wv == 0 && w_nxt < n_win && (long long)w_nxt + stride < n_win) {
+            w_after = next_active_window(wt.win_active, w_nxt + stride, n_win, stride);
+            if (w_after < n_win) d_after = desc[w_after];
+        }
+        if (wv < 2 * K) {
+            const int kk = wv >> 1;
+            const double* src = (wv & 1) ? s_b : s_a;
+            double acc = 0.0;
+            for (int m = lane; m < TPB / K; m += 32) acc += src[kk + K * m];
+            acc = warp_sum(acc);
+            if (lane == 0) s_fin[wv] = acc;
+        }
+        if (precond) {
+            const RowInfo* sri = st_ri(stage);
+            const uint16_t* sent = st_ent(stage);
+            const unsigned* sbeg = st_beg(stage);
+            const int* snode = st_node(stage);
+            const unsigned ent0 = d.ent0;
+            constexpr int KT = (K == 2) ? 2 : 1;              // rhs per task
+            constexpr int TPN = K / KT;                       // tasks per node
+            for (int t = tid; t < ((ncn * TPN * 4 + 31) & ~31); t += TPB) {
+                const int task = t >> 2, sub = t & 3;
+                const int jn = task / TPN, k0 = (task % TPN) * KT;
+                double a[KT][2];
+#pragma unroll
+                for (int kk = 0; kk < KT; ++kk) { a[kk][0] = 0.0; a[kk][1] = 0.0; }
+                if (jn < ncn) {
+                    const unsigned b0 = sbeg[jn] - ent0, b1 = sbeg[jn + 1] - ent0;
+                    for (unsigned e = b0 + sub; e < b1; e += 4) {
+                        const int en = sent[e];
+                        const int rl = en >> 2, c = en & 3;
+                        const RowInfo ri = sri[rl];
+                        const double wgt = (double)((c & 1) ? ri.s : 1.0f - ri.s) * (double)((c & 2) ? ri.t : 1.0f - ri.t);
+#pragma unroll
+                        for (int kk = 0; kk < KT; ++kk) {
+                            const double2 v = sr[rl * K + k0 + kk];
+                            a[kk][0] += wgt * v.x; a[kk][1] += wgt * v.y;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        a[kk][c] += __shfl_xor_sync(0xffffffffu, a[kk][c], 1);
+                        a[kk][c] += __shfl_xor_sync(0xffffffffu, a[kk][c], 2);
+                    }
+                if (jn < ncn && sub == 0) {
+                    float* dd = rc1 + (((size_t)sys * G + snode[jn]) * K + k0) * 2;
+                    if (KT == 2) atomicAdd((float4*)dd, make_float4((float)a[0][0], (float)a[0][1], (float)a[KT - 1][0], (float)a[KT - 1][1]));
+                    else atomicAdd((float2*)dd, make_float2((float)a[0][0], (float)a[0][1]));
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 8) part[(size_t)win * 8 + tid] = s_fin[tid];    // [rhs][rr, r.Dinv r]; k_fin_update adds them per system
+        __syncthreads();        // the stage is free again; s_win / s_desc of the other stage are visible
+        w_nxt = w_after; d_nxt = d_after;
+    }
+}
