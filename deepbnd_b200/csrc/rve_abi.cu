@@ -286,14 +286,15 @@ template <int K>
 static void launch_update(rve_batch_s* h, const PcgArgs& a, int init, int iter, cudaStream_t st) {
     if (use_pipeline()) {
         const int cn_pad = ((h->max_cn + 3) & ~3) + 4;
-        const size_t sm = RVE_PIPE_STAGES * updp_stage_bytes(K, cn_pad, a.precond != 0);
+        const size_t sm = RVE_PIPE_STAGES(K) * updp_stage_bytes(K, cn_pad, a.precond != 0);
         int& per_sm = h->updp_blocks[K][a.precond ? 1 : 0];
         if (per_sm == 0) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_update_p<K>, RVE_UPDP_THREADS(K), sm);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_update_p<K>, RVE_UPDP_THREADS(K) + 32, sm);
             if (per_sm < 1) per_sm = 1;
+            if (std::getenv("RVE_DEBUG_TIMING")) fprintf(stderr, "[k_update_p<%d>] %d CTA(s) per SM, %zu bytes of dynamic shared memory\n", K, per_sm, sm);
         }
         const int grid = std::min(a.n_win, per_sm * h->n_sm);
-        k_update_p<K><<<grid, RVE_UPDP_THREADS(K), sm, st>>>(a.wt, h->win_desc.p, a.n_win, (const double2*)h->p.p, (const double2*)h->q.p,
+        k_update_p<K><<<grid, RVE_UPDP_THREADS(K) + 32, sm, st>>>(a.wt, h->win_desc.p, a.n_win, (const double2*)h->p.p, (const double2*)h->q.p,
                                                               (double2*)h->x.p, (double2*)h->r.p, h->dinv.p, h->rowinfo.p, h->cn_node.p,
                                                               h->cn_beg.p, h->cn_ent.p, a.LV.rc[0], a.LV.g[0].G, h->part.p, h->sc.p, init,
                                                               a.precond, cn_pad);

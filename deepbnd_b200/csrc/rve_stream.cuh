@@ -6,11 +6,13 @@
 // Here a CTA is persistent (grid = resident CTAs), walks the windows w = blockIdx.x, += gridDim.x and keeps the NEXT
 // window's operands in flight while it works on the current one:
 //
-//   producer = lane 0 of warp 0: one 32-byte WinDesc load, then cp.async.bulk (UBLKCP, the 1-D TMA path) of the
-//   contiguous per-window pieces r, p, q, x, dinv, rowinfo, restriction lists into a 2-stage shared-memory ring,
-//   completion counted in bytes by an mbarrier per stage;
-//   consumers = all threads: mbarrier wait, elementwise update out of shared memory, coalesced stores of x and r,
-//   the new residual stays in the stage for the restriction.
+//   producer = one extra warp (warp specialisation): finds the CTA's next active window (32 candidates per ballot), loads
+//   its 32-byte WinDesc, waits for the stage to be released ("empty" mbarrier) and issues cp.async.bulk (UBLKCP, the
+//   1-D TMA path) of the contiguous per-window pieces r, p, q, x, dinv, rowinfo, restriction lists into a 2-stage
+//   shared-memory ring, completion counted in bytes by the "full" mbarrier of the stage;
+//   consumers = the other warps: mbarrier wait, elementwise update out of shared memory, coalesced stores of x and
+//   r, the new residual stays in the stage for the restriction; they synchronise among themselves on a named barrier
+//   (the producer never joins), so issuing copies is never on their critical path.
 //
 // No register staging, no per-thread address arithmetic for the loads, and the copy engine keeps HBM busy during the
 // reduction phases.
@@ -45,6 +47,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 }
 // order generic-proxy accesses of shared memory before the async proxy overwrites it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among the consumer warps only (id 1; the producer warp never joins)
+__device__ __forceinline__ void consumer_sync(int nthreads) { asm volatile("bar.sync 1, %0;\n" ::"r"(nthreads) : "memory"); }
 
 // first active window at or after w in the sequence w, w+stride, ... (whole warp; returns n_win when there is none)
 __device__ __forceinline__ int next_active_window(const unsigned char* __restrict__ act, int w, int n_win, int stride) {
@@ -60,7 +67,12 @@ __device__ __forceinline__ int next_active_window(const unsigned char* __restric
     return n_win;
 }
 
-#define RVE_PIPE_STAGES 2
+// stages of the shared-memory ring (measured): K <= 2: two stages and two CTAs per SM; K = 3: three stages, one CTA per SM
+#define RVE_PIPE_STAGES(K) ((K) == 3 ? 3 : 2)
+#define RVE_UPDP_MINB(K) ((K) == 3 ? 1 : 2)
+#ifndef RVE_RESTRICT_SUB
+#define RVE_RESTRICT_SUB 2      // threads sharing the (row, corner) list of one level-1 node in the restriction (2 or 4)
+#endif
 #define RVE_UPDP_THREADS(K) ((K) == 3 ? 384 : 256)
 
 // shared-memory footprint of one stage (bytes); cn_pad = level-1 nodes per window rounded up to 4, + 4
@@ -71,22 +83,23 @@ __host__ __device__ inline size_t updp_stage_bytes(int K, int cn_pad, bool preco
 }
 
 // x += alpha p ; r -= alpha q ; per-window partials of r.r and r.Dinv r ; rc += Z^T r.
-// Same arithmetic as k_update (rve_kernels.cuh), persistent + bulk-copy pipelined.
+// Same arithmetic as k_update (rve_kernels.cuh), persistent + bulk-copy pipelined; launch with RVE_UPDP_THREADS(K) + 32 threads.
 template <int K>
-__global__ void __launch_bounds__(RVE_UPDP_THREADS(K), 1)
+__global__ void __launch_bounds__(RVE_UPDP_THREADS(K) + 32, RVE_UPDP_MINB(K))
 k_update_p(WinTab wt, const WinDesc* __restrict__ desc, int n_win, const double2* __restrict__ p, const double2* __restrict__ q,
            double2* __restrict__ x, double2* __restrict__ r, const float4* __restrict__ dinv32, const RowInfo* __restrict__ rowinfo,
            const int* __restrict__ cn_node, const unsigned* __restrict__ cn_beg, const uint16_t* __restrict__ cn_ent,
            float* __restrict__ rc1, int G, double* __restrict__ part, const double* __restrict__ sc, int init, int precond, int cn_pad) {
     extern __shared__ __align__(128) unsigned char s_raw[];
-    constexpr int TPB = RVE_UPDP_THREADS(K);
-    __shared__ __align__(8) uint64_t s_full[RVE_PIPE_STAGES];
-    __shared__ WinDesc s_desc[RVE_PIPE_STAGES];
-    __shared__ int s_win[RVE_PIPE_STAGES];
+    constexpr int TPB = RVE_UPDP_THREADS(K);              // consumer threads
+    constexpr int NST = RVE_PIPE_STAGES(K);
+    __shared__ __align__(8) uint64_t s_full[NST], s_empty[NST];
+    __shared__ WinDesc s_desc[NST];
+    __shared__ int s_win[NST];
+    __shared__ double s_alpha[NST][4];
     __shared__ double s_a[TPB], s_b[TPB];
     __shared__ double s_fin[8];
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
-    const int k = tid % K;
     const size_t stage_bytes = updp_stage_bytes(K, cn_pad, precond != 0);
     const int stride = (int)gridDim.x;
 
@@ -102,66 +115,72 @@ k_update_p(WinTab wt, const WinDesc* __restrict__ desc, int n_win, const double2
     auto st_node = [&](int s) { return (int*)(st_beg(s) + cn_pad); };
 
     if (tid == 0) {
-        for (int s = 0; s < RVE_PIPE_STAGES; ++s) mbar_init(&s_full[s], 1);
+        for (int s = 0; s < NST; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
         mbar_fence_init();
     }
     __syncthreads();
 
-    // producer (lane 0 of warp 0): descriptor of window w -> bulk copies into stage s
-    auto issue = [&](int s, int w, const WinDesc& d) {
-        s_win[s] = w;
-        s_desc[s] = d;
-        if (w >= n_win) return;
-        fence_proxy_async();
-        const unsigned vb = (unsigned)d.n * K * 16, rb = (unsigned)d.n * 16;
-        unsigned tot = vb + rb + (init ? 0u : 3u * vb);
-        unsigned eb = 0, bb = 0, nb = 0;
-        if (precond) {
-            eb = ((d.nent + 7u) & ~7u) * 2u; bb = (((unsigned)d.ncn + 1u + 3u) & ~3u) * 4u; nb = (((unsigned)d.ncn + 3u) & ~3u) * 4u;
-            tot += rb + eb + bb + nb;
+    if (wv == TPB / 32) {
+        // ---------------- producer warp ----------------
+        int w = (int)blockIdx.x;
+        for (int it = 0;; ++it) {
+            const int s = it % NST;
+            w = (w < n_win) ? next_active_window(wt.win_active, w, n_win, stride) : n_win;
+            WinDesc d;
+            d.n = -1;
+            if (w < n_win) d = desc[w];
+            double al = 0.0;                                 // alpha of the window's system: read here, off the consumers' critical path
+            if (w < n_win && lane < K) al = sc[((size_t)d.sys * 4 + lane) * SC_N + SC_ALPHA];
+            if (it >= NST) mbar_wait(&s_empty[s], ((it / NST) - 1) & 1);
+            if (lane < K) s_alpha[s][lane] = al;
+            __syncwarp();
+            if (lane == 0) {
+                s_win[s] = w;
+                s_desc[s] = d;
+                if (w >= n_win) {
+                    mbar_arrive(&s_full[s]);                 // end marker: consumers wake up and leave
+                } else {
+                    fence_proxy_async();
+                    const unsigned vb = (unsigned)d.n * K * 16, rb = (unsigned)d.n * 16;
+                    unsigned tot = vb + rb + (init ? 0u : 3u * vb);
+                    unsigned eb = 0, bb = 0, nb = 0;
+                    if (precond) {
+                        eb = ((d.nent + 7u) & ~7u) * 2u; bb = (((unsigned)d.ncn + 1u + 3u) & ~3u) * 4u; nb = (((unsigned)d.ncn + 3u) & ~3u) * 4u;
+                        tot += rb + eb + bb + nb;
+                    }
+                    mbar_expect_tx(&s_full[s], tot);
+                    const size_t base = (size_t)d.row0 * K;
+                    bulk_g2s(st_r(s), r + base, vb, &s_full[s]);
+                    if (!init) {
+                        bulk_g2s(st_p(s), p + base, vb, &s_full[s]);
+                        bulk_g2s(st_q(s), q + base, vb, &s_full[s]);
+                        bulk_g2s(st_x(s), x + base, vb, &s_full[s]);
+                    }
+                    bulk_g2s(st_d(s), dinv32 + d.row0, rb, &s_full[s]);
+                    if (precond) {
+                        bulk_g2s(st_ri(s), rowinfo + d.row0, rb, &s_full[s]);
+                        if (eb) bulk_g2s(st_ent(s), cn_ent + d.ent0, eb, &s_full[s]);
+                        bulk_g2s(st_beg(s), cn_beg + d.cn0, bb, &s_full[s]);
+                        if (nb) bulk_g2s(st_node(s), cn_node + d.cn0, nb, &s_full[s]);
+                    }
+                }
+            }
+            if (w >= n_win) break;
+            w += stride;
         }
-        mbar_expect_tx(&s_full[s], tot);
-        const size_t base = (size_t)d.row0 * K;
-        bulk_g2s(st_r(s), r + base, vb, &s_full[s]);
-        if (!init) {
-            bulk_g2s(st_p(s), p + base, vb, &s_full[s]);
-            bulk_g2s(st_q(s), q + base, vb, &s_full[s]);
-            bulk_g2s(st_x(s), x + base, vb, &s_full[s]);
-        }
-        bulk_g2s(st_d(s), dinv32 + d.row0, rb, &s_full[s]);
-        if (precond) {
-            bulk_g2s(st_ri(s), rowinfo + d.row0, rb, &s_full[s]);
-            if (eb) bulk_g2s(st_ent(s), cn_ent + d.ent0, eb, &s_full[s]);
-            bulk_g2s(st_beg(s), cn_beg + d.cn0, bb, &s_full[s]);
-            if (nb) bulk_g2s(st_node(s), cn_node + d.cn0, nb, &s_full[s]);
-        }
-    };
-
-    // prologue: first two windows of this CTA
-    int w_cur = n_win, w_nxt = n_win;
-    WinDesc d_nxt;
-    d_nxt.n = -1;
-    if (wv == 0) {
-        w_cur = next_active_window(wt.win_active, (int)blockIdx.x, n_win, stride);
-        WinDesc d0;
-        d0.n = -1;
-        if (w_cur < n_win) d0 = desc[w_cur];
-        if (lane == 0) issue(0, w_cur, d0);
-        w_nxt = (w_cur < n_win && (long long)w_cur + stride < n_win) ? next_active_window(wt.win_active, w_cur + stride, n_win, stride) : n_win;
-        if (w_nxt < n_win) d_nxt = desc[w_nxt];
+        return;
     }
-    __syncthreads();
-    unsigned phase_bits = 0;
-    for (int stage = 0;; stage ^= 1) {
+
+    // ---------------- consumer warps ----------------
+    const int k = tid % K;
+    for (int it = 0;; ++it) {
+        const int stage = it % NST;
+        mbar_wait(&s_full[stage], (it / NST) & 1);
         const int win = s_win[stage];
         if (win >= n_win) break;
-        // next window's operands first
-        if (wv == 0 && lane == 0) issue(stage ^ 1, w_nxt, d_nxt);
         const WinDesc d = s_desc[stage];
         const int sys = d.sys, row0 = d.row0, n = d.n, ncn = d.ncn;
-        const double alpha = sc[((size_t)sys * 4 + k) * SC_N + SC_ALPHA];
-        mbar_wait(&s_full[stage], (phase_bits >> stage) & 1u);
-        phase_bits ^= 1u << stage;
+        const double alpha = s_alpha[stage][k];
         double2* sr = st_r(stage);
         double rr = 0.0, rdr = 0.0;
         {
@@ -185,15 +204,7 @@ k_update_p(WinTab wt, const WinDesc* __restrict__ desc, int n_win, const double2
         }
         s_a[tid] = rr; s_b[tid] = rdr;
         if (tid < 8) s_fin[tid] = 0.0;
-        __syncthreads();
-        // look for the window after next while the reductions run (consumed at the end of this iteration)
-        int w_after = n_win;
-        WinDesc d_after;
-        d_after.n = -1;
-        if (wv == 0 && w_nxt < n_win && (long long)w_nxt + stride < n_win) {
-            w_after = next_active_window(wt.win_active, w_nxt + stride, n_win, stride);
-            if (w_after < n_win) d_after = desc[w_after];
-        }
+        consumer_sync(TPB);
         if (wv < 2 * K) {
             const int kk = wv >> 1;
             const double* src = (wv & 1) ? s_b : s_a;
@@ -210,15 +221,15 @@ k_update_p(WinTab wt, const WinDesc* __restrict__ desc, int n_win, const double2
             const unsigned ent0 = d.ent0;
             constexpr int KT = (K == 2) ? 2 : 1;              // rhs per task
             constexpr int TPN = K / KT;                       // tasks per node
-            for (int t = tid; t < ((ncn * TPN * 4 + 31) & ~31); t += TPB) {
-                const int task = t >> 2, sub = t & 3;
+            for (int t = tid; t < ((ncn * TPN * RVE_RESTRICT_SUB + 31) & ~31); t += TPB) {
+                const int task = t / RVE_RESTRICT_SUB, sub = t % RVE_RESTRICT_SUB;
                 const int jn = task / TPN, k0 = (task % TPN) * KT;
                 double a[KT][2];
 #pragma unroll
                 for (int kk = 0; kk < KT; ++kk) { a[kk][0] = 0.0; a[kk][1] = 0.0; }
                 if (jn < ncn) {
                     const unsigned b0 = sbeg[jn] - ent0, b1 = sbeg[jn + 1] - ent0;
-                    for (unsigned e = b0 + sub; e < b1; e += 4) {
+                    for (unsigned e = b0 + sub; e < b1; e += RVE_RESTRICT_SUB) {
                         const int en = sent[e];
                         const int rl = en >> 2, c = en & 3;
                         const RowInfo ri = sri[rl];
@@ -235,7 +246,7 @@ k_update_p(WinTab wt, const WinDesc* __restrict__ desc, int n_win, const double2
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         a[kk][c] += __shfl_xor_sync(0xffffffffu, a[kk][c], 1);
-                        a[kk][c] += __shfl_xor_sync(0xffffffffu, a[kk][c], 2);
+                        if (RVE_RESTRICT_SUB == 4) a[kk][c] += __shfl_xor_sync(0xffffffffu, a[kk][c], 2);
                     }
                 if (jn < ncn && sub == 0) {
                     float* dd = rc1 + (((size_t)sys * G + snode[jn]) * K + k0) * 2;
@@ -244,9 +255,8 @@ k_update_p(WinTab wt, const WinDesc* __restrict__ desc, int n_win, const double2
                 }
             }
         }
-        __syncthreads();
+        consumer_sync(TPB);                                   // the stage has been read for the last time
+        if (tid == 0) mbar_arrive(&s_empty[stage]);
         if (tid < 8) part[(size_t)win * 8 + tid] = s_fin[tid];    // [rhs][rr, r.Dinv r]; k_fin_update adds them per system
-        __syncthreads();        // the stage is free again; s_win / s_desc of the other stage are visible
-        w_nxt = w_after; d_nxt = d_after;
     }
 }
