@@ -122,6 +122,7 @@ struct rve_batch_s {
     int max_words = 0;
     DBuf<RowInfo> rowinfo;
     DBuf<WinDesc> win_desc;
+    DBuf<double> win_scal;             // [n_win][8] alpha / beta of the window's system (written by the k_fin_* kernels)
     DBuf<double> lvA[RVE_MAXLEV], lvD[RVE_MAXLEV];
     DBuf<float> lvR[RVE_MAXLEV], lvX[RVE_MAXLEV], lvT[RVE_MAXLEV];   // V-cycle vectors (fp32)
     DBuf<stv> lvA4[RVE_MAXLEV], lvH4[RVE_MAXLEV];
@@ -130,7 +131,8 @@ struct rve_batch_s {
     DBuf<double> MWt, transl, Yd, gradT;
     int opt_sym_B = 0;
     int n_sm = 148;
-    int updp_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};   // resident CTAs per SM of k_update_p<K> (by precond), 0 = not asked yet
+    int updp_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    int dirp_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};   // resident CTAs per SM of k_update_p<K> (by precond), 0 = not asked yet
     // matrix-free operator (rve_matfree.cuh): window-element tables; the SELL values (bval) are built on demand only
     int opt_operator = RVE_OPERATOR_MATFREE;
     bool have_bval = false;
@@ -247,6 +249,7 @@ static cudaError_t raise_smem_limits(int device) {
     RAISE_(k_sym_window); RAISE_(k_sym_coarse); RAISE_(k_sym_elems);
     RAISE_(k_apply<1>); RAISE_(k_apply<2>); RAISE_(k_apply<3>);
     RAISE_(k_update_p<1>); RAISE_(k_update_p<2>); RAISE_(k_update_p<3>);
+    RAISE_(k_direction_p<1>); RAISE_(k_direction_p<2>); RAISE_(k_direction_p<3>);
 #undef RAISE_
     return cudaSuccess;
 }
@@ -273,7 +276,7 @@ static void launch_spmv(rve_batch_s* h, const PcgArgs& a, const double* p, doubl
                                                                    h->max_slots, part);
     else
         k_spmv<K><<<a.n_win, RVE_SPMV_THREADS, a.sm_spmv, st>>>(a.wt, a.sl, (const double2*)h->bval.p, (const double2*)p, (double2*)q, part);
-    k_fin_alpha<<<cdiv(a.n_sys, 8), 256, 0, st>>>(a.n_sys, K, a.wt.sys_win0, part, active, sc);
+    k_fin_alpha<<<cdiv(a.n_sys, 8), 256, 0, st>>>(a.n_sys, K, a.wt.sys_win0, part, active, sc, h->win_scal.p);
 }
 
 // persistent bulk-copy-pipelined vector kernels (rve_stream.cuh); RVE_PIPELINE=0 selects the one-window-per-CTA kernels
@@ -296,7 +299,7 @@ static void launch_update(rve_batch_s* h, const PcgArgs& a, int init, int iter, 
         const int grid = std::min(a.n_win, per_sm * h->n_sm);
         k_update_p<K><<<grid, RVE_UPDP_THREADS(K) + 32, sm, st>>>(a.wt, h->win_desc.p, a.n_win, (const double2*)h->p.p, (const double2*)h->q.p,
                                                               (double2*)h->x.p, (double2*)h->r.p, h->dinv.p, h->rowinfo.p, h->cn_node.p,
-                                                              h->cn_beg.p, h->cn_ent.p, a.LV.rc[0], a.LV.g[0].G, h->part.p, h->sc.p, init,
+                                                              h->cn_beg.p, h->cn_ent.p, a.LV.rc[0], a.LV.g[0].G, h->part.p, h->win_scal.p, init,
                                                               a.precond, cn_pad);
     } else {
         k_update<K><<<a.n_win, RVE_UPD_THREADS(K), a.sm_upd, st>>>(a.wt, (const double2*)h->p.p, (const double2*)h->q.p, (double2*)h->x.p,
@@ -304,7 +307,7 @@ static void launch_update(rve_batch_s* h, const PcgArgs& a, int init, int iter, 
                                                                    h->cn_ent.p, a.LV.rc[0], a.LV.g[0].G, h->part.p, h->sc.p, init, a.precond);
     }
     k_fin_update<<<cdiv(a.n_sys, 8), 256, 0, st>>>(a.n_sys, K, a.wt.sys_win0, h->part.p, h->active.p, a.wt.win_active, h->sc.p, init, iter,
-                                                   a.rtol2, a.precond, h->d_iters.p, h->n_active.p);
+                                                   a.rtol2, a.precond, h->d_iters.p, h->n_active.p, h->win_scal.p);
 }
 
 // coarse V-cycle: the large levels (always level 1) as grid-wide kernels (thread per coarse node), the small
@@ -333,12 +336,27 @@ static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStrea
     }
     k_vc_up1<K><<<grid(0), 256, 0, st>>>(LV, h->active.p, h->cpart.p);
     const int nb = (LV.g[0].G + 255) / 256;
-    k_fin_beta<<<cdiv(a.n_sys, 8), 256, 0, st>>>(a.n_sys, K, nb, h->cpart.p, h->active.p, h->sc.p, first);
+    k_fin_beta<<<cdiv(a.n_sys, 8), 256, 0, st>>>(a.n_sys, K, nb, a.wt.sys_win0, h->cpart.p, h->active.p, h->sc.p, first, h->win_scal.p);
     h->launches += nk + 1;
 }
 
 template <int K>
 static void launch_direction(rve_batch_s* h, const PcgArgs& a, cudaStream_t st) {
+    if (use_pipeline()) {
+        const int cn_pad = ((h->max_cn + 3) & ~3) + 4;
+        const size_t sm = RVE_DIRP_STAGES * dirp_stage_bytes(K, cn_pad, a.precond != 0);
+        int& per_sm = h->dirp_blocks[K][a.precond ? 1 : 0];
+        if (per_sm == 0) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_direction_p<K>, RVE_UPDP_THREADS(K) + 32, sm);
+            if (per_sm < 1) per_sm = 1;
+            if (std::getenv("RVE_DEBUG_TIMING")) fprintf(stderr, "[k_direction_p<%d>] %d CTA(s) per SM, %zu bytes of dynamic shared memory\n", K, per_sm, sm);
+        }
+        const int grid = std::min(a.n_win, per_sm * h->n_sm);
+        k_direction_p<K><<<grid, RVE_UPDP_THREADS(K) + 32, sm, st>>>(a.wt, h->win_desc.p, a.n_win, (double2*)h->p.p, (const double2*)h->r.p,
+                                                                      h->dinv.p, h->rowinfo.p, h->cn_node.p, (const cvec*)a.LV.tc[0],
+                                                                      a.LV.g[0].G, h->win_scal.p, a.precond, cn_pad);
+        return;
+    }
     k_direction<K><<<a.n_win, RVE_DIR_THREADS(K), a.sm_dir, st>>>(a.wt, (double2*)h->p.p, (const double2*)h->r.p, h->dinv.p, h->rowinfo.p,
                                                       h->cn_node.p, (const cvec*)a.LV.tc[0], a.LV.g[0].G, h->active.p,
                                                       h->sc.p, a.precond);
@@ -633,7 +651,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     CU(cudaMemsetAsync(h->sym_cnt.p, 0, 8 * sizeof(int), st));
     const long long cn_cap = h->R + 5LL * n_win + 4096;      // level-1 nodes touched per window are far fewer than its rows
     CU(h->win_cn0.alloc(n_win)); CU(h->win_ncn.alloc(n_win)); CU(h->win_active.alloc(n_win)); CU(h->cn_node.alloc((size_t)cn_cap)); CU(h->cn_beg.alloc((size_t)cn_cap));
-    CU(h->cn_ent.alloc(4 * (size_t)h->R + 8 * (size_t)n_win + 64)); CU(h->rowinfo.alloc((size_t)h->R)); CU(h->win_desc.alloc((size_t)n_win));
+    CU(h->cn_ent.alloc(4 * (size_t)h->R + 8 * (size_t)n_win + 64)); CU(h->rowinfo.alloc((size_t)h->R)); CU(h->win_desc.alloc((size_t)n_win)); CU(h->win_scal.alloc(8 * (size_t)n_win));
     {
         WinTab wt = win_tab(h);
         k_sym_cols<<<n_win, RVE_WIN, 0, st>>>(wt, h->d_row_ptr.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->node_row.p,

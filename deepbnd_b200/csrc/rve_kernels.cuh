@@ -1346,17 +1346,18 @@ __device__ __forceinline__ double sys_sum(const double* __restrict__ v, int firs
 // alpha = r.z / p.q after the operator application
 __global__ void __launch_bounds__(256)
 k_fin_alpha(int n_sys, int K, const int* __restrict__ sys_win0, const double* __restrict__ part, const int* __restrict__ active,
-            double* __restrict__ sc) {
+            double* __restrict__ sc, double* __restrict__ win_scal) {
     const int sys = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (sys >= n_sys || !active[sys]) return;
+    const int lane = threadIdx.x & 31;
     const int w0 = sys_win0[sys], w1 = sys_win0[sys + 1];
     for (int k = 0; k < K; ++k) {
         const double pq = sys_sum(part, w0, w1, 4, k);
-        if ((threadIdx.x & 31) == 0) {
-            double* s_ = sc + ((size_t)sys * 4 + k) * SC_N;
-            s_[SC_PQ] = pq;
-            s_[SC_ALPHA] = (pq > 0.0) ? s_[SC_RZ] / pq : 0.0;
-        }
+        double* s_ = sc + ((size_t)sys * 4 + k) * SC_N;
+        const double alpha = (pq > 0.0) ? s_[SC_RZ] / pq : 0.0;
+        if (lane == 0) { s_[SC_PQ] = pq; s_[SC_ALPHA] = alpha; }
+        // per-window copy ([window][8]: alpha[0..3], beta[4..7]): the persistent kernels read it next to the descriptor
+        for (int w = w0 + lane; w < w1; w += 32) win_scal[(size_t)w * 8 + k] = alpha;
     }
 }
 
@@ -1364,7 +1365,7 @@ k_fin_alpha(int n_sys, int K, const int* __restrict__ sys_win0, const double* __
 __global__ void __launch_bounds__(256)
 k_fin_update(int n_sys, int K, const int* __restrict__ sys_win0, const double* __restrict__ part, int* __restrict__ active,
              unsigned char* __restrict__ win_active, double* __restrict__ sc, int init, int iter, double rtol2, int precond,
-             int* __restrict__ iters, int* n_active) {
+             int* __restrict__ iters, int* n_active, double* __restrict__ win_scal) {
     const int sys = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (sys >= n_sys || !active[sys]) return;
     const int lane = threadIdx.x & 31;
@@ -1375,15 +1376,16 @@ k_fin_update(int n_sys, int K, const int* __restrict__ sys_win0, const double* _
         double* s = sc + ((size_t)sys * 4 + k) * SC_N;
         const double bb = init ? vrr : s[SC_BB];
         if (!(vrr <= rtol2 * bb || vrr <= 1e-28 * s[SC_BREF])) done = false;
+        if (precond == 0) {  // block Jacobi: z = Dinv r, finish the scalar recurrences here
+            const double rzold = s[SC_RZ];
+            const double beta = (!init && rzold > 0.0) ? vrdr / rzold : 0.0;
+            __syncwarp();
+            if (lane == 0) { s[SC_RZOLD] = rzold; s[SC_RZ] = vrdr; s[SC_BETA] = beta; }
+            for (int w = w0 + lane; w < w1; w += 32) win_scal[(size_t)w * 8 + 4 + k] = beta;
+        }
         if (lane == 0) {
             if (init) s[SC_BB] = vrr;
             s[SC_RR] = vrr; s[SC_RDR] = vrdr;
-            if (precond == 0) {  // block Jacobi: z = Dinv r, finish the scalar recurrences here
-                const double rzold = s[SC_RZ];
-                s[SC_RZOLD] = rzold;
-                s[SC_RZ] = vrdr;
-                s[SC_BETA] = (!init && rzold > 0.0) ? vrdr / rzold : 0.0;
-            }
         }
     }
     if (!done) return;
@@ -1397,20 +1399,21 @@ k_fin_update(int n_sys, int K, const int* __restrict__ sys_win0, const double* _
 
 // r.z = r.Dinv r + rc.z1 after the V-cycle; beta
 __global__ void __launch_bounds__(256)
-k_fin_beta(int n_sys, int K, int nb, const double* __restrict__ cpart, const int* __restrict__ active, double* __restrict__ sc,
-           int first) {
+k_fin_beta(int n_sys, int K, int nb, const int* __restrict__ sys_win0, const double* __restrict__ cpart,
+           const int* __restrict__ active, double* __restrict__ sc, int first, double* __restrict__ win_scal) {
     const int sys = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (sys >= n_sys || !active[sys]) return;
+    const int lane = threadIdx.x & 31;
+    const int w0 = sys_win0[sys], w1 = sys_win0[sys + 1];
     for (int k = 0; k < K; ++k) {
         const double cz = sys_sum(cpart, sys * nb, sys * nb + nb, 4, k);
-        if ((threadIdx.x & 31) == 0) {
-            double* s = sc + ((size_t)sys * 4 + k) * SC_N;
-            const double rz = s[SC_RDR] + cz;
-            const double rzold = s[SC_RZ];
-            s[SC_RZOLD] = rzold;
-            s[SC_RZ] = rz;
-            s[SC_BETA] = (!first && rzold > 0.0) ? rz / rzold : 0.0;
-        }
+        double* s = sc + ((size_t)sys * 4 + k) * SC_N;
+        const double rz = s[SC_RDR] + cz;
+        const double rzold = s[SC_RZ];
+        const double beta = (!first && rzold > 0.0) ? rz / rzold : 0.0;
+        __syncwarp();
+        if (lane == 0) { s[SC_RZOLD] = rzold; s[SC_RZ] = rz; s[SC_BETA] = beta; }
+        for (int w = w0 + lane; w < w1; w += 32) win_scal[(size_t)w * 8 + 4 + k] = beta;
     }
 }
 
