@@ -2,20 +2,24 @@
 """bench.py — RVE solves/sec of the batched B200 path (and of the CPU reference arm).
 
 Contract (task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
-A "step" is one pass of the hot path (assemble -> multi-RHS PCG -> constraint post-processing ->
+A "step" is one pass of the hot path (preconditioner set-up -> multi-RHS PCG -> constraint post-processing ->
 fused epilogues [-> RB projection]) over one batch of synthetic RVEs.  Default workload = BASELINE.json
 configs[1] ("C2"): 1k extended 6x6 ('full') RVEs, periodic model, loads S and A, internal-boundary
 DOF extraction + projection onto a (synthetic, orthonormal) Wbasis.
 
   value : whole-job RVE solves/s with the batch already resident in HBM (device-resident loop)
-  e2e   : same metric through the C-ABI with HOST mesh buffers: symbolic phase, H2D of the batch,
+  e2e   : same metric through the C-ABI with HOST mesh buffers: H2D of the raw meshes, GPU symbolic phase,
           device work, D2H of every output inside the timed region
-  roofline : the SpMV kernel (k_spmv_dot) — algorithmic CSR bytes B_spmv(k) / CUDA-event time of the
-          launches inside the timed PCG loops, against MEASURED_PEAKS.json hbm_gbs
+  roofline : the operator application q = A p inside the PCG (k_apply, matrix-free; k_spmv with
+          --operator assembled) — algorithmic CSR bytes B_spmv(k) of SURVEY 8d / CUDA-event time of its launches
+          inside the timed solves, against MEASURED_PEAKS.json hbm_gbs.  `roofline.spmv_assembled` is the stored
+          SELL-32 SpMV kernel timed alone in the same run (rve_bench_spmv).
   cpu_baseline : the CPU oracle (scipy sparse LU restatement of the reference path) timed on the
           host cores, rank-strided worker processes like the reference's MPI launch
+  extra_workloads : the other BASELINE configs (C3 dnn 10k, C4 lin, C2 MR) measured in the same run with fewer
+          steps (N = 1 only; --no-extra skips them)
 
-`--impl reference` times only that CPU arm.  Multi-GPU (torchrun): RVEs shard by rank, no data-path
+`--impl reference` times only the CPU arm.  Multi-GPU (torchrun): RVEs shard by rank, no data-path
 collective, one final gather of the per-RVE outputs ("weak" scaling: per-GPU batch fixed).
 """
 import argparse
@@ -34,14 +38,19 @@ sys.path.insert(0, ROOT)
 
 PARAM_MAT = (0.3, 10.0, 0.3, 1.0)           # simulation_snapshots.py:120-123
 WORKLOADS = {
-    # name: (ns per GPU, mesh size, model, loads (Voigt ids), project?)
+    # name: RVEs per GPU, mesh size, model, loads (Voigt ids), project?, [lcar, mesher, e2e chunk size]
     "C2_snapshots_1k_full_per": dict(ns=1000, size="full", model="per", loads=(2, 0), project=True),
     "C2_snapshots_1k_full_MR": dict(ns=1000, size="full", model="MR", loads=(2, 0), project=True),
     "C3_tangents_10k_reduced_dnn": dict(ns=10000, size="reduced", model="dnn", loads=(0, 1, 2), project=False),
     "C4_tangents_10k_reduced_per": dict(ns=10000, size="reduced", model="per", loads=(0, 1, 2), project=False),
     "C4_tangents_10k_reduced_lin": dict(ns=10000, size="reduced", model="lin", loads=(0, 1, 2), project=False),
     "C4_tangents_10k_reduced_MR": dict(ns=10000, size="reduced", model="MR", loads=(0, 1, 2), project=False),
+    # BASELINE config 5 per GPU: "refined" = lcar 1/30 (4x the DOFs of C2), meshes morphed from one template,
+    # streamed through the two handles in device-sized chunks
+    "C5_snapshots_refined_per": dict(ns=512, size="full", model="per", loads=(2, 0), project=True, lcar=1.0 / 30.0,
+                                     mesher="morph", chunk=128),
 }
+EXTRA = {"C3_tangents_10k_reduced_dnn": 10000, "C4_tangents_10k_reduced_lin": 4000, "C2_snapshots_1k_full_MR": 1000}
 
 
 def _mesh_worker(args):
@@ -50,7 +59,11 @@ def _mesh_worker(args):
     return buildRVEmesh_arrays(row.copy(), size=size, lcar=lcar)
 
 
-def make_meshes(param, size, lcar, nproc):
+def make_meshes(param, size, lcar, nproc, mesher="delaunay"):
+    if mesher == "morph":                           # one template, every RVE morphed from it (rve_morph.py)
+        from deepbnd_b200.mesh.rve_morph import MorphTemplate, buildRVEmesh_morphed
+        tpl = MorphTemplate(param[0], size=size, lcar=lcar)
+        return [buildRVEmesh_morphed(param[i].copy(), tpl) for i in range(len(param))]
     jobs = [(param[i], size, lcar) for i in range(len(param))]
     if nproc <= 1 or len(jobs) < 4:
         return [_mesh_worker(j) for j in jobs]
@@ -140,7 +153,6 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if sm:
-            # median of the samples under load (top half)
             srt = sorted(sm)
             out["sm_mhz"] = srt[len(srt) // 2]
             out["sm_max_mhz"] = max(smax)
@@ -150,6 +162,138 @@ class ClockSampler:
         except OSError:
             pass
         return out
+
+
+def synthetic_inputs(wl, ns, nuniq, rank, lcar, nproc):
+    """meshes (at most `nuniq` distinct ones, cycled to ns — every copy is set up and solved as an independent
+    system), macro strains, Dirichlet data, projection basis of one workload"""
+    from deepbnd_b200.synthetic import synthetic_param, smooth_uD
+    from deepbnd_b200.elasticity import macro_strain_voigt
+    param = synthetic_param(nuniq, seed=2 + 1000 * rank)
+    t0 = time.perf_counter()
+    meshes = make_meshes(param, wl["size"], lcar, nproc, wl.get("mesher", "delaunay"))
+    meshes = [meshes[i % nuniq] for i in range(ns)]
+    t_mesh = time.perf_counter() - t0
+    nl = len(wl["loads"])
+    uD = None
+    if wl["model"] == "dnn":
+        rng = np.random.RandomState(5 + rank)
+        base = np.stack([smooth_uD(81, 17 + i) for i in range(3)])
+        uD = base[None] * (1.0 + 0.1 * rng.randn(ns, 1, 1))
+    eps = np.broadcast_to(np.stack([macro_strain_voigt(i) for i in wl["loads"]]), (ns, nl, 3)).copy()
+    W = M = None
+    if wl["project"]:
+        rng = np.random.RandomState(0)
+        Wq = np.linalg.qr(rng.randn(162, 160))[0].T                   # synthetic orthonormal basis (160,162)
+        W = np.stack([Wq] * nl)
+        n = 80
+        M = np.zeros((162, 162))
+        for k in range(n):                                             # boundary mass of Vref (h = 0.1)
+            k2 = (k + 1) % n
+            for c in range(2):
+                M[2 * k + c, 2 * k + c] += 0.1 / 3; M[2 * k2 + c, 2 * k2 + c] += 0.1 / 3
+                M[2 * k + c, 2 * k2 + c] += 0.1 / 6; M[2 * k2 + c, 2 * k + c] += 0.1 / 6
+    return dict(meshes=meshes, flat=flatten(meshes), eps=eps, uD=uD, W=W, M=M, t_mesh=t_mesh, nl=nl)
+
+
+class Runner:
+    """device-resident and end-to-end passes of one workload on the two handles of this rank"""
+
+    def __init__(self, hb, pool, wl, inp, args, barrier):
+        self.hb, self.pool, self.wl, self.inp, self.args, self.barrier = hb, pool, wl, inp, args, barrier
+        self.ns = len(inp["meshes"])
+        voff, toff, xy, tri, reg = inp["flat"]
+        csz = wl.get("chunk", 0)
+        nchunk = max(1, -(-self.ns // csz)) if csz else max(1, min(args.chunks, self.ns // 64))
+        cb = [self.ns * c // nchunk for c in range(nchunk + 1)]
+        self.chunks = [(voff[a:z + 1] - voff[a], toff[a:z + 1] - toff[a], xy[voff[a]:voff[z]], tri[toff[a]:toff[z]],
+                        reg[toff[a]:toff[z]], slice(a, z)) for a, z in zip(cb[:-1], cb[1:])]
+        self.nchunk = nchunk
+        self.vref_box = (-1.0, -1.0, 2.0, 2.0)
+
+    def set_pass(self, bb, c=None):
+        arr = self.inp["flat"] if c is None else self.chunks[c][:5]
+        bb.set_batch(*arr, param=PARAM_MAT, model=self.wl["model"], vref_nb=21, vref_box=self.vref_box)
+
+    def solve_pass(self, bb, sl_=slice(None)):
+        inp, wl = self.inp, self.wl
+        bb.assemble()
+        status, iters = bb.solve(inp["eps"][sl_], uD=None if inp["uD"] is None else inp["uD"][sl_], rtol=self.args.rtol,
+                                 maxit=4000, precond=self.args.precond)
+        if inp["nl"] == 3:
+            out = bb.tangent()
+        else:
+            out = bb.snapshot()
+            if wl["project"]:
+                out["Y"] = bb.project(inp["W"], inp["M"], translate=out["a"])
+        return out, iters
+
+    def e2e_steps(self, nsteps):
+        """nsteps full passes from HOST mesh arrays.  Two host workers, one per handle, each run set_batch (H2D of the
+        raw meshes + GPU symbolic phase) -> set-up -> solve -> epilogues -> D2H for every other chunk; the kernels of
+        the two handles interleave on the GPU (deepbnd_b200.batch.DoubleBuffer does the same for the drop-in scripts)."""
+        jobs = [c for _ in range(nsteps) for c in range(self.nchunk)]
+        outs = [None] * len(jobs)
+
+        def worker(k):
+            for i in range(k, len(jobs), 2):
+                self.set_pass(self.hb[k], jobs[i])
+                outs[i] = self.solve_pass(self.hb[k], self.chunks[jobs[i]][5])
+
+        futs = [self.pool.submit(worker, k) for k in range(min(2, len(jobs)))]
+        for f_ in futs:
+            f_.result()
+        last = outs[-self.nchunk:]
+        iters = np.concatenate([o[1] for o in last])
+        if self.inp["nl"] == 3:
+            return np.concatenate([o[0] for o in last]), iters
+        return {k_: np.concatenate([o[0][k_] for o in last]) for k_ in last[0][0]}, iters
+
+    def timed(self, fn, *a):
+        self.barrier()
+        t = time.perf_counter()
+        r = fn(*a)
+        self.barrier()
+        return time.perf_counter() - t, r
+
+    def counters(self):
+        c0_, c1_ = self.hb[0].timings()[1], self.hb[1].timings()[1]
+        return {k_: c0_[k_] + c1_[k_] for k_ in c0_}
+
+    def measure(self, steps, warmup, do_e2e=True):
+        res = {}
+        b = self.hb[0]
+        if do_e2e:
+            self.timed(self.e2e_steps, max(3, warmup))
+            cnt0 = self.counters()
+            res["t_e2e"], (res["out"], res["iters"]) = self.timed(self.e2e_steps, steps)
+            cnt1 = self.counters()
+            res["h2d"] = (cnt1["h2d_bytes"] - cnt0["h2d_bytes"]) / steps
+            res["d2h"] = (cnt1["d2h_bytes"] - cnt0["d2h_bytes"]) / steps
+        # device-resident loop (batch already in HBM): `value`
+        self.set_pass(b)
+        for _ in range(1 if do_e2e else max(1, warmup)):
+            self.timed(self.solve_pass, b)
+        launches0 = b.timings()[1]["kernel_launches"]
+        spmv_ms = spmv_bytes = 0.0
+        phase = {}
+        self.barrier()
+        t = time.perf_counter()
+        for _ in range(steps):
+            out, iters = self.solve_pass(b)
+            tt, cc = b.timings()
+            spmv_ms += tt["spmv"]; spmv_bytes += cc["spmv_alg_bytes"]
+            for k_, v_ in tt.items():
+                phase[k_] = phase.get(k_, 0.0) + v_ / steps
+            spmv_launches = cc["spmv_launches"]
+        self.barrier()
+        res["t_dev"] = time.perf_counter() - t
+        res.update(spmv_ms=spmv_ms, spmv_bytes=spmv_bytes, spmv_launches=spmv_launches, phase=phase,
+                   launches=b.timings()[1]["kernel_launches"] - launches0)
+        if not do_e2e:
+            res["out"], res["iters"] = out, iters
+        res["dof"] = int(np.mean([2 * b.sizes(s)["n_rows"] for s in range(min(self.ns, 8))]))
+        return res
 
 
 def main():
@@ -166,7 +310,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2_snapshots_1k_full_per", choices=sorted(WORKLOADS))
     ap.add_argument("--ns", type=int, default=0, help="override RVEs per GPU")
-    ap.add_argument("--lcar", type=float, default=0.0, help="override mesh size (default 2/30)")
+    ap.add_argument("--lcar", type=float, default=0.0, help="override mesh size (default 2/30; C5: 1/30)")
     ap.add_argument("--rtol", type=float, default=1e-10)
     ap.add_argument("--precond", default="twolevel", choices=["twolevel", "jacobi"])
     ap.add_argument("--unique", type=int, default=256, help="distinct synthetic RVEs meshed per rank (cycled to --ns); 0 = all")
@@ -174,6 +318,7 @@ def main():
     ap.add_argument("--operator", default="matfree", choices=["matfree", "assembled"],
                     help="q = A p inside the PCG: element-wise (default) or the assembled SELL-32 SpMV")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads block")
     ap.add_argument("--cpu-sample", type=int, default=0, help="RVEs in the CPU baseline sample (default: one per core)")
     args = ap.parse_args()
 
@@ -183,7 +328,7 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.ns:
         wl["ns"] = args.ns
-    lcar = args.lcar if args.lcar > 0 else None
+    lcar = args.lcar if args.lcar > 0 else wl.get("lcar")
     ncpu = os.cpu_count() or 1
     nproc_local = max(1, ncpu // max(1, world))
     if world > 1:                                   # ranks share the host cores of the box
@@ -215,10 +360,11 @@ def main():
         line = {"impl": "reference", "metric": "RVE solves/sec", "value": val, "unit": "RVE/s", "n_gpus": args.gpus,
                 "steps": nst, "warmup": args.warmup, "ms_per_step": 1e3 * tot / nst, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "mesh": wl["size"], "model": wl["model"], "loads": list(wl["loads"]),
-                           "lcar": lcar or 2 / 30},
+                "config": {"workload": args.workload, "rves_per_gpu": wl["ns"], "mesh": wl["size"], "model": wl["model"],
+                           "loads": list(wl["loads"]), "lcar": lcar or 2 / 30},
                 "cpu_baseline": {"value": val, "unit": "RVE/s", "cores": ncpu, "kind": "port",
-                                 "sample": "%d RVEs per step, %d serial worker processes, scipy splu" % (nsamp, ncpu)},
+                                 "sample": "%d RVEs per step (one per core) of the %d-RVE workload, %d serial worker processes, "
+                                           "oracle port: scipy splu on the bordered KKT system" % (nsamp, wl["ns"], ncpu)},
                 "e2e": {"value": val, "unit": "RVE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         _OUT.write(json.dumps(line) + "\n")
         _OUT.flush()
@@ -229,27 +375,22 @@ def main():
     # meshing is outside the path ("generated once and cached"): at most --unique distinct RVEs are meshed per
     # rank and cycled to the batch size; every copy is still set up and solved as an independent system
     nuniq = min(ns, args.unique) if args.unique > 0 else ns
-    param = synthetic_param(nuniq, seed=2 + 1000 * rank)
-    t0 = time.perf_counter()
-    meshes = make_meshes(param, wl["size"], lcar, nproc_local)   # fork BEFORE any CUDA initialisation
-    meshes = [meshes[i % nuniq] for i in range(ns)]
-    t_mesh = time.perf_counter() - t0
-    voff, toff, xy, tri, reg = flatten(meshes)
-
-    nl = len(wl["loads"])
-    uD = None
-    if wl["model"] == "dnn":
-        rng = np.random.RandomState(5 + rank)
-        base = np.stack([smooth_uD(81, 17 + i) for i in range(3)])
-        uD = base[None] * (1.0 + 0.1 * rng.randn(ns, 1, 1))
+    inp = synthetic_inputs(wl, ns, nuniq, rank, lcar, nproc_local)       # forks BEFORE any CUDA initialisation
+    extra_inp = {}
+    do_extra = world == 1 and not args.no_extra and args.workload == "C2_snapshots_1k_full_per" and not args.ns
+    if do_extra:
+        for name, n2 in EXTRA.items():
+            w2 = WORKLOADS[name]
+            extra_inp[name] = synthetic_inputs(w2, n2, min(n2, args.unique or n2), rank, w2.get("lcar"), nproc_local)
     # CPU baseline first (worker processes are forked before CUDA is initialised)
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         nsamp = min(ns, args.cpu_sample or ncpu)
-        uDs = None if uD is None else [list(uD[s]) for s in range(nsamp)]
-        rate, dt = cpu_reference_rate(meshes[:nsamp], wl["model"], wl["loads"], uDs, ncpu)
+        uDs = None if inp["uD"] is None else [list(inp["uD"][s]) for s in range(nsamp)]
+        rate, dt = cpu_reference_rate(inp["meshes"][:nsamp], wl["model"], wl["loads"], uDs, ncpu)
         cpu = {"value": rate, "unit": "RVE/s", "cores": ncpu, "kind": "port",
-               "sample": "first %d RVEs of the same batch, %d serial worker processes (scipy splu), %.1f s" % (nsamp, ncpu, dt)}
+               "sample": "first %d RVEs of the same batch, %d serial worker processes (oracle port: scipy splu on the "
+                         "bordered KKT system), %.1f s" % (nsamp, ncpu, dt)}
 
     import torch
     import torch.distributed as dist
@@ -257,103 +398,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from deepbnd_b200.batch import RVEBatch
-    from deepbnd_b200.elasticity import macro_strain_voigt
-
-    eps = np.broadcast_to(np.stack([macro_strain_voigt(i) for i in wl["loads"]]), (ns, nl, 3)).copy()
-    vref_box = (-1.0, -1.0, 2.0, 2.0)
-    W = M = None
-    if wl["project"]:
-        rng = np.random.RandomState(0)
-        Wq = np.linalg.qr(rng.randn(162, 160))[0].T                   # synthetic orthonormal basis (160,162)
-        W = np.stack([Wq] * nl)
-        n = 80
-        M = np.zeros((162, 162))
-        for k in range(n):                                             # boundary mass of Vref (h = 0.1)
-            k2 = (k + 1) % n
-            for c in range(2):
-                M[2 * k + c, 2 * k + c] += 0.1 / 3; M[2 * k2 + c, 2 * k2 + c] += 0.1 / 3
-                M[2 * k + c, 2 * k2 + c] += 0.1 / 6; M[2 * k2 + c, 2 * k + c] += 0.1 / 6
-
-    # two handles: while one batch is being solved, a second host thread uploads the next one and runs its symbolic phase
-    # one on the other handle from a second host thread (ctypes releases the GIL)
     from concurrent.futures import ThreadPoolExecutor
+
+    # two handles: while one chunk is being solved, a second host thread uploads the next one and runs its symbolic
+    # phase on the other handle (ctypes releases the GIL)
     hb = [RVEBatch(local_rank).set_operator(args.operator), RVEBatch(local_rank).set_operator(args.operator)]
-    b = hb[0]
     pool = ThreadPoolExecutor(max_workers=2)
-    maxit = 4000
-
-    def device_pass(bb=None):
-        bb = bb or b
-        bb.assemble()
-        status, iters = bb.solve(eps, uD=uD, rtol=args.rtol, maxit=maxit, precond=args.precond)
-        if nl == 3:
-            out = bb.tangent()
-        else:
-            out = bb.snapshot()
-            if wl["project"]:
-                out["Y"] = bb.project(W, M, translate=out["a"])
-        return out, iters
-
-    def set_pass(bb, c=None):
-        if c is None:
-            bb.set_batch(voff, toff, xy, tri, reg, param=PARAM_MAT, model=wl["model"], vref_nb=21, vref_box=vref_box)
-        else:
-            bb.set_batch(*chunks[c][:5], param=PARAM_MAT, model=wl["model"], vref_nb=21, vref_box=vref_box)
-
-    # e2e streams every step's batch through the two handles in `nchunk` chunks, so that the pipeline
-    # fill/drain costs one chunk, not one batch
-    nchunk = max(1, min(args.chunks, ns // 64))
-    cb = [ns * c // nchunk for c in range(nchunk + 1)]
-    chunks = []
-    for c in range(nchunk):
-        a, z = cb[c], cb[c + 1]
-        chunks.append((voff[a:z + 1] - voff[a], toff[a:z + 1] - toff[a], xy[voff[a]:voff[z]], tri[toff[a]:toff[z]],
-                       reg[toff[a]:toff[z]], slice(a, z)))
-
-    def chunk_pass(bb, c):
-        sl_ = chunks[c][5]
-        bb.assemble()
-        status, iters = bb.solve(eps[sl_], uD=None if uD is None else uD[sl_], rtol=args.rtol, maxit=maxit, precond=args.precond)
-        if nl == 3:
-            out = bb.tangent()
-        else:
-            out = bb.snapshot()
-            if wl["project"]:
-                out["Y"] = bb.project(W, M, translate=out["a"])
-        return out, iters
-
-    def e2e_steps(nsteps):
-        """nsteps full passes from HOST mesh arrays.  Two host workers, one per handle, each run set_batch (H2D of the
-        raw meshes + GPU symbolic phase) -> assemble -> solve -> epilogues -> D2H for every other chunk; the kernels of
-        the two handles interleave on the GPU (deepbnd_b200.batch.DoubleBuffer does the same for the drop-in scripts)."""
-        jobs = [c for _ in range(nsteps) for c in range(nchunk)]
-        outs = [None] * len(jobs)
-        dbg = os.environ.get("BENCH_E2E_DEBUG") == "1"
-        acc = [{}, {}]
-
-        def worker(k):
-            for i in range(k, len(jobs), 2):
-                tc0 = time.perf_counter()
-                set_pass(hb[k], jobs[i])
-                tc1 = time.perf_counter()
-                outs[i] = chunk_pass(hb[k], jobs[i])
-                if dbg:                                        # where the wall time of a chunk goes (stderr only)
-                    for k_, v_ in hb[k].timings()[0].items():
-                        acc[k][k_] = acc[k].get(k_, 0.0) + v_
-                    acc[k]["wall_set_batch"] = acc[k].get("wall_set_batch", 0.0) + 1e3 * (tc1 - tc0)
-                    acc[k]["wall_chunk_pass"] = acc[k].get("wall_chunk_pass", 0.0) + 1e3 * (time.perf_counter() - tc1)
-
-        futs = [pool.submit(worker, k) for k in range(min(2, len(jobs)))]
-        for f_ in futs:
-            f_.result()
-        if dbg:
-            tot = {k_: acc[0].get(k_, 0.0) + acc[1].get(k_, 0.0) for k_ in set(acc[0]) | set(acc[1])}
-            print("[e2e debug] per step (ms, both workers): " + json.dumps({k_: round(v_ / nsteps, 2) for k_, v_ in sorted(tot.items())}), file=sys.stderr)
-        last = outs[-nchunk:]
-        iters = np.concatenate([o[1] for o in last])
-        if nl == 3:
-            return np.concatenate([o[0] for o in last]), iters
-        return {k_: np.concatenate([o[0][k_] for o in last]) for k_ in last[0][0]}, iters
 
     def barrier():
         torch.cuda.synchronize()
@@ -361,95 +411,99 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, *a):
-        barrier()
-        t = time.perf_counter()
-        r = fn(*a)
-        barrier()
-        return time.perf_counter() - t, r
-
-    def counters():
-        t0_, c0_ = hb[0].timings()
-        t1_, c1_ = hb[1].timings()
-        return {k_: c0_[k_] + c1_[k_] for k_ in c0_}
-
-    # e2e loop (host buffers in, outputs out)
-    timed(e2e_steps, max(3, args.warmup))
-    cnt0 = counters()
+    run = Runner(hb, pool, wl, inp, args, barrier)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    t_e2e, (out, iters) = timed(e2e_steps, args.steps)
-    cnt1 = counters()
-    # device-resident loop (batch already in HBM): `value`
-    set_pass(b)
-    timed(device_pass)
-    spmv_ms, spmv_bytes, launches0 = 0.0, 0.0, b.timings()[1]["kernel_launches"]
-    barrier()
-    t = time.perf_counter()
-    phase = {}
-    for _ in range(args.steps):
-        device_pass()
-        tt, cc = b.timings()
-        spmv_ms += tt["spmv"]; spmv_bytes += cc["spmv_alg_bytes"]
-        for k_, v_ in tt.items():
-            phase[k_] = phase.get(k_, 0.0) + v_ / args.steps
-        spmv_launches = cc["spmv_launches"]
-    barrier()
-    t_dev = time.perf_counter() - t
+    res = run.measure(args.steps, args.warmup, do_e2e=True)
     clocks = sampler.stop()
-    launches = b.timings()[1]["kernel_launches"] - launches0
 
-    tmax = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+    # assembled SELL-32 SpMV of the same batch, timed alone (the stored-matrix kernel BASELINE's "SpMV HBM GB/s" names)
+    spmv_as = None
+    if rank == 0:
+        try:
+            bs = hb[1]
+            nsp = min(ns, 256 if wl["size"] == "full" else 2000)
+            bs.set_operator("assembled")
+            bs.set_batch(*flatten(inp["meshes"][:nsp]), param=PARAM_MAT, model=wl["model"], vref_nb=21, vref_box=run.vref_box)
+            bs.assemble()
+            kk = 3 if (wl["model"] == "MR" or inp["nl"] == 3) else inp["nl"]
+            ms_, by_ = bs.bench_spmv(n_rhs=kk, reps=20)
+            spmv_as = {"kernel": "k_spmv<%d>" % kk, "rves": nsp, "ms_per_launch": ms_, "alg_bytes_per_launch": by_,
+                       "achieved": by_ / (ms_ * 1e-3) / 1e9, "unit": "GB/s"}
+            bs.set_operator(args.operator)
+        except Exception as e:                       # noqa: BLE001 - diagnostics only
+            spmv_as = {"error": str(e)}
+
+    tmax = torch.tensor([res["t_dev"], res["t_e2e"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         # the only exchange of the path: final gather of the per-RVE outputs on rank 0
+        out = res["out"]
         flat = torch.from_numpy(np.ascontiguousarray(
-            out.reshape(ns, -1) if nl == 3 else np.concatenate([out[k].reshape(ns, -1) for k in ("sol", "sigma", "a", "B", "sigmaT")], 1))).cuda()
+            out.reshape(ns, -1) if inp["nl"] == 3 else np.concatenate([out[k].reshape(ns, -1) for k in ("sol", "sigma", "a", "B", "sigmaT")], 1))).cuda()
         gathered = [torch.empty_like(flat) for _ in range(world)] if rank == 0 else None
         dist.gather(flat, gathered, dst=0)
     t_dev_max, t_e2e_max = tmax.tolist()
     total = ns * world
     value = total * args.steps / t_dev_max
     e2e_val = total * args.steps / t_e2e_max
-    h2d = (cnt1["h2d_bytes"] - cnt0["h2d_bytes"]) / args.steps
-    d2h = (cnt1["d2h_bytes"] - cnt0["d2h_bytes"]) / args.steps
+
+    extras = []
+    if do_extra and rank == 0:
+        for name, n2 in EXTRA.items():
+            r2 = Runner(hb, pool, WORKLOADS[name], extra_inp[name], args, barrier).measure(2, 1, do_e2e=False)
+            extras.append({"workload": name, "rves_per_gpu": n2, "value": n2 * 2 / r2["t_dev"], "unit": "RVE/s", "steps": 2, "warmup": 1,
+                           "ms_per_step": 1e3 * r2["t_dev"] / 2, "mean_pcg_iters": float(np.mean(r2["iters"])),
+                           "dofs_per_rve": r2["dof"], "operator_alg_gbs": r2["spmv_bytes"] / (r2["spmv_ms"] * 1e-3) / 1e9,
+                           "phase_ms": {k_: round(v_, 2) for k_, v_ in r2["phase"].items()}})
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
-    # DRAM traffic of one SpMV launch from the committed ncu --set full capture (per RVE, scaled to this batch)
-    traffic = None
+    achieved = res["spmv_bytes"] / (res["spmv_ms"] * 1e-3) / 1e9 if res["spmv_ms"] > 0 else 0.0
+    # DRAM bytes of one operator launch from the committed ncu --set full capture (per RVE): reported next to the
+    # algorithmic figure, NOT measured in this run
+    traffic_ncu = None
     tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(tpath):
-        tj = json.load(open(tpath)).get(args.workload)
+        tj = json.load(open(tpath)).get(args.workload + ":" + args.operator)
         if tj and not args.lcar:
-            traffic = tj["dram_bytes_per_rve_per_launch"] * ns
+            traffic_ncu = dict(tj)
+            ms_launch = res["spmv_ms"] / max(1.0, res["spmv_launches"] * args.steps)
+            traffic_ncu["dram_gbs_at_this_run"] = tj["dram_bytes_per_rve_per_launch"] * ns / (ms_launch * 1e-3) / 1e9
+    if spmv_as and "achieved" in spmv_as:
+        spmv_as["frac"] = spmv_as["achieved"] / peak
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    dof = int(np.mean([2 * b.sizes(s)["n_rows"] for s in range(min(ns, 8))]))
+    opname = "k_apply (matrix-free element-wise operator)" if args.operator == "matfree" else "k_spmv (assembled SELL-32)"
     line = {"metric": "RVE solves/sec", "value": value, "unit": "RVE/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "rves_per_gpu": ns, "mesh": wl["size"], "lcar": lcar or 2 / 30,
-                       "model": wl["model"], "loads": list(wl["loads"]), "dofs_per_rve": dof, "rtol": args.rtol,
-                       "precond": args.precond, "mean_pcg_iters": float(np.mean(iters)),
+                       "model": wl["model"], "loads": list(wl["loads"]), "dofs_per_rve": res["dof"], "rtol": args.rtol,
+                       "precond": args.precond, "operator": args.operator, "mean_pcg_iters": float(np.mean(res["iters"])),
                        "l2": "per-iteration working set >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                       "unique_meshes": nuniq, "mesh_gen_s": t_mesh, "phase_ms": phase},
-            "e2e": {"value": e2e_val, "unit": "RVE/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "pipeline": "2 handles / 2 host workers, %d chunks per step: each worker runs H2D of the raw meshes + GPU symbolic phase + solve + D2H for every other chunk; the two streams interleave on the GPU" % nchunk},
-            "gpu_launches": int(launches),
+                       "unique_meshes": nuniq, "mesher": wl.get("mesher", "delaunay"), "mesh_gen_s": inp["t_mesh"],
+                       "phase_ms": res["phase"]},
+            "e2e": {"value": e2e_val, "unit": "RVE/s", "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
+                    "pipeline": "2 handles / 2 host workers, %d chunks per step: each worker runs H2D of the raw meshes + GPU symbolic phase + solve + D2H for every other chunk; the two streams interleave on the GPU" % run.nchunk},
+            "gpu_launches": int(res["launches"]),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "launches_timed": int(spmv_launches * args.steps),
-                         "alg_bytes_per_launch": spmv_bytes / max(1.0, spmv_launches * args.steps)},
-            "cpu_baseline": cpu}
+            "roofline": {"bound": "hbm", "kernel": opname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "alg_bytes_model": "B_spmv(K) = 12 nnz + 4 (n+1) + 16 n K per RVE (scalar-CSR accounting of SURVEY 8d); the "
+                                            "matrix-free kernel moves several times fewer bytes, so frac > 1 is the format advantage, not a bandwidth claim",
+                         "traffic_ncu": traffic_ncu,
+                         "launches_timed": int(res["spmv_launches"] * args.steps),
+                         "alg_bytes_per_launch": res["spmv_bytes"] / max(1.0, res["spmv_launches"] * args.steps),
+                         "spmv_assembled": spmv_as},
+            "cpu_baseline": cpu,
+            "extra_workloads": extras}
     _OUT.write(json.dumps(line) + "\n")
     _OUT.flush()
     if world > 1:

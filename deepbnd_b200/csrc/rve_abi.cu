@@ -315,9 +315,9 @@ static void launch_update(rve_batch_s* h, const PcgArgs& a, int init, int iter, 
 template <int K>
 static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStream_t st) {
     const Levels& LV = a.LV;
+    auto grid = [&](int l) { return dim3((unsigned)((LV.g[l].G + 255) / 256), (unsigned)a.n_sys); };
     int W = 1;                                         // number of wide levels; the coarsest level stays in k_vc_mid
     while (W < LV.L - 1 && LV.g[W].G >= RVE_WIDE_NODES) ++W;
-    auto grid = [&](int l) { return dim3((unsigned)((LV.g[l].G + 255) / 256), (unsigned)a.n_sys); };
     k_vc_down1<K><<<grid(0), 256, 0, st>>>(LV, 0, h->active.p);
     for (int l = 1; l < W; ++l) {
         k_vc_restrict<K><<<grid(l), 256, 0, st>>>(LV, l, h->active.p);
