@@ -12,7 +12,7 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 
 MODEL = {"lin": 0, "dnn": 1, "per": 2, "MR": 3}
 PRECOND = {"jacobi": 0, "twolevel": 1}
-OPT_SYM_B, OPT_OPERATOR = 1, 2
+OPT_SYM_B, OPT_OPERATOR, OPT_RESIDUAL_REPLACE = 1, 2, 3
 OPERATOR = {"assembled": 0, "matfree": 1}
 
 # every symbol include/rve_b200.h declares (checked by tests/test_abi.py)

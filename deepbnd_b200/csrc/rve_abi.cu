@@ -130,6 +130,7 @@ struct rve_batch_s {
     DBuf<double> eps, eps_eff, Bmat, uD, gval, d_vbox, U, acc, sigL, sigT, aout, Bout, sol, Mx, Gaff, aaff;
     DBuf<double> MWt, transl, Yd, gradT;
     int opt_sym_B = 0;
+    int opt_resid_replace = 0;         // > 0: every so many iterations r is recomputed as b - A x (RVE_OPT_RESIDUAL_REPLACE)
     int n_sm = 148;
     int updp_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     int dirp_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};   // resident CTAs per SM of k_update_p<K> (by precond), 0 = not asked yet
@@ -935,16 +936,16 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     if (uD)
         k_bnd_values<<<cdiv(h->NBN * NL, 256), 256, 0, st>>>((int)h->NBN, NL, nside, h->bnd_sys.p, h->bnd_node.p, h->bnd_s.p,
                                                               h->node_xy.p, h->uD.p, h->Bmat.p, h->gval.p);
-    CU(cudaMemsetAsync(h->b.p, 0, RK * sizeof(double), st));
     CU(cudaMemsetAsync(h->sc.p, 0, h->sc.n * sizeof(double), st));
-    if (h->model == RVE_MODEL_MR)
+    if (h->model == RVE_MODEL_MR) {
+        // (each boundary node receives at most two edge terms: the sum is order-independent)
+        CU(cudaMemsetAsync(h->b.p, 0, RK * sizeof(double), st));
         k_rhs_mr<<<cdiv(h->NBE, 256), 256, 0, st>>>((int)h->NBE, h->bedge.p, h->bedge_nl.p, h->node_row.p, h->b.p);
-    else if (!uD)
-        k_rhs_load<<<cdiv(h->E, 40), 256, 0, st>>>((int)h->E, K, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
-                                                   h->node_row.p, h->eps_eff.p, h->b.p, h->sc.p, h->mat);
-    else
-        k_rhs<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, K, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
-                                              h->node_row.p, h->node_bnd.p, h->eps_eff.p, uD ? h->gval.p : nullptr, h->b.p, h->sc.p, h->mat);
+    } else {
+        k_rhs_rows<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), K, h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->elem_reg.p, h->node_xy.p,
+                                                  h->node_row.p, h->node_bnd.p, h->eps_eff.p, uD ? h->gval.p : nullptr, h->b.p, h->part.p, h->mat);
+        k_fin_bref<<<cdiv(n_sys, 8), 256, 0, st>>>(n_sys, K, h->sys_win0.p, h->part.p, h->sc.p);
+    }
     CU(cudaEventRecord(h->ev[1], st));
     // ---- PCG
     CU(cudaMemsetAsync(h->p.p, 0, h->p.n * sizeof(double), st));
@@ -1001,6 +1002,19 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
 #define UPD_(KK) launch_update<KK>(h, pa, 0, it, st)
             K_DISPATCH(K, UPD_);
 #undef UPD_
+            if (h->opt_resid_replace > 0 && (it + 1) % h->opt_resid_replace == 0) {
+                // residual replacement: the recurrence residual is replaced by the true one, r = b - A x, and its norms and
+                // restriction are recomputed (the alpha k_fin_alpha derives from this application is never used)
+#define RSP_(KK) launch_spmv<KK>(h, pa, h->x.p, h->q.p, h->active.p, h->part.p, h->sc.p, st)
+                K_DISPATCH(K, RSP_);
+#undef RSP_
+                k_true_residual<<<pa.n_win, 256, 0, st>>>(pa.wt, K, (const double2*)h->b.p, (const double2*)h->q.p, (double2*)h->r.p);
+                if (precond) CU(cudaMemsetAsync(LV.rc[0], 0, h->lvR[0].n * sizeof(float), st));
+#define UPD2_(KK) launch_update<KK>(h, pa, 2, it, st)
+                K_DISPATCH(K, UPD2_);
+#undef UPD2_
+                h->launches += 4;
+            }
             if (ktime) cudaEventRecord(dbg_event(3 * (size_t)it + 2), st);
             ++launched;
             h->launches += 5;
@@ -1134,6 +1148,11 @@ int rve_epilogue_snapshot(rve_handle_t h, double* sol, double* sigma, double* a,
 int rve_set_option(rve_handle_t h, int32_t option, int32_t value) {
     H_CHECK(h);
     if (option == RVE_OPT_SYM_B) { h->opt_sym_B = value ? 1 : 0; return 0; }
+    if (option == RVE_OPT_RESIDUAL_REPLACE) {
+        if (value < 0) FAIL(RVE_E_ARG, "residual replacement interval must be >= 0");
+        h->opt_resid_replace = value;
+        return 0;
+    }
     if (option == RVE_OPT_OPERATOR) {
         if (value != RVE_OPERATOR_ASSEMBLED && value != RVE_OPERATOR_MATFREE) FAIL(RVE_E_ARG, "unknown operator");
         if (value == RVE_OPERATOR_MATFREE && h->assembled && h->opt_operator != RVE_OPERATOR_MATFREE) h->assembled = false;   // needs k_we_geo

@@ -1374,27 +1374,40 @@ k_fin_update(int n_sys, int K, const int* __restrict__ sys_win0, const double* _
     for (int k = 0; k < K; ++k) {
         const double vrr = sys_sum(part, w0, w1, 8, 2 * k), vrdr = sys_sum(part, w0, w1, 8, 2 * k + 1);
         double* s = sc + ((size_t)sys * 4 + k) * SC_N;
-        const double bb = init ? vrr : s[SC_BB];
+        // init: 0 = after an update, 1 = first residual (sets the reference norm), 2 = after a residual replacement
+        const double bb = (init == 1) ? vrr : s[SC_BB];
         if (!(vrr <= rtol2 * bb || vrr <= 1e-28 * s[SC_BREF])) done = false;
         if (precond == 0) {  // block Jacobi: z = Dinv r, finish the scalar recurrences here
-            const double rzold = s[SC_RZ];
-            const double beta = (!init && rzold > 0.0) ? vrdr / rzold : 0.0;
+            const double rzold = (init == 2) ? s[SC_RZOLD] : s[SC_RZ];
+            const double beta = (init != 1 && rzold > 0.0) ? vrdr / rzold : 0.0;
             __syncwarp();
             if (lane == 0) { s[SC_RZOLD] = rzold; s[SC_RZ] = vrdr; s[SC_BETA] = beta; }
             for (int w = w0 + lane; w < w1; w += 32) win_scal[(size_t)w * 8 + 4 + k] = beta;
         }
         if (lane == 0) {
-            if (init) s[SC_BB] = vrr;
+            if (init == 1) s[SC_BB] = vrr;
             s[SC_RR] = vrr; s[SC_RDR] = vrdr;
         }
     }
     if (!done) return;
     if (lane == 0) {
         active[sys] = 0;
-        iters[sys] = init ? 0 : iter + 1;
+        iters[sys] = (init == 1) ? 0 : iter + 1;
         atomicSub(n_active, 1);
     }
     for (int wq = w0 + lane; wq < w1; wq += 32) win_active[wq] = 0;
+}
+
+// residual replacement: r = b - q with q = A x just applied (thread per (row, rhs) value pair of the active windows)
+__global__ void __launch_bounds__(256)
+k_true_residual(WinTab wt, int K, const double2* __restrict__ b, const double2* __restrict__ q, double2* __restrict__ r) {
+    const int w = blockIdx.x;
+    if (!wt.win_active[w]) return;
+    const size_t base = (size_t)wt.win_row0[w] * K;
+    for (int e = threadIdx.x; e < wt.win_n[w] * K; e += 256) {
+        const double2 bv = b[base + e], qv = q[base + e];
+        r[base + e] = make_double2(bv.x - qv.x, bv.y - qv.y);
+    }
 }
 
 // r.z = r.Dinv r + rc.z1 after the V-cycle; beta
@@ -1545,156 +1558,87 @@ __global__ void k_bnd_values(int n_bnd, int K, int nside, const int* __restrict_
     gval[2 * (size_t)gid + 1] = g1 + B[2] * x + B[3] * y;
 }
 
-// b = -int B^T D eps  - K_fb g : warp per element.  First term in closed form per node
-// (sigma0 . int grad phi_a), second only where an element touches Dirichlet nodes with data.
-__global__ void __launch_bounds__(256)
-k_rhs(int n_elem, int K, const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
-      const int* __restrict__ elem_sys, const double* __restrict__ node_xy, const int* __restrict__ node_row,
-      const int* __restrict__ node_bnd, const double* __restrict__ eps_eff, const double* __restrict__ gval,
-      double* __restrict__ b, double* __restrict__ sc, Mat8 mat) {
+// Deterministic load vector: thread per block row (CTA per window) walks the elements around its row, like k_assemble:
+// b_row = sum_e [ -(sigma(eps) . int grad phi_a) - sum_{b prescribed} K_e[a][b] g_b ], one writer per row, no atomics,
+// the same summation order on every run.  The per-window partial of the squared unassembled contributions (absolute
+// convergence floor) goes to part[win][8]; k_fin_bref adds them per system in a fixed order.
+__global__ void __launch_bounds__(RVE_WIN)
+k_rhs_rows(WinTab wt, int K, const unsigned* __restrict__ adjf_ptr, const int* __restrict__ adjf, const int* __restrict__ elem_node,
+           const unsigned char* __restrict__ elem_reg, const double* __restrict__ node_xy, const int* __restrict__ node_row,
+           const int* __restrict__ node_bnd, const double* __restrict__ eps_eff, const double* __restrict__ gval,
+           double* __restrict__ b, double* __restrict__ part, Mat8 mat) {
     __shared__ double s_mat[8];
+    __shared__ double s_m2[RVE_WIN / 32][4];
     if (threadIdx.x < 8) s_mat[threadIdx.x] = mat.v[threadIdx.x];
     __syncthreads();
-    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-    const int e = blockIdx.x * (blockDim.x >> 5) + wv;
-    __shared__ double s_m2[8][3];
-    __shared__ int s_sys[8];
-    const bool valid = e < n_elem;
-    const int sys = valid ? elem_sys[e] : -1;
-    if (lane == 0) { s_sys[wv] = sys; s_m2[wv][0] = s_m2[wv][1] = s_m2[wv][2] = 0.0; }
-    int node = 0, row = -1, bnd = -1;
-    double px = 0, py = 0, lam = 0, mu = 0;
-    TriGeom g;
-    if (valid) {
-    if (lane < 6) {
-        node = elem_node[(size_t)e * 6 + lane];
-        row = node_row[node];
-        bnd = (gval && row < 0) ? node_bnd[node] : -1;
-        px = node_xy[2 * (size_t)node];
-        py = node_xy[2 * (size_t)node + 1];
-    }
-    double x0 = __shfl_sync(0xffffffffu, px, 0), y0 = __shfl_sync(0xffffffffu, py, 0);
-    double x1 = __shfl_sync(0xffffffffu, px, 1), y1 = __shfl_sync(0xffffffffu, py, 1);
-    double x2 = __shfl_sync(0xffffffffu, px, 2), y2 = __shfl_sync(0xffffffffu, py, 2);
-    tri_geom(x0, y0, x1, y1, x2, y2, g);
-    const int reg = elem_reg[e];
-    lam = s_mat[2 * reg]; mu = s_mat[2 * reg + 1];
-    {
-        double gx = 0, gy = 0;
-        if (lane < 6) p2_grad_int(g, lane, gx, gy);
-        for (int k = 0; k < K; ++k) {
-            const double* ev = eps_eff + 3 * ((size_t)sys * K + k);
-            const double s00 = (lam + 2 * mu) * ev[0] + lam * ev[1];
-            const double s11 = lam * ev[0] + (lam + 2 * mu) * ev[1];
-            const double s01 = mu * ev[2];
-            const double f0 = -(s00 * gx + s01 * gy), f1 = -(s01 * gx + s11 * gy);
-            if (lane < 6 && row >= 0) {
-                atomicAdd(b + ((size_t)row * K + k) * 2, f0);
-                atomicAdd(b + ((size_t)row * K + k) * 2 + 1, f1);
-            }
-            // reference magnitude of the load before cancellation (absolute convergence floor)
-            double m2 = (lane < 6 && row >= 0) ? f0 * f0 + f1 * f1 : 0.0;
+    const int w = blockIdx.x, t = threadIdx.x, lane = t & 31, wv = t >> 5;
+    const int sys = wt.win_sys[w];
+    double acc[RVE_MAX_RHS][2], m2[RVE_MAX_RHS];
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
-            if (lane == 0) s_m2[wv][k] = m2;
-        }
-    }
-    }
-    // reference magnitude: one atomic per CTA and rhs when its 8 elements belong to one system
-    __syncthreads();
-    if (threadIdx.x < 3 * 8) {
-        const int w2 = threadIdx.x / 3, k = threadIdx.x % 3;
-        bool same = true;
-        for (int i = 1; i < 8; ++i) same = same && (s_sys[i] == s_sys[0] || s_sys[i] < 0);
-        if (k < K) {
-            if (same) {
-                if (w2 == 0 && s_sys[0] >= 0) {
-                    double t = 0.0;
-                    for (int i = 0; i < 8; ++i) t += s_m2[i][k];
-                    atomicAdd(sc + ((size_t)s_sys[0] * 4 + k) * SC_N + SC_BREF, t);
+    for (int k = 0; k < RVE_MAX_RHS; ++k) { acc[k][0] = acc[k][1] = 0.0; m2[k] = 0.0; }
+    if (t < wt.win_n[w]) {
+        const int r = wt.win_row0[w] + t;
+        for (unsigned i = adjf_ptr[r]; i < adjf_ptr[r + 1]; ++i) {
+            const int e = adjf[i];
+            const int* en = elem_node + 6 * (size_t)e;
+            int a = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) if (node_row[en[k]] == r) a = k;
+            const double* p0 = node_xy + 2 * (size_t)en[0]; const double* p1 = node_xy + 2 * (size_t)en[1]; const double* p2 = node_xy + 2 * (size_t)en[2];
+            TriGeom g;
+            tri_geom(p0[0], p0[1], p1[0], p1[1], p2[0], p2[1], g);
+            const int reg = elem_reg[e];
+            const double lam = s_mat[2 * reg], mu = s_mat[2 * reg + 1];
+            double gx, gy;
+            p2_grad_int(g, a, gx, gy);
+            for (int k = 0; k < K; ++k) {
+                const double* ev = eps_eff + 3 * ((size_t)sys * K + k);
+                const double s00 = (lam + 2 * mu) * ev[0] + lam * ev[1];
+                const double s11 = lam * ev[0] + (lam + 2 * mu) * ev[1];
+                const double s01 = mu * ev[2];
+                const double f0 = -(s00 * gx + s01 * gy), f1 = -(s01 * gx + s11 * gy);
+                acc[k][0] += f0; acc[k][1] += f1;
+                m2[k] += f0 * f0 + f1 * f1;
+            }
+            if (gval) {
+                for (int bb = 0; bb < 6; ++bb) {
+                    if (bb == a) continue;
+                    const int nb = en[bb];
+                    if (node_row[nb] >= 0) continue;
+                    const int ib = node_bnd[nb];
+                    if (ib < 0) continue;
+                    double Kb[4];
+                    p2_stiff_block(g, a, bb, lam, mu, Kb);
+                    for (int k = 0; k < K; ++k) {
+                        const double g0 = gval[((size_t)ib * K + k) * 2], g1 = gval[((size_t)ib * K + k) * 2 + 1];
+                        acc[k][0] -= Kb[0] * g0 + Kb[1] * g1;
+                        acc[k][1] -= Kb[2] * g0 + Kb[3] * g1;
+                    }
                 }
-            } else if (s_sys[w2] >= 0) {
-                atomicAdd(sc + ((size_t)s_sys[w2] * 4 + k) * SC_N + SC_BREF, s_m2[w2][k]);
             }
         }
+        for (int k = 0; k < K; ++k) { b[((size_t)r * K + k) * 2] = acc[k][0]; b[((size_t)r * K + k) * 2 + 1] = acc[k][1]; }
     }
-    if (!valid) return;
-    const unsigned anyb = __ballot_sync(0xffffffffu, bnd >= 0);
-    if (anyb == 0) return;
-    int a = 0, bb = 0;
-    pair_ab(lane < 21 ? lane : 0, a, bb);
-    const int ra = __shfl_sync(0xffffffffu, row, a), rb = __shfl_sync(0xffffffffu, row, bb);
-    const int ba = __shfl_sync(0xffffffffu, bnd, a), bnb = __shfl_sync(0xffffffffu, bnd, bb);
-    if (lane < 21 && a != bb) {
-        double Kb[4];
-        p2_stiff_block(g, a, bb, lam, mu, Kb);
-        if (ra >= 0 && bnb >= 0) {  // row a free, column b prescribed
-            for (int k = 0; k < K; ++k) {
-                const double g0 = gval[((size_t)bnb * K + k) * 2], g1 = gval[((size_t)bnb * K + k) * 2 + 1];
-                atomicAdd(b + ((size_t)ra * K + k) * 2, -(Kb[0] * g0 + Kb[1] * g1));
-                atomicAdd(b + ((size_t)ra * K + k) * 2 + 1, -(Kb[2] * g0 + Kb[3] * g1));
-            }
-        }
-        if (rb >= 0 && ba >= 0) {  // row b free, column a prescribed: K_ba = K_ab^T
-            for (int k = 0; k < K; ++k) {
-                const double g0 = gval[((size_t)ba * K + k) * 2], g1 = gval[((size_t)ba * K + k) * 2 + 1];
-                atomicAdd(b + ((size_t)rb * K + k) * 2, -(Kb[0] * g0 + Kb[2] * g1));
-                atomicAdd(b + ((size_t)rb * K + k) * 2 + 1, -(Kb[1] * g0 + Kb[3] * g1));
-            }
-        }
+    for (int k = 0; k < K; ++k) {
+        const double v = warp_sum(m2[k]);
+        if (lane == 0) s_m2[wv][k] = v;
+    }
+    __syncthreads();
+    if (t < 4) {
+        double tot = 0.0;
+        if (t < K) for (int i = 0; i < RVE_WIN / 32; ++i) tot += s_m2[i][t];
+        part[(size_t)w * 8 + t] = tot;
     }
 }
 
-// Load vector without Dirichlet data (lin with zero fluctuation, per): b = -int B^T D eps in closed form per node.
-// Thread per (element, node): 5 elements per warp, no idle element lanes.
 __global__ void __launch_bounds__(256)
-k_rhs_load(int n_elem, int K, const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
-           const int* __restrict__ elem_sys, const double* __restrict__ node_xy, const int* __restrict__ node_row,
-           const double* __restrict__ eps_eff, double* __restrict__ b, double* __restrict__ sc, Mat8 mat) {
-    __shared__ double s_mat[8];
-    if (threadIdx.x < 8) s_mat[threadIdx.x] = mat.v[threadIdx.x];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-    const int slot = lane / 6, a = lane - 6 * slot;
-    const long long e = ((long long)blockIdx.x * 8 + wv) * 5 + slot;
-    const bool valid = lane < 30 && e < n_elem;
-    const int sys0 = __shfl_sync(0xffffffffu, valid ? elem_sys[e] : -1, 0);
-    if (sys0 < 0) return;                                   // whole warp past the end
-    const int sys = valid ? elem_sys[e] : sys0;
-    const bool uniform = __all_sync(0xffffffffu, sys == sys0);
-    double gx = 0.0, gy = 0.0, lam = 0.0, mu = 0.0;
-    int row = -1;
-    if (valid) {
-        const int* en = elem_node + 6 * (size_t)e;
-        const int n0 = en[0], n1 = en[1], n2 = en[2];
-        TriGeom g;
-        tri_geom(node_xy[2 * (size_t)n0], node_xy[2 * (size_t)n0 + 1], node_xy[2 * (size_t)n1], node_xy[2 * (size_t)n1 + 1],
-                 node_xy[2 * (size_t)n2], node_xy[2 * (size_t)n2 + 1], g);
-        p2_grad_int(g, a, gx, gy);
-        row = node_row[en[a]];
-        const int reg = elem_reg[e];
-        lam = s_mat[2 * reg]; mu = s_mat[2 * reg + 1];
-    }
+k_fin_bref(int n_sys, int K, const int* __restrict__ sys_win0, const double* __restrict__ part, double* __restrict__ sc) {
+    const int sys = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (sys >= n_sys) return;
+    const int w0 = sys_win0[sys], w1 = sys_win0[sys + 1];
     for (int k = 0; k < K; ++k) {
-        const double* ev = eps_eff + 3 * ((size_t)sys * K + k);
-        const double s00 = (lam + 2 * mu) * ev[0] + lam * ev[1];
-        const double s11 = lam * ev[0] + (lam + 2 * mu) * ev[1];
-        const double s01 = mu * ev[2];
-        const double f0 = -(s00 * gx + s01 * gy), f1 = -(s01 * gx + s11 * gy);
-        double m2 = 0.0;
-        if (row >= 0) {
-            atomicAdd(b + ((size_t)row * K + k) * 2, f0);
-            atomicAdd(b + ((size_t)row * K + k) * 2 + 1, f1);
-            m2 = f0 * f0 + f1 * f1;
-        }
-        // reference magnitude of the load before cancellation (absolute convergence floor)
-        double* dst = sc + ((size_t)sys * 4 + k) * SC_N + SC_BREF;
-        if (uniform) {
-            m2 = warp_sum(m2);
-            if (lane == 0) atomicAdd(dst, m2);
-        } else if (row >= 0) {
-            atomicAdd(dst, m2);
-        }
+        const double v = sys_sum(part, w0, w1, 8, k);
+        if ((threadIdx.x & 31) == 0) sc[((size_t)sys * 4 + k) * SC_N + SC_BREF] = v;
     }
 }
 

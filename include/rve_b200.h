@@ -133,6 +133,10 @@ int rve_epilogue_homogenisation(rve_handle_t h, double* sigmaL, double* sigmaT, 
 #define RVE_OPT_OPERATOR 2
 #define RVE_OPERATOR_ASSEMBLED 0
 #define RVE_OPERATOR_MATFREE 1
+/* RVE_OPT_RESIDUAL_REPLACE = N > 0: every N PCG iterations the recurrence residual is replaced by the true residual
+ * b - A x (one extra operator application) and its norms are recomputed, so that the stopping test cannot drift away
+ * from the true residual on badly conditioned systems (high contrast); 0 (default) = never. */
+#define RVE_OPT_RESIDUAL_REPLACE 3
 int rve_set_option(rve_handle_t h, int32_t option, int32_t value);
 
 /* replaces getAlphas_fast (creation_model/RB/RB_utils.py:211-213): Y = U M W[:nmax]^T on the

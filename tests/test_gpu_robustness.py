@@ -1,0 +1,78 @@
+"""Determinism and robustness of the CUDA path: run-to-run spread, the atomics-free load vector,
+residual replacement at high stiffness contrast."""
+import numpy as np
+import pytest
+
+from conftest import smooth_uD
+
+pytestmark = pytest.mark.gpu
+
+PARAM = (0.3, 10.0, 0.3, 1.0)
+
+
+@pytest.mark.parametrize("model", ["lin", "dnn", "per"])
+def test_load_vector_is_bitwise_reproducible(coarse_reduced_meshes, model):
+    """k_rhs_rows has one writer per row and a fixed summation order: b is identical on every run."""
+    from deepbnd_b200.batch import RVEBatch
+    n = len(coarse_reduced_meshes)
+    eps = np.broadcast_to(np.eye(3), (n, 3, 3)).copy()
+    uD = None
+    if model == "dnn":
+        uD = np.stack([np.stack([smooth_uD(81, 3 * s + i) for i in range(3)]) for s in range(n)])
+    rhs = []
+    for _ in range(3):
+        b = RVEBatch().set_meshes(coarse_reduced_meshes, PARAM, model=model).assemble()
+        b.solve(eps, uD=uD, rtol=1e-6)
+        rhs.append([b.rhs(s).copy() for s in range(n)])
+        b.close()
+    for s in range(n):
+        assert np.array_equal(rhs[0][s], rhs[1][s]) and np.array_equal(rhs[0][s], rhs[2][s])
+
+
+@pytest.mark.parametrize("model,size", [("per", "full"), ("dnn", "reduced"), ("MR", "reduced")])
+def test_run_to_run_spread_is_bounded(reduced_meshes, full_mesh, model, size):
+    """The only non-reproducible pieces left are fp32 REDs in the restriction of the preconditioner and the epilogue
+    accumulators: the same batch solved 5 times gives tangents / stresses within 1e-12 relative and iteration counts
+    within one iteration."""
+    from deepbnd_b200.batch import RVEBatch
+    meshes = [full_mesh] * 2 if size == "full" else list(reduced_meshes)
+    n = len(meshes)
+    eps = np.broadcast_to(np.eye(3), (n, 3, 3)).copy()
+    uD = None
+    if model == "dnn":
+        uD = np.stack([np.stack([smooth_uD(81, 11 * s + i) for i in range(3)]) for s in range(n)])
+    b = RVEBatch().set_meshes(meshes, PARAM, model=model, vref_box=(-1.0, -1.0, 2.0, 2.0))
+    Cs, its = [], []
+    for _ in range(5):
+        b.assemble()
+        st, it = b.solve(eps, uD=uD, rtol=1e-10)
+        Cs.append(b.tangent().copy()); its.append(it.copy())
+    b.close()
+    Cs, its = np.array(Cs), np.array(its)
+    spread = np.abs(Cs - Cs[0]).max() / np.abs(Cs[0]).max()
+    assert spread <= 1e-12, spread
+    assert (its.max(0) - its.min(0)).max() <= 1
+
+
+@pytest.mark.parametrize("model", ["lin", "per"])
+def test_residual_replacement_at_contrast_1000(coarse_reduced_meshes, model):
+    """Stiffness contrast 1000 (reference default: 10): with RVE_OPT_RESIDUAL_REPLACE the stopping test is re-anchored on the
+    true residual b - A x every 10 iterations; with and without it the tangents agree with sparse LU to 1e-8."""
+    from deepbnd_b200 import _lib as L
+    from deepbnd_b200.batch import RVEBatch
+    from oracle.rve_oracle import OracleRVE
+    param = (0.3, 1000.0, 0.3, 1.0)
+    meshes = coarse_reduced_meshes[:3]
+    eps = np.broadcast_to(np.eye(3), (3, 3, 3)).copy()
+    ref = [OracleRVE(*m, param=param, model=model).compute_tangent() for m in meshes]
+    its = {}
+    for every in (0, 10):
+        b = RVEBatch().set_meshes(meshes, param, model=model)
+        b.set_option(L.OPT_RESIDUAL_REPLACE, every).assemble()
+        st, it = b.solve(eps, rtol=1e-11, maxit=4000)
+        C = b.tangent()
+        its[every] = it.copy()
+        b.close()
+        for s in range(3):
+            assert np.abs(C[s] - ref[s]).max() <= 1e-8 * np.abs(ref[s]).max(), (every, s)
+    assert its[10].max() <= 2 * its[0].max() + 10      # the restarts may cost iterations, not convergence
