@@ -20,7 +20,7 @@ import numpy as np
 
 from . import wrapper_h5py as myhd
 from .simulation_snapshots import vref_box_from_mesh
-from .vref import vref_points
+from .vref import COMP_LABEL, COORD_LABEL, load_vref_vectors, vref_order_datasets, vref_points
 
 DEVICE = "cuda"
 
@@ -161,7 +161,7 @@ class NNElast:
         self.labels = list(net.keys())
         self.Wbasis, self.scalerX, self.scalerY, self.model = {}, {}, {}, {}
         for l in self.labels:
-            self.Wbasis[l] = myhd.loadhd5(nameWbasis, 'Wbasis_%s' % l)
+            self.Wbasis[l] = load_vref_vectors(nameWbasis, 'Wbasis_%s' % l)     # library Vref DOF order (deepbnd_b200/vref.py)
             self.scalerX[l], self.scalerY[l] = importScale(net[l].files['scaler'], net[l].nX, net[l].nY, scalertype)
             self.model[l] = net[l].getModel(device=device)
 
@@ -192,5 +192,6 @@ def predictBCs(namefiles, net, device=None):
     S_p = model.predict(paramRVEdata[:, :, 2], nameMeshRefBnd)
     if os.path.exists(bcs_namefile):
         os.remove(bcs_namefile)
-    myhd.savehd5(bcs_namefile, S_p, ['u0', 'u1', 'u2'], mode='w')
+    coords, comps = vref_order_datasets(*vref_box_from_mesh(nameMeshRefBnd))
+    myhd.savehd5(bcs_namefile, S_p + [coords, comps], ['u0', 'u1', 'u2', COORD_LABEL, COMP_LABEL], mode='w')
     return S_p

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import wrapper_h5py as myhd
 from .simulation_snapshots import vref_box_from_mesh
-from .vref import vref_mass, vref_points
+from .vref import COMP_LABEL, COORD_LABEL, load_vref_vectors, vref_mass, vref_order_datasets, vref_points
 
 
 DEVICE = "cuda"
@@ -34,7 +34,8 @@ def getMassMatrix(nameMeshRefBnd=None):
 def translateSolution(nameSnaps, nameMeshRefBnd=None):
     """solutions_trans_partial_X = solutions_X + a_X at every Vref node (reference :36-51, B = 0)."""
     for load_flag in ['A', 'S']:
-        Isol, a = myhd.loadhd5(nameSnaps, ['solutions_%s' % load_flag, 'a_%s' % load_flag])
+        Isol = load_vref_vectors(nameSnaps, 'solutions_%s' % load_flag, *vref_box_from_mesh(nameMeshRefBnd))
+        a = myhd.loadhd5(nameSnaps, 'a_%s' % load_flag)
         trans = Isol + np.tile(a, (1, Isol.shape[1] // 2))
         myhd.addDataset(nameSnaps, trans, 'solutions_trans_partial_%s' % load_flag)
 
@@ -62,7 +63,8 @@ def computingBasis(nameSnaps, nameWbasis, Nmax, Nh=None, nameMeshRefBnd=None, de
         W, sig2 = computingBasis_svd(Isol, M, Nmax, device)
         out['Wbasis_%s' % load_flag] = W
         out['sig_%s' % load_flag] = sig2[:Nmax]
-    labels = ['Wbasis_A', 'Wbasis_S', 'sig_A', 'sig_S', 'massMat']
+    out[COORD_LABEL], out[COMP_LABEL] = vref_order_datasets(*vref_box_from_mesh(nameMeshRefBnd))
+    labels = ['Wbasis_A', 'Wbasis_S', 'sig_A', 'sig_S', 'massMat', COORD_LABEL, COMP_LABEL]
     myhd.savehd5(nameWbasis, [out[l] for l in labels], labels, 'w')
 
 

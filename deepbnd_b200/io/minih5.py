@@ -10,10 +10,12 @@ Specification v1/v2 subset):
           v1 object headers, CONTIGUOUS little-endian f8/f4/i8/i4/u1 datasets in the root group —
           the most conservative layout; h5py/libhdf5 open it in 'r' and 'a' mode and can add
           datasets to it (build_inout.py:39,50 does that to snapshots.hd5).
-  reader  superblock v0/v1, v1 object headers with continuation blocks, old-style groups (nested),
-          datatypes int/float of any size/endianness, layouts compact / contiguous / chunked
-          (B-tree v1) with the deflate, shuffle and fletcher32 filters — what h5py's default
-          (libver='earliest') writes for the reference's files.
+  reader  superblock v0/v1, v1 and v2 object headers with continuation blocks, old-style groups (nested) and
+          new-style groups with compact link storage (hard, soft and EXTERNAL links: the `_regions.h5` files of
+          wrapper_io.py:124-127), datatypes int/float of any size/endianness, layouts compact / contiguous /
+          chunked (B-tree v1) with the deflate, shuffle and fletcher32 filters — what h5py's default
+          (libver='earliest') writes for the reference's files.  tests/golden/make_h5_fixtures.py assembles
+          such files byte by byte from the format specification, independently of the writer below.
 
 Only whole-dataset reads and writes are supported (that is all the reference does).
 """
@@ -61,12 +63,51 @@ def _object_header(messages):
     return struct.pack("<BBHII", 1, 0, len(messages), 1, len(body)) + b"\x00" * 4 + body
 
 
-class Writer:
-    """Collects root-group datasets and writes the file on close()."""
+def _chunk_btree(out_append, keys, rank, end_offsets):
+    """version-1 B-tree of chunk records (node type 1) over `keys` = [(nbytes, offsets, address)], at most 64 entries
+    per node (the default 'indexed storage internal node K' = 32); `out_append(bytes) -> address`; returns the root."""
+    CAP = 64
+    level = 0
+    nodes = [(k[1], k[0], k[2]) for k in keys]            # (first chunk offsets, nbytes of the first chunk, child address)
+    while True:
+        groups = [nodes[i:i + CAP] for i in range(0, len(nodes), CAP)]
+        addrs, sizes = [], []
+        for g in groups:
+            sizes.append(24 + len(g) * (8 + 8 * (rank + 1) + 8) + 8 + 8 * (rank + 1))
+        base = out_append(b"\x00" * 0)                     # current end (aligned)
+        pos = base
+        for sz in sizes:
+            addrs.append(pos)
+            pos += sz + (-sz % 8)
+        new_nodes = []
+        for gi, g in enumerate(groups):
+            left = addrs[gi - 1] if gi > 0 else _UNDEF
+            right = addrs[gi + 1] if gi + 1 < len(groups) else _UNDEF
+            node = b"TREE" + struct.pack("<BBH", 1, level, len(g)) + struct.pack("<QQ", left, right)
+            for offs, nbytes, child in g:
+                node += struct.pack("<II", nbytes, 0) + b"".join(struct.pack("<Q", o) for o in offs) + struct.pack("<Q", child)
+            last = groups[gi + 1][0][0] if gi + 1 < len(groups) else end_offsets
+            node += struct.pack("<II", 0, 0) + b"".join(struct.pack("<Q", o) for o in last)
+            a = out_append(_pad8(node))
+            assert a == addrs[gi]
+            new_nodes.append((g[0][0], g[0][1], a))
+        if len(new_nodes) == 1:
+            return new_nodes[0][2]
+        nodes = new_nodes
+        level += 1
 
-    def __init__(self, path):
+
+class Writer:
+    """Collects root-group datasets and writes the file on close().  layout='contiguous' (default) or 'chunked' =
+    the reference's dataset creation properties (wrapper_h5py.py:30-34): chunks (1, ...), deflate level 0."""
+
+    def __init__(self, path, layout="contiguous"):
+        if layout not in ("contiguous", "chunked"):
+            raise ValueError("layout must be 'contiguous' or 'chunked'")
         self.path = path
         self.items = {}
+        self.layout = layout
+        self.data_addr = {}               # name -> file offset of the raw data (contiguous layout), after close()
 
     def create_dataset(self, name, data):
         a = np.asarray(data)
@@ -127,25 +168,54 @@ class Writer:
         for _ in groups:
             snods.append(pos)
             pos += snod_size
-        obj_hdr, obj_bytes, data_addr = {}, {}, {}
+        obj_hdr, obj_bytes, data_addr, chunked = {}, {}, {}, {}
         for n in names:
             a = self.items[n]
             obj_hdr[n] = pos
             shape = a.shape if a.ndim else ()
             space = struct.pack("<BBBBI", 1, len(shape), 0, 0, 0) + b"".join(struct.pack("<Q", d) for d in shape)
-            msgs = [_message(0x0001, space), _message(0x0003, _dtype_message(a.dtype), flags=1),
-                    _message(0x0005, struct.pack("<BBBB", 2, 2, 2, 0)),
-                    _message(0x0008, struct.pack("<BBQQ", 3, 1, 0, 0)),                    # patched below
-                    _message(0x0000, b"\x00" * 64)]                                        # NIL: room for attributes
+            chunked[n] = self.layout == "chunked" and a.ndim >= 1 and a.size > 0
+            if chunked[n]:
+                cd = (1,) + tuple(shape[1:]) + (a.dtype.itemsize,)
+                lay = struct.pack("<BBBQ", 3, 2, len(cd), 0) + b"".join(struct.pack("<I", c) for c in cd)   # B-tree address patched below
+                filt = struct.pack("<BB6x", 1, 1) + struct.pack("<HHHHI4x", 1, 0, 0, 1, 0)                   # deflate, level 0
+                msgs = [_message(0x0001, space), _message(0x0003, _dtype_message(a.dtype), flags=1),
+                        _message(0x0005, struct.pack("<BBBB", 2, 1, 0, 0)), _message(0x000B, filt),
+                        _message(0x0008, lay), _message(0x0000, b"\x00" * 64)]
+            else:
+                msgs = [_message(0x0001, space), _message(0x0003, _dtype_message(a.dtype), flags=1),
+                        _message(0x0005, struct.pack("<BBBB", 2, 2, 2, 0)),
+                        _message(0x0008, struct.pack("<BBQQ", 3, 1, 0, 0)),                # patched below
+                        _message(0x0000, b"\x00" * 64)]                                    # NIL: room for attributes
             obj_bytes[n] = bytearray(_object_header(msgs))
             pos += len(obj_bytes[n])
         for n in names:
+            if chunked[n]:
+                continue
             pos += -pos % 8
             data_addr[n] = pos if self.items[n].nbytes else _UNDEF
             pos += self.items[n].nbytes
         eof = pos
 
         out = bytearray(eof)
+        tail = bytearray()                                # chunk data and chunk B-trees follow the fixed part
+
+        def append(b):
+            tail.extend(b"\x00" * (-(eof + len(tail)) % 8))
+            a = eof + len(tail)
+            tail.extend(b)
+            return a
+
+        for n in names:
+            if not chunked[n]:
+                continue
+            a = self.items[n]
+            rank = a.ndim
+            keys = []
+            for i in range(a.shape[0]):
+                comp = zlib.compress(a[i:i + 1].tobytes(), 0)
+                keys.append((len(comp), (i,) + (0,) * rank, append(comp)))
+            data_addr[n] = _chunk_btree(append, keys, rank, (a.shape[0],) + (0,) * rank)
         # ---- superblock v0
         sb = _SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, LEAF_K, INT_K, 0)
         sb += struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF)
@@ -185,13 +255,22 @@ class Writer:
         for n in names:
             a = self.items[n]
             ob = obj_bytes[n]
+            if chunked[n]:
+                idx = ob.find(struct.pack("<BBB", 3, 2, a.ndim + 1), 16)
+                struct.pack_into("<Q", ob, idx + 3, data_addr[n])
+                out[obj_hdr[n]:obj_hdr[n] + len(ob)] = ob
+                continue
             idx = ob.find(struct.pack("<HH", 0x0008, 24))
             struct.pack_into("<QQ", ob, idx + 8 + 2, data_addr[n], a.nbytes)
             out[obj_hdr[n]:obj_hdr[n] + len(ob)] = ob
             if a.nbytes:
                 out[data_addr[n]:data_addr[n] + a.nbytes] = a.tobytes()
+        if tail:
+            struct.pack_into("<Q", out, 24 + 16, eof + len(tail))          # end-of-file address of the superblock
+        self.data_addr = {n: data_addr[n] for n in names if not chunked[n]}
         with open(self.path, "wb") as f:
             f.write(out)
+            f.write(tail)
 
 
 # =================================================================================================
@@ -322,6 +401,7 @@ class File:
     """Read-only view: `f[name]` -> dataset (np.array(f[name]) reads it) or sub-group; `keys()`."""
 
     def __init__(self, path):
+        self.path = path
         with open(path, "rb") as fh:
             self.buf = fh.read()
         # the superblock may sit at 0, 512, 1024, ... (user block, e.g. MATLAB v7.3 files)
@@ -354,7 +434,7 @@ class File:
     def _read_header(self, addr):
         hd = self._read(addr, 16)
         if hd[:4] == b"OHDR":
-            raise NotImplementedError("minih5: version-2 object headers (write the file with libver='earliest')")
+            return self._read_header_v2(addr)
         ver, _, nmsgs, refc, hsize = struct.unpack_from("<BBHII", hd, 0)
         if ver != 1:
             raise ValueError("minih5: bad object header")
@@ -373,6 +453,67 @@ class File:
                     blocks.append((ca, cs))
                 msgs.append((mtype, data))
         return msgs
+
+    def _read_header_v2(self, addr):
+        """version-2 object header ('OHDR'; groups that hold link messages, files written with libver='latest')"""
+        hd = self._read(addr, 6)
+        if hd[4] != 2:
+            raise ValueError("minih5: bad version-2 object header")
+        flags = hd[5]
+        o = addr + 6
+        if flags & 0x20:
+            o += 16                                    # access / modification / change / birth times
+        if flags & 0x10:
+            o += 4                                     # max compact / min dense attributes
+        nsz = 1 << (flags & 3)
+        size = int.from_bytes(self._read(o, nsz), "little")
+        o += nsz
+        msgs = []
+        blocks = [(o, size)]
+        while blocks:
+            a, size = blocks.pop(0)
+            blk = self._read(a, size)
+            p = 0
+            while p + 4 <= size:
+                mtype = blk[p]
+                msize, mflags = struct.unpack_from("<HB", blk, p + 1)
+                p += 4 + (2 if flags & 0x04 else 0)    # creation order
+                data = blk[p:p + msize]
+                p += msize
+                if mtype == 0x10:                      # continuation: 'OCHK' + messages + checksum
+                    ca, cs = struct.unpack_from("<QQ", data, 0)
+                    blocks.append((ca + 4, cs - 8))
+                elif mtype != 0:
+                    msgs.append((mtype, data))
+        return msgs
+
+    @staticmethod
+    def _parse_link(d):
+        """Link message -> (name, kind, payload): ('hard', address) | ('soft', path) | ('external', (file, path))"""
+        ver, flags = d[0], d[1]
+        o = 2
+        ltype = 0
+        if flags & 0x08:
+            ltype = d[o]; o += 1
+        if flags & 0x04:
+            o += 8                                     # creation order
+        if flags & 0x10:
+            o += 1                                     # character set
+        nsz = 1 << (flags & 3)
+        nlen = int.from_bytes(d[o:o + nsz], "little")
+        o += nsz
+        name = bytes(d[o:o + nlen]).decode()
+        o += nlen
+        if ltype == 0:
+            return name, "hard", struct.unpack_from("<Q", d, o)[0]
+        ilen = struct.unpack_from("<H", d, o)[0]
+        info = bytes(d[o + 2:o + 2 + ilen])
+        if ltype == 1:
+            return name, "soft", info.decode()
+        if ltype == 64:
+            fn, obj = info[1:].split(b"\x00")[:2]
+            return name, "external", (fn.decode(), obj.decode())
+        raise NotImplementedError("minih5: link type %d" % ltype)
 
     @staticmethod
     def _parse_dataspace(d):
@@ -451,15 +592,27 @@ class File:
 
 
 class _Group:
+    """old-style groups (symbol table) and new-style groups with compact link storage (link messages in the object
+    header — what libhdf5 turns a group into when an ExternalLink is added, wrapper_io.py:124-127)"""
+
     def __init__(self, f, addr):
         self.f = f
-        self.entries = {}
+        self.entries = {}                 # name -> object header address
+        self.links = {}                   # name -> ('soft', path) | ('external', (file, path))
         for t, d in f._read_header(addr):
             if t == 0x0011:
                 btree, heap = struct.unpack_from("<QQ", d, 0)
                 self._load(btree, heap)
-            elif t in (0x0002, 0x0006):
-                raise NotImplementedError("minih5: new-style groups (write the file with libver='earliest')")
+            elif t == 0x0002:
+                o = 2 + (8 if d[1] & 1 else 0)
+                if struct.unpack_from("<Q", d, o)[0] != _UNDEF:
+                    raise NotImplementedError("minih5: groups with dense link storage (fractal heap)")
+            elif t == 0x0006:
+                name, kind, payload = f._parse_link(d)
+                if kind == "hard":
+                    self.entries[name] = payload
+                else:
+                    self.links[name] = (kind, payload)
 
     def _load(self, btree, heap):
         f = self.f
@@ -494,13 +647,23 @@ class _Group:
             walk(btree)
 
     def keys(self):
-        return list(self.entries)
+        return list(self.entries) + list(self.links)
 
     def __getitem__(self, name):
+        if name in self.links:
+            kind, payload = self.links[name]
+            if kind == "soft":
+                return self.f[payload]
+            import os
+            fn, obj = payload                               # external link: relative to the directory of this file
+            target = fn if os.path.isabs(fn) else os.path.join(os.path.dirname(os.path.abspath(self.f.path)), fn)
+            if not os.path.exists(target):
+                raise KeyError("%s -> external link to missing file %s" % (name, target))
+            return File(target)[obj]
         if name not in self.entries:
             raise KeyError(name)
         addr = self.entries[name]
         msgs = self.f._read_header(addr)
-        if any(t == 0x0011 for t, _ in msgs):
+        if any(t in (0x0011, 0x0002, 0x0006) for t, _ in msgs):
             return _Group(self.f, addr)
         return _Dataset(self.f, addr)

@@ -27,6 +27,16 @@ def _dataitems(xdmf_path):
     return out
 
 
+def read_xdmf_points(meshFile):
+    """vertex coordinates (nv, 2) of an XDMF mesh; no cell markers needed (the boundary reference mesh Vref)"""
+    for fn, ds, dims in _dataitems(meshFile):
+        with minih5.File(fn) as f:
+            a = np.array(f[ds])
+        if a.dtype.kind == "f" and a.ndim == 2:
+            return np.ascontiguousarray(a[:, :2].astype(np.float64))
+    raise ValueError("read_xdmf_points: no coordinate array in %s" % meshFile)
+
+
 def read_xdmf_mesh(meshFile):
     """-> (points (nv,2) f8, triangles (nt,3) i4, region (nt,) i4)."""
     items = _dataitems(meshFile)
@@ -44,9 +54,9 @@ def read_xdmf_mesh(meshFile):
         for fn, ds, dims in _dataitems(rfile):
             try:
                 with minih5.File(fn) as f:
-                    a = np.array(f[ds])
-            except (KeyError, NotImplementedError, ValueError):
-                continue                      # the ExternalLink back to mesh.h5 (geometry is read from there)
+                    a = np.array(f[ds])           # data1 of *_regions.h5 is an ExternalLink back to mesh.h5 (resolved)
+            except KeyError:
+                continue                      # link target missing: the geometry is read from mesh.h5 anyway
             if a.dtype.kind in "iu" and (a.ndim == 1 or (a.ndim == 2 and a.shape[1] == 1)) and tri is not None \
                     and a.shape[0] == tri.shape[0]:
                 reg = a.reshape(-1).astype(np.int32)

@@ -17,8 +17,9 @@ import numpy as np
 from . import wrapper_h5py as myhd
 from .batch import DoubleBuffer
 from .elasticity import macro_strain_voigt
-from .mesh.mesh_io import cache_name, load_mesh, read_xdmf_mesh, save_mesh_cache
+from .mesh.mesh_io import cache_name, load_mesh, read_xdmf_points, save_mesh_cache
 from .mesh.rve_mesher import buildRVEmesh_arrays, paramRVE_default
+from .vref import COMP_LABEL, COORD_LABEL, vref_order_datasets
 
 LABELS = ['id', 'solutions_S', 'sigma_S', 'a_S', 'B_S', 'sigmaTotal_S',
           'solutions_A', 'sigma_A', 'a_A', 'B_A', 'sigmaTotal_A']
@@ -26,26 +27,30 @@ LABELS = ['id', 'solutions_S', 'sigma_S', 'a_S', 'B_S', 'sigmaTotal_S',
 
 def vref_box_from_mesh(bndMeshname):
     """Bounding box (x0, y0, Lx, Ly) and Nb of the internal-boundary reference mesh
-    (degeneratedBoundaryRectangleMesh, core/mesh/degenerated_rectangle_mesh.py:3-35).  Falls back to the
-    reference's constants (paramRVE_default: [-1,1]^2, Nb = 21) when the file is absent."""
+    (degeneratedBoundaryRectangleMesh, core/mesh/degenerated_rectangle_mesh.py:3-35).  The reference's constants
+    (paramRVE_default: [-1,1]^2, Nb = 21) are used ONLY when no file is given / the file does not exist; a file
+    that exists but cannot be read raises (a silently different Vref box would change nh and every sample)."""
     p = paramRVE_default()
-    box, nb = (p.x0L, p.y0L, p.LxL, p.LyL), 21
-    if bndMeshname and os.path.exists(bndMeshname):
-        try:
-            pts, tri, _ = read_xdmf_mesh(bndMeshname)
-            x0, y0 = pts.min(axis=0)
-            Lx, Ly = np.ptp(pts[:, 0]), np.ptp(pts[:, 1])
-            box, nb = (x0, y0, Lx, Ly), (len(pts) - 1) // 4 + 1
-        except Exception:                                       # noqa: BLE001 - markers are optional for Vref
-            pass
-    return box, nb
+    if not bndMeshname or not os.path.exists(bndMeshname):
+        return (p.x0L, p.y0L, p.LxL, p.LyL), 21
+    pts = read_xdmf_points(bndMeshname)                         # no cell markers needed for Vref
+    x0, y0 = pts.min(axis=0)
+    Lx, Ly = np.ptp(pts[:, 0]), np.ptp(pts[:, 1])
+    if (len(pts) - 1) % 4:
+        raise ValueError("%s: %d vertices is not 4 (Nb - 1) + 1: not a degeneratedBoundaryRectangleMesh" % (bndMeshname, len(pts)))
+    return (float(x0), float(y0), float(Lx), float(Ly)), (len(pts) - 1) // 4 + 1
 
 
 def _mesh_job(args):
+    """createMesh=True: mesh and hand the arrays back (the reference overwrites ONE temporary mesh per rank; nothing
+    is left on disk here unless DEEPBND_KEEP_MESHES=1).  createMesh=False: the cached / XDMF mesh of that name, meshed
+    and cached on first use ("generated once and cached")."""
     row, meshname, size, createMesh = args
-    if createMesh or not (os.path.exists(cache_name(meshname)) or os.path.exists(meshname)):
+    have = os.path.exists(cache_name(meshname)) or os.path.exists(meshname)
+    if createMesh or not have:
         mesh = buildRVEmesh_arrays(row, isOrdered=False, size=size)        # permutes `row` in place
-        save_mesh_cache(meshname, mesh)
+        if not createMesh or os.environ.get("DEEPBND_KEEP_MESHES") == "1":
+            save_mesh_cache(meshname, mesh)
         return mesh, row
     return load_mesh(meshname), row
 
@@ -53,8 +58,26 @@ def _mesh_job(args):
 def make_mesh_pool(nproc=None):
     """Process pool for the meshing jobs, to be created BEFORE the GPU handles and their host worker threads exist
     (the workers are forked from a single-threaded, CUDA-free parent and re-used for every batch).  None = serial."""
-    nproc = nproc or (os.cpu_count() or 1)
+    nproc = nproc or default_nproc()
     return mp.get_context("fork").Pool(nproc) if nproc > 1 else None
+
+
+def default_nproc():
+    """meshing workers of this rank: the host cores divided among the ranks of the node"""
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+    return max(1, (os.cpu_count() or 1) // max(1, local_world))
+
+
+def default_device(run):
+    """CUDA device of rank `run`: LOCAL_RANK under torchrun, else the rank modulo the visible devices"""
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
+    try:
+        import torch
+        n = torch.cuda.device_count()
+    except Exception:                                               # noqa: BLE001
+        n = 0
+    return int(run) % n if n > 0 else int(run)
 
 
 def get_meshes(paramRVEdata, meshnames, size, createMesh, nproc=None, template=None, pool=None):
@@ -65,7 +88,7 @@ def get_meshes(paramRVEdata, meshnames, size, createMesh, nproc=None, template=N
         from .mesh.rve_morph import buildRVEmesh_morphed
         return [buildRVEmesh_morphed(paramRVEdata[i], template) for i in range(len(meshnames))]
     jobs = [(paramRVEdata[i], meshnames[i], size, createMesh) for i in range(len(meshnames))]
-    nproc = nproc or min(len(jobs), os.cpu_count() or 1)
+    nproc = nproc or min(len(jobs), default_nproc())
     if pool is not None and len(jobs) >= 4:
         res = pool.map(_mesh_job, jobs, chunksize=max(1, len(jobs) // (4 * nproc)))
     elif nproc <= 1 or len(jobs) < 4:
@@ -124,6 +147,10 @@ def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs
                                             shape=[(nrun,)] + 2 * [(nrun, nh), (nrun, 3), (nrun, 2), (nrun, 2, 2), (nrun, 3)],
                                             label=LABELS, mode='w-')
     ids = snapshots[0]
+    # DOF order of the solutions_* vectors, self-described in the file (deepbnd_b200/vref.py)
+    coords, comps = vref_order_datasets(box, nb)
+    myhd.addDataset(fsnaps, coords, COORD_LABEL)
+    myhd.addDataset(fsnaps, comps, COMP_LABEL)
     paramRVEdata = myhd.loadhd5(paramRVEname, 'param')[ids_run]
 
     template = None
@@ -146,10 +173,10 @@ def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs
     def store(rows, out):
         ids[rows] = ids_run[rows]
         _store_snapshots(rows, out, snapshots)
-        fsnaps.flush()
+        fsnaps.flush(rows)
 
     pool = make_mesh_pool(nproc) if template is None else None             # forked before the GPU threads exist
-    db = DoubleBuffer(run if device is None else device)
+    db = DoubleBuffer(default_device(run) if device is None else device)
     try:
         db.run([np.arange(b0, min(nrun, b0 + batch_size)) for b0 in range(0, nrun, batch_size)], prepare, solve, store)
     finally:

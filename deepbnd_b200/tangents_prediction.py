@@ -14,7 +14,8 @@ import numpy as np
 from . import wrapper_h5py as myhd
 from .batch import DoubleBuffer
 from .elasticity import macro_strain_voigt
-from .simulation_snapshots import get_meshes, make_mesh_pool, vref_box_from_mesh
+from .simulation_snapshots import default_device, get_meshes, make_mesh_pool, vref_box_from_mesh
+from .vref import load_vref_vectors
 
 
 def predictTangents(num, num_runs, modelBnd, namefiles, createMesh, meshSize, device=None, batch_size=2048,
@@ -39,7 +40,10 @@ def predictTangents(num, num_runs, modelBnd, namefiles, createMesh, meshSize, de
                                                       ['id', 'tangent', 'center'], mode='w')
     uD_all = None
     if modelBnd == 'dnn':
-        uD_all = np.stack([myhd.loadhd5(BCname, 'u%d' % k)[run::num_runs, :] for k in range(3)], axis=1)
+        # bcs.hd5 in the library's Vref DOF order: permuted if the file (or a sidecar) describes another order, refused
+        # if it describes none (deepbnd_b200/vref.py)
+        u012 = load_vref_vectors(BCname, ['u0', 'u1', 'u2'], box=vref[0], Nb=vref[1])
+        uD_all = np.stack([u[run::num_runs, :] for u in u012], axis=1)
 
     contrast, E2, nu = 10.0, 1.0, 0.3
     param = [nu, E2 * contrast, nu, E2]
@@ -68,11 +72,11 @@ def predictTangents(num, num_runs, modelBnd, namefiles, createMesh, meshSize, de
         Iid[rows] = ids[rows]
         Itangent[rows, :, :] = tangents
         Icenter[rows, :] = centers[rows, :]
-        f.flush()
+        f.flush(rows)
         sys.stdout.flush()
 
     pool = make_mesh_pool(nproc) if template is None else None             # forked before the GPU threads exist
-    db = DoubleBuffer(run if device is None else device)
+    db = DoubleBuffer(default_device(run) if device is None else device)
     try:
         db.run([np.arange(b0, min(ns, b0 + batch_size)) for b0 in range(0, ns, batch_size)], prepare, solve, store)
     finally:

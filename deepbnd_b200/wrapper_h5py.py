@@ -1,8 +1,10 @@
 """Numpy-facing dataset I/O with the call signatures of the reference's
 core/data_manipulation/wrapper_h5py.py (loadhd5 :38-49, savehd5 :64-72, addDataset :75-78,
 zeros_openFile :82-96, checkExistenceDataset :159-161, merge :105-122), implemented on the in-tree
-HDF5 reader/writer (deepbnd_b200/io/minih5.py) because h5py is not part of this image.  When h5py
-is importable it is used instead, with the reference's exact dataset creation properties."""
+HDF5 reader/writer (deepbnd_b200/io/minih5.py) because h5py is not part of this image: reads always go through
+minih5; writes use h5py with the reference's exact dataset creation properties when it is importable, else
+minih5.Writer — contiguous datasets by default, the reference's chunked (1, ...) + deflate-0 layout
+(wrapper_h5py.py:30-34) with DEEPBND_H5_LAYOUT=chunked."""
 import os
 
 import numpy as np
@@ -73,10 +75,12 @@ def _write(filename, items):
                     f.create_dataset(k, data=v)
         return
     tmp = filename + ".tmp%d" % os.getpid()
-    with minih5.Writer(tmp) as w:
-        for k, v in items.items():
-            w.create_dataset(k, v)
+    w = minih5.Writer(tmp, layout=os.environ.get("DEEPBND_H5_LAYOUT", "contiguous"))
+    for k, v in items.items():
+        w.create_dataset(k, v)
+    w.close()
     os.replace(tmp, filename)
+    return w.data_addr
 
 
 class ZerosFile:
@@ -87,9 +91,29 @@ class ZerosFile:
         self.filename = filename
         self.arrays = arrays
         self.closed = False
+        self._addr = None                  # dataset -> file offset of its (contiguous) data after the first write
+        self._rowwise = list(arrays)       # the datasets the caller fills row by row (addDataset adds static ones)
 
-    def flush(self):
-        _write(self.filename, self.arrays)
+    def flush(self, rows=None):
+        """rows=None: (re)write the whole file; rows = indices along axis 0 that changed since the last flush: only
+        those rows are written in place (a 100k-snapshot campaign flushes per batch without rewriting the file)"""
+        if rows is None or not self._addr or not os.path.exists(self.filename):
+            self._addr = _write(self.filename, self.arrays)
+            return
+        rows = np.unique(np.asarray(rows, dtype=np.int64))
+        if len(rows) == 0:
+            return
+        runs = np.split(rows, np.flatnonzero(np.diff(rows) != 1) + 1)
+        with open(self.filename, "r+b") as fh:
+            for k in self._rowwise:
+                a = self.arrays[k]
+                if k not in self._addr or a.ndim == 0 or a.dtype != np.float64:
+                    self._addr = _write(self.filename, self.arrays)      # layout not updatable in place
+                    return
+                rb = a[0:1].nbytes
+                for r in runs:
+                    fh.seek(self._addr[k] + int(r[0]) * rb)
+                    fh.write(np.ascontiguousarray(a[r[0]:r[-1] + 1]).tobytes())
 
     def close(self):
         if not self.closed:

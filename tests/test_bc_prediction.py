@@ -116,7 +116,9 @@ def test_predictBCs_writes_bcs_file(tmp_path):
         keep[l] = (w, tab)
     Wb = {l: rs.randn(20, 162) for l in ('A', 'S')}
     nameW = str(tmp_path / "Wbasis.hd5")
-    myhd.savehd5(nameW, [Wb['A'], Wb['S']], ['Wbasis_A', 'Wbasis_S'], mode='w')
+    from deepbnd_b200.vref import COMP_LABEL, COORD_LABEL, vref_order_datasets
+    coords, comps = vref_order_datasets()
+    myhd.savehd5(nameW, [Wb['A'], Wb['S'], coords, comps], ['Wbasis_A', 'Wbasis_S', COORD_LABEL, COMP_LABEL], mode='w')
     param = np.zeros((ns, 36, 5))
     param[:, :, 2] = 0.2 + 0.2 * rs.rand(ns, 36)
     nameP = str(tmp_path / "paramRVEdataset.hd5")

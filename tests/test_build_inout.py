@@ -22,6 +22,8 @@ def _fake_snapshots(path, ns=300, seed=0):
         data["solutions_" + lab] = U
         data["a_" + lab] = 0.01 * rng.randn(ns, 2)
         data["B_" + lab] = np.zeros((ns, 2, 2))
+    from deepbnd_b200.vref import COMP_LABEL, COORD_LABEL, vref_order_datasets
+    data[COORD_LABEL], data[COMP_LABEL] = vref_order_datasets()
     myhd.savehd5(path, list(data.values()), list(data.keys()), 'w')
     return data
 

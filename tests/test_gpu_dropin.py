@@ -55,7 +55,9 @@ def test_predictTangents_matches_oracle(tmp_path, modelBnd):
     pfile, tfile, bfile = (str(tmp_path / n) for n in ("paramRVEdataset.hd5", "tangents.hd5", "bcs.hd5"))
     myhd.savehd5(pfile, [par, np.arange(ns, dtype=float), np.arange(2.0 * ns).reshape(ns, 2)], ['param', 'id', 'center'], 'w')
     uD = np.stack([np.stack([smooth_uD(81, 10 * s + i) for s in range(ns)]) for i in range(3)])   # (3, ns, 162)
-    myhd.savehd5(bfile, [uD[0], uD[1], uD[2]], ['u0', 'u1', 'u2'], 'w')
+    from deepbnd_b200.vref import COMP_LABEL, COORD_LABEL, vref_order_datasets
+    coords, comps = vref_order_datasets()
+    myhd.savehd5(bfile, [uD[0], uD[1], uD[2], coords, comps], ['u0', 'u1', 'u2', COORD_LABEL, COMP_LABEL], 'w')
     mname = str(tmp_path / "meshes" / "mesh_micro_{0}_{1}.xdmf")
     predictTangents(0, 1, modelBnd, ["", pfile, tfile, bfile, mname], True, 'reduced', device=0)
     T, ids, cen = myhd.loadhd5(tfile, 'tangent'), myhd.loadhd5(tfile, 'id'), myhd.loadhd5(tfile, 'center')

@@ -1,9 +1,12 @@
 """CPU tests of the dataset I/O layer (the reference's wrapper_h5py.py call surface on the in-tree
 HDF5 reader/writer) and of the mesh cache."""
 import os
+import struct
 
 import numpy as np
 import pytest
+
+import deepbnd_b200.wrapper_h5py as myhd
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -101,3 +104,113 @@ def test_xdmf_triplet_reader(tmp_path, coarse_reduced_meshes):
     open(base + "_regions.xdmf", "w").write(xr)
     p2, t2, r2 = read_xdmf_mesh(base + ".xdmf")
     assert np.array_equal(p2, p) and np.array_equal(t2, t) and np.array_equal(r2, r)
+
+
+# ---- interop with files this package did not write (N1, a17) -------------------------------------------
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_reader_on_hand_assembled_chunked_deflate_file():
+    """tests/golden/make_h5_fixtures.py builds this file byte by byte from the HDF5 specification (not with
+    minih5.Writer): chunks (1, ...) + deflate level 0, chunk B-tree v1 — the layout of wrapper_h5py.py:30-34."""
+    e = np.load(os.path.join(GOLD, "h5_fixtures_expected.npz"))
+    fn = os.path.join(GOLD, "chunked_deflate0.h5")
+    assert sorted(myhd.minih5.File(fn).keys()) == ["B_S", "id", "solutions_S"]
+    for k in ("solutions_S", "B_S", "id"):
+        a = myhd.loadhd5(fn, k)
+        assert a.shape == e[k].shape and np.array_equal(a, e[k]), k
+    assert myhd.checkExistenceDataset(fn, "id") and not myhd.checkExistenceDataset(fn, "nope")
+
+
+@pytest.mark.parametrize("ver", [1, 2])
+def test_reader_follows_external_links_in_new_style_groups(ver):
+    """the `_regions.h5` of wrapper_io.py:124-127: link messages (v1 and v2 object headers), data1 -> mesh.h5:/data1"""
+    e = np.load(os.path.join(GOLD, "h5_fixtures_expected.npz"))
+    f = myhd.minih5.File(os.path.join(GOLD, "link_regions_v%d.h5" % ver))
+    assert sorted(f.keys()) == ["data0", "data1", "data2"]
+    assert np.array_equal(np.array(f["data1"]), e["tri"])          # through the external link, chunked + deflate 4
+    assert np.array_equal(np.array(f["data2"]), e["tags"])
+    assert np.array(f["data0"]).shape == (1, 2)
+
+
+def test_xdmf_triplet_with_external_link_is_read(tmp_path):
+    """meshio-3.3-style triplet around the hand-assembled files: mesh.xdmf -> link_mesh.h5, mesh_regions.xdmf ->
+    link_regions.h5 whose topology item is the ExternalLink"""
+    import shutil
+    from deepbnd_b200.mesh.mesh_io import read_xdmf_mesh
+    e = np.load(os.path.join(GOLD, "h5_fixtures_expected.npz"))
+    shutil.copy(os.path.join(GOLD, "link_mesh.h5"), tmp_path / "link_mesh.h5")
+    shutil.copy(os.path.join(GOLD, "link_regions_v1.h5"), tmp_path / "mesh_regions.h5")
+    (tmp_path / "mesh.xdmf").write_text(
+        '<Xdmf Version="3.0"><Domain><Grid Name="Grid"><Geometry GeometryType="XY"><DataItem DataType="Float" Dimensions="9 2" '
+        'Format="HDF" Precision="8">link_mesh.h5:/data0</DataItem></Geometry><Topology NumberOfElements="7" TopologyType="Triangle">'
+        '<DataItem DataType="Int" Dimensions="7 3" Format="HDF" Precision="8">link_mesh.h5:/data1</DataItem></Topology></Grid></Domain></Xdmf>')
+    (tmp_path / "mesh_regions.xdmf").write_text(
+        '<Xdmf Version="3.0"><Domain><Grid Name="Grid"><Geometry GeometryType="XY"><DataItem DataType="Float" Dimensions="1 2" '
+        'Format="HDF" Precision="8">mesh_regions.h5:/data0</DataItem></Geometry><Topology NumberOfElements="7" TopologyType="Triangle">'
+        '<DataItem DataType="Int" Dimensions="7 3" Format="HDF" Precision="8">mesh_regions.h5:/data1</DataItem></Topology>'
+        '<Attribute AttributeType="Scalar" Center="Cell" Name="regions"><DataItem DataType="Int" Dimensions="7" Format="HDF" '
+        'Precision="8">mesh_regions.h5:/data2</DataItem></Attribute></Grid></Domain></Xdmf>')
+    pts, tri, reg = read_xdmf_mesh(str(tmp_path / "mesh.xdmf"))
+    assert np.array_equal(pts, e["pts"]) and np.array_equal(tri, e["tri"]) and np.array_equal(reg, e["tags"])
+
+
+def test_chunked_writer_layout_roundtrip_and_structure(tmp_path, monkeypatch):
+    """DEEPBND_H5_LAYOUT=chunked writes the reference's dataset creation properties (chunks (1, ...), deflate 0): the
+    file reads back, and its dataset header carries the same layout / filter messages as the hand-assembled fixture"""
+    monkeypatch.setenv("DEEPBND_H5_LAYOUT", "chunked")
+    rng = np.random.RandomState(0)
+    A, B = rng.randn(200, 5), rng.randn(3, 2, 2)
+    fn = str(tmp_path / "c.hd5")
+    myhd.savehd5(fn, [A, B], ["A", "B"], "w")
+    assert np.array_equal(myhd.loadhd5(fn, "A"), A) and np.array_equal(myhd.loadhd5(fn, "B"), B)
+
+    def layout_and_filter(path, name):
+        ds = myhd.minih5.File(path)[name]
+        lay = [bytes(d) for t, d in ds.msgs if t == 0x0008][0]
+        fil = [bytes(d) for t, d in ds.msgs if t == 0x000B][0]
+        return lay[:3], lay[11:], fil[:20]          # (version, class, rank), chunk dims, filter description
+    mine = layout_and_filter(fn, "B")
+    ref = layout_and_filter(os.path.join(GOLD, "chunked_deflate0.h5"), "B_S")
+    assert mine[0] == ref[0] == bytes([3, 2, 4]) and mine[2] == ref[2]
+    assert struct.unpack("<4I", mine[1][:16]) == (1, 2, 2, 8)
+
+
+def test_zerosfile_flushes_rows_in_place(tmp_path):
+    """buildSnapshots / predictTangents flush per batch: only the rows of the batch are rewritten"""
+    fn = str(tmp_path / "z.hd5")
+    (a, b), f = myhd.zeros_openFile(fn, [(6, 3), (6,)], ["a", "b"], mode="w")
+    myhd.addDataset(f, np.arange(4.0).reshape(2, 2), "static")
+    a[0:2] = 1.0; b[0:2] = 2.0
+    f.flush([0, 1])                                   # first flush: whole file
+    size0 = os.path.getsize(fn)
+    a[4:6] = 5.0; b[4] = 7.0
+    f.flush([4, 5])
+    assert os.path.getsize(fn) == size0
+    assert np.array_equal(myhd.loadhd5(fn, "a"), a) and np.array_equal(myhd.loadhd5(fn, "b"), b)
+    assert np.array_equal(myhd.loadhd5(fn, "static"), np.arange(4.0).reshape(2, 2))
+    f.close()
+
+
+def test_vref_vectors_are_permuted_or_refused(tmp_path, monkeypatch):
+    """a file with Vref vectors but no DOF-order description is refused; with a description (in the file or
+    the exporter's sidecar) the vectors come back in the library's order"""
+    from deepbnd_b200 import vref
+    rng = np.random.RandomState(3)
+    U = rng.randn(4, 162)
+    coords, comps = vref.vref_order_datasets()
+    shuffle = rng.permutation(162)                     # a "dolfin" order: file DOF d = library DOF shuffle[d]
+    fn = str(tmp_path / "bcs.hd5")
+    myhd.savehd5(fn, [U[:, shuffle]], ["u0"], "w")
+    with pytest.raises(vref.VrefOrderError):
+        vref.load_vref_vectors(fn, "u0")
+    monkeypatch.setenv("DEEPBND_ASSUME_LIBRARY_VREF_ORDER", "1")
+    assert np.array_equal(vref.load_vref_vectors(fn, "u0"), U[:, shuffle])
+    monkeypatch.delenv("DEEPBND_ASSUME_LIBRARY_VREF_ORDER")
+    myhd.savehd5(str(tmp_path / vref.SIDECAR), [coords[shuffle], comps[shuffle]], [vref.COORD_LABEL, vref.COMP_LABEL], "w")
+    assert np.array_equal(vref.load_vref_vectors(fn, "u0"), U)                      # sidecar of the FEniCS exporter
+    fn2 = str(tmp_path / "sub" / "Wbasis.hd5")
+    os.makedirs(os.path.dirname(fn2))
+    myhd.savehd5(fn2, [U, coords, comps], ["Wbasis_A", vref.COORD_LABEL, vref.COMP_LABEL], "w")
+    assert np.array_equal(vref.load_vref_vectors(fn2, ["Wbasis_A"])[0], U)          # self-described, identity
