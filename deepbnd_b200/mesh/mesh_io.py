@@ -5,6 +5,8 @@
   `data0` = points, `data1` = triangles, and `mesh_regions.xdmf` + `mesh_regions.h5` holding the
   per-triangle physical tags; `mesh_faces.*` is not needed by the RVE models) without meshio/h5py:
   the XML is parsed for its `DataItem` references and the heavy data is read with minih5.
+* `write_xdmf_mesh`: the same triplet, written (for meshes that must leave this package: the boundary reference
+  mesh `boundaryMesh.xdmf`, RVE meshes handed to the reference's FEniCS scripts).
 * `save_mesh_cache` / `load_mesh_cache`: the array triple our own mesher produces, cached next to the
   name the reference would have used ("generated once and cached", BASELINE.json north_star).
 """
@@ -63,6 +65,47 @@ def read_xdmf_mesh(meshFile):
     if pts is None or tri is None or reg is None:
         raise ValueError("read_xdmf_mesh: could not find points/triangles/regions in %s" % meshFile)
     return np.ascontiguousarray(pts), np.ascontiguousarray(tri), np.ascontiguousarray(reg)
+
+
+def _xdmf(path, h5name, npts, ncell, cell, ncol, attr=None):
+    a = ""
+    if attr:
+        a = ('<Attribute AttributeType="Scalar" Center="Cell" Name="%s"><DataItem DataType="Int" Dimensions="%d" Format="HDF" '
+             'Precision="8">%s:/data2</DataItem></Attribute>' % (attr, ncell, h5name))
+    with open(path, "w") as f:
+        f.write('<Xdmf Version="3.0"><Domain><Grid Name="Grid"><Geometry GeometryType="XY"><DataItem DataType="Float" '
+                'Dimensions="%d 2" Format="HDF" Precision="8">%s:/data0</DataItem></Geometry><Topology NumberOfElements="%d" '
+                'TopologyType="%s"><DataItem DataType="Int" Dimensions="%d %d" Format="HDF" Precision="8">%s:/data1</DataItem>'
+                '</Topology>%s</Grid></Domain></Xdmf>\n' % (npts, h5name, ncell, cell, ncell, ncol, h5name, a))
+
+
+def write_xdmf_mesh(meshFile, points, triangles, region, lines=None, line_tags=None):
+    """The triplet exportMeshHDF5_fromGMSH leaves on disk (wrapper_io.py:78-134), readable by readXDMF_with_markers
+    (:31-49): `mesh.xdmf/.h5` (data0 points, data1 triangles), `mesh_regions.xdmf/.h5` (data1 triangles, data2 the
+    physical tag per triangle, named 'regions') and `mesh_faces.xdmf/.h5` (data1 boundary lines, data2 their tags,
+    named 'faces').  The reference replaces data1 of the regions file by an ExternalLink to save space; here it is a
+    plain copy (old-style groups cannot hold link messages, and every reader resolves both the same way)."""
+    rad = meshFile[:-5] if meshFile.endswith(".xdmf") else meshFile
+    os.makedirs(os.path.dirname(os.path.abspath(rad)), exist_ok=True)
+    base = os.path.basename(rad)
+    pts = np.asarray(points, dtype=np.float64)[:, :2]
+    tri = np.asarray(triangles, dtype=np.int64)
+    with minih5.Writer(rad + ".h5") as w:
+        w["data0"] = pts; w["data1"] = tri
+    _xdmf(rad + ".xdmf", base + ".h5", len(pts), len(tri), "Triangle", 3)
+    with minih5.Writer(rad + "_regions.h5") as w:
+        w["data0"] = np.zeros((1, 2)); w["data1"] = tri; w["data2"] = np.asarray(region, dtype=np.int64).ravel()
+    _xdmf(rad + "_regions.xdmf", base + "_regions.h5", 1, len(tri), "Triangle", 3, "regions")
+    if lines is None:                                    # boundary edges of the triangulation, one tag
+        e = np.vstack([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]])
+        es = np.sort(e, axis=1)
+        key, idx, cnt = np.unique(es[:, 0] * (len(pts) + 1) + es[:, 1], return_index=True, return_counts=True)
+        lines = e[idx[cnt == 1]]
+        line_tags = np.full(len(lines), int(np.max(region)) + 1)
+    lines = np.asarray(lines, dtype=np.int64)
+    with minih5.Writer(rad + "_faces.h5") as w:
+        w["data0"] = np.zeros((1, 2)); w["data1"] = lines; w["data2"] = np.asarray(line_tags, dtype=np.int64).ravel()
+    _xdmf(rad + "_faces.xdmf", base + "_faces.h5", 1, len(lines), "Polyline", 2, "faces")
 
 
 def cache_name(meshname):

@@ -87,6 +87,47 @@ def _circle_points(cx, cy, r, lcar):
     return np.stack([cx + r * np.cos(t), cy + r * np.sin(t)], 1)
 
 
+def _ellipse_points(cx, cy, l, e, theta, lcar):
+    """Boundary nodes of the ellipse of ellipse2_mesh.py:27-39 (semi-axis l along theta, e*l across): the four axis
+    end points (gmsh's arc end points) and, on every quarter arc, nodes at equal arc-length spacing of about lcar."""
+    a, b = float(l), float(e) * float(l)
+    tt = np.linspace(0.0, 0.5 * np.pi, 513)
+    seg = np.hypot(np.diff(a * np.cos(tt)), np.diff(b * np.sin(tt)))
+    s = np.concatenate([[0.0], np.cumsum(seg)])                    # arc length along the first quadrant
+    nq = max(2, int(np.ceil(s[-1] / lcar)))
+    tq = np.interp(np.arange(nq) * s[-1] / nq, s, tt)              # nq nodes, the quadrant's last point belongs to the next
+    # the other quadrants are mirror images
+    t = np.concatenate([[0.0], tq[1:], [0.5 * np.pi], (np.pi - tq[1:])[::-1], [np.pi], np.pi + tq[1:], [1.5 * np.pi],
+                        (2 * np.pi - tq[1:])[::-1]])
+    c, sn = np.cos(theta), np.sin(theta)
+    x, y = a * np.cos(t), b * np.sin(t)
+    return np.stack([cx + c * x - sn * y, cy + sn * x + c * y], 1)
+
+
+def _dist_to_ellipse(p, cx, cy, l, e, theta):
+    """first-order distance of points to the ellipse curve (exact for a circle): (F - 1) / |grad F|, F = |(x'/a, y'/b)|"""
+    a, b = float(l), float(e) * float(l)
+    c, sn = np.cos(theta), np.sin(theta)
+    dx, dy = p[:, 0] - cx, p[:, 1] - cy
+    xl, yl = c * dx + sn * dy, -sn * dx + c * dy
+    F = np.sqrt((xl / a) ** 2 + (yl / b) ** 2)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        g = np.hypot(xl / a ** 2, yl / b ** 2) / F
+        d = np.abs(F - 1.0) / g
+    return np.where(F > 1e-12, d, min(a, b))
+
+
+def _in_polygon(pts, poly):
+    """crossing-number test of points against a closed polygon (vertices in order)"""
+    x, y = pts[:, 0][:, None], pts[:, 1][:, None]
+    x0, y0 = poly[:, 0][None, :], poly[:, 1][None, :]
+    x1, y1 = np.roll(poly[:, 0], -1)[None, :], np.roll(poly[:, 1], -1)[None, :]
+    cond = (y0 > y) != (y1 > y)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        xint = x0 + (y - y0) * (x1 - x0) / (y1 - y0)
+    return (np.sum(cond & (x < xint), axis=1) % 2) == 1
+
+
 def _dist_to_box(p, x0, y0, Lx, Ly):
     """Unsigned distance of points to the boundary lines of a box (inside or outside)."""
     dx = np.maximum(np.maximum(x0 - p[:, 0], p[:, 0] - (x0 + Lx)), 0)
@@ -101,7 +142,8 @@ def mesh_circles_in_box(circles, box, lcar, n_side, inner_box=None, n_side_inner
                         n_inner_incl=0, smooth_iters=3):
     """Triangulate box minus/with circular inclusions.
 
-    circles: (nc,3) [cx,cy,r]; box=(x0,y0,Lx,Ly); inner_box likewise (conforming interface).
+    circles: (nc,3) [cx,cy,r] or (nc,5) [cx,cy,l,e,theta] (elliptical inclusions, ellipse2_mesh.py:27-39);
+    box=(x0,y0,Lx,Ly); inner_box likewise (conforming interface).
     Returns points (nv,2) f8, triangles (nt,3) i4 (CCW), region (nt,) i4 with the reference's
     tags (0/1 and, with an inner box, 2/3)."""
     x0, y0, Lx, Ly = box
@@ -120,8 +162,14 @@ def mesh_circles_in_box(circles, box, lcar, n_side, inner_box=None, n_side_inner
         fixed.append(pin)
         add_loop(nfix, pin.shape[0])
         nfix += pin.shape[0]
-    for cx, cy, r in circles:
-        pc = _circle_points(cx, cy, r, lcar)
+    circles = np.asarray(circles, dtype=float)
+    circles = circles.reshape(-1, circles.shape[-1] if circles.ndim == 2 else 3)
+    if circles.shape[1] == 3:
+        circles = np.hstack([circles, np.ones((len(circles), 1)), np.zeros((len(circles), 1))])
+    polys = []
+    for cx, cy, r, ecc, th in circles:
+        pc = _circle_points(cx, cy, r, lcar) if ecc == 1.0 else _ellipse_points(cx, cy, r, ecc, th, lcar)
+        polys.append(pc)
         fixed.append(pc)
         add_loop(nfix, pc.shape[0])
         nfix += pc.shape[0]
@@ -141,9 +189,11 @@ def mesh_circles_in_box(circles, box, lcar, n_side, inner_box=None, n_side_inner
     keep &= (cand[:, 0] > x0) & (cand[:, 0] < x0 + Lx) & (cand[:, 1] > y0) & (cand[:, 1] < y0 + Ly)
     if inner_box is not None:
         keep &= _dist_to_box(cand, *inner_box) > dmin
-    circles = np.asarray(circles, dtype=float).reshape(-1, 3)
-    for cx, cy, r in circles:
-        d = np.abs(np.hypot(cand[:, 0] - cx, cand[:, 1] - cy) - r)
+    for cx, cy, r, ecc, th in circles:
+        if ecc == 1.0:
+            d = np.abs(np.hypot(cand[:, 0] - cx, cand[:, 1] - cy) - r)
+        else:
+            d = _dist_to_ellipse(cand, cx, cy, r, ecc, th)
         keep &= d > dmin
     free = cand[keep]
 
@@ -181,8 +231,13 @@ def mesh_circles_in_box(circles, box, lcar, n_side, inner_box=None, n_side_inner
     # region tags by centroid-in-polygon (exact for the inscribed regular polygons)
     cen = (pts[T[:, 0]] + pts[T[:, 1]] + pts[T[:, 2]]) / 3.0
     incl = -np.ones(T.shape[0], dtype=np.int64)
-    for k, (cx, cy, r) in enumerate(circles):
-        n = _circle_points(cx, cy, r, lcar).shape[0]
+    for k, (cx, cy, r, ecc, tht) in enumerate(circles):
+        if ecc != 1.0:                                      # polygon of the ellipse nodes: crossing-number test nearby
+            rmax = r * max(1.0, ecc)
+            near = np.flatnonzero(np.hypot(cen[:, 0] - cx, cen[:, 1] - cy) < rmax * 1.01)
+            incl[near[_in_polygon(cen[near], polys[k])]] = k
+            continue
+        n = polys[k].shape[0]
         d = np.hypot(cen[:, 0] - cx, cen[:, 1] - cy)
         th = np.arctan2(cen[:, 1] - cy, cen[:, 0] - cx)
         rel = np.mod(th, 2 * np.pi / n) - np.pi / n
@@ -210,12 +265,12 @@ def buildRVEmesh_arrays(paramRVEdata, isOrdered=False, size='reduced', NxL=2, Ny
     paramRVEdata[:, :] = paramRVEdata[perm, :]
     npl = int(round(p.LxL / p.lcar)) + 1 if lcar is not None else p.NpLxL
     npt = int(round(p.Lxt / p.lcar)) + 1 if lcar is not None else p.NpLxt
-    if np.any(np.abs(paramRVEdata[:, 3] - 1.0) > 1e-12):
-        raise NotImplementedError("only circular inclusions (e=1) are meshed; the reference datasets use e=1")
+    # columns: cx, cy, l (radius / semi-axis along theta), e (excentricity: second semi-axis e*l), theta
+    # (ellipse2_mesh.py:27-39; the reference datasets use e = 1, theta = 0: generation_inclusions.py:29-30,42)
     if size == 'reduced':
-        return mesh_circles_in_box(paramRVEdata[:p.NL, :3], (p.x0L, p.y0L, p.LxL, p.LyL), p.lcar, npl)
+        return mesh_circles_in_box(paramRVEdata[:p.NL, :5], (p.x0L, p.y0L, p.LxL, p.LyL), p.lcar, npl)
     elif size == 'full':
-        return mesh_circles_in_box(paramRVEdata[:, :3], (p.x0, p.y0, p.Lxt, p.Lyt), p.lcar, npt,
+        return mesh_circles_in_box(paramRVEdata[:, :5], (p.x0, p.y0, p.Lxt, p.Lyt), p.lcar, npt,
                                    inner_box=(p.x0L, p.y0L, p.LxL, p.LyL), n_side_inner=npl,
                                    n_inner_incl=p.NL)
     raise ValueError(size)

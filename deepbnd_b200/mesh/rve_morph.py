@@ -70,14 +70,23 @@ class MorphTemplate:
         if np.intersect1d(np.flatnonzero(on), self.moving).size:
             raise ValueError("an inclusion's zone of influence reaches the box or the internal interface")
 
-    def mesh(self, radii):
-        """points of the RVE with inclusion radii `radii` (mesher order); triangles and regions are the template's"""
+    def mesh(self, radii, e=None, theta=None):
+        """points of the RVE with inclusion radii `radii` (mesher order); triangles and regions are the template's.
+        With excentricities `e` and angles `theta` the inclusions become the ellipses of ellipse2_mesh.py:27-39
+        (semi-axis radii along theta, e*radii across): the target radius of a node is the ellipse radius in its direction."""
         radii = np.asarray(radii, dtype=float)
         if radii.shape != (self.n_incl,):
             raise ValueError("expected %d radii" % self.n_incl)
+        r = radii[self.k]
+        if e is not None and np.any(np.abs(np.asarray(e, dtype=float) - 1.0) > 1e-12):
+            e = np.asarray(e, dtype=float)
+            theta = np.zeros(self.n_incl) if theta is None else np.asarray(theta, dtype=float)
+            a, b, th = radii[self.k], (e * radii)[self.k], theta[self.k]
+            phi = np.arctan2(self.dir[:, 1], self.dir[:, 0]) - th
+            r = a * b / np.sqrt((b * np.cos(phi)) ** 2 + (a * np.sin(phi)) ** 2)
+            radii = np.maximum(radii, e * radii)
         if np.any(radii <= 0) or np.any(radii >= self.R):
             raise ValueError("radii must lie in (0, %g)" % self.R)
-        r = radii[self.k]
         dn = np.where(self.d <= self.r0, self.d * r / self.r0, r + (self.d - self.r0) * (self.R - r) / (self.R - self.r0))
         pts = self.points.copy()
         pts[self.moving] = self.centres[self.k] + self.dir * dn[:, None]
@@ -88,9 +97,7 @@ def buildRVEmesh_morphed(paramRVEdata, template):
     """Twin of buildRVEmesh_arrays on a MorphTemplate: permutes paramRVEdata IN PLACE like the reference
     (mesh_RVE.py:45-50), checks that the centres are the template's and returns (points, triangles, region)."""
     paramRVEdata[:, :] = paramRVEdata[template.perm, :]
-    if np.any(np.abs(paramRVEdata[:, 3] - 1.0) > 1e-12):
-        raise NotImplementedError("only circular inclusions (e=1)")
     n = template.n_incl
     if np.abs(paramRVEdata[:n, :2] - template.centres).max() > 1e-9:
         raise ValueError("the inclusion centres differ from the template's: re-mesh (buildRVEmesh_arrays) instead")
-    return template.mesh(paramRVEdata[:n, 2])
+    return template.mesh(paramRVEdata[:n, 2], paramRVEdata[:n, 3], paramRVEdata[:n, 4])
