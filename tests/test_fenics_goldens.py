@@ -54,3 +54,36 @@ def test_cuda_path_against_fenics(size, model):
             comp = d % 2                           # dolfin interleaves the components of a vector CG1 space per node
             assert abs(mine[k, comp] - refv[d]) < 1e-8 * max(np.abs(refv).max(), 1e-12), (d, k, comp)
     b.close()
+
+
+def test_dnn_export_settles_the_two_ext_switches():
+    """tangent_dnn of the exporter (smooth non-zero uD) against the four oracle variants: exactly one combination of
+    dirichlet_semantics x zero_average_for_dirichlet may reproduce it to 1e-8; the test fails, naming the best variant,
+    if it is not the library's choice ('p1_vertex', no zero-average block)."""
+    g = _load("reduced")
+    if "tangent_dnn" not in g.files:
+        pytest.skip("export predates the dnn case")
+    from deepbnd_b200.vref import permutation_to_library
+    from oracle.rve_oracle import OracleRVE, vref_points
+    perm = permutation_to_library(g["vref_dof_coordinates"], g["vref_dof_component"])
+    uD = [g["dnn_uD%d_dolfin_order" % i][perm] for i in range(3)]
+    pts = vref_points(-1, -1, 2, 2, 21)
+    ref = g["tangent_dnn"]
+    errs = {}
+    for sem in ("p1_vertex", "p2_nodal"):
+        for za in (False, True):
+            o = OracleRVE(g["points"][:, :2], g["triangles"], g["region"], param=PARAM, model="dnn",
+                          dirichlet_semantics=sem, zero_average_for_dirichlet=za)
+            errs[(sem, za)] = np.abs(o.compute_tangent(uD, pts) - ref).max() / np.abs(ref).max()
+    best = min(errs, key=errs.get)
+    assert errs[best] < 1e-8, errs
+    assert best == ("p1_vertex", False), "the reference runs %s: switch the library (k_bnd_values) accordingly; %s" % (best, errs)
+
+
+def test_vref_dof_order_of_the_export_is_a_permutation():
+    g = _load("reduced")
+    if "vref_dof_component" not in g.files:
+        pytest.skip("export predates the DOF-order sidecar")
+    from deepbnd_b200.vref import permutation_to_library
+    perm = permutation_to_library(g["vref_dof_coordinates"], g["vref_dof_component"])
+    assert sorted(perm.tolist()) == list(range(162))
