@@ -210,8 +210,17 @@ class Runner:
                         reg[toff[a]:toff[z]], slice(a, z)) for a, z in zip(cb[:-1], cb[1:])]
         self.nchunk = nchunk
         self.vref_box = (-1.0, -1.0, 2.0, 2.0)
+        self.shared = None
+        if wl.get("mesher") == "morph" and not args.no_shared_topology:
+            m = inp["meshes"]
+            self.shared = (np.ascontiguousarray(np.stack([x[0] for x in m])), m[0][1], m[0][2])
 
     def set_pass(self, bb, c=None):
+        if self.shared is not None:                      # morphed meshes: one topology, one symbolic phase (rve_set_batch_shared)
+            pts, tri, reg = self.shared
+            bb.set_shared(pts if c is None else pts[self.chunks[c][5]], tri, reg, param=PARAM_MAT, model=self.wl["model"],
+                          vref_nb=21, vref_box=self.vref_box)
+            return
         arr = self.inp["flat"] if c is None else self.chunks[c][:5]
         bb.set_batch(*arr, param=PARAM_MAT, model=self.wl["model"], vref_nb=21, vref_box=self.vref_box)
 
@@ -319,6 +328,8 @@ def main():
                     help="q = A p inside the PCG: element-wise (default) or the assembled SELL-32 SpMV")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads block")
+    ap.add_argument("--mesher", default="", choices=["", "delaunay", "morph"], help="override the workload's mesher")
+    ap.add_argument("--no-shared-topology", action="store_true", help="morph mesher: still run the symbolic phase per RVE")
     ap.add_argument("--cpu-sample", type=int, default=0, help="RVEs in the CPU baseline sample (default: one per core)")
     args = ap.parse_args()
 
@@ -328,6 +339,8 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.ns:
         wl["ns"] = args.ns
+    if args.mesher:
+        wl["mesher"] = args.mesher
     lcar = args.lcar if args.lcar > 0 else wl.get("lcar")
     ncpu = os.cpu_count() or 1
     nproc_local = max(1, ncpu // max(1, world))
@@ -488,10 +501,12 @@ def main():
                        "model": wl["model"], "loads": list(wl["loads"]), "dofs_per_rve": res["dof"], "rtol": args.rtol,
                        "precond": args.precond, "operator": args.operator, "mean_pcg_iters": float(np.mean(res["iters"])),
                        "l2": "per-iteration working set >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                       "unique_meshes": nuniq, "mesher": wl.get("mesher", "delaunay"), "mesh_gen_s": inp["t_mesh"],
+                       "unique_meshes": nuniq, "mesher": wl.get("mesher", "delaunay"),
+                       "shared_topology": run.shared is not None, "mesh_gen_s": inp["t_mesh"],
                        "phase_ms": res["phase"]},
             "e2e": {"value": e2e_val, "unit": "RVE/s", "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
-                    "pipeline": "2 handles / 2 host workers, %d chunks per step: each worker runs H2D of the raw meshes + GPU symbolic phase + solve + D2H for every other chunk; the two streams interleave on the GPU" % run.nchunk},
+                    "pipeline": "2 handles / 2 host workers, %d chunks per step: each worker runs H2D of the %s + solve + D2H for every other chunk; the two streams interleave on the GPU" % (
+                        run.nchunk, "vertex coordinates + ONE GPU symbolic phase per chunk (shared topology)" if run.shared is not None else "raw meshes + GPU symbolic phase")},
             "gpu_launches": int(res["launches"]),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": opname, "achieved": achieved, "peak": peak, "unit": "GB/s",

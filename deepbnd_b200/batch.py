@@ -62,6 +62,23 @@ class RVEBatch:
                                            L.iptr(reg), L.dptr(mat), L.MODEL[model], int(vref_nb), L.dptr(vb)))
         return self
 
+    def set_shared(self, points, tri, region, param=(0.3, 10.0, 0.3, 1.0), model="lin", vref_nb=21, vref_box=None, mat=None):
+        """n_sys meshes with ONE topology: points (n_sys, nv, 2), triangles (nt, 3), region (nt,) — what
+        deepbnd_b200.mesh.rve_morph produces.  The symbolic phase runs once (rve_set_batch_shared)."""
+        mat = L.f64(getLameTable(*param) if mat is None else mat)
+        vb = None if vref_box is None else L.f64(vref_box)
+        xy = L.f64(points)
+        if xy.ndim != 3 or xy.shape[2] != 2:
+            raise ValueError("points must be (n_sys, nv, 2)")
+        tri, reg = L.i32(np.asarray(tri).reshape(-1, 3)), L.i32(np.asarray(region).ravel())
+        self.n_sys = xy.shape[0]
+        self.model = model
+        self.nvref = 4 * (vref_nb - 1) + 1 if vref_nb else 0
+        self._keep = (xy, tri, reg, mat, vb)
+        self._check(self.lib.rve_set_batch_shared(self.h, self.n_sys, xy.shape[1], len(tri), L.dptr(xy), L.iptr(tri), L.iptr(reg),
+                                                  L.dptr(mat), L.MODEL[model], int(vref_nb), L.dptr(vb)))
+        return self
+
     def assemble(self):
         self._check(self.lib.rve_assemble(self.h))
         return self

@@ -138,7 +138,7 @@ struct rve_batch_s {
     int opt_operator = RVE_OPERATOR_MATFREE;
     bool have_bval = false;
     int max_slots = 0;
-    long long n_we = 0;
+    long long n_we = 0, n_halo = 0;
     DBuf<int> win_we0, win_nwe, we_elem;
     DBuf<unsigned char> win_sw, row_nadj;
     DBuf<uint32_t> we_idx;
@@ -369,6 +369,41 @@ static void launch_direction(rve_batch_s* h, const PcgArgs& a, cudaStream_t st) 
         else if ((K) == 2) { call(2); }  \
         else { call(3); }                \
     } while (0)
+
+// per-batch solver state (sizes known after the numbering): vectors of the PCG scalars, the coarse hierarchy
+static int alloc_solver_state(rve_batch_s* h, int n_sys, int model, int ncx, int ncy) {
+    h->have_bval = false;                       // SELL values: rve_assemble (assembled operator) or on demand
+    CU(h->dinv.alloc((size_t)h->R)); CU(h->wmean.alloc(h->R));
+    CU(h->active.alloc(n_sys)); CU(h->cnt.alloc(n_sys)); CU(h->d_iters.alloc(n_sys)); CU(h->n_active.alloc(1));
+    CU(h->err_flag.alloc(1));
+    CU(h->part.alloc((size_t)h->n_win * 8));  CU(h->sc.alloc((size_t)n_sys * 4 * SC_N));
+    CU(h->Mx.alloc((size_t)n_sys * 16)); CU(h->Gaff.alloc((size_t)n_sys * 16)); CU(h->aaff.alloc((size_t)n_sys * 8));
+    CU(h->acc.alloc((size_t)n_sys * ACC_PER_SYS));
+    // coarse hierarchy
+    Levels& LV = h->LV;
+    memset(&LV, 0, sizeof(Levels));
+    int lcx = ncx, lcy = ncy, L = 0;
+    while (L < RVE_MAXLEV) {
+        Grid& g = LV.g[L];
+        g.ncx = lcx; g.ncy = lcy; g.nx = lcx + 1; g.ny = lcy + 1; g.G = g.nx * g.ny;
+        g.wrap = (model == RVE_MODEL_PER);
+        if (model == RVE_MODEL_LIN || model == RVE_MODEL_DNN) { g.lox = 1; g.loy = 1; g.hix = lcx - 1; g.hiy = lcy - 1; }
+        else if (model == RVE_MODEL_PER) { g.lox = 0; g.loy = 0; g.hix = lcx - 1; g.hiy = lcy - 1; }
+        else { g.lox = 0; g.loy = 0; g.hix = lcx; g.hiy = lcy; }
+        CU(h->lvA[L].alloc((size_t)n_sys * 100 * g.G)); CU(h->lvD[L].alloc((size_t)n_sys * 4 * g.G));
+        CU(h->lvR[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2)); CU(h->lvX[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2));
+        CU(h->lvT[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2));
+        CU(h->lvA4[L].alloc((size_t)n_sys * 25 * g.G)); CU(h->lvH4[L].alloc((size_t)n_sys * 25 * g.G));
+        LV.A[L] = h->lvA[L].p; LV.dinv[L] = h->lvD[L].p; LV.rc[L] = h->lvR[L].p; LV.xc[L] = h->lvX[L].p; LV.tc[L] = h->lvT[L].p;
+        LV.A4[L] = h->lvA4[L].p; LV.H4[L] = h->lvH4[L].p;
+        ++L;
+        if ((lcx % 2) || (lcy % 2) || lcx / 2 < 2 || lcy / 2 < 2) break;
+        lcx /= 2; lcy /= 2;
+    }
+    LV.L = L;
+    CU(h->cpart.alloc((size_t)n_sys * ((LV.g[0].G + 255) / 256) * 4));
+    return 0;
+}
 
 extern "C" {
 
@@ -613,36 +648,8 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     if (std::getenv("RVE_DEBUG_TIMING"))
         fprintf(stderr, "[rve_set_batch] n_sys %d: copy + edges %.1f ms, rows + finish (enqueue) %.1f ms\n", n_sys,
                 std::chrono::duration<double, std::milli>(tp1 - t0).count(), std::chrono::duration<double, std::milli>(t1 - tp1).count());
-    h->have_bval = false;                       // SELL values: rve_assemble (assembled operator) or on demand
-    CU(h->dinv.alloc((size_t)h->R)); CU(h->wmean.alloc(h->R));
-    CU(h->active.alloc(n_sys)); CU(h->cnt.alloc(n_sys)); CU(h->d_iters.alloc(n_sys)); CU(h->n_active.alloc(1));
-    CU(h->err_flag.alloc(1));
-    CU(h->part.alloc((size_t)h->n_win * 8));  CU(h->sc.alloc((size_t)n_sys * 4 * SC_N));
-    CU(h->Mx.alloc((size_t)n_sys * 16)); CU(h->Gaff.alloc((size_t)n_sys * 16)); CU(h->aaff.alloc((size_t)n_sys * 8));
-    CU(h->acc.alloc((size_t)n_sys * ACC_PER_SYS));
-    // coarse hierarchy
+    if (int rc = alloc_solver_state(h, n_sys, model, ncx, ncy)) return rc;
     Levels& LV = h->LV;
-    memset(&LV, 0, sizeof(Levels));
-    int lcx = ncx, lcy = ncy, L = 0;
-    while (L < RVE_MAXLEV) {
-        Grid& g = LV.g[L];
-        g.ncx = lcx; g.ncy = lcy; g.nx = lcx + 1; g.ny = lcy + 1; g.G = g.nx * g.ny;
-        g.wrap = (model == RVE_MODEL_PER);
-        if (model == RVE_MODEL_LIN || model == RVE_MODEL_DNN) { g.lox = 1; g.loy = 1; g.hix = lcx - 1; g.hiy = lcy - 1; }
-        else if (model == RVE_MODEL_PER) { g.lox = 0; g.loy = 0; g.hix = lcx - 1; g.hiy = lcy - 1; }
-        else { g.lox = 0; g.loy = 0; g.hix = lcx; g.hiy = lcy; }
-        CU(h->lvA[L].alloc((size_t)n_sys * 100 * g.G)); CU(h->lvD[L].alloc((size_t)n_sys * 4 * g.G));
-        CU(h->lvR[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2)); CU(h->lvX[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2));
-        CU(h->lvT[L].alloc((size_t)n_sys * g.G * RVE_MAX_RHS * 2));
-        CU(h->lvA4[L].alloc((size_t)n_sys * 25 * g.G)); CU(h->lvH4[L].alloc((size_t)n_sys * 25 * g.G));
-        LV.A[L] = h->lvA[L].p; LV.dinv[L] = h->lvD[L].p; LV.rc[L] = h->lvR[L].p; LV.xc[L] = h->lvX[L].p; LV.tc[L] = h->lvT[L].p;
-        LV.A4[L] = h->lvA4[L].p; LV.H4[L] = h->lvH4[L].p;
-        ++L;
-        if ((lcx % 2) || (lcy % 2) || lcx / 2 < 2 || lcy / 2 < 2) break;
-        lcx /= 2; lcy /= 2;
-    }
-    LV.L = L;
-    CU(h->cpart.alloc((size_t)n_sys * ((LV.g[0].G + 255) / 256) * 4));
     // block columns, halo lists, SELL columns, restriction lists
     const long long halo_cap = h->R + h->R / 2 + 4096;
     if (halo_cap > 2000000000LL) FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
@@ -708,10 +715,152 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     if (scnt[2] == 3) FAIL(RVE_E_MESH, "device pattern build: halo list overflow");
     if (scnt[2] == 4) FAIL(RVE_E_MESH, "device pattern build: coarse-node list overflow");
     if (scnt[2] == 5) FAIL(RVE_E_MESH, "device pattern build: a window touches more than 1024 elements");
-    h->max_tile = scnt[1]; h->max_cn = scnt[5];
+    h->max_tile = scnt[1]; h->max_cn = scnt[5]; h->n_halo = scnt[0];
     if (((size_t)h->max_tile + h->max_slots) * 3 * sizeof(double2) > 200 * 1024) FAIL(RVE_E_MESH, "window halo too large for shared memory");
     auto t2 = std::chrono::steady_clock::now();
     h->t_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    h->have_batch = true;
+    return 0;
+}
+
+// One topology, n_sys coordinate sets (meshes morphed from one template, deepbnd_b200/mesh/rve_morph.py): the symbolic
+// phase runs for system 0 only; its index arrays are replicated with shifted indices, the coordinate-dependent pieces
+// (node coordinates, level-1 cells of the rows, restriction lists) are rebuilt for every system.
+int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, const double* xy, const int32_t* tri,
+                         const int32_t* region, const double* mat, int32_t model, int32_t vref_nb, const double* vref_box) {
+    H_CHECK(h);
+    if (n_sys <= 0 || nv <= 0 || nt <= 0 || !xy || !tri || !region || !mat) FAIL(RVE_E_ARG, "null/empty argument");
+    if (n_sys > 65535) FAIL(RVE_E_ARG, "more than 65535 systems in one batch: split it");
+    auto t0 = std::chrono::steady_clock::now();
+    const int64_t voff1[2] = {0, nv}, toff1[2] = {0, nt};
+    if (int rc = rve_set_batch(h, 1, voff1, toff1, xy, tri, region, mat, model, vref_nb, vref_box)) return rc;
+    if (n_sys == 1) return 0;
+    h->have_batch = false;
+    cudaStream_t st = h->stream;
+    const SysInfo Y = h->info[0];
+    const long long nn = Y.nn, na = Y.na, nb = Y.nb, nbe = Y.nbe, nwin = Y.nwin, nsl = Y.nsl, nblk = Y.nblk, ngrp = Y.ngrp,
+                    nadj = Y.nadj, H1 = h->n_halo, WE1 = h->n_we, nvref = h->nvref;
+    if (nn * n_sys > 2000000000LL || nblk * n_sys > 4000000000LL || ngrp * n_sys > 4000000000LL || 6 * WE1 * n_sys > 2000000000LL ||
+        6LL * nt * n_sys > 2000000000LL)
+        FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
+    // ---- the pieces copied from system 0 are only valid if the mesh boundary and the Vref interface do not move
+    {
+        std::vector<int> nbnd(nv), se(nvref);
+        CU(cudaMemcpyAsync(nbnd.data(), h->node_bnd.p, nv * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (nvref) CU(cudaMemcpyAsync(se.data(), h->samp_elem.p, nvref * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(stream_wait(h));
+        std::vector<char> fixed(nv, 0);
+        for (int v = 0; v < nv; ++v) fixed[v] = nbnd[v] >= 0;
+        for (int k = 0; k < nvref; ++k)
+            for (int c = 0; c < 3; ++c) fixed[tri[3 * (size_t)se[k] + c]] |= 2;      // candidates: on the interface if they stay put
+        const double tol = 1e-12 * std::max(h->h_box[2], h->h_box[3]);
+        const double* vb = h->vref_box;
+        for (int v = 0; v < nv; ++v)
+            if ((fixed[v] & 2) && !(fixed[v] & 1)) {          // vertex of a sampled element: fixed if it lies on the Vref outline
+                const double x = xy[2 * (size_t)v], y = xy[2 * (size_t)v + 1];
+                const bool on = ((std::fabs(x - vb[0]) < 1e-9 * vb[2] || std::fabs(x - vb[0] - vb[2]) < 1e-9 * vb[2]) && y > vb[1] - 1e-9 * vb[3] && y < vb[1] + vb[3] * (1 + 1e-9)) ||
+                                ((std::fabs(y - vb[1]) < 1e-9 * vb[3] || std::fabs(y - vb[1] - vb[3]) < 1e-9 * vb[3]) && x > vb[0] - 1e-9 * vb[2] && x < vb[0] + vb[2] * (1 + 1e-9));
+                fixed[v] = on ? 1 : 0;
+            }
+        for (int s = 1; s < n_sys; ++s)
+            for (int v = 0; v < nv; ++v)
+                if (fixed[v] & 1) {
+                    const double dx = xy[2 * ((size_t)s * nv + v)] - xy[2 * (size_t)v], dy = xy[2 * ((size_t)s * nv + v) + 1] - xy[2 * (size_t)v + 1];
+                    if (std::fabs(dx) > tol || std::fabs(dy) > tol)
+                        FAIL(RVE_E_MESH, "system " + std::to_string(s) + ": a vertex of the mesh boundary / Vref outline differs from system 0 (shared topology needs them fixed)");
+                }
+    }
+    // ---- replicate the index arrays
+    std::vector<void*> old;                              // freed after the stream has finished with them
+    auto rep_i = [&](DBuf<int>& d, long long n1, long long add, int keep_neg) -> cudaError_t {
+        int* src = d.p; d.p = nullptr; d.cap = d.n = 0; old.push_back(src);
+        cudaError_t e = d.alloc((size_t)(n1 * n_sys));
+        if (e != cudaSuccess || n1 == 0) return e;
+        k_rep_add<int><<<cdiv(n1 * n_sys, 256), 256, 0, st>>>(d.p, src, n1, n_sys, add, keep_neg);
+        return cudaSuccess;
+    };
+    auto rep_p = [&](DBuf<unsigned>& d, long long n1, long long add) -> cudaError_t {
+        unsigned* src = d.p; d.p = nullptr; d.cap = d.n = 0; old.push_back(src);
+        cudaError_t e = d.alloc((size_t)(n1 * n_sys + 1));
+        if (e != cudaSuccess) return e;
+        k_rep_ptr<<<cdiv(n1 * n_sys + 1, 256), 256, 0, st>>>(d.p, src, n1, n_sys, add);
+        return cudaSuccess;
+    };
+    auto rep_s = [&](DBuf<int>& d, long long n1) -> cudaError_t {
+        cudaError_t e = d.alloc((size_t)(n1 * n_sys));
+        if (e != cudaSuccess || n1 == 0) return e;
+        k_rep_sys<<<cdiv(n1 * n_sys, 256), 256, 0, st>>>(d.p, n1, n_sys);
+        return cudaSuccess;
+    };
+#define REP_COPY(d, n1)                                                                                        \
+    do {                                                                                                       \
+        auto* src_ = (d).p; (d).p = nullptr; (d).cap = (d).n = 0; old.push_back((void*)src_);                   \
+        CU((d).alloc((size_t)((n1) * n_sys)));                                                                 \
+        for (int s_ = 0; s_ < n_sys && (n1) > 0; ++s_)                                                         \
+            CU(cudaMemcpyAsync((d).p + (size_t)s_ * (n1), src_, (size_t)(n1) * sizeof(*src_), cudaMemcpyDeviceToDevice, st)); \
+    } while (0)
+    CU(rep_i(h->node_va, nn, 0, 0)); CU(rep_i(h->node_vb, nn, 0, 0));
+    CU(rep_i(h->node_bnd, nn, nb, 1)); CU(rep_i(h->node_row, nn, na, 1)); CU(rep_i(h->elem_node, 6LL * nt, nn, 0));
+    CU(rep_i(h->bnd_node, nb, nn, 0)); CU(rep_i(h->bedge, 3 * nbe, nn, 0)); CU(rep_i(h->samp_elem, nvref, nt, 0));
+    CU(rep_i(h->row_node, na, nn, 0)); CU(rep_i(h->adjf, nadj, nt, 0)); CU(rep_i(h->csr_col, nblk, na, 0));
+    CU(rep_i(h->win_row0, nwin, na, 0)); CU(rep_i(h->win_n, nwin, 0, 0)); CU(rep_i(h->win_slice0, nwin, nsl, 0));
+    CU(rep_i(h->win_halo0, nwin, H1, 0)); CU(rep_i(h->win_nhalo, nwin, 0, 0)); CU(rep_i(h->win_we0, nwin, WE1, 0));
+    CU(rep_i(h->win_nwe, nwin, 0, 0)); CU(rep_i(h->halo, H1, na, 0)); CU(rep_i(h->we_elem, WE1, nt, 1));
+    CU(rep_s(h->node_sys, nn)); CU(rep_s(h->elem_sys, nt)); CU(rep_s(h->bnd_sys, nb)); CU(rep_s(h->win_sys, nwin));
+    CU(rep_p(h->d_row_ptr, na, nblk)); CU(rep_p(h->adjf_ptr, na, nadj)); CU(rep_p(h->slice_ptr, nsl, ngrp));
+    REP_COPY(h->elem_reg, (long long)nt); REP_COPY(h->emap, 36LL * nt); REP_COPY(h->rlen, na); REP_COPY(h->row_nadj, na);
+    REP_COPY(h->win_sw, 8 * nwin); REP_COPY(h->scol, 32 * ngrp); REP_COPY(h->we_idx, 6 * WE1);
+    REP_COPY(h->bedge_nl, 2 * nbe); REP_COPY(h->samp_lam, 2 * nvref); REP_COPY(h->box, 4LL);
+    if (model == RVE_MODEL_DNN) REP_COPY(h->bnd_s, 2 * nb);
+#undef REP_COPY
+    // ---- host bookkeeping
+    h->n_sys = n_sys;
+    h->info.assign(n_sys, Y);
+    h->true_blocks.assign(n_sys, h->true_blocks[0]);
+    auto mult = [&](std::vector<int>& v, long long n1) { v.resize(n_sys + 1); for (int s = 0; s <= n_sys; ++s) v[s] = (int)(s * n1); };
+    auto multl = [&](std::vector<long long>& v, long long n1) { v.resize(n_sys + 1); for (int s = 0; s <= n_sys; ++s) v[s] = s * n1; };
+    mult(h->voff, nv); mult(h->toff, nt); mult(h->node_base, nn); mult(h->bnd_base, nb); mult(h->bedge_base, nbe);
+    mult(h->row_base, na); mult(h->win_base, nwin); mult(h->slice_base, nsl);
+    multl(h->blk_base, nblk); multl(h->grp_base, ngrp); multl(h->adjf_base, nadj);
+    h->elem_base = h->toff;
+    h->h_box.resize(4 * (size_t)n_sys);
+    for (int s = 1; s < n_sys; ++s) for (int k = 0; k < 4; ++k) h->h_box[4 * (size_t)s + k] = h->h_box[k];
+    h->N = nn * n_sys; h->E = (long long)nt * n_sys; h->R = na * n_sys; h->NB = nblk * n_sys; h->NG = ngrp * n_sys;
+    h->NBN = nb * n_sys; h->NBE = nbe * n_sys; h->n_win = (int)(nwin * n_sys); h->n_halo = H1 * n_sys; h->n_we = WE1 * n_sys;
+    UPL(h->sys_win0, h->win_base); UPL(h->d_row_base, h->row_base); UPL(h->d_bedge_base, h->bedge_base);
+    UPL(h->d_node_base, h->node_base); UPL(h->d_bnd_base, h->bnd_base); UPL(h->d_toff, h->toff);
+    // ---- coordinates of every system
+    {
+        const size_t cnt = 2 * (size_t)nv * n_sys;
+        CU(h->arena.reserve(PinnedArena::need(cnt, 8)));
+        Span<double> a_xy = h->arena.take<double>(cnt);
+        parallel_for(n_sys, [&](int s) { memcpy(a_xy.p + 2 * (size_t)s * nv, xy + 2 * (size_t)s * nv, 2 * sizeof(double) * (size_t)nv); });
+        UPL(h->d_xy, a_xy);
+        CU(h->node_xy.alloc(2 * (size_t)h->N));
+        k_shared_node_xy<<<cdiv(h->N, 256), 256, 0, st>>>(n_sys, (int)nn, nv, h->d_xy.p, h->node_va.p, h->node_vb.p, h->node_xy.p);
+    }
+    // ---- solver state and the coordinate-dependent symbolic pieces for all systems
+    if (int rc = alloc_solver_state(h, n_sys, model, h->ncx, h->ncy)) return rc;
+    CU(h->we_geo.alloc(3 * (size_t)std::max<long long>(h->n_we, 1)));
+    const int n_win = h->n_win;
+    const long long cn_cap = h->R + 5LL * n_win + 4096;
+    CU(h->win_cn0.alloc(n_win)); CU(h->win_ncn.alloc(n_win)); CU(h->win_active.alloc(n_win)); CU(h->cn_node.alloc((size_t)cn_cap));
+    CU(h->cn_beg.alloc((size_t)cn_cap)); CU(h->cn_ent.alloc(4 * (size_t)h->R + 8 * (size_t)n_win + 64)); CU(h->rowinfo.alloc((size_t)h->R));
+    CU(h->win_desc.alloc((size_t)n_win)); CU(h->win_scal.alloc(8 * (size_t)n_win)); CU(h->sys_blocks.alloc(n_sys));
+    CU(cudaMemsetAsync(h->sym_cnt.p + 2, 0, 4 * sizeof(int), st));
+    const size_t smc = 2 * (size_t)((h->LV.g[0].G + 31) / 32) * sizeof(unsigned);
+    k_sym_coarse<<<n_win, RVE_WIN, smc, st>>>(win_tab(h), h->win_cn0.p, h->win_ncn.p, h->row_node.p, h->node_xy.p, h->box.p, h->LV.g[0],
+                                              model, h->rowinfo.p, h->cn_node.p, h->cn_beg.p, h->cn_ent.p, (int)cn_cap, h->sym_cnt.p, h->win_desc.p);
+    h->launches += 40;
+    int scnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(stream_wait(h));
+    CU(cudaGetLastError());
+    for (void* q : old) cudaFree(q);
+    if (scnt[2] == 4) FAIL(RVE_E_MESH, "device pattern build: coarse-node list overflow");
+    h->max_cn = scnt[5];
+    h->t_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    h->t_ms[1] = 0.0;
     h->have_batch = true;
     return 0;
 }

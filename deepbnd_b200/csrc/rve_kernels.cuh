@@ -408,6 +408,42 @@ k_sym_coarse(WinTab wt, int* __restrict__ win_cn0, int* __restrict__ win_ncn, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// (0b) shared topology (rve_set_batch_shared): the symbolic phase ran for system 0; its index arrays are replicated for
+//      the other systems by shifting the global indices, the node coordinates are rebuilt from every system's vertices
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__global__ void k_rep_add(T* __restrict__ dst, const T* __restrict__ src, long long n1, int n_sys, long long add, int keep_neg) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n1 * n_sys) return;
+    const long long s = gid / n1;
+    const T v = src[gid - s * n1];
+    dst[gid] = (keep_neg && v < (T)0) ? v : (T)(v + s * add);
+}
+// row-pointer style arrays (n1 + 1 entries per system, the last one = the next system's first)
+__global__ void k_rep_ptr(unsigned* __restrict__ dst, const unsigned* __restrict__ src, long long n1, int n_sys, long long add) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid > n1 * n_sys) return;
+    if (gid == n1 * n_sys) { dst[gid] = (unsigned)(src[n1] + (n_sys - 1) * add); return; }
+    const long long s = gid / n1;
+    dst[gid] = (unsigned)(src[gid - s * n1] + s * add);
+}
+__global__ void k_rep_sys(int* __restrict__ dst, long long n1, int n_sys) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n1 * n_sys) dst[gid] = (int)(gid / n1);
+}
+// node coordinates of every system from its own vertices: vertex nodes first, then the mid-edge nodes (va, vb)
+__global__ void k_shared_node_xy(int n_sys, int nn, int nv, const double* __restrict__ xy /*[n_sys][nv][2]*/,
+                                 const int* __restrict__ node_va, const int* __restrict__ node_vb, double* __restrict__ node_xy) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n_sys * nn) return;
+    const int s = (int)(gid / nn), n = (int)(gid - (long long)s * nn);
+    const double* x = xy + 2 * (size_t)s * nv;
+    const int a = node_va[n], b = node_vb[n];
+    node_xy[2 * gid] = 0.5 * (x[2 * a] + x[2 * b]);
+    node_xy[2 * gid + 1] = 0.5 * (x[2 * a + 1] + x[2 * b + 1]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // (1) numeric assembly, row-wise: thread per block row (CTA per window, warp per 32-row SELL slice).  A thread
 //     zeroes the slots of its row, walks the elements around the row (adjf), computes the 6 blocks K_e[a][0..5] of
 //     its own local node a (closed-form P2, branch-free gradient table) and adds them into the SELL slots named

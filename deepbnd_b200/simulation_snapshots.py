@@ -101,6 +101,14 @@ def get_meshes(paramRVEdata, meshnames, size, createMesh, nproc=None, template=N
     return [m for m, _ in res]
 
 
+def set_batch_meshes(batch, meshes, template, param, model, nb, box):
+    """morphed meshes share the template's topology: one symbolic phase for the whole batch (rve_set_batch_shared)"""
+    if template is not None:
+        batch.set_shared(np.stack([m[0] for m in meshes]), template.tri, template.region, param, model=model, vref_nb=nb, vref_box=box)
+    else:
+        batch.set_meshes(meshes, param, model=model, vref_nb=nb, vref_box=box)
+
+
 def solve_snapshot_batch(rows, batch, datasets, rtol=1e-10):
     """Batch twin of solve_snapshot (reference :42-64) on a batch already set on the GPU: fills rows `rows`
     of the 11 datasets."""
@@ -164,7 +172,7 @@ def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs
         # the reference reuses ONE temporary mesh name per rank; a batch needs one cache entry per snapshot
         names = [meshname.replace(".xdmf", "_%d.xdmf" % int(ids_run[i])) for i in rows]
         meshes = get_meshes(paramRVEdata[rows], names, 'full', createMesh, nproc, template, pool)
-        batch.set_meshes(meshes, tuple(paramMaterial), model=opModel, vref_nb=nb, vref_box=box)
+        set_batch_meshes(batch, meshes, template, tuple(paramMaterial), opModel, nb, box)
 
     def solve(rows, batch, _):
         print("Solving snapshots", int(ids_run[rows[0]]), "..", int(ids_run[rows[-1]]))

@@ -14,7 +14,7 @@ import numpy as np
 from . import wrapper_h5py as myhd
 from .batch import DoubleBuffer
 from .elasticity import macro_strain_voigt
-from .simulation_snapshots import default_device, get_meshes, make_mesh_pool, vref_box_from_mesh
+from .simulation_snapshots import default_device, get_meshes, make_mesh_pool, set_batch_meshes, vref_box_from_mesh
 from .vref import load_vref_vectors
 
 
@@ -60,7 +60,7 @@ def predictTangents(num, num_runs, modelBnd, namefiles, createMesh, meshSize, de
     def prepare(rows, batch):
         names = [meshMicroName.format(int(ids[i]) if np.any(ids) else int(i), meshSize) for i in rows]
         meshes = get_meshes(paramRVEdata[rows], names, meshSize, createMesh, nproc, template, pool)
-        batch.set_meshes(meshes, tuple(param), model=modelBnd, vref_nb=nb, vref_box=box)
+        set_batch_meshes(batch, meshes, template, tuple(param), modelBnd, nb, box)
 
     def solve(rows, batch, _):
         print(run, rows[0], rows[-1], ids[rows[0]])

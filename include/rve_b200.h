@@ -69,6 +69,15 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
                   const double* xy, const int32_t* tri, const int32_t* region, const double* mat,
                   int32_t model, int32_t vref_nb, const double* vref_box);
 
+/* rve_set_batch for n_sys meshes that share ONE topology (triangles, region tags) and differ only in their vertex
+ * coordinates xy[n_sys][nv][2] — the meshes deepbnd_b200/mesh/rve_morph.py derives from one template, the reference's
+ * datasets vary only the inclusion radii (build_snapshots_param.py:21-41).  The symbolic phase runs once; per system only
+ * the coordinates, the level-1 cell of every row and the restriction lists are rebuilt.  The boundary vertices must be
+ * the same in every system (checked).  Results equal those of rve_set_batch on the same meshes up to the row order
+ * (taken from system 0), i.e. to rounding. */
+int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, const double* xy, const int32_t* tri,
+                         const int32_t* region, const double* mat, int32_t model, int32_t vref_nb, const double* vref_box);
+
 /* replaces: A = mp.block_assemble(a); bcs.apply(A) (micro_model.py:60-62, micro_model_dnn.py:65-67).
  * Numeric P2 stiffness assembly of every system into the SELL-32 node-block matrix + preconditioner set-up. */
 int rve_assemble(rve_handle_t h);

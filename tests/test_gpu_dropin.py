@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 PARAM = [0.3, 10.0, 0.3, 1.0]
 
 
-def test_buildSnapshots_writes_reference_layout_and_matches_oracle(tmp_path):
+def test_buildSnapshots_writes_reference_layout_and_matches_oracle(tmp_path, monkeypatch):
+    monkeypatch.setenv("DEEPBND_KEEP_MESHES", "1")        # keep the meshes of createMesh=True: the oracle solves the same ones
     import deepbnd_b200.wrapper_h5py as myhd
     from deepbnd_b200.simulation_snapshots import buildSnapshots, LABELS
     from deepbnd_b200.mesh.mesh_io import load_mesh
@@ -45,7 +46,8 @@ def test_buildSnapshots_writes_reference_layout_and_matches_oracle(tmp_path):
 
 
 @pytest.mark.parametrize("modelBnd", ["dnn", "lin", "per", "MR"])
-def test_predictTangents_matches_oracle(tmp_path, modelBnd):
+def test_predictTangents_matches_oracle(tmp_path, modelBnd, monkeypatch):
+    monkeypatch.setenv("DEEPBND_KEEP_MESHES", "1")
     import deepbnd_b200.wrapper_h5py as myhd
     from deepbnd_b200.tangents_prediction import predictTangents
     from deepbnd_b200.mesh.mesh_io import load_mesh

