@@ -121,6 +121,7 @@ struct rve_batch_s {
     std::vector<long long> adjf_base;
     int max_words = 0;
     DBuf<RowInfo> rowinfo;
+    DBuf<unsigned char> rep_scratch;   // rve_set_batch_shared: system-0 copies of the index arrays while they are replicated
     DBuf<WinDesc> win_desc;
     DBuf<double> win_scal;             // [n_win][8] alpha / beta of the window's system (written by the k_fin_* kernels)
     DBuf<double> lvA[RVE_MAXLEV], lvD[RVE_MAXLEV];
@@ -770,17 +771,34 @@ int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, 
                         FAIL(RVE_E_MESH, "system " + std::to_string(s) + ": a vertex of the mesh boundary / Vref outline differs from system 0 (shared topology needs them fixed)");
                 }
     }
-    // ---- replicate the index arrays
-    std::vector<void*> old;                              // freed after the stream has finished with them
+    // ---- replicate the index arrays.  The system-0 copy of every array goes to one grow-only scratch buffer first, so
+    //      that the arrays themselves can grow in place: no cudaMalloc / cudaFree (device-wide synchronisation) once the
+    //      handle has seen a batch of this size
+    {
+        size_t need = 0;
+        auto acc = [&](long long cnt, size_t elem) { need += (((size_t)cnt * elem + 255) & ~(size_t)255); };
+        acc(2 * nn, 4); acc(2 * nn, 4); acc(6LL * nt, 4); acc(nb, 4); acc(3 * nbe, 4); acc(nvref, 4); acc(na, 4); acc(nadj, 4); acc(nblk, 4);
+        acc(6 * nwin, 4); acc(2 * nwin, 4); acc(H1, 4); acc(WE1, 4); acc(3 * (na + 1) + nsl + 1, 4);
+        acc(nt, 1); acc(36LL * nt, 1); acc(2 * na, 1); acc(8 * nwin, 1); acc(32 * ngrp, 2); acc(6 * WE1, 4);
+        acc(2 * nbe + 2 * nvref + 4 + 2 * nb, 8);
+        CU(h->rep_scratch.alloc(need + 64 * 256));
+    }
+    size_t rep_off = 0;
+    auto stash = [&](const void* src, size_t bytes) -> void* {       // system-0 data -> scratch (device to device)
+        void* dst = h->rep_scratch.p + rep_off;
+        rep_off += (bytes + 255) & ~(size_t)255;
+        if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st);
+        return dst;
+    };
     auto rep_i = [&](DBuf<int>& d, long long n1, long long add, int keep_neg) -> cudaError_t {
-        int* src = d.p; d.p = nullptr; d.cap = d.n = 0; old.push_back(src);
+        const int* src = (const int*)stash(d.p, (size_t)n1 * sizeof(int));
         cudaError_t e = d.alloc((size_t)(n1 * n_sys));
         if (e != cudaSuccess || n1 == 0) return e;
         k_rep_add<int><<<cdiv(n1 * n_sys, 256), 256, 0, st>>>(d.p, src, n1, n_sys, add, keep_neg);
         return cudaSuccess;
     };
     auto rep_p = [&](DBuf<unsigned>& d, long long n1, long long add) -> cudaError_t {
-        unsigned* src = d.p; d.p = nullptr; d.cap = d.n = 0; old.push_back(src);
+        const unsigned* src = (const unsigned*)stash(d.p, (size_t)(n1 + 1) * sizeof(unsigned));
         cudaError_t e = d.alloc((size_t)(n1 * n_sys + 1));
         if (e != cudaSuccess) return e;
         k_rep_ptr<<<cdiv(n1 * n_sys + 1, 256), 256, 0, st>>>(d.p, src, n1, n_sys, add);
@@ -792,12 +810,13 @@ int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, 
         k_rep_sys<<<cdiv(n1 * n_sys, 256), 256, 0, st>>>(d.p, n1, n_sys);
         return cudaSuccess;
     };
+    // plain copies (no index shift), any element type: byte-wise
 #define REP_COPY(d, n1)                                                                                        \
     do {                                                                                                       \
-        auto* src_ = (d).p; (d).p = nullptr; (d).cap = (d).n = 0; old.push_back((void*)src_);                   \
+        const long long bytes_ = (long long)(n1) * (long long)sizeof(*(d).p);                                  \
+        const unsigned char* src_ = (const unsigned char*)stash((d).p, (size_t)bytes_);                        \
         CU((d).alloc((size_t)((n1) * n_sys)));                                                                 \
-        for (int s_ = 0; s_ < n_sys && (n1) > 0; ++s_)                                                         \
-            CU(cudaMemcpyAsync((d).p + (size_t)s_ * (n1), src_, (size_t)(n1) * sizeof(*src_), cudaMemcpyDeviceToDevice, st)); \
+        if (bytes_ > 0) k_rep_add<unsigned char><<<cdiv(bytes_ * n_sys, 256), 256, 0, st>>>((unsigned char*)(d).p, src_, bytes_, n_sys, 0, 0); \
     } while (0)
     CU(rep_i(h->node_va, nn, 0, 0)); CU(rep_i(h->node_vb, nn, 0, 0));
     CU(rep_i(h->node_bnd, nn, nb, 1)); CU(rep_i(h->node_row, nn, na, 1)); CU(rep_i(h->elem_node, 6LL * nt, nn, 0));
@@ -856,7 +875,6 @@ int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, 
     CU(cudaMemcpyAsync(scnt, h->sym_cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(stream_wait(h));
     CU(cudaGetLastError());
-    for (void* q : old) cudaFree(q);
     if (scnt[2] == 4) FAIL(RVE_E_MESH, "device pattern build: coarse-node list overflow");
     h->max_cn = scnt[5];
     h->t_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
