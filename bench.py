@@ -59,10 +59,14 @@ def _mesh_worker(args):
     return buildRVEmesh_arrays(row.copy(), size=size, lcar=lcar)
 
 
+MORPH = {}                                          # template + (l, e, theta) of the last make_meshes(mesher="morph")
+
+
 def make_meshes(param, size, lcar, nproc, mesher="delaunay"):
     if mesher == "morph":                           # one template, every RVE morphed from it (rve_morph.py)
-        from deepbnd_b200.mesh.rve_morph import MorphTemplate, buildRVEmesh_morphed
+        from deepbnd_b200.mesh.rve_morph import MorphTemplate, buildRVEmesh_morphed, morph_parameters
         tpl = MorphTemplate(param[0], size=size, lcar=lcar)
+        MORPH["template"], MORPH["prm"] = tpl, morph_parameters(param.copy(), tpl)
         return [buildRVEmesh_morphed(param[i].copy(), tpl) for i in range(len(param))]
     jobs = [(param[i], size, lcar) for i in range(len(param))]
     if nproc <= 1 or len(jobs) < 4:
@@ -173,6 +177,9 @@ def synthetic_inputs(wl, ns, nuniq, rank, lcar, nproc):
     t0 = time.perf_counter()
     meshes = make_meshes(param, wl["size"], lcar, nproc, wl.get("mesher", "delaunay"))
     meshes = [meshes[i % nuniq] for i in range(ns)]
+    morph = None
+    if wl.get("mesher") == "morph":
+        morph = (MORPH["template"], np.ascontiguousarray(MORPH["prm"][np.arange(ns) % nuniq]))
     t_mesh = time.perf_counter() - t0
     nl = len(wl["loads"])
     uD = None
@@ -193,7 +200,7 @@ def synthetic_inputs(wl, ns, nuniq, rank, lcar, nproc):
             for c in range(2):
                 M[2 * k + c, 2 * k + c] += 0.1 / 3; M[2 * k2 + c, 2 * k2 + c] += 0.1 / 3
                 M[2 * k + c, 2 * k2 + c] += 0.1 / 6; M[2 * k2 + c, 2 * k + c] += 0.1 / 6
-    return dict(meshes=meshes, flat=flatten(meshes), eps=eps, uD=uD, W=W, M=M, t_mesh=t_mesh, nl=nl)
+    return dict(meshes=meshes, flat=flatten(meshes), eps=eps, uD=uD, W=W, M=M, t_mesh=t_mesh, nl=nl, morph=morph)
 
 
 class Runner:
@@ -212,14 +219,13 @@ class Runner:
         self.vref_box = (-1.0, -1.0, 2.0, 2.0)
         self.shared = None
         if wl.get("mesher") == "morph" and not args.no_shared_topology:
-            m = inp["meshes"]
-            self.shared = (np.ascontiguousarray(np.stack([x[0] for x in m])), m[0][1], m[0][2])
+            self.shared = inp["morph"]
 
     def set_pass(self, bb, c=None):
-        if self.shared is not None:                      # morphed meshes: one topology, one symbolic phase (rve_set_batch_shared)
-            pts, tri, reg = self.shared
-            bb.set_shared(pts if c is None else pts[self.chunks[c][5]], tri, reg, param=PARAM_MAT, model=self.wl["model"],
-                          vref_nb=21, vref_box=self.vref_box)
+        if self.shared is not None:                      # morphed meshes: one symbolic phase, coordinates made on the GPU
+            tpl, prm = self.shared
+            bb.set_morphed(tpl, prm if c is None else prm[self.chunks[c][5]], param=PARAM_MAT, model=self.wl["model"],
+                           vref_nb=21, vref_box=self.vref_box)
             return
         arr = self.inp["flat"] if c is None else self.chunks[c][:5]
         bb.set_batch(*arr, param=PARAM_MAT, model=self.wl["model"], vref_nb=21, vref_box=self.vref_box)
@@ -506,7 +512,7 @@ def main():
                        "phase_ms": res["phase"]},
             "e2e": {"value": e2e_val, "unit": "RVE/s", "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
                     "pipeline": "2 handles / 2 host workers, %d chunks per step: each worker runs H2D of the %s + solve + D2H for every other chunk; the two streams interleave on the GPU" % (
-                        run.nchunk, "vertex coordinates + ONE GPU symbolic phase per chunk (shared topology)" if run.shared is not None else "raw meshes + GPU symbolic phase")},
+                        run.nchunk, "inclusion parameters (the meshes are morphed from one template on the GPU) + ONE GPU symbolic phase per chunk" if run.shared is not None else "raw meshes + GPU symbolic phase")},
             "gpu_launches": int(res["launches"]),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": opname, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -16,7 +16,7 @@ OPT_SYM_B, OPT_OPERATOR, OPT_RESIDUAL_REPLACE = 1, 2, 3
 OPERATOR = {"assembled": 0, "matfree": 1}
 
 # every symbol include/rve_b200.h declares (checked by tests/test_abi.py)
-SYMBOLS = ["rve_create", "rve_destroy", "rve_last_error", "rve_set_batch", "rve_set_batch_shared", "rve_assemble", "rve_get_sizes",
+SYMBOLS = ["rve_create", "rve_destroy", "rve_last_error", "rve_set_batch", "rve_set_batch_shared", "rve_set_batch_morphed", "rve_assemble", "rve_get_sizes",
            "rve_get_csr", "rve_get_rowmap", "rve_get_nodemap", "rve_get_rhs", "rve_get_solution",
            "rve_get_coarse_dim", "rve_get_coarse_dense", "rve_solve", "rve_epilogue_tangent",
            "rve_epilogue_snapshot", "rve_epilogue_homogenisation", "rve_set_option", "rve_project", "rve_timings", "rve_bench_spmv", "rve_apply_operator", "rve_host_symbolic"]
@@ -48,6 +48,10 @@ def load():
                                   c_int32_p, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p]
     lib.rve_set_batch_shared.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_double_p, c_int32_p,
                                          c_int32_p, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p]
+    lib.rve_set_batch_morphed.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_double_p, c_int32_p,
+                                          c_int32_p, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p, ctypes.c_int32, c_int32_p,
+                                          c_int32_p, c_double_p, c_double_p, ctypes.c_int32, c_double_p, ctypes.c_double,
+                                          ctypes.c_double, c_double_p]
     lib.rve_assemble.argtypes = [ctypes.c_void_p]
     lib.rve_get_sizes.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_int64_p, c_int64_p, c_int64_p, c_int64_p]
     lib.rve_get_csr.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_int32_p, c_int32_p, c_double_p]

@@ -79,6 +79,26 @@ class RVEBatch:
                                                   L.dptr(mat), L.MODEL[model], int(vref_nb), L.dptr(vb)))
         return self
 
+    def set_morphed(self, template, prm, param=(0.3, 10.0, 0.3, 1.0), model="lin", vref_nb=21, vref_box=None, mat=None):
+        """n_sys RVEs morphed ON THE GPU from a deepbnd_b200.mesh.rve_morph.MorphTemplate: prm (n_sys, n_incl, 3) =
+        (l, e, theta) of every inclusion in the mesher's (permuted) order; only these travel to the device."""
+        mat = L.f64(getLameTable(*param) if mat is None else mat)
+        vb = None if vref_box is None else L.f64(vref_box)
+        prm = L.f64(prm)
+        if prm.ndim != 3 or prm.shape[1:] != (template.n_incl, 3):
+            raise ValueError("prm must be (n_sys, %d, 3)" % template.n_incl)
+        xy, tri, reg = L.f64(template.points), L.i32(template.tri), L.i32(template.region)
+        mv, inc = L.i32(template.moving), L.i32(template.k)
+        d, u, c = L.f64(template.d), L.f64(template.dir), L.f64(template.centres)
+        self.n_sys = prm.shape[0]
+        self.model = model
+        self.nvref = 4 * (vref_nb - 1) + 1 if vref_nb else 0
+        self._keep = (xy, tri, reg, mat, vb, prm, mv, inc, d, u, c)
+        self._check(self.lib.rve_set_batch_morphed(self.h, self.n_sys, len(xy), len(tri), L.dptr(xy), L.iptr(tri), L.iptr(reg), L.dptr(mat),
+                                                   L.MODEL[model], int(vref_nb), L.dptr(vb), len(mv), L.iptr(mv), L.iptr(inc), L.dptr(d),
+                                                   L.dptr(u), len(c), L.dptr(c), float(template.r0), float(template.R), L.dptr(prm)))
+        return self
+
     def assemble(self):
         self._check(self.lib.rve_assemble(self.h))
         return self

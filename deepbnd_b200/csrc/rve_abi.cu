@@ -121,6 +121,8 @@ struct rve_batch_s {
     std::vector<long long> adjf_base;
     int max_words = 0;
     DBuf<RowInfo> rowinfo;
+    DBuf<int> m_node, m_incl;          // rve_set_batch_morphed: the template's moving nodes
+    DBuf<double> m_d, m_dir, m_centre, m_prm;
     DBuf<unsigned char> rep_scratch;   // rve_set_batch_shared: system-0 copies of the index arrays while they are replicated
     DBuf<WinDesc> win_desc;
     DBuf<double> win_scal;             // [n_win][8] alpha / beta of the window's system (written by the k_fin_* kernels)
@@ -727,15 +729,22 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
 // One topology, n_sys coordinate sets (meshes morphed from one template, deepbnd_b200/mesh/rve_morph.py): the symbolic
 // phase runs for system 0 only; its index arrays are replicated with shifted indices, the coordinate-dependent pieces
 // (node coordinates, level-1 cells of the rows, restriction lists) are rebuilt for every system.
-int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, const double* xy, const int32_t* tri,
-                         const int32_t* region, const double* mat, int32_t model, int32_t vref_nb, const double* vref_box) {
+struct MorphHost {                 // rve_set_batch_morphed: template description + per-system inclusion parameters (host pointers)
+    int n_mov, n_incl;
+    const int32_t* node; const int32_t* incl; const double* d; const double* dir; const double* centre; const double* prm;
+    double r0, R;
+};
+
+static int set_batch_shared_impl(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, const double* xy, const int32_t* tri,
+                                 const int32_t* region, const double* mat, int32_t model, int32_t vref_nb, const double* vref_box,
+                                 const MorphHost* morph) {
     H_CHECK(h);
     if (n_sys <= 0 || nv <= 0 || nt <= 0 || !xy || !tri || !region || !mat) FAIL(RVE_E_ARG, "null/empty argument");
     if (n_sys > 65535) FAIL(RVE_E_ARG, "more than 65535 systems in one batch: split it");
     auto t0 = std::chrono::steady_clock::now();
     const int64_t voff1[2] = {0, nv}, toff1[2] = {0, nt};
     if (int rc = rve_set_batch(h, 1, voff1, toff1, xy, tri, region, mat, model, vref_nb, vref_box)) return rc;
-    if (n_sys == 1) return 0;
+    if (n_sys == 1 && !morph) return 0;
     h->have_batch = false;
     cudaStream_t st = h->stream;
     const SysInfo Y = h->info[0];
@@ -745,7 +754,8 @@ int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, 
         6LL * nt * n_sys > 2000000000LL)
         FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
     // ---- the pieces copied from system 0 are only valid if the mesh boundary and the Vref interface do not move
-    {
+    //      (morphing on the device never moves them: the template's moving set excludes those nodes)
+    if (!morph) {
         std::vector<int> nbnd(nv), se(nvref);
         CU(cudaMemcpyAsync(nbnd.data(), h->node_bnd.p, nv * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (nvref) CU(cudaMemcpyAsync(se.data(), h->samp_elem.p, nvref * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -780,7 +790,7 @@ int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, 
         acc(2 * nn, 4); acc(2 * nn, 4); acc(6LL * nt, 4); acc(nb, 4); acc(3 * nbe, 4); acc(nvref, 4); acc(na, 4); acc(nadj, 4); acc(nblk, 4);
         acc(6 * nwin, 4); acc(2 * nwin, 4); acc(H1, 4); acc(WE1, 4); acc(3 * (na + 1) + nsl + 1, 4);
         acc(nt, 1); acc(36LL * nt, 1); acc(2 * na, 1); acc(8 * nwin, 1); acc(32 * ngrp, 2); acc(6 * WE1, 4);
-        acc(2 * nbe + 2 * nvref + 4 + 2 * nb, 8);
+        acc(2 * nbe + 2 * nvref + 4 + 2 * nb, 8); acc(2LL * nv, 8);
         CU(h->rep_scratch.alloc(need + 64 * 256));
     }
     size_t rep_off = 0;
@@ -851,10 +861,32 @@ int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, 
     // ---- coordinates of every system
     {
         const size_t cnt = 2 * (size_t)nv * n_sys;
+        if (morph) {
+            // template coordinates (already on the device as system 0) replicated, moving nodes recomputed per system
+            const size_t nm = (size_t)morph->n_mov, ni = (size_t)morph->n_incl;
+            CU(h->arena.reserve(PinnedArena::need(nm, 4) * 2 + PinnedArena::need(nm, 8) + PinnedArena::need(2 * nm, 8) +
+                                PinnedArena::need(2 * ni, 8) + PinnedArena::need(3 * ni * n_sys, 8)));
+            Span<int> a_node = h->arena.take<int>(nm), a_incl = h->arena.take<int>(nm);
+            Span<double> a_d = h->arena.take<double>(nm), a_dir = h->arena.take<double>(2 * nm), a_c = h->arena.take<double>(2 * ni),
+                         a_prm = h->arena.take<double>(3 * ni * n_sys);
+            memcpy(a_node.p, morph->node, nm * sizeof(int)); memcpy(a_incl.p, morph->incl, nm * sizeof(int));
+            memcpy(a_d.p, morph->d, nm * sizeof(double)); memcpy(a_dir.p, morph->dir, 2 * nm * sizeof(double));
+            memcpy(a_c.p, morph->centre, 2 * ni * sizeof(double)); memcpy(a_prm.p, morph->prm, 3 * ni * n_sys * sizeof(double));
+            UPL(h->m_node, a_node); UPL(h->m_incl, a_incl); UPL(h->m_d, a_d); UPL(h->m_dir, a_dir); UPL(h->m_centre, a_c); UPL(h->m_prm, a_prm);
+            const unsigned char* src = (const unsigned char*)stash(h->d_xy.p, 2 * (size_t)nv * sizeof(double));
+            CU(h->d_xy.alloc(cnt));
+            const long long bytes = 2LL * nv * (long long)sizeof(double);
+            k_rep_add<unsigned char><<<cdiv(bytes * n_sys, 256), 256, 0, st>>>((unsigned char*)h->d_xy.p, src, bytes, n_sys, 0, 0);
+            MorphDev MD;
+            MD.node = h->m_node.p; MD.incl = h->m_incl.p; MD.d = h->m_d.p; MD.dir = h->m_dir.p; MD.centre = h->m_centre.p; MD.prm = h->m_prm.p;
+            MD.n_mov = morph->n_mov; MD.n_incl = morph->n_incl; MD.r0 = morph->r0; MD.R = morph->R;
+            if (nm) k_morph<<<cdiv((long long)nm * n_sys, 256), 256, 0, st>>>(n_sys, nv, MD, h->d_xy.p);
+        } else {
         CU(h->arena.reserve(PinnedArena::need(cnt, 8)));
         Span<double> a_xy = h->arena.take<double>(cnt);
         parallel_for(n_sys, [&](int s) { memcpy(a_xy.p + 2 * (size_t)s * nv, xy + 2 * (size_t)s * nv, 2 * sizeof(double) * (size_t)nv); });
         UPL(h->d_xy, a_xy);
+        }
         CU(h->node_xy.alloc(2 * (size_t)h->N));
         k_shared_node_xy<<<cdiv(h->N, 256), 256, 0, st>>>(n_sys, (int)nn, nv, h->d_xy.p, h->node_va.p, h->node_vb.p, h->node_xy.p);
     }
@@ -881,6 +913,28 @@ int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, 
     h->t_ms[1] = 0.0;
     h->have_batch = true;
     return 0;
+}
+
+int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, const double* xy, const int32_t* tri,
+                         const int32_t* region, const double* mat, int32_t model, int32_t vref_nb, const double* vref_box) {
+    return set_batch_shared_impl(h, n_sys, nv, nt, xy, tri, region, mat, model, vref_nb, vref_box, nullptr);
+}
+
+int rve_set_batch_morphed(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, const double* xy_template, const int32_t* tri,
+                          const int32_t* region, const double* mat, int32_t model, int32_t vref_nb, const double* vref_box,
+                          int32_t n_mov, const int32_t* mov_node, const int32_t* mov_incl, const double* mov_d, const double* mov_dir,
+                          int32_t n_incl, const double* centre, double r0, double R, const double* prm) {
+    if (!h) return RVE_E_ARG;
+    if (n_mov < 0 || n_incl <= 0 || !centre || !prm || (n_mov > 0 && (!mov_node || !mov_incl || !mov_d || !mov_dir)) || !(r0 > 0) || !(R > r0))
+        FAIL(RVE_E_ARG, "bad morphing description");
+    for (long long i = 0; i < (long long)n_sys * n_incl; ++i) {
+        const double l = prm[3 * i], e = prm[3 * i + 1];
+        if (!(l > 0) || !(e > 0) || !(std::max(l, e * l) < R)) FAIL(RVE_E_MESH, "inclusion " + std::to_string(i % n_incl) + " of system " + std::to_string(i / n_incl) + ": radius outside (0, R)");
+    }
+    MorphHost M;
+    M.n_mov = n_mov; M.n_incl = n_incl; M.node = mov_node; M.incl = mov_incl; M.d = mov_d; M.dir = mov_dir; M.centre = centre; M.prm = prm;
+    M.r0 = r0; M.R = R;
+    return set_batch_shared_impl(h, n_sys, nv, nt, xy_template, tri, region, mat, model, vref_nb, vref_box, &M);
 }
 
 int rve_assemble(rve_handle_t h) {

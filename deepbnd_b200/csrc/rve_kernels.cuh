@@ -443,6 +443,40 @@ __global__ void k_shared_node_xy(int n_sys, int nn, int nv, const double* __rest
     node_xy[2 * gid + 1] = 0.5 * (x[2 * a + 1] + x[2 * b + 1]);
 }
 
+// Radial morphing of a template mesh on the device (deepbnd_b200/mesh/rve_morph.py): a moving node at distance d and
+// direction u from the centre c of its nearest inclusion goes to c + u d', d' = d r / r0 inside the template radius r0 and
+// r + (d - r0)(R - r)/(R - r0) in the annulus up to R; r = the inclusion's radius, or the radius of its ellipse
+// (semi-axes l, e l, angle theta: ellipse2_mesh.py:27-39) in the direction u.  Thread per (system, moving node).
+struct MorphDev {
+    const int* node;       // [n_mov] vertex id
+    const int* incl;       // [n_mov] nearest inclusion
+    const double* d;       // [n_mov]
+    const double* dir;     // [n_mov][2]
+    const double* centre;  // [n_incl][2]
+    const double* prm;     // [n_sys][n_incl][3]  l, e, theta
+    int n_mov, n_incl;
+    double r0, R;
+};
+__global__ void k_morph(int n_sys, int nv, MorphDev M, double* __restrict__ xy /*[n_sys][nv][2], pre-filled with the template*/) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n_sys * M.n_mov) return;
+    const int s = (int)(gid / M.n_mov), j = (int)(gid - (long long)s * M.n_mov);
+    const int k = M.incl[j];
+    const double* pr = M.prm + 3 * ((size_t)s * M.n_incl + k);
+    const double ux = M.dir[2 * j], uy = M.dir[2 * j + 1], d = M.d[j];
+    double r = pr[0];
+    if (pr[1] != 1.0) {
+        const double a = pr[0], b = pr[1] * pr[0];
+        const double phi = atan2(uy, ux) - pr[2];
+        const double cb = b * cos(phi), sa = a * sin(phi);
+        r = a * b / sqrt(cb * cb + sa * sa);
+    }
+    const double dn = (d <= M.r0) ? d * r / M.r0 : r + (d - M.r0) * (M.R - r) / (M.R - M.r0);
+    double* o = xy + 2 * ((size_t)s * nv + M.node[j]);
+    o[0] = M.centre[2 * k] + ux * dn;
+    o[1] = M.centre[2 * k + 1] + uy * dn;
+}
+
 // ---------------------------------------------------------------------------------------------
 // (1) numeric assembly, row-wise: thread per block row (CTA per window, warp per 32-row SELL slice).  A thread
 //     zeroes the slots of its row, walks the elements around the row (adjf), computes the 6 blocks K_e[a][0..5] of

@@ -101,3 +101,14 @@ def buildRVEmesh_morphed(paramRVEdata, template):
     if np.abs(paramRVEdata[:n, :2] - template.centres).max() > 1e-9:
         raise ValueError("the inclusion centres differ from the template's: re-mesh (buildRVEmesh_arrays) instead")
     return template.mesh(paramRVEdata[:n, 2], paramRVEdata[:n, 3], paramRVEdata[:n, 4])
+
+
+
+def morph_parameters(paramRVEdata, template):
+    """(l, e, theta) of every inclusion of a batch in the mesher's order, for RVEBatch.set_morphed (the morphing then runs
+    on the GPU): paramRVEdata (B, Nx*Ny, 5) is permuted IN PLACE, every row like the reference (mesh_RVE.py:45-50)."""
+    paramRVEdata[:, :, :] = paramRVEdata[:, template.perm, :]
+    n = template.n_incl
+    if np.abs(paramRVEdata[:, :n, :2] - template.centres[None]).max() > 1e-9:
+        raise ValueError("the inclusion centres differ from the template's: re-mesh (buildRVEmesh_arrays) instead")
+    return np.ascontiguousarray(paramRVEdata[:, :n, 2:5])

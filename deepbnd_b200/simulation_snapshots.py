@@ -140,7 +140,7 @@ def _store_snapshots(rows, out, datasets):
 
 
 def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs, comm_self=None,
-                   device=None, batch_size=256, rtol=1e-10, nproc=None, mesher="delaunay"):
+                   device=None, batch_size=256, rtol=1e-10, nproc=None, mesher="delaunay", lcar=None):
     bndMeshname, paramRVEname, snapshotsname, meshname = filesnames
     box, nb = vref_box_from_mesh(bndMeshname)
     nh = 2 * (4 * (nb - 1) + 1)                                             # Vref.dim()
@@ -163,14 +163,20 @@ def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs
 
     template = None
     if mesher == "morph":                     # one template mesh per rank, every snapshot morphed from it (rve_morph.py)
-        from .mesh.rve_morph import MorphTemplate
-        template = MorphTemplate(paramRVEdata[0], size='full')
+        from .mesh.rve_morph import MorphTemplate, morph_parameters
+        template = MorphTemplate(paramRVEdata[0], size='full', lcar=lcar)          # lcar: None = the reference's 2/30
     elif mesher != "delaunay":
         raise ValueError("mesher must be 'delaunay' or 'morph'")
 
     def prepare(rows, batch):
         # the reference reuses ONE temporary mesh name per rank; a batch needs one cache entry per snapshot
         names = [meshname.replace(".xdmf", "_%d.xdmf" % int(ids_run[i])) for i in rows]
+        if template is not None:              # morphing on the GPU from the template: only (l, e, theta) per inclusion travel
+            sub = paramRVEdata[rows]
+            prm = morph_parameters(sub, template)
+            paramRVEdata[rows] = sub              # keep the reference's in-place permutation of the rows
+            batch.set_morphed(template, prm, tuple(paramMaterial), model=opModel, vref_nb=nb, vref_box=box)
+            return
         meshes = get_meshes(paramRVEdata[rows], names, 'full', createMesh, nproc, template, pool)
         set_batch_meshes(batch, meshes, template, tuple(paramMaterial), opModel, nb, box)
 

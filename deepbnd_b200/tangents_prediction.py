@@ -52,13 +52,19 @@ def predictTangents(num, num_runs, modelBnd, namefiles, createMesh, meshSize, de
 
     template = None
     if mesher == "morph":
-        from .mesh.rve_morph import MorphTemplate
+        from .mesh.rve_morph import MorphTemplate, morph_parameters
         template = MorphTemplate(paramRVEdata[0], size=meshSize)
     elif mesher != "delaunay":
         raise ValueError("mesher must be 'delaunay' or 'morph'")
 
     def prepare(rows, batch):
         names = [meshMicroName.format(int(ids[i]) if np.any(ids) else int(i), meshSize) for i in rows]
+        if template is not None:              # morphing on the GPU from the template: only (l, e, theta) per inclusion travel
+            sub = paramRVEdata[rows]
+            prm = morph_parameters(sub, template)
+            paramRVEdata[rows] = sub              # keep the reference's in-place permutation of the rows
+            batch.set_morphed(template, prm, tuple(param), model=modelBnd, vref_nb=nb, vref_box=box)
+            return
         meshes = get_meshes(paramRVEdata[rows], names, meshSize, createMesh, nproc, template, pool)
         set_batch_meshes(batch, meshes, template, tuple(param), modelBnd, nb, box)
 

@@ -78,6 +78,17 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
 int rve_set_batch_shared(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, const double* xy, const int32_t* tri,
                          const int32_t* region, const double* mat, int32_t model, int32_t vref_nb, const double* vref_box);
 
+/* rve_set_batch_shared with the coordinates generated ON THE DEVICE by radial morphing of one template mesh
+ * (deepbnd_b200/mesh/rve_morph.py; the reference re-meshes every snapshot with gmsh, mesh_RVE.py:38-64): per RVE only
+ * its inclusion parameters travel to the GPU.  xy_template[nv][2] is the template mesh; the moving nodes are described
+ * by mov_node (vertex id), mov_incl (nearest inclusion), mov_d / mov_dir (distance and unit direction from its centre);
+ * centre[n_incl][2], template radius r0 and influence radius R; prm[n_sys][n_incl][3] = (l, e, theta) of every inclusion
+ * (circle: e = 1). */
+int rve_set_batch_morphed(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt, const double* xy_template, const int32_t* tri,
+                          const int32_t* region, const double* mat, int32_t model, int32_t vref_nb, const double* vref_box,
+                          int32_t n_mov, const int32_t* mov_node, const int32_t* mov_incl, const double* mov_d, const double* mov_dir,
+                          int32_t n_incl, const double* centre, double r0, double R, const double* prm);
+
 /* replaces: A = mp.block_assemble(a); bcs.apply(A) (micro_model.py:60-62, micro_model_dnn.py:65-67).
  * Numeric P2 stiffness assembly of every system into the SELL-32 node-block matrix + preconditioner set-up. */
 int rve_assemble(rve_handle_t h);

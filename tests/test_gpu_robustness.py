@@ -120,3 +120,27 @@ def test_shared_topology_refuses_a_moving_boundary(coarse_reduced_meshes):
     pts[1, k, 1] += 1e-3
     with pytest.raises(L.RVEError):
         RVEBatch().set_shared(pts, T, R, PARAM, model="lin")
+
+
+def test_device_morphing_equals_host_morphing():
+    """rve_set_batch_morphed (coordinates generated on the GPU from the template + (l, e, theta)) against set_shared with the
+    coordinates morphed on the host: same meshes to rounding, hence the same tangents; circles and ellipses"""
+    from conftest import synthetic_param
+    from deepbnd_b200.batch import RVEBatch
+    from deepbnd_b200.mesh.rve_morph import MorphTemplate, buildRVEmesh_morphed, morph_parameters
+    n = 4
+    par = synthetic_param(n, seed=17)
+    par[2:, 3] = 0.8
+    par[2:, 4] = 0.6
+    par[2:, 2] *= 0.9
+    tpl = MorphTemplate(par[0], size="reduced")
+    pts = np.stack([buildRVEmesh_morphed(par[i].copy(), tpl)[0] for i in range(n)])
+    prm = morph_parameters(par.copy(), tpl)
+    eps = np.broadcast_to(np.eye(3), (n, 3, 3)).copy()
+    a = RVEBatch().set_shared(pts, tpl.tri, tpl.region, PARAM, model="per").assemble()
+    a.solve(eps, rtol=1e-11)
+    b = RVEBatch().set_morphed(tpl, prm, PARAM, model="per").assemble()
+    b.solve(eps, rtol=1e-11)
+    Ca, Cb = a.tangent(), b.tangent()
+    assert np.abs(Ca - Cb).max() <= 1e-10 * np.abs(Ca).max()
+    a.close(); b.close()
