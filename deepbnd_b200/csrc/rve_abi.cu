@@ -319,13 +319,15 @@ static void launch_update(rve_batch_s* h, const PcgArgs& a, int init, int iter, 
 template <int K>
 static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStream_t st) {
     const Levels& LV = a.LV;
-    auto grid = [&](int l) { return dim3((unsigned)((LV.g[l].G + 255) / 256), (unsigned)a.n_sys); };
+    // thread per (system, node); small grids take 128-thread blocks so that the last block of a system is not mostly idle
+    auto bs = [&](int l) { return LV.g[l].G < 2048 ? 128 : 256; };
+    auto grid = [&](int l) { return dim3((unsigned)((LV.g[l].G + bs(l) - 1) / bs(l)), (unsigned)a.n_sys); };
     int W = 1;                                         // number of wide levels; the coarsest level stays in k_vc_mid
     while (W < LV.L - 1 && LV.g[W].G >= RVE_WIDE_NODES) ++W;
-    k_vc_down1<K><<<grid(0), 256, 0, st>>>(LV, 0, h->active.p);
+    k_vc_down1<K><<<grid(0), bs(0), 0, st>>>(LV, 0, h->active.p);
     for (int l = 1; l < W; ++l) {
-        k_vc_restrict<K><<<grid(l), 256, 0, st>>>(LV, l, h->active.p);
-        k_vc_down1<K><<<grid(l), 256, 0, st>>>(LV, l, h->active.p);
+        k_vc_restrict<K><<<grid(l), bs(l), 0, st>>>(LV, l, h->active.p);
+        k_vc_down1<K><<<grid(l), bs(l), 0, st>>>(LV, l, h->active.p);
     }
     int nk = 2 + 2 * (W - 1);
     if (LV.L > 1) {
@@ -333,13 +335,13 @@ static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStrea
         k_vc_mid<K><<<a.n_sys, Gm <= 128 ? 128 : (Gm <= 256 ? 256 : 320), 0, st>>>(LV, W, h->active.p);
         for (int l = W - 1; l >= 0; --l) {
             const float* src = (l + 1 == W) ? LV.xc[W] : LV.tc[l + 1];
-            k_vc_prolong<K><<<grid(l), 256, 0, st>>>(LV, l, src, h->active.p);
-            if (l > 0) k_vc_upl<K><<<grid(l), 256, 0, st>>>(LV, l, h->active.p);
+            k_vc_prolong<K><<<grid(l), bs(l), 0, st>>>(LV, l, src, h->active.p);
+            if (l > 0) k_vc_upl<K><<<grid(l), bs(l), 0, st>>>(LV, l, h->active.p);
         }
         nk += 1 + W + (W - 1);
     }
-    k_vc_up1<K><<<grid(0), 256, 0, st>>>(LV, h->active.p, h->cpart.p);
-    const int nb = (LV.g[0].G + 255) / 256;
+    k_vc_up1<K><<<grid(0), bs(0), 0, st>>>(LV, h->active.p, h->cpart.p);
+    const int nb = (int)grid(0).x * (bs(0) / 32);      // per-warp partials of rc.z1
     k_fin_beta<<<cdiv(a.n_sys, 8), 256, 0, st>>>(a.n_sys, K, nb, a.wt.sys_win0, h->cpart.p, h->active.p, h->sc.p, first, h->win_scal.p);
     h->launches += nk + 1;
 }
@@ -404,7 +406,7 @@ static int alloc_solver_state(rve_batch_s* h, int n_sys, int model, int ncx, int
         lcx /= 2; lcy /= 2;
     }
     LV.L = L;
-    CU(h->cpart.alloc((size_t)n_sys * ((LV.g[0].G + 255) / 256) * 4));
+    CU(h->cpart.alloc((size_t)n_sys * ((LV.g[0].G + 127) / 128 + 1) * 8 * 4));      // per-warp partials of k_vc_up1
     return 0;
 }
 

@@ -1357,7 +1357,7 @@ k_vc_upl(Levels LV, int l, const int* __restrict__ active) {
 // r.z = rc . z1, beta; clears rc for the next restriction.  grid (ceil(G/256), n_sys)
 template <int K>
 __global__ void __launch_bounds__(256)
-k_vc_up1(Levels LV, const int* __restrict__ active, double* __restrict__ part) {
+k_vc_up1(Levels LV, const int* __restrict__ active, double* __restrict__ part) {   // block size 128 or 256
     const int sys = blockIdx.y;
     if (!active[sys]) return;
     const Grid g = LV.g[0];
@@ -1388,17 +1388,12 @@ k_vc_up1(Levels LV, const int* __restrict__ active, double* __restrict__ part) {
             rc[(size_t)idx * K + k] = make_float2(0.f, 0.f);
         }
     }
-    __shared__ double s_dot[8][4];
+    // per-WARP partial of rc.z1 (no block barrier: finished warps retire); k_fin_beta adds them per system in a fixed order
+    const int nwp = blockDim.x >> 5;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const double v = warp_sum(dot[k]);
-        if (lane == 0) s_dot[wv][k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < K) {                           // per-CTA partial of rc.z1; k_fin_beta adds them per system
-        double my = 0.0;
-        for (int i = 0; i < 8; ++i) my += s_dot[i][threadIdx.x];
-        part[((size_t)sys * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = my;
+        if (lane == 0) part[(((size_t)sys * gridDim.x + blockIdx.x) * nwp + wv) * 4 + k] = v;
     }
 }
 
