@@ -332,7 +332,8 @@ static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStrea
     int nk = 2 + 2 * (W - 1);
     if (LV.L > 1) {
         const int Gm = LV.g[W].G;
-        k_vc_mid<K><<<a.n_sys, Gm <= 128 ? 128 : (Gm <= 256 ? 256 : 320), 0, st>>>(LV, W, h->active.p);
+        // one CTA per system, as few idle threads as the largest level allows: more systems resident per SM (the kernel is latency-bound)
+        k_vc_mid<K><<<a.n_sys, std::min(320, std::max(64, (Gm + 31) & ~31)), 0, st>>>(LV, W, h->active.p);
         for (int l = W - 1; l >= 0; --l) {
             const float* src = (l + 1 == W) ? LV.xc[W] : LV.tc[l + 1];
             k_vc_prolong<K><<<grid(l), bs(l), 0, st>>>(LV, l, src, h->active.p);
