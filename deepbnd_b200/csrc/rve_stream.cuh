@@ -307,6 +307,7 @@ k_update_p(WinTab wt, const WinDesc* __restrict__ desc, int n_win, const double2
 // nor the dependent gather are on the critical path.  Launch with RVE_UPDP_THREADS(K) + 32 threads.
 // ------------------------------------------------------------------------------------------------------------------
 #define RVE_DIRP_STAGES 3
+#define RVE_DIRP_MINB(K) 2             // two CTAs per SM for every K (3 stages of r, p, dinv, rowinfo fit twice)
 __host__ __device__ inline size_t dirp_stage_bytes(int K, int cn_pad, bool precond) {
     size_t b = 2 * (size_t)RVE_WIN * K * 16 + (size_t)RVE_WIN * 16;                                   // r p, dinv
     if (precond) b += (size_t)RVE_WIN * 16 + (size_t)cn_pad * 4 + (size_t)cn_pad * K * 8;             // rowinfo, node list, xc (float2)
@@ -321,7 +322,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 template <int K>
-__global__ void __launch_bounds__(RVE_UPDP_THREADS(K) + 32, RVE_UPDP_MINB(K))
+__global__ void __launch_bounds__(RVE_UPDP_THREADS(K) + 32, RVE_DIRP_MINB(K))
 k_direction_p(WinTab wt, const WinDesc* __restrict__ desc, int n_win, double2* __restrict__ p, const double2* __restrict__ r,
               const float4* __restrict__ dinv32, const RowInfo* __restrict__ rowinfo, const int* __restrict__ cn_node,
               const cvec* __restrict__ xc1, int G, const double* __restrict__ win_scal, int precond, int cn_pad) {
