@@ -773,14 +773,18 @@ __global__ void k_coarse_dinv(int n_sys, Grid g, const double* __restrict__ A, d
 // (3) PCG kernels (one CTA of RVE_WIN threads per window)
 // ---------------------------------------------------------------------------------------------
 
-// q = A p, pq = p.q.  CTA of RVE_SPMV_WARPS (=2) warps per window.  The CTA first stages the p entries
+// q = A p, per-window partial of p.q.  CTA of RVE_SPMV_WARPS (= 4) warps per window.  The CTA first stages the p entries
 // its window needs (own rows: one coalesced copy; halo rows: list-driven gather) in shared memory.
-// Then every lane owns one row of a SELL-32 slice and each warp walks the slices w, w+2, w+4, w+6 of the
-// window: rows are sorted by length inside a window (2 long vertex slices, 6 short mid-edge slices), so
-// both warps get the same number of slots — no warp idles at a barrier.  Per slot: one coalesced 2-byte
+// Then every lane owns one row of a SELL-32 slice and warp w walks the slices w and w+4 of the window: rows are sorted
+// by length inside a window (2 long vertex slices, 6 short mid-edge slices), warps 0-1 get a long and a short slice,
+// warps 2-3 two short ones.  Per slot: one coalesced 2-byte
 // column load, two coalesced LDG.128 of the 2x2 block and K LDS.128 gathers from the tile; the loads of
 // the next slot pair (also across a slice boundary) are in flight while the current pair is multiplied.
 // No cross-lane reduction; q leaves through shared memory so the global store is coalesced.
+// (K = 3: the 48-byte pitch of the tile was suspected of the 38-43 % conflict wavefronts ncu shows; a 64-byte pitch was measured
+// in round 2 and is WORSE — 67 % conflict wavefronts, +20 % time: with 4 x 16 B per row only two bank groups are reachable per
+// rhs, while 3 is coprime with 8.  The conflicts are birthday collisions of 8 random rows per quarter warp, not a stride artefact:
+// profiles/r02e_ncu_spmv_k3_pitch64_rejected_summary.csv.)
 // warps per CTA (window): measured 2 -> 4: SpMV -4 % (K = 2) / -7 % (K = 3), the p-tile is shared by more warps and the
 // shared-memory-limited occupancy doubles; 8 (one slice per warp: 2 long + 6 short slices) is 15-30 % slower
 #ifndef RVE_SPMV_WARPS
