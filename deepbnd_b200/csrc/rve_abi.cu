@@ -88,6 +88,7 @@ struct rve_batch_s {
     // host-side batch description
     int n_sys = 0, model = 0, vref_nb = 0, nvref = 0;
     bool have_batch = false, assembled = false, solved = false;
+    bool have_samples = false;          // the Vref samples / epilogue buffers belong to the last solve (rve_project needs them)
     int K = 0, NL = 0;  // solver rhs count, load count of the last solve
     Mat8 mat;
     double vref_box[4];
@@ -106,7 +107,7 @@ struct rve_batch_s {
     DBuf<float4> dinv;
     DBuf<int> node_row, node_bnd, node_sys, elem_node, elem_sys, d_row_base, bnd_sys, bnd_node,
         bedge, d_bedge_base, samp_elem, win_sys, win_row0, win_n, win_slice0, win_halo0, win_cn0, sys_win0, halo,
-        cn_node, active, cnt, d_iters, n_active, err_flag;
+        cn_node, active, cnt, d_iters, n_active;
     DBuf<unsigned char> elem_reg;
     DBuf<unsigned> slice_ptr, cn_beg;
     DBuf<uint16_t> scol, cn_ent;
@@ -381,7 +382,6 @@ static int alloc_solver_state(rve_batch_s* h, int n_sys, int model, int ncx, int
     h->have_bval = false;                       // SELL values: rve_assemble (assembled operator) or on demand
     CU(h->dinv.alloc((size_t)h->R)); CU(h->wmean.alloc(h->R));
     CU(h->active.alloc(n_sys)); CU(h->cnt.alloc(n_sys)); CU(h->d_iters.alloc(n_sys)); CU(h->n_active.alloc(1));
-    CU(h->err_flag.alloc(1));
     CU(h->part.alloc((size_t)h->n_win * 8));  CU(h->sc.alloc((size_t)n_sys * 4 * SC_N));
     CU(h->Mx.alloc((size_t)n_sys * 16)); CU(h->Gaff.alloc((size_t)n_sys * 16)); CU(h->aaff.alloc((size_t)n_sys * 8));
     CU(h->acc.alloc((size_t)n_sys * ACC_PER_SYS));
@@ -475,7 +475,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     if (model < RVE_MODEL_LIN || model > RVE_MODEL_MR) FAIL(RVE_E_ARG, "unknown model");
     if (vref_nb != 0 && vref_nb < 2) FAIL(RVE_E_ARG, "vref_nb must be 0 or >= 2");
     auto t0 = std::chrono::steady_clock::now();
-    h->have_batch = h->assembled = h->solved = false;
+    h->have_batch = h->assembled = h->solved = h->have_samples = false;
     h->n_sys = n_sys; h->model = model; h->vref_nb = vref_nb;
     h->nvref = vref_nb > 0 ? 4 * (vref_nb - 1) + 1 : 0;
     for (int k = 0; k < 8; ++k) h->mat.v[k] = mat[k];
@@ -945,7 +945,6 @@ int rve_assemble(rve_handle_t h) {
     if (!h->have_batch) FAIL(RVE_E_STATE, "rve_assemble before rve_set_batch");
     cudaStream_t st = h->stream;
     CU(cudaEventRecord(h->ev[0], st));
-    CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), st));
     if (h->opt_operator == RVE_OPERATOR_MATFREE) {
         // matrix-free operator: geometry x material of the window elements, block-Jacobi diagonal from the element fans
         k_we_geo<<<h->n_win, RVE_WIN, 0, st>>>(h->n_win, h->win_we0.p, h->win_nwe.p, h->we_elem.p, h->elem_node.p, h->elem_reg.p,
@@ -965,7 +964,7 @@ int rve_assemble(rve_handle_t h) {
     Levels& LV = h->LV;
     for (int l = 0; l < LV.L; ++l) CU(cudaMemsetAsync(LV.A[l], 0, h->lvA[l].n * sizeof(double), st));
     k_galerkin1<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
-                                                h->node_row.p, h->box.p, LV.g[0], LV.A[0], h->mat, h->err_flag.p);
+                                                h->node_row.p, h->box.p, LV.g[0], LV.A[0], h->mat);
     k_galerkin_mirror<<<cdiv((long long)h->n_sys * 12 * LV.g[0].G, 256), 256, 0, st>>>(h->n_sys, LV.g[0], LV.A[0]);
     for (int l = 0; l + 1 < LV.L; ++l) {
         long long n = (long long)h->n_sys * LV.g[l + 1].G * 25;
@@ -978,8 +977,6 @@ int rve_assemble(rve_handle_t h) {
     }
     h->launches += 4 + (LV.L - 1) + 2 * LV.L;
     CU(cudaEventRecord(h->ev[2], st));
-    int flag = 0;
-    CU(cudaMemcpyAsync(&flag, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(stream_wait(h));
     CU(cudaGetLastError());
     float ms = 0;
@@ -1139,7 +1136,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     const int K = (h->model == RVE_MODEL_MR) ? 3 : n_rhs;
     const int n_sys = h->n_sys;
     if (h->opt_operator == RVE_OPERATOR_ASSEMBLED) { if (int rc = ensure_bval(h)) return rc; }
-    h->K = K; h->NL = NL; h->solved = false;
+    h->K = K; h->NL = NL; h->solved = false; h->have_samples = false;
     cudaStream_t st = h->stream;
     const size_t RK = (size_t)h->R * K * 2;
     CU(h->p.alloc(RK)); CU(h->q.alloc(RK)); CU(h->x.alloc(RK)); CU(h->r.alloc(RK)); CU(h->b.alloc(RK));
@@ -1327,6 +1324,7 @@ static int run_epilogue(rve_handle_t h) {
         k_epi_sample<<<cdiv(n, 256), 256, 0, st>>>(n, h->nvref, NL, h->samp_elem.p, h->samp_lam.p, h->elem_node.p, h->U.p, h->sol.p);
     }
     h->launches += 2 + (h->nvref ? 1 : 0);
+    h->have_samples = h->nvref > 0;
     CU(cudaEventRecord(h->ev[1], st));
     return 0;
 }
@@ -1409,7 +1407,7 @@ int rve_epilogue_homogenisation(rve_handle_t h, double* sigmaL, double* sigmaT, 
 
 int rve_project(rve_handle_t h, int32_t nmax, int32_t nh, const double* W, const double* M, const double* translate, double* Y) {
     H_CHECK(h);
-    if (!h->solved || !h->sol.p) FAIL(RVE_E_STATE, "rve_project needs rve_epilogue_snapshot first");
+    if (!h->solved || !h->have_samples || !h->nvref) FAIL(RVE_E_STATE, "rve_project needs rve_epilogue_snapshot of the current solve first");
     if (nh != 2 * h->nvref || nmax < 1 || !W || !M || !Y) FAIL(RVE_E_ARG, "bad projection arguments");
     const int NL = h->NL;
     // MWt[l][q][j] = sum_k M[q][k] W[l][j][k]

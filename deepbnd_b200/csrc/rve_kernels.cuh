@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(256)
 k_galerkin1(int n_elem, const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
             const int* __restrict__ elem_sys, const double* __restrict__ node_xy,
             const int* __restrict__ node_row, const double* __restrict__ box, Grid g1,
-            double* __restrict__ A1, Mat8 mat, int* __restrict__ err_flag) {
+            double* __restrict__ A1, Mat8 mat) {
     __shared__ double s_mat[8];
     __shared__ double s_W[8][6][9];
     __shared__ double s_G[8][3][9][2];          // coarse gradients gI(q)

@@ -144,3 +144,55 @@ def test_device_morphing_equals_host_morphing():
     Ca, Cb = a.tangent(), b.tangent()
     assert np.abs(Ca - Cb).max() <= 1e-10 * np.abs(Ca).max()
     a.close(); b.close()
+
+
+def test_project_refuses_stale_samples(coarse_reduced_meshes):
+    """the epilogue buffers survive rve_solve; rve_project must not project the samples of an older solve"""
+    from deepbnd_b200 import _lib as L
+    from deepbnd_b200.batch import RVEBatch
+    meshes = coarse_reduced_meshes[:2]
+    b = RVEBatch().set_meshes(meshes, PARAM, model="per").assemble()
+    eps = np.broadcast_to(np.eye(3)[[2, 0]], (2, 2, 3)).copy()
+    W, M = np.eye(160, 162), np.eye(162)
+    b.solve(eps)
+    b.snapshot()
+    assert b.project(W, M).shape == (2, 2, 160)
+    b.solve(eps)                                   # new solve, no epilogue yet
+    with pytest.raises(L.RVEError):
+        b.project(W, M)
+    b.close()
+
+
+def test_bench_sized_batch_at_the_shipped_tolerance_matches_oracle():
+    """What the bench and the drop-in drivers actually run (matrix-free operator, two-level preconditioner, rtol = 1e-10)
+    on `full` RVEs at the reference resolution lcar = 2/30 (70k DOFs): a ragged batch of different meshes, two of its
+    systems compared with sparse LU — snapshot outputs (per) and tangents with non-zero boundary data (dnn)."""
+    from conftest import synthetic_param
+    from deepbnd_b200.batch import RVEBatch
+    from deepbnd_b200.elasticity import macro_strain_voigt
+    from deepbnd_b200.mesh.rve_mesher import buildRVEmesh_arrays
+    from oracle.rve_oracle import OracleRVE, vref_points
+    par = synthetic_param(6, seed=2)
+    meshes = [buildRVEmesh_arrays(par[i].copy(), size="full") for i in range(6)]
+    box, pts = (-1.0, -1.0, 2.0, 2.0), vref_points(-1, -1, 2, 2, 21)
+    eps = np.broadcast_to(np.stack([macro_strain_voigt(2), macro_strain_voigt(0)]), (6, 2, 3)).copy()
+    b = RVEBatch().set_meshes(meshes, PARAM, model="per", vref_box=box).assemble()
+    st, it = b.solve(eps, rtol=1e-10)
+    out = b.snapshot()
+    b.close()
+    assert st.max() == 0 and it.max() < 90
+    s = 4
+    ref = OracleRVE(*meshes[s], param=PARAM, model="per").snapshot(pts)
+    for j, lab in enumerate(("S", "A")):
+        for key, mine in (("solutions_" + lab, out["sol"][s, j]), ("sigma_" + lab, out["sigma"][s, j]),
+                          ("sigmaTotal_" + lab, out["sigmaT"][s, j]), ("a_" + lab, out["a"][s, j]), ("B_" + lab, out["B"][s, j])):
+            r = np.asarray(ref[key])
+            assert np.abs(mine.reshape(r.shape) - r).max() <= 1e-8 * max(np.abs(r).max(), 1e-3), key
+    # dnn on the internal box of the same size class is the `reduced` mesh; on a `full` mesh the Dirichlet boundary is the
+    # outer box: lin (zero data) at full size
+    b = RVEBatch().set_meshes(meshes[:2], PARAM, model="lin", vref_box=box).assemble()
+    b.solve(np.broadcast_to(np.eye(3), (2, 3, 3)).copy(), rtol=1e-10)
+    C = b.tangent()
+    b.close()
+    Co = OracleRVE(*meshes[1], param=PARAM, model="lin").compute_tangent()
+    assert np.abs(C[1] - Co).max() <= 1e-8 * np.abs(Co).max()
