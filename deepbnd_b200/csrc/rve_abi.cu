@@ -1190,7 +1190,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
     K_DISPATCH(K, UPD0_);
 #undef UPD0_
     int it = 0, launched = 0;
-    const int CHECK = 8;
+    int CHECK = 8;                     // iterations between two reads of the active-systems counter; 2 once systems start to converge
     h->launches += 3 + (uD ? 1 : 0);
     auto pool_event = [&](size_t i) -> cudaEvent_t {
         while (h->evpool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); h->evpool.push_back(e); }
@@ -1243,6 +1243,7 @@ int rve_solve(rve_handle_t h, int32_t n_rhs, const double* eps, const double* uD
         CU(cudaMemcpyAsync(h->h_nactive, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(stream_wait(h));
         if (*h->h_nactive <= 0) break;
+        if (*h->h_nactive < n_sys) CHECK = 2;      // the tail: stop within two iterations of the last system
     }
     CU(cudaEventRecord(h->ev[2], st));
     // ---- constraint post-processing + nodal field
