@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "rve_abi.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("rve_kernels.cuh", "rve_devsym.cuh", "rve_math.cuh", "rve_symbolic.hpp")] + \
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("rve_kernels.cuh", "rve_devsym.cuh", "rve_math.cuh", "rve_symbolic.hpp", "rve_matfree.cuh", "rve_stream.cuh")] + \
        [os.path.join(HERE, "..", "include", "rve_b200.h")]
 LIB = os.environ.get("DEEPBND_RVE_LIB") or os.path.join(HERE, "lib", "librve_b200.so")   # override: kernel-variant experiments
 
@@ -25,7 +25,8 @@ def build_lib(force=False, verbose=False):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    extra = os.environ.get("DEEPBND_NVCC_EXTRA", "").split()          # kernel-variant experiments: -DRVE_...=...
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

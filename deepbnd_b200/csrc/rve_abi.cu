@@ -229,7 +229,7 @@ static Sell sell_tab(rve_batch_s* h) {
 static size_t smem_spmv(rve_batch_s* h, int K) { return (size_t)h->max_tile * K * sizeof(double2); }
 static size_t smem_update(int K) { return (size_t)RVE_WIN * K * sizeof(double2) + RVE_WIN * sizeof(float2) + 4 * RVE_WIN * sizeof(uint16_t); }
 static size_t smem_direction(rve_batch_s* h, int K) { return (size_t)h->max_cn * K * sizeof(double2); }
-static size_t smem_apply(rve_batch_s* h, int K) { return ((size_t)h->max_tile + h->max_slots) * K * sizeof(double2); }
+static size_t smem_apply(rve_batch_s* h, int K) { return ((size_t)apply_tile_pitch(h->max_tile) + h->max_slots) * K * sizeof(double2); }
 
 // Opt-in dynamic shared memory of the kernels that size their tiles at run time.  The attribute belongs to the
 // FUNCTION (shared by every handle and host thread of the process), so it is raised once, to the device limit
@@ -722,7 +722,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     if (scnt[2] == 4) FAIL(RVE_E_MESH, "device pattern build: coarse-node list overflow");
     if (scnt[2] == 5) FAIL(RVE_E_MESH, "device pattern build: a window touches more than 1024 elements");
     h->max_tile = scnt[1]; h->max_cn = scnt[5]; h->n_halo = scnt[0];
-    if (((size_t)h->max_tile + h->max_slots) * 3 * sizeof(double2) > 200 * 1024) FAIL(RVE_E_MESH, "window halo too large for shared memory");
+    if (((size_t)h->max_tile + 8 + h->max_slots) * 3 * sizeof(double2) > 200 * 1024) FAIL(RVE_E_MESH, "window halo too large for shared memory");
     auto t2 = std::chrono::steady_clock::now();
     h->t_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
     h->have_batch = true;

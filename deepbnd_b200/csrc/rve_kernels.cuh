@@ -1074,9 +1074,54 @@ __device__ __forceinline__ void stencil_apply(const Grid& g, const stv* __restri
         }
 }
 
+// Same sum for the grid-wide kernels of the large levels (thread per coarse node, nothing to amortise a latency with):
+// the 25 stencil blocks of the node (the only DRAM stream, 200 B per node and pass, read once per V-cycle, hence
+// evict-first loads) are ALL requested before the first one is used -- with the loop above the compiler keeps two
+// slots in flight and the node pays about twelve dependent round trips; the neighbours' vectors (L1 / L2 hits) follow,
+// both right-hand sides of K = 2 in one 16-byte load.
+#ifndef RVE_VC_PRELOAD
+#define RVE_VC_PRELOAD 1
+#endif
+#ifndef RVE_VC_MINB
+#define RVE_VC_MINB 3
+#endif
+template <int K>
+__device__ __forceinline__ void stencil_apply_wide(const Grid& g, const stv* __restrict__ S4,
+                                                   const cvec* __restrict__ x, int i, int j, cvec* out) {
+#if RVE_VC_PRELOAD
+    const int idx = j * g.nx + i;
+    stv s[25];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) s[t] = __ldcs(S4 + (size_t)t * g.G + idx);
+#pragma unroll
+    for (int dj = -2; dj <= 2; ++dj)
+#pragma unroll
+        for (int di = -2; di <= 2; ++di) {
+            int nb;
+            if (!grid_node_fast(g, i + di, j + dj, nb)) nb = idx;
+            const float4 a = st_unpack(s[(dj + 2) * 5 + (di + 2)]);
+            const cvec* xn = x + (size_t)nb * K;
+            if (K == 2) {
+                const float4 xv = *(const float4*)xn;
+                out[0].x += a.x * xv.x + a.y * xv.y; out[0].y += a.z * xv.x + a.w * xv.y;
+                out[K - 1].x += a.x * xv.z + a.y * xv.w; out[K - 1].y += a.z * xv.z + a.w * xv.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const cvec xv = xn[k];
+                    out[k].x += a.x * xv.x + a.y * xv.y;
+                    out[k].y += a.z * xv.x + a.w * xv.y;
+                }
+            }
+        }
+#else
+    stencil_apply<K>(g, S4, x, i, j, out);
+#endif
+}
+
 // wide level l, down: x_l = om Dinv rc_l ; t_l = rc_l - H rc_l.   thread per (sys, node), grid (ceil(G_l/256), n_sys)
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RVE_VC_MINB)
 k_vc_down1(Levels LV, int l, const int* __restrict__ active) {
     const int sys = blockIdx.y;
     if (!active[sys]) return;
@@ -1092,7 +1137,7 @@ k_vc_down1(Levels LV, int l, const int* __restrict__ active) {
     cvec acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
-    stencil_apply<K>(g, LV.H4[l] + (size_t)sys * 25 * g.G, rc, idx % g.nx, idx / g.nx, acc);
+    stencil_apply_wide<K>(g, LV.H4[l] + (size_t)sys * 25 * g.G, rc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const cvec rv = rc[(size_t)idx * K + k];
@@ -1330,7 +1375,7 @@ k_vc_prolong(Levels LV, int l, const float* __restrict__ src, const int* __restr
 
 // post-smoothing of a wide level l >= 1: tc_l = x_l + om Dinv (rc_l - A x_l)
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RVE_VC_MINB)
 k_vc_upl(Levels LV, int l, const int* __restrict__ active) {
     const int sys = blockIdx.y;
     if (!active[sys]) return;
@@ -1346,7 +1391,7 @@ k_vc_upl(Levels LV, int l, const int* __restrict__ active) {
     cvec acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
-    stencil_apply<K>(g, LV.A4[l] + (size_t)sys * 25 * g.G, xc, idx % g.nx, idx / g.nx, acc);
+    stencil_apply_wide<K>(g, LV.A4[l] + (size_t)sys * 25 * g.G, xc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const cvec rv = rc[(size_t)idx * K + k];
@@ -1360,7 +1405,7 @@ k_vc_upl(Levels LV, int l, const int* __restrict__ active) {
 // level-1 up: z1 = x1 + om Dinv (rc - A x1) written to tc[0] (k_direction prolongs it), coarse part of
 // r.z = rc . z1, beta; clears rc for the next restriction.  grid (ceil(G/256), n_sys)
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RVE_VC_MINB)
 k_vc_up1(Levels LV, const int* __restrict__ active, double* __restrict__ part) {   // block size 128 or 256
     const int sys = blockIdx.y;
     if (!active[sys]) return;
@@ -1380,7 +1425,7 @@ k_vc_up1(Levels LV, const int* __restrict__ active, double* __restrict__ part) {
         cvec acc[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
-        stencil_apply<K>(g, LV.A4[0] + (size_t)sys * 25 * g.G, xc, idx % g.nx, idx / g.nx, acc);
+        stencil_apply_wide<K>(g, LV.A4[0] + (size_t)sys * 25 * g.G, xc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const cvec rv = rc[(size_t)idx * K + k];

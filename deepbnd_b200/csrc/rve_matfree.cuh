@@ -213,6 +213,13 @@ k_diag(WinTab wt, const unsigned* __restrict__ adjf_ptr, const int* __restrict__
 }
 
 #define RVE_APPLY_THREADS 256
+// p-tile layout in shared memory.  Interleaved [row][rhs] puts the K = 2 gathers of one rhs on every other 16-byte
+// bank group (4 of the 8 groups a quarter-warp can hit in one wavefront); planar [rhs][row] spreads them over all 8.
+// The planes are pitched by tile_cap rounded up to 4 mod 8 rows, so that the two planes of a row land 64 bytes apart.
+#ifndef RVE_APPLY_PLANAR
+#define RVE_APPLY_PLANAR 1
+#endif
+__host__ __device__ inline int apply_tile_pitch(int tile_cap) { return RVE_APPLY_PLANAR ? ((tile_cap + 3) & ~7) + 4 : tile_cap; }
 #ifndef RVE_APPLY_MINB
 #define RVE_APPLY_MINB(K) ((K) == 3 ? 3 : 4)
 #endif
@@ -239,7 +246,13 @@ k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
     const int h0 = wt.win_halo0[win], nh = wt.win_nhalo[win];
     const int we0 = mf.win_we0[win], nwe = mf.win_nwe[win], nep = (nwe + 31) & ~31;
-    double2* s_f = s_tile + (size_t)tile_cap * K;
+    const int pitch = apply_tile_pitch(tile_cap);
+#if RVE_APPLY_PLANAR
+#define TIDX(c, k) ((k) * pitch + (c))
+#else
+#define TIDX(c, k) ((c) * K + (k))
+#endif
+    double2* s_f = s_tile + (size_t)pitch * K;
     __shared__ int s_sb[RVE_WIN / 32];
     // halo row ids first (the gather below depends on them)
     int hr[2];
@@ -253,7 +266,7 @@ k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __
     }
     {   // own rows: one contiguous copy
         const double2* src = p + (size_t)row0 * K;
-        for (int e = tid; e < n * K; e += TPB) cp_async16(s_tile + e, src + e);
+        for (int e = tid; e < n * K; e += TPB) cp_async16(s_tile + TIDX(e / K, e % K), src + e);
     }
     // element record of the first element of this thread, rows' fan sizes
     const uint32_t* idx = mf.we_idx + 6 * (size_t)we0;
@@ -268,19 +281,18 @@ k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __
     }
     const int na = (tid < n) ? mf.row_nadj[row0 + tid] : 0;
     {   // halo rows
-        double2* dstt = s_tile + n * K;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
             const int e = tid + it * TPB;
             if (e < nh) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) cp_async16(dstt + e * K + k, p + (size_t)hr[it] * K + k);
+                for (int k = 0; k < K; ++k) cp_async16(s_tile + TIDX(n + e, k), p + (size_t)hr[it] * K + k);
             }
         }
         for (int e = tid + 2 * TPB; e < nh; e += TPB) {           // (a window has fewer than 512 halo rows in practice)
             const int h = sl.halo[h0 + e];
 #pragma unroll
-            for (int k = 0; k < K; ++k) cp_async16(dstt + e * K + k, p + (size_t)h * K + k);
+            for (int k = 0; k < K; ++k) cp_async16(s_tile + TIDX(n + e, k), p + (size_t)h * K + k);
         }
     }
     cp_async_wait_all();
@@ -300,7 +312,7 @@ k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
                 const unsigned c = (ix[a >> 1] >> (16 * (a & 1))) & 0xffffu;
-                const double2 v = (c != 0xffffu) ? s_tile[c * K + k] : make_double2(0.0, 0.0);
+                const double2 v = (c != 0xffffu) ? s_tile[TIDX(c, k)] : make_double2(0.0, 0.0);
                 u[2 * a] = v.x; u[2 * a + 1] = v.y;
             }
             p2_apply(g6, u, f);
@@ -329,7 +341,7 @@ k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             qd[k] = acc[k];
-            const double2 pv = s_tile[tid * K + k];
+            const double2 pv = s_tile[TIDX(tid, k)];
             dot[k] = acc[k].x * pv.x + acc[k].y * pv.y;
         }
     }
@@ -345,4 +357,5 @@ k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __
         for (int i = 0; i < TPB / 32; ++i) my += s_dot[i][tid];
         part[(size_t)win * 4 + tid] = my;
     }
+#undef TIDX
 }
