@@ -137,6 +137,7 @@ struct rve_batch_s {
     int opt_resid_replace = 0;         // > 0: every so many iterations r is recomputed as b - A x (RVE_OPT_RESIDUAL_REPLACE)
     int n_sm = 148;
     int updp_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    int applyp_blocks[4] = {0, 0, 0, 0};
     int dirp_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};   // resident CTAs per SM of k_update_p<K> (by precond), 0 = not asked yet
     // matrix-free operator (rve_matfree.cuh): window-element tables; the SELL values (bval) are built on demand only
     int opt_operator = RVE_OPERATOR_MATFREE;
@@ -255,6 +256,10 @@ static cudaError_t raise_smem_limits(int device) {
     RAISE_(k_apply<1>); RAISE_(k_apply<2>); RAISE_(k_apply<3>);
     RAISE_(k_update_p<1>); RAISE_(k_update_p<2>); RAISE_(k_update_p<3>);
     RAISE_(k_direction_p<1>); RAISE_(k_direction_p<2>); RAISE_(k_direction_p<3>);
+#if RVE_APPLY_PERSISTENT
+    RAISE_(k_apply_p<1>); RAISE_(k_apply_p<2>); RAISE_(k_apply_p<3>);
+#endif
+    RAISE_(k_vc_mid_s<1>); RAISE_(k_vc_mid_s<2>); RAISE_(k_vc_mid_s<3>);
 #undef RAISE_
     return cudaSuccess;
 }
@@ -274,20 +279,32 @@ static MfTab mf_tab(rve_batch_s* h) {
     return mf;
 }
 
+// persistent bulk-copy-pipelined vector kernels (rve_stream.cuh); RVE_PIPELINE=0 selects the one-window-per-CTA kernels
+static bool use_pipeline() {
+    static const bool on = [] { const char* e = std::getenv("RVE_PIPELINE"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <int K>
 static void launch_spmv(rve_batch_s* h, const PcgArgs& a, const double* p, double* q, int* active, double* part, double* sc, cudaStream_t st) {
+#if RVE_APPLY_PERSISTENT
+    if (a.op == RVE_OPERATOR_MATFREE && use_pipeline()) {
+        int& per_sm = h->applyp_blocks[K];
+        if (per_sm == 0) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_apply_p<K>, RVE_APPLY_THREADS, a.sm_apply);
+            if (per_sm < 1) per_sm = 1;
+            if (std::getenv("RVE_DEBUG_TIMING")) fprintf(stderr, "[k_apply_p<%d>] %d CTA(s) per SM, %zu bytes of dynamic shared memory\n", K, per_sm, a.sm_apply);
+        }
+        k_apply_p<K><<<std::min(a.n_win, per_sm * h->n_sm), RVE_APPLY_THREADS, a.sm_apply, st>>>(a.wt, a.sl, mf_tab(h), (const double2*)p, (double2*)q,
+                                                                                             h->max_tile, h->max_slots, part, a.n_win);
+    } else
+#endif
     if (a.op == RVE_OPERATOR_MATFREE)
         k_apply<K><<<a.n_win, RVE_APPLY_THREADS, a.sm_apply, st>>>(a.wt, a.sl, mf_tab(h), (const double2*)p, (double2*)q, h->max_tile,
                                                                    h->max_slots, part);
     else
         k_spmv<K><<<a.n_win, RVE_SPMV_THREADS, a.sm_spmv, st>>>(a.wt, a.sl, (const double2*)h->bval.p, (const double2*)p, (double2*)q, part);
     k_fin_alpha<<<cdiv(a.n_sys, 8), 256, 0, st>>>(a.n_sys, K, a.wt.sys_win0, part, active, sc, h->win_scal.p);
-}
-
-// persistent bulk-copy-pipelined vector kernels (rve_stream.cuh); RVE_PIPELINE=0 selects the one-window-per-CTA kernels
-static bool use_pipeline() {
-    static const bool on = [] { const char* e = std::getenv("RVE_PIPELINE"); return !(e && e[0] == '0'); }();
-    return on;
 }
 
 template <int K>
@@ -334,7 +351,11 @@ static void launch_vcycle(rve_batch_s* h, const PcgArgs& a, int first, cudaStrea
     if (LV.L > 1) {
         const int Gm = LV.g[W].G;
         // one CTA per system, as few idle threads as the largest level allows: more systems resident per SM (the kernel is latency-bound)
+#if RVE_VC_MID_SMEM
+        k_vc_mid_s<K><<<a.n_sys, std::min(320, std::max(64, (Gm + 31) & ~31)), vc_mid_smem(LV, W, K), st>>>(LV, W, h->active.p);
+#else
         k_vc_mid<K><<<a.n_sys, std::min(320, std::max(64, (Gm + 31) & ~31)), 0, st>>>(LV, W, h->active.p);
+#endif
         for (int l = W - 1; l >= 0; --l) {
             const float* src = (l + 1 == W) ? LV.xc[W] : LV.tc[l + 1];
             k_vc_prolong<K><<<grid(l), bs(l), 0, st>>>(LV, l, src, h->active.p);
@@ -664,7 +685,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     CU(h->win_halo0.alloc(n_win)); CU(h->win_nhalo.alloc(n_win)); CU(h->sym_cnt.alloc(8));
     CU(cudaMemsetAsync(h->sym_cnt.p, 0, 8 * sizeof(int), st));
     const long long cn_cap = h->R + 5LL * n_win + 4096;      // level-1 nodes touched per window are far fewer than its rows
-    CU(h->win_cn0.alloc(n_win)); CU(h->win_ncn.alloc(n_win)); CU(h->win_active.alloc(n_win)); CU(h->cn_node.alloc((size_t)cn_cap)); CU(h->cn_beg.alloc((size_t)cn_cap));
+    CU(h->win_cn0.alloc(n_win)); CU(h->win_ncn.alloc(n_win)); CU(h->win_active.alloc((size_t)n_win + 4)); CU(h->cn_node.alloc((size_t)cn_cap)); CU(h->cn_beg.alloc((size_t)cn_cap));
     CU(h->cn_ent.alloc(4 * (size_t)h->R + 8 * (size_t)n_win + 64)); CU(h->rowinfo.alloc((size_t)h->R)); CU(h->win_desc.alloc((size_t)n_win)); CU(h->win_scal.alloc(8 * (size_t)n_win));
     {
         WinTab wt = win_tab(h);
@@ -898,7 +919,7 @@ static int set_batch_shared_impl(rve_handle_t h, int32_t n_sys, int32_t nv, int3
     CU(h->we_geo.alloc(3 * (size_t)std::max<long long>(h->n_we, 1)));
     const int n_win = h->n_win;
     const long long cn_cap = h->R + 5LL * n_win + 4096;
-    CU(h->win_cn0.alloc(n_win)); CU(h->win_ncn.alloc(n_win)); CU(h->win_active.alloc(n_win)); CU(h->cn_node.alloc((size_t)cn_cap));
+    CU(h->win_cn0.alloc(n_win)); CU(h->win_ncn.alloc(n_win)); CU(h->win_active.alloc((size_t)n_win + 4)); CU(h->cn_node.alloc((size_t)cn_cap));
     CU(h->cn_beg.alloc((size_t)cn_cap)); CU(h->cn_ent.alloc(4 * (size_t)h->R + 8 * (size_t)n_win + 64)); CU(h->rowinfo.alloc((size_t)h->R));
     CU(h->win_desc.alloc((size_t)n_win)); CU(h->win_scal.alloc(8 * (size_t)n_win)); CU(h->sys_blocks.alloc(n_sys));
     CU(cudaMemsetAsync(h->sym_cnt.p + 2, 0, 4 * sizeof(int), st));

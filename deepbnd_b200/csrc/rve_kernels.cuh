@@ -1085,14 +1085,15 @@ __device__ __forceinline__ void stencil_apply(const Grid& g, const stv* __restri
 #ifndef RVE_VC_MINB
 #define RVE_VC_MINB 3
 #endif
-template <int K>
-__device__ __forceinline__ void stencil_apply_wide(const Grid& g, const stv* __restrict__ S4,
-                                                   const cvec* __restrict__ x, int i, int j, cvec* out) {
-#if RVE_VC_PRELOAD
-    const int idx = j * g.nx + i;
-    stv s[25];
+// the 25 stencil blocks of node idx (evict-first: every block is read once per V-cycle)
+__device__ __forceinline__ void stencil_load(const stv* __restrict__ S4, int G, int idx, stv* s) {
 #pragma unroll
-    for (int t = 0; t < 25; ++t) s[t] = __ldcs(S4 + (size_t)t * g.G + idx);
+    for (int t = 0; t < 25; ++t) s[t] = __ldcs(S4 + (size_t)t * G + idx);
+}
+// out += S x with the stencil blocks in registers; x in global or shared memory (K = 2: 16-byte aligned)
+template <int K>
+__device__ __forceinline__ void stencil_apply_regs(const Grid& g, const stv* s, const cvec* x, int i, int j, cvec* out) {
+    const int idx = j * g.nx + i;
 #pragma unroll
     for (int dj = -2; dj <= 2; ++dj)
 #pragma unroll
@@ -1114,6 +1115,14 @@ __device__ __forceinline__ void stencil_apply_wide(const Grid& g, const stv* __r
                 }
             }
         }
+}
+template <int K>
+__device__ __forceinline__ void stencil_apply_wide(const Grid& g, const stv* __restrict__ S4,
+                                                   const cvec* __restrict__ x, int i, int j, cvec* out) {
+#if RVE_VC_PRELOAD
+    stv s[25];
+    stencil_load(S4, g.G, j * g.nx + i, s);
+    stencil_apply_regs<K>(g, s, x, i, j, out);
 #else
     stencil_apply<K>(g, S4, x, i, j, out);
 #endif
@@ -1299,6 +1308,194 @@ k_vc_mid(Levels LV, int l0, const int* __restrict__ active) {
             }
         }
         __syncthreads();
+    }
+}
+
+// The same V-cycle tail with every vector of the levels >= l0 in SHARED memory (rc, xc, tc per level: 3 K G_l float2),
+// so that the ~20 barrier-separated phases of a system no longer pay a global round trip each: the only global
+// accesses left are the restriction input t_{l0-1}, the stencil blocks + Dinv of each pass -- requested BEFORE the
+// barrier-separated phase that precedes their use -- and the result xc[l0].  Residual and damped-Jacobi update of the
+// post-smoothing are done by the node's own thread (one barrier in between: the neighbours read x).
+// Bitwise the same arithmetic as k_vc_mid.  Dynamic shared memory: vc_mid_smem(LV, l0, K).
+#ifndef RVE_VC_MID_SMEM
+#define RVE_VC_MID_SMEM 1
+#endif
+#ifndef RVE_VC_MID_MINB
+#define RVE_VC_MID_MINB(K) ((K) == 3 ? 3 : 2)      // measured: K = 3 prefers three CTAs per SM with a few spilled words
+#endif
+__host__ inline size_t vc_mid_smem(const Levels& LV, int l0, int K) {
+    size_t n = 0;
+    for (int l = l0; l < LV.L; ++l) n += (size_t)LV.g[l].G;
+    return n * 3 * K * sizeof(cvec) + 16;
+}
+template <int K>
+__global__ void __launch_bounds__(320, RVE_VC_MID_MINB(K))
+k_vc_mid_s(Levels LV, int l0, const int* __restrict__ active) {
+    extern __shared__ __align__(16) unsigned char s_mid_raw[];
+    cvec* s_v = (cvec*)s_mid_raw;
+    const int sys = blockIdx.x;
+    if (!active[sys]) return;
+    const int nth = blockDim.x, tid = threadIdx.x;
+    const float om = (float)RVE_OMEGA;
+    stv s[25];
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    auto load_node = [&](const stv* __restrict__ S4, const double* __restrict__ Di, int G, int idx) {
+        stencil_load(S4, G, idx, s);
+        const double2 da = *(const double2*)(Di + 4 * (size_t)idx), db = *(const double2*)(Di + 4 * (size_t)idx + 2);
+        d0 = om * (float)da.x; d1 = om * (float)da.y; d2 = om * (float)db.x; d3 = om * (float)db.y;
+    };
+    int off = 0, off_f = 0;                          // float2 offsets of level l and of level l-1 in s_v
+    // ---- down: rc_l = P^T t_{l-1} ; x_l = om Dinv rc_l ; t_l = rc_l - H rc_l
+    for (int l = l0; l < LV.L; ++l) {
+        const Grid g = LV.g[l], gf = LV.g[l - 1];
+        cvec* rc = s_v + off; cvec* xc = rc + g.G * K; cvec* tc = xc + g.G * K;
+        const stv* H4 = LV.H4[l] + (size_t)sys * 25 * g.G;
+        const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
+        const bool single = g.G <= nth;              // one node per thread: its stencil is requested a phase ahead
+        if (single && tid < g.G) load_node(H4, Di, g.G, tid);
+        const cvec* tf = (l == l0) ? (const cvec*)LV.tc[l - 1] + (size_t)sys * gf.G * K : s_v + off_f + 2 * gf.G * K;
+        for (int idx = tid; idx < g.G; idx += nth) {
+            const int I = idx % g.nx, J = idx / g.nx;
+            cvec acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
+            if (grid_valid(g, I, J)) {
+#pragma unroll
+                for (int aj = -1; aj <= 1; ++aj)
+#pragma unroll
+                    for (int ai = -1; ai <= 1; ++ai) {
+                        int nf;
+                        if (!grid_node_fast(gf, 2 * I + ai, 2 * J + aj, nf)) continue;
+                        const float wgt = (ai ? 0.5f : 1.0f) * (aj ? 0.5f : 1.0f);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const cvec tv = tf[(size_t)nf * K + k];
+                            acc[k].x += wgt * tv.x; acc[k].y += wgt * tv.y;
+                        }
+                    }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) rc[idx * K + k] = acc[k];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < g.G; idx += nth) {
+            if (!single) load_node(H4, Di, g.G, idx);
+            cvec acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
+            stencil_apply_regs<K>(g, s, rc, idx % g.nx, idx / g.nx, acc);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const cvec rv = rc[idx * K + k];
+                xc[idx * K + k] = make_float2(d0 * rv.x + d1 * rv.y, d2 * rv.x + d3 * rv.y);
+                tc[idx * K + k] = make_float2(rv.x - acc[k].x, rv.y - acc[k].y);
+            }
+        }
+        if (l + 1 < LV.L) { off_f = off; off += 3 * g.G * K; }
+        else {
+            // ---- coarsest level: two more damped-Jacobi sweeps.  x += om Dinv t (own node) ; t = rc - A x ; x += om Dinv t
+            const stv* A4 = LV.A4[l] + (size_t)sys * 25 * g.G;
+            for (int idx = tid; idx < g.G; idx += nth) {
+                if (!single) load_node(A4, Di, g.G, idx);           // (for Dinv; never taken in practice: the coarsest level is tiny)
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const cvec tv = tc[idx * K + k];
+                    cvec xv = xc[idx * K + k];
+                    xv.x += d0 * tv.x + d1 * tv.y; xv.y += d2 * tv.x + d3 * tv.y;
+                    xc[idx * K + k] = xv;
+                }
+            }
+            if (single && tid < g.G) load_node(A4, Di, g.G, tid);
+            __syncthreads();
+            for (int idx = tid; idx < g.G; idx += nth) {
+                if (!single) load_node(A4, Di, g.G, idx);
+                cvec acc[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
+                stencil_apply_regs<K>(g, s, xc, idx % g.nx, idx / g.nx, acc);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const cvec rv = rc[idx * K + k];
+                    const float t0 = rv.x - acc[k].x, t1 = rv.y - acc[k].y;
+                    tc[idx * K + k] = make_float2(d0 * t0 + d1 * t1, d2 * t0 + d3 * t1);     // the update, applied after the barrier
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < g.G; idx += nth)
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const cvec uv = tc[idx * K + k];
+                    cvec xv = xc[idx * K + k];
+                    xv.x += uv.x; xv.y += uv.y;
+                    xc[idx * K + k] = xv;
+                }
+        }
+        __syncthreads();
+    }
+    // ---- up: x_l += P x_{l+1} ; x_l += om Dinv (rc_l - A x_l)
+    for (int l = LV.L - 2; l >= l0; --l) {
+        const Grid g = LV.g[l], gc = LV.g[l + 1];
+        const int off_c = off;                        // level l+1
+        off -= 3 * g.G * K;                           // level l
+        cvec* rc = s_v + off; cvec* xc = rc + g.G * K; cvec* tc = xc + g.G * K;
+        const cvec* xcc = s_v + off_c + gc.G * K;
+        const stv* A4 = LV.A4[l] + (size_t)sys * 25 * g.G;
+        const double* Di = LV.dinv[l] + (size_t)sys * g.G * 4;
+        const bool single = g.G <= nth;
+        if (single && tid < g.G) load_node(A4, Di, g.G, tid);
+        for (int idx = tid; idx < g.G; idx += nth) {
+            const int i = idx % g.nx, j = idx / g.nx;
+            if (!grid_valid(g, i, j)) continue;
+            const int I0 = i >> 1, J0 = j >> 1;
+            const int ni = (i & 1) ? 2 : 1, nj = (j & 1) ? 2 : 1;
+            const float wgt = ((i & 1) ? 0.5f : 1.0f) * ((j & 1) ? 0.5f : 1.0f);
+            cvec acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = xc[idx * K + k];
+            for (int bj = 0; bj < nj; ++bj)
+                for (int bi = 0; bi < ni; ++bi) {
+                    int nc;
+                    if (!grid_node_fast(gc, I0 + bi, J0 + bj, nc)) continue;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const cvec v = xcc[nc * K + k];
+                        acc[k].x += wgt * v.x; acc[k].y += wgt * v.y;
+                    }
+                }
+#pragma unroll
+            for (int k = 0; k < K; ++k) xc[idx * K + k] = acc[k];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < g.G; idx += nth) {
+            if (!single) load_node(A4, Di, g.G, idx);
+            cvec acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
+            stencil_apply_regs<K>(g, s, xc, idx % g.nx, idx / g.nx, acc);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const cvec rv = rc[idx * K + k];
+                const float t0 = rv.x - acc[k].x, t1 = rv.y - acc[k].y;
+                tc[idx * K + k] = make_float2(d0 * t0 + d1 * t1, d2 * t0 + d3 * t1);
+            }
+        }
+        __syncthreads();
+        cvec* xg = (cvec*)LV.xc[l] + (size_t)sys * g.G * K;
+        for (int idx = tid; idx < g.G; idx += nth)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const cvec uv = tc[idx * K + k];
+                cvec xv = xc[idx * K + k];
+                xv.x += uv.x; xv.y += uv.y;
+                if (l == l0) xg[(size_t)idx * K + k] = xv; else xc[idx * K + k] = xv;
+            }
+        if (l > l0) __syncthreads();
+    }
+    if (LV.L - 1 == l0) {                             // a single small level: its result is the coarsest sweep's
+        const Grid g = LV.g[l0];
+        const cvec* xc = s_v + off + g.G * K;
+        cvec* xg = (cvec*)LV.xc[l0] + (size_t)sys * g.G * K;
+        for (int idx = tid; idx < g.G * K; idx += nth) xg[idx] = xc[idx];
     }
 }
 

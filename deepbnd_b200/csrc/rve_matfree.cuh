@@ -213,11 +213,11 @@ k_diag(WinTab wt, const unsigned* __restrict__ adjf_ptr, const int* __restrict__
 }
 
 #define RVE_APPLY_THREADS 256
-// p-tile layout in shared memory.  Interleaved [row][rhs] puts the K = 2 gathers of one rhs on every other 16-byte
-// bank group (4 of the 8 groups a quarter-warp can hit in one wavefront); planar [rhs][row] spreads them over all 8.
-// The planes are pitched by tile_cap rounded up to 4 mod 8 rows, so that the two planes of a row land 64 bytes apart.
+// p-tile layout in shared memory: interleaved [row][rhs] (default) or planar [rhs][row] with the planes pitched to
+// 4 mod 8 rows.  Planar was meant to spread the K = 2 gathers of one rhs over all 8 16-byte bank groups instead of
+// every other one; measured (r02f, 1000 full / 10k reduced RVEs): K = 2 +1 %, K = 3 +5 % time per launch -> not used.
 #ifndef RVE_APPLY_PLANAR
-#define RVE_APPLY_PLANAR 1
+#define RVE_APPLY_PLANAR 0
 #endif
 __host__ __device__ inline int apply_tile_pitch(int tile_cap) { return RVE_APPLY_PLANAR ? ((tile_cap + 3) & ~7) + 4 : tile_cap; }
 #ifndef RVE_APPLY_MINB
@@ -241,6 +241,8 @@ k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __
     extern __shared__ double2 s_tile[];           // [tile_cap * K] p-tile (row-major, rhs interleaved), then K planes [slot_cap] of nodal forces
     constexpr int TPB = RVE_APPLY_THREADS;
     const int win = blockIdx.x;
+    // (requesting the window metadata together with the active flag -- volatile loads ahead of the early exit -- was
+    //  measured: no change, r02f)
     if (!wt.win_active[win]) return;
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int row0 = wt.win_row0[win], n = wt.win_n[win];
@@ -359,3 +361,195 @@ k_apply(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __
     }
 #undef TIDX
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent k_apply -- MEASURED AND NOT USED (compiled with -DRVE_APPLY_PERSISTENT=1 only).
+// With one window per CTA every window pays four dependent global round trips before its first element product
+// (active flag -> window metadata -> halo row ids -> halo rows of p): 31 % of the stall samples of k_apply<2>
+// (profiles/r02f_ncu_apply2_source_top.txt).  Here a CTA walks the windows w = blockIdx.x, += gridDim.x and requests,
+// together with the p-tile of window i, the halo ids of window i+1 and the metadata of window i+2 -- all with cp.async
+// into small shared-memory rings, no registers -- so that every window only waits for ONE round trip (its tile).
+// Same results (tests green), but 20 % (K = 2) / 6 % (K = 3) SLOWER per launch on 1000 full / 10k reduced RVEs
+// (r02f: 1756 vs 1457 us, 2315 vs 2180 us): the resident CTAs of an SM start together and stay in step, so their
+// tile waits coincide instead of being covered by each other's element products the way the staggered one-window CTAs
+// cover them; hiding the tile wait inside one CTA needs a second tile buffer = one CTA per SM less.
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef RVE_APPLY_PERSISTENT
+#define RVE_APPLY_PERSISTENT 0
+#endif
+#if RVE_APPLY_PERSISTENT
+#define RVE_APPLY_HCAP 512           // halo ids staged per window (more: read straight from global memory)
+#ifndef RVE_APPLYP_MINB
+#define RVE_APPLYP_MINB(K) ((K) == 3 ? 3 : 4)
+#endif
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8b(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+// metadata words of a window in shared memory
+enum { AM_ACT = 0, AM_ROW0, AM_N, AM_H0, AM_NH, AM_WE0, AM_NWE, AM_PAD, AM_SW0, AM_SW1, AM_WORDS = 12 };
+
+template <int K>
+__global__ void __launch_bounds__(RVE_APPLY_THREADS, RVE_APPLYP_MINB(K))
+k_apply_p(WinTab wt, Sell sl, MfTab mf, const double2* __restrict__ p, double2* __restrict__ q, int tile_cap, int slot_cap,
+          double* __restrict__ part, int n_win) {
+    extern __shared__ double2 s_tile[];           // p-tile, then K planes [slot_cap] of nodal forces (as in k_apply)
+    constexpr int TPB = RVE_APPLY_THREADS;
+    __shared__ int s_halo[2][RVE_APPLY_HCAP];
+    __shared__ __align__(8) int s_meta[2][AM_WORDS];
+    __shared__ double s_dot[2][TPB / 32][4];
+    __shared__ int s_sb[RVE_WIN / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int stride = (int)gridDim.x;
+    const int pitch = apply_tile_pitch(tile_cap);
+#if RVE_APPLY_PLANAR
+#define TIDX(c, k) ((k) * pitch + (c))
+#else
+#define TIDX(c, k) ((c) * K + (k))
+#endif
+    double2* s_f = s_tile + (size_t)pitch * K;
+    // request the metadata of window w into ring slot `slot` (threads 0..7; the flag word holds 4 neighbouring flags)
+    auto fetch_meta = [&](int w, int slot) {
+        if (w >= n_win) { if (tid == 0) s_meta[slot][AM_N] = -1; return; }
+        int* m = s_meta[slot];
+        switch (tid) {
+            case 0: cp_async4(m + AM_ACT, (const int*)(wt.win_active + (w & ~3))); break;
+            case 1: cp_async4(m + AM_ROW0, wt.win_row0 + w); break;
+            case 2: cp_async4(m + AM_N, wt.win_n + w); break;
+            case 3: cp_async4(m + AM_H0, wt.win_halo0 + w); break;
+            case 4: cp_async4(m + AM_NH, wt.win_nhalo + w); break;
+            case 5: cp_async4(m + AM_WE0, mf.win_we0 + w); break;
+            case 6: cp_async4(m + AM_NWE, mf.win_nwe + w); break;
+            case 7: cp_async8b(m + AM_SW0, mf.win_sw + (size_t)w * 8); break;
+            default: break;
+        }
+    };
+    auto is_active = [&](const int* m, int w) { return m[AM_N] >= 0 && ((((unsigned)m[AM_ACT]) >> (8 * (w & 3))) & 0xffu) != 0u; };
+    auto fetch_halo = [&](const int* m, int w, int slot) {
+        if (!is_active(m, w)) return;
+        const int h0 = m[AM_H0], nh = min(m[AM_NH], RVE_APPLY_HCAP);
+        for (int e = tid; e < nh; e += TPB) cp_async4(&s_halo[slot][e], sl.halo + h0 + e);
+    };
+    // prologue: metadata of the first two windows, halo ids of the first
+    int w = (int)blockIdx.x;
+    fetch_meta(w, 0);
+    fetch_meta(w + stride, 1);
+    cp_async_wait_all();
+    __syncthreads();
+    fetch_halo(s_meta[0], w, 0);
+    int prev_win = -1;
+    for (int it = 0; w < n_win; ++it, w += stride) {
+        const int cur = it & 1;
+        cp_async_wait_all();                      // (prologue halo ids; otherwise nothing is pending here)
+        __syncthreads();                          // (A) rings of this window visible; the previous window's tile, forces and dots are free / final
+        if (prev_win >= 0 && tid < K) {           // p.q partial of the previous window
+            double my = 0.0;
+            for (int i = 0; i < TPB / 32; ++i) my += s_dot[cur ^ 1][i][tid];
+            part[(size_t)prev_win * 4 + tid] = my;
+        }
+        const int* m = s_meta[cur];
+        const bool act = is_active(m, w);
+        const int row0 = m[AM_ROW0], n = m[AM_N], h0 = m[AM_H0], nh = m[AM_NH], we0 = m[AM_WE0], nwe = m[AM_NWE];
+        const int nep = (nwe + 31) & ~31;
+        const uint32_t* idx = mf.we_idx + 6 * (size_t)we0;
+        const double2* geo = mf.we_geo + 3 * (size_t)we0;
+        uint32_t ix[6];
+        double2 gv[3];
+        int na = 0;
+        if (act) {
+            if (tid == 0) {
+                int tot = 0;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) { s_sb[s] = tot; tot += 32 * (int)((((unsigned)m[AM_SW0 + (s >> 2)]) >> (8 * (s & 3))) & 0xffu); }
+            }
+            const double2* src = p + (size_t)row0 * K;
+            for (int e = tid; e < n * K; e += TPB) cp_async16(s_tile + TIDX(e / K, e % K), src + e);
+            for (int e = tid; e < nh; e += TPB) {
+                const int hrow = e < RVE_APPLY_HCAP ? s_halo[cur][e] : sl.halo[h0 + e];
+#pragma unroll
+                for (int k = 0; k < K; ++k) cp_async16(s_tile + TIDX(n + e, k), p + (size_t)hrow * K + k);
+            }
+            if (tid < nwe) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) ix[j] = idx[j * nep + tid];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) gv[j] = geo[j * nep + tid];
+            }
+            na = (tid < n) ? mf.row_nadj[row0 + tid] : 0;
+        }
+        // the next window's halo ids and the metadata of the one after it travel with this window's tile
+        fetch_halo(s_meta[cur ^ 1], w + stride, cur ^ 1);
+        cp_async_wait_all();
+        __syncthreads();                          // (B) tile complete; s_meta[cur] has been read by every thread
+        fetch_meta(w + 2 * stride, cur);          // lands during the phases below, waited for at the top of the next window
+        if (!act) { prev_win = -1; continue; }    // (uniform)
+        // phase 1: element products
+        for (int e = tid; e < nwe; e += TPB) {
+            if (e != tid) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) ix[j] = idx[j * nep + e];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) gv[j] = geo[j * nep + e];
+            }
+            const double g6[6] = {gv[0].x, gv[0].y, gv[1].x, gv[1].y, gv[2].x, gv[2].y};
+#pragma unroll 1
+            for (int k = 0; k < K; ++k) {
+                double u[12], f[12];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    const unsigned c = (ix[a >> 1] >> (16 * (a & 1))) & 0xffffu;
+                    const double2 v = (c != 0xffffu) ? s_tile[TIDX(c, k)] : make_double2(0.0, 0.0);
+                    u[2 * a] = v.x; u[2 * a + 1] = v.y;
+                }
+                p2_apply(g6, u, f);
+                double2* fk = s_f + (size_t)k * slot_cap;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    const unsigned d = (ix[3 + (a >> 1)] >> (16 * (a & 1))) & 0xffffu;
+                    if (d != 0xffffu) fk[d] = make_double2(f[2 * a], f[2 * a + 1]);
+                }
+            }
+        }
+        __syncthreads();                          // (C)
+        // phase 2: row sums, p.q partials per warp
+        double dot[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) dot[k] = 0.0;
+        if (tid < n) {
+            const int sb = s_sb[wv] + lane;
+            double2 acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = make_double2(0.0, 0.0);
+            for (int j = 0; j < na; ++j)
+#pragma unroll
+                for (int k = 0; k < K; ++k) { const double2 v = s_f[(size_t)k * slot_cap + sb + j * 32]; acc[k].x += v.x; acc[k].y += v.y; }
+            double2* qd = q + ((size_t)row0 + tid) * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                qd[k] = acc[k];
+                const double2 pv = s_tile[TIDX(tid, k)];
+                dot[k] = acc[k].x * pv.x + acc[k].y * pv.y;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double v = warp_sum(dot[k]);
+            if (lane == 0) s_dot[cur][wv][k] = v;
+        }
+        prev_win = w;
+    }
+    __syncthreads();
+    if (prev_win >= 0 && tid < K) {
+        const int it_last = (prev_win - (int)blockIdx.x) / stride;
+        double my = 0.0;
+        for (int i = 0; i < TPB / 32; ++i) my += s_dot[it_last & 1][i][tid];
+        part[(size_t)prev_win * 4 + tid] = my;
+    }
+#undef TIDX
+}
+#endif  // RVE_APPLY_PERSISTENT
