@@ -259,6 +259,7 @@ static cudaError_t raise_smem_limits(int device) {
 #if RVE_APPLY_PERSISTENT
     RAISE_(k_apply_p<1>); RAISE_(k_apply_p<2>); RAISE_(k_apply_p<3>);
 #endif
+    RAISE_(k_galerkin1_t);
     RAISE_(k_vc_mid_s<1>); RAISE_(k_vc_mid_s<2>); RAISE_(k_vc_mid_s<3>);
 #undef RAISE_
     return cudaSuccess;
@@ -984,8 +985,13 @@ int rve_assemble(rve_handle_t h) {
     // two-level preconditioner: Galerkin hierarchy
     Levels& LV = h->LV;
     for (int l = 0; l < LV.L; ++l) CU(cudaMemsetAsync(LV.A[l], 0, h->lvA[l].n * sizeof(double), st));
+#if RVE_GALERKIN_THREAD
+    k_galerkin1_t<<<cdiv(h->E, RVE_GAL_THREADS), RVE_GAL_THREADS, 54 * RVE_GAL_THREADS * sizeof(double), st>>>((int)h->E, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
+                                                h->node_row.p, h->box.p, LV.g[0], LV.A[0], h->mat);
+#else
     k_galerkin1<<<cdiv(h->E, 8), 256, 0, st>>>((int)h->E, h->elem_node.p, h->elem_reg.p, h->elem_sys.p, h->node_xy.p,
                                                 h->node_row.p, h->box.p, LV.g[0], LV.A[0], h->mat);
+#endif
     k_galerkin_mirror<<<cdiv((long long)h->n_sys * 12 * LV.g[0].G, 256), 256, 0, st>>>(h->n_sys, LV.g[0], LV.A[0]);
     for (int l = 0; l + 1 < LV.L; ++l) {
         long long n = (long long)h->n_sys * LV.g[l + 1].G * 25;

@@ -691,6 +691,104 @@ k_galerkin1(int n_elem, const int* __restrict__ elem_node, const unsigned char* 
     }
 }
 
+// Thread-per-element version of k_galerkin1 (same sums, default).  The warp-per-element kernel above spends 855 warp
+// instructions per element with 6 to 27 lanes busy and is issue-bound (67 % issue-active, 4.9 ms per 250 full RVEs:
+// profiles/r02f_ncu_galerkin1_summary.csv); here a thread owns an element, its 3 x 9 coarse gradients live in a
+// shared-memory column (54 doubles, [entry][thread]: conflict-free) and the weighted window nodes are walked as bit sets.
+#ifndef RVE_GALERKIN_THREAD
+#define RVE_GALERKIN_THREAD 1
+#endif
+#define RVE_GAL_THREADS 128
+__global__ void __launch_bounds__(RVE_GAL_THREADS)
+k_galerkin1_t(int n_elem, const int* __restrict__ elem_node, const unsigned char* __restrict__ elem_reg,
+              const int* __restrict__ elem_sys, const double* __restrict__ node_xy,
+              const int* __restrict__ node_row, const double* __restrict__ box, Grid g1,
+              double* __restrict__ A1, Mat8 mat) {
+    extern __shared__ double s_gal[];             // [54][RVE_GAL_THREADS]: gI(q) = entry (q * 9 + I) * 2 + component
+    const int tid = threadIdx.x;
+    const int e = blockIdx.x * RVE_GAL_THREADS + tid;
+    if (e >= n_elem) return;
+    double* sg = s_gal + tid;
+#define SG(q, I, c) sg[(((q) * 9 + (I)) * 2 + (c)) * RVE_GAL_THREADS]
+    const int sys = elem_sys[e];
+    int row[6], ci[6], cj[6];
+    double cs[6], ct[6];
+    double vx[3], vy[3];
+    const double bx0 = box[4 * sys], by0 = box[4 * sys + 1];
+    const double invHx = g1.ncx / box[4 * sys + 2], invHy = g1.ncy / box[4 * sys + 3];
+    int imin = 1 << 20, jmin = 1 << 20;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        const int node = elem_node[(size_t)e * 6 + a];
+        row[a] = node_row[node];
+        const double px = node_xy[2 * (size_t)node], py = node_xy[2 * (size_t)node + 1];
+        if (a < 3) { vx[a] = px; vy[a] = py; }
+        coarse_cell(px, py, bx0, by0, invHx, invHy, g1.ncx, g1.ncy, ci[a], cj[a], cs[a], ct[a]);
+        imin = min(imin, ci[a]); jmin = min(jmin, cj[a]);
+    }
+    TriGeom g;
+    tri_geom(vx[0], vy[0], vx[1], vy[1], vx[2], vy[2], g);
+    const int reg = elem_reg[e];
+    const double lam = mat.v[2 * reg], mu = mat.v[2 * reg + 1];
+#pragma unroll
+    for (int i = 0; i < 54; ++i) sg[i * RVE_GAL_THREADS] = 0.0;
+    unsigned am = 0u;                             // window nodes that carry weight
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        if (row[a] < 0) continue;
+        // an element larger than a coarse cell can reach a third cell: its far nodes are snapped onto the
+        // last coarse-node line of the element's 3x3 window (the operator stays a sum of SPSD terms)
+        int oi = ci[a] - imin, oj = cj[a] - jmin;
+        double sa = cs[a], ta = ct[a];
+        if (oi > 1) { oi = 1; sa = 1.0; }
+        if (oj > 1) { oj = 1; ta = 1.0; }
+        const int I0 = oj * 3 + oi;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const double wgt = ((c & 1) ? sa : 1.0 - sa) * ((c & 2) ? ta : 1.0 - ta);
+            if (wgt == 0.0) continue;
+            const int I = I0 + (c & 1) + 3 * (c >> 1);
+            am |= 1u << I;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                double ax, ay;
+                p2_grad(g, q, a, ax, ay);
+                SG(q, I, 0) += wgt * ax; SG(q, I, 1) += wgt * ay;
+            }
+        }
+    }
+    double* Asys = A1 + (size_t)sys * 100 * g1.G;
+    const double wq = g.area * (1.0 / 3.0);
+    for (unsigned mi = am; mi; mi &= mi - 1) {
+        const int I = __ffs(mi) - 1;
+        const int Ii = imin + I % 3, Ij = jmin + I / 3;
+        int nI;
+        if (!grid_node(g1, Ii, Ij, nI)) continue;
+        double gi[3][2];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { gi[q][0] = SG(q, I, 0); gi[q][1] = SG(q, I, 1); }
+        for (unsigned mj = am & ~((1u << I) - 1u); mj; mj &= mj - 1) {       // upper half: J >= I in window order = (j, i) order
+            const int J = __ffs(mj) - 1;
+            const int Ji = imin + J % 3, Jj = jmin + J / 3;
+            int nJ;
+            if (!grid_node(g1, Ji, Jj, nJ)) continue;
+            double G00 = 0, G01 = 0, G10 = 0, G11 = 0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const double jx = SG(q, J, 0), jy = SG(q, J, 1);
+                G00 += gi[q][0] * jx; G01 += gi[q][0] * jy; G10 += gi[q][1] * jx; G11 += gi[q][1] * jy;
+            }
+            G00 *= wq; G01 *= wq; G10 *= wq; G11 *= wq;
+            const double tr = G00 + G11;
+            const int slot = (Jj - Ij + 2) * 5 + (Ji - Ii + 2);
+            double* d = Asys + (size_t)slot * 4 * g1.G + nI;
+            atomicAdd(d, lam * G00 + mu * G00 + mu * tr); atomicAdd(d + g1.G, lam * G01 + mu * G10);
+            atomicAdd(d + 2 * (size_t)g1.G, lam * G10 + mu * G01); atomicAdd(d + 3 * (size_t)g1.G, lam * G11 + mu * G11 + mu * tr);
+        }
+    }
+#undef SG
+}
+
 // lower half of the level-1 stencils from the upper half: A[n][-d] = A[n - d][d]^T.  thread per (sys, lower slot, node)
 __global__ void k_galerkin_mirror(int n_sys, Grid g, double* __restrict__ A) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
