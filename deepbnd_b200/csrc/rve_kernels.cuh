@@ -1181,7 +1181,7 @@ __device__ __forceinline__ void stencil_apply(const Grid& g, const stv* __restri
 #define RVE_VC_PRELOAD 1
 #endif
 #ifndef RVE_VC_MINB
-#define RVE_VC_MINB 3
+#define RVE_VC_MINB 4              // CTAs of 256 threads per SM (64 registers, a few spilled words): measured against 3
 #endif
 // the 25 stencil blocks of node idx (evict-first: every block is read once per V-cycle)
 __device__ __forceinline__ void stencil_load(const stv* __restrict__ S4, int G, int idx, stv* s) {
@@ -1683,14 +1683,13 @@ k_vc_upl(Levels LV, int l, const int* __restrict__ active) {
     const double* d = LV.dinv[l] + ((size_t)sys * g.G + idx) * 4;
     const float om = (float)RVE_OMEGA;
     const float d0 = om * (float)d[0], d1 = om * (float)d[1], d2 = om * (float)d[2], d3 = om * (float)d[3];
-    cvec acc[K];
+    cvec acc[K], rv[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
+    for (int k = 0; k < K; ++k) { acc[k] = make_float2(0.f, 0.f); rv[k] = rc[(size_t)idx * K + k]; }    // (requested with the stencil, not after it)
     stencil_apply_wide<K>(g, LV.A4[l] + (size_t)sys * 25 * g.G, xc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const cvec rv = rc[(size_t)idx * K + k];
-        const float t0 = rv.x - acc[k].x, t1 = rv.y - acc[k].y;
+        const float t0 = rv[k].x - acc[k].x, t1 = rv[k].y - acc[k].y;
         cvec xv = xc[(size_t)idx * K + k];
         xv.x += d0 * t0 + d1 * t1; xv.y += d2 * t0 + d3 * t1;
         zc[(size_t)idx * K + k] = xv;
@@ -1717,18 +1716,17 @@ k_vc_up1(Levels LV, const int* __restrict__ active, double* __restrict__ part) {
         const double* d = LV.dinv[0] + ((size_t)sys * g.G + idx) * 4;
         const float om = (float)RVE_OMEGA;
         const float d0 = om * (float)d[0], d1 = om * (float)d[1], d2 = om * (float)d[2], d3 = om * (float)d[3];
-        cvec acc[K];
+        cvec acc[K], rv[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
+        for (int k = 0; k < K; ++k) { acc[k] = make_float2(0.f, 0.f); rv[k] = rc[(size_t)idx * K + k]; }   // (requested with the stencil, not after it)
         stencil_apply_wide<K>(g, LV.A4[0] + (size_t)sys * 25 * g.G, xc, idx % g.nx, idx / g.nx, acc);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const cvec rv = rc[(size_t)idx * K + k];
-            const float t0 = rv.x - acc[k].x, t1 = rv.y - acc[k].y;
+            const float t0 = rv[k].x - acc[k].x, t1 = rv[k].y - acc[k].y;
             cvec xv = xc[(size_t)idx * K + k];
             xv.x += d0 * t0 + d1 * t1; xv.y += d2 * t0 + d3 * t1;
             zc[(size_t)idx * K + k] = xv;
-            dot[k] = (double)rv.x * (double)xv.x + (double)rv.y * (double)xv.y;
+            dot[k] = (double)rv[k].x * (double)xv.x + (double)rv[k].y * (double)xv.y;
             rc[(size_t)idx * K + k] = make_float2(0.f, 0.f);
         }
     }
