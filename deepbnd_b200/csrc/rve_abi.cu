@@ -690,7 +690,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     CU(h->cn_ent.alloc(4 * (size_t)h->R + 8 * (size_t)n_win + 64)); CU(h->rowinfo.alloc((size_t)h->R)); CU(h->win_desc.alloc((size_t)n_win)); CU(h->win_scal.alloc(8 * (size_t)n_win));
     {
         WinTab wt = win_tab(h);
-        k_sym_cols<<<n_win, RVE_WIN, 0, st>>>(wt, h->d_row_ptr.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->node_row.p,
+        k_sym_cols<<<n_win * RVE_SYMCOLS_SPLIT, RVE_WIN / RVE_SYMCOLS_SPLIT, 0, st>>>(wt, h->d_row_ptr.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->node_row.p,
                                                h->csr_col.p, h->rlen.p, h->emap.p, h->sys_blocks.p, h->sym_cnt.p);
         DBG_SYNC("k_sym_cols");
         const size_t sm = 2 * (size_t)h->max_words * sizeof(unsigned);

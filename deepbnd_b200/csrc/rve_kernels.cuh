@@ -154,12 +154,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 //     window), then the level-1 nodes a window touches and its restriction lists (k_sym_coarse).
 // ---------------------------------------------------------------------------------------------
 // counters: [0] halo entries used, [1] max rows of a p-tile (own + halo), [2] error code
-__global__ void __launch_bounds__(RVE_WIN)
+// Launched with RVE_SYMCOLS_SPLIT CTAs of RVE_WIN / RVE_SYMCOLS_SPLIT threads per window: the rows of a window are sorted by
+// length, so its two vertex-row warps work 5-10x longer than its six mid-edge warps; as one 256-thread CTA the six wait
+// at the final barrier and hold the SM's warp slots (62 % of the stall samples, r02h), as 64-thread CTAs heavy and light
+// pieces of different windows mix freely.
+#define RVE_SYMCOLS_SPLIT 4
+__global__ void __launch_bounds__(RVE_WIN / RVE_SYMCOLS_SPLIT)
 k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __restrict__ adjf_ptr,
            const int* __restrict__ adjf, const int* __restrict__ elem_node, const int* __restrict__ node_row,
            int* __restrict__ csr_col, unsigned char* __restrict__ rlen, unsigned char* __restrict__ emap,
            int* __restrict__ sys_blocks, int* counters) {
-    const int w = blockIdx.x, t = threadIdx.x;
+    constexpr int TPB = RVE_WIN / RVE_SYMCOLS_SPLIT;
+    constexpr int SC = 32;
+    __shared__ int s_cols[SC * TPB];
+    const int w = blockIdx.x / RVE_SYMCOLS_SPLIT, t = (blockIdx.x % RVE_SYMCOLS_SPLIT) * TPB + threadIdx.x;
     int cnt = 0;
     if (t < wt.win_n[w]) {
         const int r = wt.win_row0[w] + t;
@@ -179,27 +187,26 @@ k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __re
             for (int k = 0; k < 6; ++k) {
                 const int c = rows[k];
                 if (c < 0) { em[k] = 0xff; continue; }
+                // the columns found so far are searched in a shared-memory column of the thread (searching the global
+                // list re-read freshly written lines from L2: one L2 round trip per probe); rows longer than SC fall
+                // back to the global list for the tail
                 int j = 0;
-                while (j < cnt && j < cap && cols[j] != c) ++j;
-                if (j == cnt) { if (cnt < cap) cols[cnt] = c; ++cnt; }
+                while (j < cnt && j < cap && (j < SC ? s_cols[j * TPB + threadIdx.x] : cols[j]) != c) ++j;
+                if (j == cnt) {
+                    if (cnt < cap) { cols[cnt] = c; if (cnt < SC) s_cols[cnt * TPB + threadIdx.x] = c; }
+                    ++cnt;
+                }
                 em[k] = (unsigned char)j;
             }
         }
         if (cnt > cap) { atomicExch(counters + 2, 2); cnt = cap; }
         rlen[r] = (unsigned char)cnt;
     }
-    // true number of blocks of the system (one atomic per window)
-    __shared__ int s_w[RVE_WIN / 32];
+    // true number of blocks of the system (one integer atomic per warp, no block barrier)
     int v = cnt;
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-    if ((t & 31) == 0) s_w[t >> 5] = v;
-    __syncthreads();
-    if (t == 0) {
-        int tot = 0;
-        for (int i = 0; i < RVE_WIN / 32; ++i) tot += s_w[i];
-        atomicAdd(sys_blocks + wt.win_sys[w], tot);
-    }
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(sys_blocks + wt.win_sys[w], v);
 }
 
 __global__ void __launch_bounds__(RVE_WIN)
@@ -343,8 +350,24 @@ k_sym_coarse(WinTab wt, int* __restrict__ win_cn0, int* __restrict__ win_ncn, co
         }
     }
     __syncthreads();
-    if (tid == 0) {                               // exclusive offsets (ncn is ~50-250)
-        for (int j = 0; j < ncn; ++j) s_cnt[j + 1] += s_cnt[j];
+    {   // offsets: s_cnt[j + 1] = inclusive sum of the counts (4 consecutive lists per thread, warp scans, 8 warp totals)
+        __shared__ int s_wsum[RVE_WIN / 32];
+        const int b4 = 4 * tid;
+        int a[4], tsum = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = (b4 + i < ncn) ? s_cnt[b4 + i + 1] : 0; tsum += a[i]; }
+        int inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += u; }
+        if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+        __syncthreads();
+        int run2 = inc - tsum;
+        for (int i = 0; i < (tid >> 5); ++i) run2 += s_wsum[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { run2 += a[i]; if (b4 + i < ncn) s_cnt[b4 + i + 1] = run2; }
+    }
+    __syncthreads();
+    if (tid == 0) {
         const int nent = s_cnt[ncn];
         // segments start on 16-byte boundaries (4 ints / 8 uint16): the persistent PCG kernels fetch them with bulk copies
         int c0 = atomicAdd(counters + 3, (ncn + 1 + 3) & ~3);
@@ -374,8 +397,11 @@ k_sym_coarse(WinTab wt, int* __restrict__ win_cn0, int* __restrict__ win_ncn, co
     __syncthreads();
     // fill in shared memory (position inside a list by atomics on a second counter array), order every list there
     // (reproducible summation order in the restriction), then write the window's entries out in one coalesced pass
+    // (the lists used to be ordered by one insertion sort per list: a few long lists kept the CTA waiting, 67 % of the
+    // stall samples at the barrier behind them, r02h; now every entry finds its rank in its list by counting the smaller
+    // ones -- four entries per thread, same work for all)
     __shared__ int s_fill[4 * RVE_WIN];
-    __shared__ uint16_t s_entl[4 * RVE_WIN];
+    __shared__ uint16_t s_entl[4 * RVE_WIN], s_ents[4 * RVE_WIN];
     for (int j = tid; j < ncn; j += RVE_WIN) s_fill[j] = 0;
     __syncthreads();
     if (tid < n) {
@@ -392,19 +418,20 @@ k_sym_coarse(WinTab wt, int* __restrict__ win_cn0, int* __restrict__ win_ncn, co
         rowinfo[r0 + tid] = ri;
     }
     __syncthreads();
-    for (int j = tid; j < ncn; j += RVE_WIN) {
-        uint16_t* L = s_entl + s_cnt[j];
-        const int len = s_cnt[j + 1] - s_cnt[j];
-        for (int i = 1; i < len; ++i) {
-            const uint16_t v = L[i];
-            int k = i - 1;
-            while (k >= 0 && L[k] > v) { L[k + 1] = L[k]; --k; }
-            L[k + 1] = v;
+    if (tid < n) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (slot[c] < 0) continue;
+            const int b = s_cnt[slot[c]], e = s_cnt[slot[c] + 1];
+            const uint16_t v = (uint16_t)((tid << 2) | c);
+            int rank = 0;
+            for (int i = b; i < e; ++i) rank += (s_entl[i] < v) ? 1 : 0;
+            s_ents[b + rank] = v;
         }
     }
     __syncthreads();
     const int nent = s_cnt[ncn];
-    for (int i = tid; i < nent; i += RVE_WIN) cn_ent[(size_t)e0 + i] = s_entl[i];
+    for (int i = tid; i < nent; i += RVE_WIN) cn_ent[(size_t)e0 + i] = s_ents[i];
 }
 
 // ---------------------------------------------------------------------------------------------
