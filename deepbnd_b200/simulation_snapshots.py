@@ -139,8 +139,12 @@ def _store_snapshots(rows, out, datasets):
         sigmaT[rows, :] = out["sigmaT"][:, k]
 
 
+LAST_TIMINGS = {}          # wall-clock phases of the last buildSnapshots call of this process (diagnostics)
+
+
 def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs, comm_self=None,
                    device=None, batch_size=256, rtol=1e-10, nproc=None, mesher="delaunay", lcar=None):
+    t_begin = timer()
     bndMeshname, paramRVEname, snapshotsname, meshname = filesnames
     box, nb = vref_box_from_mesh(bndMeshname)
     nh = 2 * (4 * (nb - 1) + 1)                                             # Vref.dim()
@@ -190,14 +194,20 @@ def buildSnapshots(paramMaterial, filesnames, opModel, createMesh, run, num_runs
         fsnaps.flush(rows)
 
     pool = make_mesh_pool(nproc) if template is None else None             # forked before the GPU threads exist
+    t_files = timer()
     db = DoubleBuffer(default_device(run) if device is None else device)
+    t_ctx = timer()
     try:
         db.run([np.arange(b0, min(nrun, b0 + batch_size)) for b0 in range(0, nrun, batch_size)], prepare, solve, store)
     finally:
+        t_run = timer()
         db.close()
         if pool is not None:
             pool.close(); pool.join()
     fsnaps.close()
+    LAST_TIMINGS.clear()
+    LAST_TIMINGS.update(files_and_template_s=t_files - t_begin, cuda_context_and_handles_s=t_ctx - t_files,
+                        pipeline_s=t_run - t_ctx, close_s=timer() - t_run)
 
 
 if __name__ == '__main__':

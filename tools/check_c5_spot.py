@@ -32,4 +32,4 @@ for k, sid in enumerate(spot["ids"][:nrows]):
         errs[key] = float(np.abs(spot[key][k].ravel() - r).max() / max(np.abs(r).max(), 1e-3))
     out.append({"id": int(sid), "rank": rank, "oracle_s": time.perf_counter() - t0, "max_rel_err": max(errs.values()), "errs": errs})
     print(json.dumps(out[-1]))
-json.dump(out, open(os.path.join(ROOT, "profiles", "r02_c5_campaign_spotcheck.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "profiles", os.environ.get("SPOT_OUT", "r02_c5_campaign_spotcheck.json")), "w"), indent=1)

@@ -47,7 +47,10 @@ def main():
     buildSnapshots([0.3, 10.0, 0.3, 1.0], [bfile, pfile, sfile, os.path.join(args.dir, "meshes", "mesh_temp_%d.xdmf" % rank)],
                    'per', True, rank, world, None, batch_size=args.batch, mesher="morph", lcar=args.lcar * 1.0)
     t_rank = time.perf_counter() - t0
-    tt = torch.tensor([t_rank], dtype=torch.float64)
+    from deepbnd_b200 import simulation_snapshots as _ss
+    phases = dict(_ss.LAST_TIMINGS)
+    tt = torch.tensor([t_rank] + [phases.get(k, 0.0) for k in ("files_and_template_s", "cuda_context_and_handles_s", "pipeline_s", "close_s")],
+                      dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     if rank == 0:
@@ -72,7 +75,9 @@ def main():
         line = {"workload": "C5 campaign through buildSnapshots (files in, files out)", "n_gpus": world, "rves": ns, "per_gpu": args.per_gpu,
                 "lcar": args.lcar, "mesher": "morph (shared topology)", "batch_size": args.batch,
                 "wall_s_max_over_ranks": float(tt[0]), "rves_per_s_incl_meshing_and_file_io": ns / float(tt[0]),
-                "merge_s": t_merge, "file_bytes_per_rank": os.path.getsize(sfile)}
+                "merge_s": t_merge, "file_bytes_per_rank": os.path.getsize(sfile),
+                "phases_max_over_ranks_s": {"files_and_template": float(tt[1]), "cuda_context_and_handles": float(tt[2]),
+                                            "double_buffered_pipeline": float(tt[3]), "close": float(tt[4])}}
         print(json.dumps(line))
         open(args.out, "w").write(json.dumps(line) + "\n")
     if world > 1:
