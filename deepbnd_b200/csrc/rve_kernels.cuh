@@ -1626,7 +1626,9 @@ k_vc_mid_s(Levels LV, int l0, const int* __restrict__ active) {
 
 // Large coarse levels (>= RVE_WIDE_NODES nodes; always level 1) run as grid-wide kernels, thread per (system,
 // node), grid (ceil(G_l/256), n_sys): restriction, pre-smoothing + residual, prolongation, post-smoothing.
+#ifndef RVE_WIDE_NODES
 #define RVE_WIDE_NODES 1024
+#endif
 
 // rc_l = P^T t_{l-1} (full weighting; t vanishes outside the coarse space)
 template <int K>
