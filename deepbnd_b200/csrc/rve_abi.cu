@@ -400,7 +400,7 @@ static void launch_direction(rve_batch_s* h, const PcgArgs& a, cudaStream_t st) 
     } while (0)
 
 #ifndef RVE_COARSEST_CELLS
-#define RVE_COARSEST_CELLS 6
+#define RVE_COARSEST_CELLS 2
 #endif
 // per-batch solver state (sizes known after the numbering): vectors of the PCG scalars, the coarse hierarchy
 static int alloc_solver_state(rve_batch_s* h, int n_sys, int model, int ncx, int ncy) {
@@ -429,9 +429,9 @@ static int alloc_solver_state(rve_batch_s* h, int n_sys, int model, int ncx, int
         LV.A[L] = h->lvA[L].p; LV.dinv[L] = h->lvD[L].p; LV.rc[L] = h->lvR[L].p; LV.xc[L] = h->lvX[L].p; LV.tc[L] = h->lvT[L].p;
         LV.A4[L] = h->lvA4[L].p; LV.H4[L] = h->lvH4[L].p;
         ++L;
-        // the coarsest level keeps >= RVE_COARSEST_CELLS cells per side: deeper levels (4 x 4, 2 x 2 cells) do not change the PCG
-        // iteration counts (62.70 vs 62.78 on the full meshes, 55.31 vs 55.26 on the reduced ones, r02h) and every level
-        // costs the one-CTA-per-RVE kernel five barrier-separated phases
+        // (stopping the hierarchy at >= 6 cells per side leaves the iteration counts of per / lin / dnn unchanged and saves
+        // a few latency-bound phases per V-cycle, but the MR model -- unconstrained stiffness, rigid-body modes -- needs the deep
+        // levels: 69.8 -> 85.0 iterations on the full meshes, r02i; the hierarchy therefore goes down to 2 x 2 cells)
         if ((lcx % 2) || (lcy % 2) || lcx / 2 < RVE_COARSEST_CELLS || lcy / 2 < RVE_COARSEST_CELLS) break;
         lcx /= 2; lcy /= 2;
     }
