@@ -142,6 +142,7 @@ struct rve_batch_s {
     // matrix-free operator (rve_matfree.cuh): window-element tables; the SELL values (bval) are built on demand only
     int opt_operator = RVE_OPERATOR_MATFREE;
     bool have_bval = false;
+    bool have_emap = false;                    // element -> SELL slot map built (assembled operator only)
     int max_slots = 0;
     long long n_we = 0, n_halo = 0;
     DBuf<int> win_we0, win_nwe, we_elem;
@@ -688,7 +689,9 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     // block columns, halo lists, SELL columns, restriction lists
     const long long halo_cap = h->R + h->R / 2 + 4096;
     if (halo_cap > 2000000000LL) FAIL(RVE_E_ARG, "batch too large for 32-bit indexing: split it");
-    CU(h->csr_col.alloc((size_t)h->NB)); CU(h->emap.alloc(36 * (size_t)h->E)); CU(h->rlen.alloc((size_t)h->R));
+    CU(h->csr_col.alloc((size_t)h->NB)); CU(h->rlen.alloc((size_t)h->R));
+    h->have_emap = h->opt_operator == RVE_OPERATOR_ASSEMBLED;     // element -> slot map: only k_assemble reads it (ensure_emap otherwise)
+    if (h->have_emap) CU(h->emap.alloc(36 * (size_t)h->E));
     CU(h->sys_blocks.alloc(n_sys)); CU(cudaMemsetAsync(h->sys_blocks.p, 0, n_sys * sizeof(int), st)); CU(h->halo.alloc((size_t)halo_cap)); CU(h->scol.alloc((size_t)h->NG * 32));
     CU(h->win_halo0.alloc(n_win)); CU(h->win_nhalo.alloc(n_win)); CU(h->sym_cnt.alloc(8));
     CU(cudaMemsetAsync(h->sym_cnt.p, 0, 8 * sizeof(int), st));
@@ -698,7 +701,7 @@ int rve_set_batch(rve_handle_t h, int32_t n_sys, const int64_t* vert_off, const 
     {
         WinTab wt = win_tab(h);
         k_sym_cols<<<n_win * RVE_SYMCOLS_SPLIT, RVE_WIN / RVE_SYMCOLS_SPLIT, 0, st>>>(wt, h->d_row_ptr.p, h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->node_row.p,
-                                               h->csr_col.p, h->rlen.p, h->emap.p, h->sys_blocks.p, h->sym_cnt.p);
+                                               h->csr_col.p, h->rlen.p, h->have_emap ? h->emap.p : nullptr, h->sys_blocks.p, h->sym_cnt.p);
         DBG_SYNC("k_sym_cols");
         const size_t sm = 2 * (size_t)h->max_words * sizeof(unsigned);
         if (sm > 200 * 1024) FAIL(RVE_E_MESH, "system too large for the halo bitmap in shared memory");
@@ -869,7 +872,8 @@ static int set_batch_shared_impl(rve_handle_t h, int32_t n_sys, int32_t nv, int3
     CU(rep_i(h->win_nwe, nwin, 0, 0)); CU(rep_i(h->halo, H1, na, 0)); CU(rep_i(h->we_elem, WE1, nt, 1));
     CU(rep_s(h->node_sys, nn)); CU(rep_s(h->elem_sys, nt)); CU(rep_s(h->bnd_sys, nb)); CU(rep_s(h->win_sys, nwin));
     CU(rep_p(h->d_row_ptr, na, nblk)); CU(rep_p(h->adjf_ptr, na, nadj)); CU(rep_p(h->slice_ptr, nsl, ngrp));
-    REP_COPY(h->elem_reg, (long long)nt); REP_COPY(h->emap, 36LL * nt); REP_COPY(h->rlen, na); REP_COPY(h->row_nadj, na);
+    REP_COPY(h->elem_reg, (long long)nt); REP_COPY(h->rlen, na); REP_COPY(h->row_nadj, na);
+    if (h->have_emap) REP_COPY(h->emap, 36LL * nt);
     REP_COPY(h->win_sw, 8 * nwin); REP_COPY(h->scol, 32 * ngrp); REP_COPY(h->we_idx, 6 * WE1);
     REP_COPY(h->bedge_nl, 2 * nbe); REP_COPY(h->samp_lam, 2 * nvref); REP_COPY(h->box, 4LL);
     if (model == RVE_MODEL_DNN) REP_COPY(h->bnd_s, 2 * nb);
@@ -969,6 +973,8 @@ int rve_set_batch_morphed(rve_handle_t h, int32_t n_sys, int32_t nv, int32_t nt,
     return set_batch_shared_impl(h, n_sys, nv, nt, xy_template, tri, region, mat, model, vref_nb, vref_box, &M);
 }
 
+static int ensure_emap(rve_handle_t h);
+
 int rve_assemble(rve_handle_t h) {
     H_CHECK(h);
     if (!h->have_batch) FAIL(RVE_E_STATE, "rve_assemble before rve_set_batch");
@@ -982,6 +988,7 @@ int rve_assemble(rve_handle_t h) {
                                               h->node_row.p, h->dinv.p, h->wmean.p, h->mat);
         h->have_bval = false;
     } else {
+        if (int rc = ensure_emap(h)) return rc;
         CU(h->bval.alloc(128 * (size_t)h->NG));
         k_assemble<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), sell_tab(h), h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->elem_reg.p,
                                                   h->node_xy.p, h->node_row.p, h->emap.p, h->bval.p, h->wmean.p, h->mat);
@@ -1021,8 +1028,23 @@ int rve_assemble(rve_handle_t h) {
 }
 
 // SELL values of the assembled operator, built on demand when the batch was set up for the matrix-free one
+// element -> slot map of the assembled operator, built on demand when the batch was set for the matrix-free one:
+// k_sym_cols once more (same columns and lengths, block counts left alone)
+static int ensure_emap(rve_handle_t h) {
+    if (h->have_emap) return 0;
+    cudaStream_t st = h->stream;
+    CU(h->emap.alloc(36 * (size_t)h->E));
+    k_sym_cols<<<h->n_win * RVE_SYMCOLS_SPLIT, RVE_WIN / RVE_SYMCOLS_SPLIT, 0, st>>>(win_tab(h), h->d_row_ptr.p, h->adjf_ptr.p, h->adjf.p,
+                                                                                    h->elem_node.p, h->node_row.p, h->csr_col.p, h->rlen.p,
+                                                                                    h->emap.p, nullptr, h->sym_cnt.p);
+    h->launches += 1;
+    h->have_emap = true;
+    return 0;
+}
+
 static int ensure_bval(rve_handle_t h) {
     if (h->have_bval) return 0;
+    if (int rc = ensure_emap(h)) return rc;
     cudaStream_t st = h->stream;
     CU(h->bval.alloc(128 * (size_t)h->NG));
     k_assemble<<<h->n_win, RVE_WIN, 0, st>>>(win_tab(h), sell_tab(h), h->adjf_ptr.p, h->adjf.p, h->elem_node.p, h->elem_reg.p,

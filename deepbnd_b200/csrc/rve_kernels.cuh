@@ -164,6 +164,8 @@ k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __re
            const int* __restrict__ adjf, const int* __restrict__ elem_node, const int* __restrict__ node_row,
            int* __restrict__ csr_col, unsigned char* __restrict__ rlen, unsigned char* __restrict__ emap,
            int* __restrict__ sys_blocks, int* counters) {
+    // emap == nullptr: columns, lengths and block counts only (the element -> slot map serves the ASSEMBLED operator; it is
+    // 36 single-byte stores per element and is built on demand, with sys_blocks == nullptr, by ensure_emap)
     constexpr int TPB = RVE_WIN / RVE_SYMCOLS_SPLIT;
     constexpr int SC = 32;
     __shared__ int s_cols[SC * TPB];
@@ -182,11 +184,11 @@ k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __re
             for (int k = 0; k < 6; ++k) { rows[k] = node_row[en[k]]; if (rows[k] == r) a = k; }
             // emap[e][a][k] = SELL slot of block (row of local node a, row of local node k): k_assemble scatters
             // without searching
-            unsigned char* em = emap + (size_t)e * 36 + a * 6;
+            unsigned char* em = emap ? emap + (size_t)e * 36 + a * 6 : nullptr;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 const int c = rows[k];
-                if (c < 0) { em[k] = 0xff; continue; }
+                if (c < 0) { if (em) em[k] = 0xff; continue; }
                 // the columns found so far are searched in a shared-memory column of the thread (searching the global
                 // list re-read freshly written lines from L2: one L2 round trip per probe); rows longer than SC fall
                 // back to the global list for the tail
@@ -196,7 +198,7 @@ k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __re
                     if (cnt < cap) { cols[cnt] = c; if (cnt < SC) s_cols[cnt * TPB + threadIdx.x] = c; }
                     ++cnt;
                 }
-                em[k] = (unsigned char)j;
+                if (em) em[k] = (unsigned char)j;
             }
         }
         if (cnt > cap) { atomicExch(counters + 2, 2); cnt = cap; }
@@ -206,7 +208,7 @@ k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __re
     int v = cnt;
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(sys_blocks + wt.win_sys[w], v);
+    if (sys_blocks && (threadIdx.x & 31) == 0 && v) atomicAdd(sys_blocks + wt.win_sys[w], v);
 }
 
 __global__ void __launch_bounds__(RVE_WIN)
