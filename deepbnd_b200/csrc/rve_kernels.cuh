@@ -176,6 +176,7 @@ k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __re
         const unsigned o = row_ptr[r];
         const int cap = (int)(row_ptr[r + 1] - o);   // capacity of the row (>= its true length)
         int* cols = csr_col + o;                     // unique rows in discovery order (same order as rve_symbolic.hpp)
+        unsigned long long seen = 0ull;
         for (unsigned i = adjf_ptr[r]; i < adjf_ptr[r + 1]; ++i) {
             const int e = adjf[i];
             const int* en = elem_node + 6 * (size_t)e;
@@ -192,8 +193,12 @@ k_sym_cols(WinTab wt, const unsigned* __restrict__ row_ptr, const unsigned* __re
                 // the columns found so far are searched in a shared-memory column of the thread (searching the global
                 // list re-read freshly written lines from L2: one L2 round trip per probe); rows longer than SC fall
                 // back to the global list for the tail
-                int j = 0;
-                while (j < cnt && j < cap && (j < SC ? s_cols[j * TPB + threadIdx.x] : cols[j]) != c) ++j;
+                // (a 64-bit filter of the columns seen so far: a column whose bit is clear is new, no search; about half of
+                // the look-ups of a fan are first sightings and used to scan the whole list)
+                const unsigned long long bit = 1ull << (c & 63);
+                int j = cnt;
+                if (seen & bit) { j = 0; while (j < cnt && j < cap && (j < SC ? s_cols[j * TPB + threadIdx.x] : cols[j]) != c) ++j; }
+                seen |= bit;
                 if (j == cnt) {
                     if (cnt < cap) { cols[cnt] = c; if (cnt < SC) s_cols[cnt * TPB + threadIdx.x] = c; }
                     ++cnt;
