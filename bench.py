@@ -492,6 +492,8 @@ def main():
             traffic_ncu = dict(tj)
             ms_launch = res["spmv_ms"] / max(1.0, res["spmv_launches"] * args.steps)
             traffic_ncu["dram_gbs_at_this_run"] = tj["dram_bytes_per_rve_per_launch"] * ns / (ms_launch * 1e-3) / 1e9
+            # the kernel's distance from the HBM roofline in bytes really moved (the CSR-accounted `frac` above is a format comparison)
+            traffic_ncu["frac_of_peak_in_dram_bytes"] = traffic_ncu["dram_gbs_at_this_run"] / peak
     if spmv_as and "achieved" in spmv_as:
         spmv_as["frac"] = spmv_as["achieved"] / peak
 
