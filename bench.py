@@ -16,8 +16,8 @@ DOF extraction + projection onto a (synthetic, orthonormal) Wbasis.
           SELL-32 SpMV kernel timed alone in the same run (rve_bench_spmv).
   cpu_baseline : the CPU oracle (scipy sparse LU restatement of the reference path) timed on the
           host cores, rank-strided worker processes like the reference's MPI launch
-  extra_workloads : the other BASELINE configs (C3 dnn 10k, C4 lin, C2 MR) measured in the same run with fewer
-          steps (N = 1 only; --no-extra skips them)
+  extra_workloads : the other BASELINE configs (C3 dnn 10k, C4 lin, C2 MR, C5 resolution) measured in the same run
+          with fewer steps (N = 1 only; --no-extra skips them)
 
 `--impl reference` times only the CPU arm.  Multi-GPU (torchrun): RVEs shard by rank, no data-path
 collective, one final gather of the per-RVE outputs ("weak" scaling: per-GPU batch fixed).
@@ -50,7 +50,8 @@ WORKLOADS = {
     "C5_snapshots_refined_per": dict(ns=512, size="full", model="per", loads=(2, 0), project=True, lcar=1.0 / 30.0,
                                      mesher="morph", chunk=128),
 }
-EXTRA = {"C3_tangents_10k_reduced_dnn": 10000, "C4_tangents_10k_reduced_lin": 4000, "C2_snapshots_1k_full_MR": 1000}
+EXTRA = {"C3_tangents_10k_reduced_dnn": 10000, "C4_tangents_10k_reduced_lin": 4000, "C2_snapshots_1k_full_MR": 1000,
+         "C5_snapshots_refined_per": 256}
 
 
 def _mesh_worker(args):
