@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from deepbnd_b200.mesh.rve_morph import MorphTemplate, buildRVEmesh_morphed   # noqa: E402
 from deepbnd_b200.synthetic import synthetic_param                              # noqa: E402
